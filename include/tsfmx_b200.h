@@ -1,0 +1,214 @@
+/*
+ * tsfmx_b200 — C ABI of the B200-native multimodal forecast hot path.
+ *
+ * Drop-in boundary for the device stages behind the TSFMx adapter API
+ * (reference: /root/reference/src/tsfmx, package `tsfmx` 1.0.1).  Every entry
+ * point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream
+ * (passed as `void*`, i.e. a `cudaStream_t`), returns an int status
+ * (0 = TSFMX_OK) and never throws.  `tsfmx_last_error()` returns the message
+ * of the last failure on the calling thread.
+ *
+ * Ownership: the caller (PyTorch on the host side) allocates and owns every
+ * buffer; the library borrows pointers for the duration of the call, enqueues
+ * work on the caller's stream, performs no cudaMalloc and no host sync and
+ * keeps no reference after return.  There is no CPU fallback: on a machine
+ * without an sm_100 device every compute entry point fails with
+ * TSFMX_ERR_NO_DEVICE.
+ *
+ * Tensor conventions: row-major contiguous unless a leading dimension is
+ * given; masks are one byte per element, non-zero = padded (the tsfmx
+ * convention, reference base.py:17).
+ *
+ * Activation storage ("precision" argument of the dense entry points):
+ *   TSFMX_PREC_BF16    operands are bf16, accumulation fp32 (throughput mode)
+ *   TSFMX_PREC_BF16X3  every operand is kept as a (hi, lo) pair of bf16 with
+ *                      x ~= hi + lo (16 mantissa bits) and each product is
+ *                      evaluated as hi*hi + hi*lo + lo*hi on the same tcgen05
+ *                      kernel, fp32 accumulate (parity mode, <= 1e-3 relative
+ *                      against the fp32 reference).
+ *   A "split" matrix of logical shape [R, K] is stored as [R, 2K] bf16:
+ *   columns [0, K) hold hi, columns [K, 2K) hold lo.
+ */
+#ifndef TSFMX_B200_H_
+#define TSFMX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSFMX_ABI_VERSION 1
+
+enum {
+  TSFMX_OK = 0,
+  TSFMX_ERR_INVALID_ARGUMENT = 1,
+  TSFMX_ERR_CUDA = 2,
+  TSFMX_ERR_NO_DEVICE = 3,
+  TSFMX_ERR_UNSUPPORTED = 4
+};
+
+enum { TSFMX_PREC_BF16 = 0, TSFMX_PREC_BF16X3 = 1 };
+
+/* element storage of an output / input matrix */
+enum { TSFMX_DT_F32 = 0, TSFMX_DT_BF16 = 1, TSFMX_DT_BF16_SPLIT = 2 };
+
+enum { TSFMX_ACT_NONE = 0, TSFMX_ACT_SILU = 1, TSFMX_ACT_RELU = 2 };
+
+int tsfmx_abi_version(void);
+const char* tsfmx_last_error(void);
+/* number of kernels this library has launched on the calling process (all threads) */
+uint64_t tsfmx_launch_count(void);
+/* 0 when an sm_100 device is usable for `device` (<0: current device) */
+int tsfmx_device_check(int device);
+
+/* ------------------------------------------------------------------------
+ * HBM-bound stages
+ * ---------------------------------------------------------------------- */
+
+/*
+ * TimesFM 2.5 patchify + running RevIN statistics + normalise + mask-concat.
+ * Replaces the first half of TimesFM2p5Adapter.preprocess
+ * (reference tsfmx/tsfm/timesfm.py:53-73: reshape to patches, the N-step
+ * update_running_stats loop, revin, where(mask, 0, x), cat([x, mask])).
+ *
+ *   x          [B, C] fp32           context values
+ *   mask       [B, C] u8             non-zero = padded
+ *   patch_len  P (32 for TimesFM 2.5); C % P == 0, N = C / P
+ *   tokens     [B*N, 2P] of tokens_dtype (F32 / BF16 / BF16_SPLIT -> [B*N, 4P])
+ *              = concat(normalised values with padded->0, mask as 0/1)
+ *   mu, sigma  [B, N] fp32           cumulative mean / std after each patch
+ *   patch_mask [B, N] u8             mask of the LAST element of each patch
+ *                                    (reference timesfm.py:97 `masks[..., -1]`)
+ *   num_masked [B] int32             sum of patch_mask per series
+ * Any of mu / sigma / patch_mask / num_masked may be NULL.
+ */
+int tsfmx_timesfm_patchify_norm(const float* x, const uint8_t* mask, int64_t batch, int32_t context,
+                                int32_t patch_len, int32_t tokens_dtype, void* tokens, float* mu, float* sigma,
+                                uint8_t* patch_mask, int32_t* num_masked, void* stream);
+
+/*
+ * Chronos-2 instance-norm + arcsinh + patch(16) + time-encoding concat.
+ * Replaces Chronos2Model._prepare_patched_context as called by
+ * Chronos2Adapter.preprocess (reference tsfmx/tsfm/chronos.py:48-52).
+ *
+ *   x, mask     [B, C] fp32 / u8 (non-zero = padded; tsfmx convention)
+ *   patch       16; C is left-padded (NaN) to Cp = ceil(C/patch)*patch, N = Cp/patch
+ *   patched     [B*N, out_cols] of out_dtype = [time_enc | values | mask | zero fill]; out_cols >= 3*patch
+ *               (64 for the 48-wide Chronos-2 patch so the row is one GEMM k-block)
+ *   attn_mask   [B, N] u8   1 = patch has at least one observed point
+ *   loc, scale  [B] fp32
+ */
+int tsfmx_chronos2_patchify_norm(const float* x, const uint8_t* mask, int64_t batch, int32_t context,
+                                 int32_t patch, int32_t use_arcsinh, float time_encoding_scale,
+                                 int32_t out_dtype, int32_t out_cols, void* patched, uint8_t* attn_mask,
+                                 float* loc, float* scale, void* stream);
+
+/*
+ * Chronos-T5 MeanScaleUniformBins tokeniser (north-star item; upstream
+ * chronos.MeanScaleUniformBins.context_input_transform, not in the reference).
+ *
+ *   x         [B, C] fp32, NaN = missing
+ *   ids       [B, C+1] int64   token ids, EOS (1) appended, PAD (0) for NaN
+ *   attn_mask [B, C+1] u8
+ *   scale     [B] fp32          mean(|x|) over observed points (1 if not > 0)
+ *   boundaries[n_boundaries] fp32 device pointer, ascending (bucketize right=True)
+ */
+int tsfmx_chronos_t5_tokenize(const float* x, int64_t batch, int32_t context, const float* boundaries,
+                              int32_t n_boundaries, int32_t n_special, int32_t n_tokens, int32_t pad_id,
+                              int32_t eos_id, int64_t* ids, uint8_t* attn_mask, float* scale, void* stream);
+
+/* ids [B, L] int64 -> values [B, L] fp32 = centers[clamp(id - n_special - 1, 0, n_centers-1)] * scale[b] */
+int tsfmx_chronos_t5_dequantize(const int64_t* ids, int64_t batch, int32_t length, const float* centers,
+                                int32_t n_centers, int32_t n_special, const float* scale, float* values,
+                                void* stream);
+
+/* fp32 [rows, cols] (leading dim ld_in) -> bf16 or split-bf16 [rows, cols | 2*cols] */
+int tsfmx_cast_rows(const float* in, int64_t rows, int32_t cols, int64_t ld_in, int32_t out_dtype, void* out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------
+ * Dense stages (tcgen05 / TMEM GEMM fed by TMA)
+ * ---------------------------------------------------------------------- */
+
+/* One K-segment of a GEMM: contributes A_s[M, k] * B_s[N, k]^T to the accumulator. */
+typedef struct {
+  const void* a;  /* bf16 [M, k] (or split [M, 2k]); K-major */
+  int64_t lda;    /* elements */
+  const void* b;  /* bf16 [N, k] (or split [N, 2k]); K-major, e.g. nn.Linear.weight */
+  int64_t ldb;    /* elements */
+  int32_t k;      /* logical K of this segment; multiple of 64 */
+  int32_t reserved;
+} tsfmx_gemm_segment;
+
+/*
+ * D = epilogue( sum_s A_s * B_s^T )   with epilogue, in this order:
+ *   v = acc + bias[col]; v = act(v); v = v * row_scale[row] + row_shift[row];
+ *   v += residual[row, col]; store columns < n_store as d_dtype.
+ * Used for every Linear on the path: TimesFM tokenizer / transformer / head
+ * ResidualBlocks (two segments: hidden path + residual path), MultimodalFusion
+ * (reference fusion.py:46-47: relu epilogue + residual add), Chronos-2 blocks.
+ */
+typedef struct {
+  int64_t m;
+  int32_t n;
+  int32_t num_segments; /* 1 or 2 */
+  tsfmx_gemm_segment seg[2];
+  int32_t precision;      /* TSFMX_PREC_* : whether A/B are split matrices */
+  int32_t act;            /* TSFMX_ACT_* */
+  const float* bias;      /* [n] or NULL */
+  const float* row_scale; /* [m] or NULL */
+  const float* row_shift; /* [m] or NULL */
+  const float* residual;  /* fp32 [m, n] (ld = ldr) or NULL */
+  int64_t ldr;
+  void* d;         /* output */
+  int64_t ldd;     /* elements of d_dtype (for BF16_SPLIT: lo half starts at column split_off) */
+  int32_t d_dtype; /* TSFMX_DT_* */
+  int32_t n_store; /* store only columns < n_store (0 = n) */
+  int32_t split_off; /* BF16_SPLIT: column offset of the lo half (0 = n) */
+  int32_t reserved;
+} tsfmx_gemm_args;
+
+int tsfmx_gemm(const tsfmx_gemm_args* args, void* stream);
+
+/* y = x * rsqrt(mean(x^2) + eps) * w, rows of `cols` fp32 -> bf16 / split / f32. */
+int tsfmx_rmsnorm(const float* x, int64_t rows, int32_t cols, const float* w, float eps, int32_t out_dtype,
+                  void* out, void* stream);
+
+/*
+ * Fused post-norm + residual + next pre-norm of a TimesFM 2.5 layer
+ * (upstream Transformer.forward: `post_ln(a) + x` followed by the next
+ * `pre_ln`; HF twin modeling_timesfm2_5.py:378-388):
+ *   y   = rmsnorm(a) * w_post + x          (fp32, written to y; may alias x)
+ *   yn  = rmsnorm(y) * w_next              (bf16 / split; w_next NULL -> yn = y cast)
+ *   a is a_dtype (F32 or BF16) [rows, cols].
+ */
+int tsfmx_norm_residual_norm(const void* a, int32_t a_dtype, const float* x, int64_t rows, int32_t cols,
+                             const float* w_post, const float* w_next, float eps, float* y, int32_t yn_dtype,
+                             void* yn, void* stream);
+
+/*
+ * TimesFM 2.5 attention core for one layer (upstream MultiHeadAttention after
+ * qkv_proj; HF twin modeling_timesfm2_5.py:304-346): RoPE(q, k) with
+ * position = n - num_masked[b], RMSNorm over head_dim on q and k, per-dim
+ * softplus query scale, softmax(q k^T + causal & key-not-padded mask) v.
+ *
+ *   qkv        [B*N, 3*H*hd] of qkv_dtype (F32 or BF16): [q | k | v], head-major inside
+ *   patch_mask [B, N] u8, num_masked [B] int32
+ *   inv_freq   [hd/2] fp32;  q_ln_w, k_ln_w [hd];  q_scale [hd] = softplus(per_dim_scale)*1.442695041/sqrt(hd)
+ *   out        [B*N, H*hd] of out_dtype (BF16 / BF16_SPLIT / F32)
+ * A query whose keys are all masked attends uniformly to all N keys (what the
+ * additive finfo.min mask of the reference produces).
+ */
+int tsfmx_timesfm_attention(const void* qkv, int32_t qkv_dtype, int64_t batch, int32_t num_patches,
+                            int32_t num_heads, int32_t head_dim, const uint8_t* patch_mask,
+                            const int32_t* num_masked, const float* inv_freq, const float* q_ln_w,
+                            const float* k_ln_w, const float* q_scale, float eps, int32_t out_dtype, void* out,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TSFMX_B200_H_ */

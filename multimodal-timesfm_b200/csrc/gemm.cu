@@ -1,0 +1,502 @@
+// tcgen05 / TMEM GEMM fed by TMA — the dense workhorse of the forecast path.
+//
+//   D[M, N] = epilogue( sum_s A_s[M, K_s] * B_s[N, K_s]^T )
+//
+// A_s, B_s are bf16, K-major (row-major [rows, K]); nn.Linear.weight is already
+// [N, K] K-major so no operand is ever transposed.  Accumulation is fp32 in
+// tensor memory.  The K loop walks a list of "segments": that one mechanism
+// gives (i) ResidualBlock fusion (hidden path + residual path accumulate into
+// the same TMEM tile; reference ResidualBlock = output_layer(act(hidden)) +
+// residual_layer(x)) and (ii) the bf16x3 parity mode (hi*hi + hi*lo + lo*hi of
+// split operands) without a second kernel.
+//
+// Kernel organisation (persistent, warp-specialised, one CTA or one CTA pair per SM):
+//   warp 0    TMA producer: cp.async.bulk.tensor 2-D tiles, 128B swizzle, STAGES-deep ring
+//   warp 1    MMA issuer:   one elected thread issues tcgen05.mma (UMMA 128xBNx16, or
+//                           256xBNx16 with cta_group::2), tcgen05.commit frees smem slots
+//   warp 2    TMEM allocator (2 x BN fp32 columns: the epilogue of tile i overlaps the
+//                           MMAs of tile i+1)
+//   warps 4-7 epilogue:     tcgen05.ld 32x32b -> registers -> bias/act/affine/residual ->
+//                           vectorised global stores (f32 / bf16 / split bf16)
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace tsfmx {
+
+namespace {
+
+constexpr int BM = 128;      // rows per CTA tile (TMEM lanes)
+constexpr int BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;   // K of one tcgen05.mma kind::f16
+constexpr int MAX_XSEG = 6;  // expanded segments (2 logical x 3 split products)
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+struct XSeg {
+  int32_t a_idx, b_idx;    // which tensor map
+  int32_t a_koff, b_koff;  // element offset along K inside that tensor
+  int32_t nkb;             // number of 64-wide k-blocks
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap tma_a[2];
+  CUtensorMap tma_b[2];
+  XSeg xseg[MAX_XSEG];
+  int32_t num_xseg;
+  int32_t n;
+  int64_t m;
+  int32_t tiles_m, tiles_n;  // tiles_m counts BM*CG-row tiles
+  int32_t act, d_dtype;
+  const float* bias;
+  const float* row_scale;
+  const float* row_shift;
+  const float* residual;
+  int64_t ldr;
+  void* d;
+  int64_t ldd;
+  int32_t n_store, split_off;
+  int32_t vec_ok;  // all pointers / leading dims allow 16-byte vector access
+};
+
+template <int BN, int CG>
+struct Cfg {
+  static constexpr int B_ROWS = BN / CG;  // B rows held by one CTA
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(2 * BN <= 512, "two accumulator stages must fit in TMEM");
+  static_assert(BN % 32 == 0 && BN <= 256, "BN");
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == TSFMX_ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == TSFMX_ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+
+// Epilogue for 32 consecutive columns [col0, col0+32) of one output row.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int64_t row,
+                                               int col0) {
+  const int n_store = p.n_store;
+  if (col0 >= n_store) return;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+
+  const bool full = (col0 + 32 <= n_store) && p.vec_ok;
+  if (p.bias != nullptr) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[4 * i + 0] += b.x, v[4 * i + 1] += b.y, v[4 * i + 2] += b.z, v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < n_store) v[i] += __ldg(p.bias + col0 + i);
+    }
+  }
+  if (p.act != TSFMX_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+  }
+  if (p.row_scale != nullptr) {
+    const float s = __ldg(p.row_scale + row);
+    const float t = p.row_shift != nullptr ? __ldg(p.row_shift + row) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = v[i] * s + t;
+  }
+  if (p.residual != nullptr) {
+    const float* rp = p.residual + row * p.ldr + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
+        v[4 * i + 0] += x.x, v[4 * i + 1] += x.y, v[4 * i + 2] += x.z, v[4 * i + 3] += x.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < n_store) v[i] += rp[i];
+    }
+  }
+
+  if (p.d_dtype == TSFMX_DT_F32) {
+    float* dp = reinterpret_cast<float*>(p.d) + row * p.ldd + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(dp + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < n_store) dp[i] = v[i];
+    }
+  } else if (p.d_dtype == TSFMX_DT_BF16) {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + row * p.ldd + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q;
+        q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(dp + 8 * i) = q;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < n_store) dp[i] = __float2bfloat16_rn(v[i]);
+    }
+  } else {  // TSFMX_DT_BF16_SPLIT
+    __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.d) + row * p.ldd + col0;
+    __nv_bfloat16* lp = hp + p.split_off;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 qh, ql;
+        split_bf16x2(v[8 * i + 0], v[8 * i + 1], qh.x, ql.x);
+        split_bf16x2(v[8 * i + 2], v[8 * i + 3], qh.y, ql.y);
+        split_bf16x2(v[8 * i + 4], v[8 * i + 5], qh.z, ql.z);
+        split_bf16x2(v[8 * i + 6], v[8 * i + 7], qh.w, ql.w);
+        *reinterpret_cast<uint4*>(hp + 8 * i) = qh;
+        *reinterpret_cast<uint4*>(lp + 8 * i) = ql;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < n_store) split_bf16(v[i], hp[i], lp[i]);
+    }
+  }
+}
+
+template <int BN, int CG>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN, CG>;
+  constexpr int STAGES = C::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte aligned bases (same offset in every CTA).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES] TMA -> MMA   (leader CTA's are used when CG == 2)
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES] MMA -> TMA
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2] MMA -> epilogue
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2] epilogue -> MMA  (leader's when CG == 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a[0]);
+    tma_prefetch_desc(&p.tma_b[0]);
+    if (p.num_xseg > 1) {
+      tma_prefetch_desc(&p.tma_a[1]);
+      tma_prefetch_desc(&p.tma_b[1]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], CG);  // one arrive(+expect_tx) per producing CTA
+      mbar_init(&empty_bar[i], 1);  // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);        // one tcgen05.commit
+      mbar_init(&tmem_empty_bar[i], 4 * CG);  // one arrive per epilogue warp (of every CTA of the pair)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int first_tile = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tile_step = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        const int32_t a_row = (m_blk * CG + static_cast<int>(cta_rank)) * BM;
+        const int32_t b_row = n_blk * BN + static_cast<int>(cta_rank) * C::B_ROWS;
+        for (int s = 0; s < p.num_xseg; ++s) {
+          const XSeg sg = p.xseg[s];
+          const CUtensorMap* ta = &p.tma_a[sg.a_idx];
+          const CUtensorMap* tb = &p.tma_b[sg.b_idx];
+          for (int kb = 0; kb < sg.nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            void* sa = smem_a + stage * C::A_BYTES;
+            void* sb = smem_b + stage * C::B_BYTES;
+            if constexpr (CG == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              tma_load_2d(sa, ta, &full_bar[stage], sg.a_koff + kb * BK, a_row);
+              tma_load_2d(sb, tb, &full_bar[stage], sg.b_koff + kb * BK, b_row);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * 2);
+              else        mbar_arrive_cluster(&full_bar[stage], 0);
+              tma_load_2d_pair(sa, ta, &full_bar[stage], sg.a_koff + kb * BK, a_row);
+              tma_load_2d_pair(sb, tb, &full_bar[stage], sg.b_koff + kb * BK, b_row);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
+      uint32_t stage = 0, phase = 0, iter = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
+        const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // epilogue drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.num_xseg; ++s) {
+          const int nkb = p.xseg[s].nkb;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_umma_desc_sw128(smem_u32(smem_a + stage * C::A_BYTES));
+            const uint64_t db = make_umma_desc_sw128(smem_u32(smem_b + stage * C::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            if constexpr (CG == 1) umma_commit(&empty_bar[stage]);
+            else                   umma_commit_pair(&empty_bar[stage], 0b11);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        if constexpr (CG == 1) umma_commit(&tmem_full_bar[as]);
+        else                   umma_commit_pair(&tmem_full_bar[as], 0b11);
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t iter = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk * CG + static_cast<int>(cta_rank)) * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const int col_base = n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);  // warp-collective: issued even for out-of-range rows
+        tmem_ld_wait();
+        if (row < p.m) epilogue_chunk(p, r, row, col_base + c * 32);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[as]);
+        else                   mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &ptr, 12000, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// bf16 [rows, cols] with row stride ld (elements); box = 64 x box_rows, 128B swizzle.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return TSFMX_ERR_NO_DEVICE;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) base=%p rows=%lld cols=%lld ld=%lld", (int)r, base,
+              (long long)rows, (long long)cols, (long long)ld);
+    return TSFMX_ERR_CUDA;
+  }
+  return TSFMX_OK;
+}
+
+template <int BN, int CG>
+int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  using C = Cfg<BN, CG>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return TSFMX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  int units = num_sms() / CG;  // CTAs (or CTA pairs) resident at once: persistent grid
+  if (units > total) units = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int nattr = 0;
+  if (CG == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    nattr = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) {
+    set_error("gemm launch failed: %s", cudaGetErrorString(e));
+    return TSFMX_ERR_CUDA;
+  }
+  return check_last_launch("gemm_bf16_tcgen05");
+}
+
+int g_force_cta_group = 0;  // test hook: 0 = auto, 1 / 2 = force
+
+}  // namespace
+}  // namespace tsfmx
+
+using namespace tsfmx;
+
+extern "C" int tsfmx_gemm_set_cta_group(int cg) {
+  if (cg < 0 || cg > 2) {
+    set_error("cta_group must be 0 (auto), 1 or 2");
+    return TSFMX_ERR_INVALID_ARGUMENT;
+  }
+  g_force_cta_group = cg;
+  return TSFMX_OK;
+}
+
+extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(a != nullptr, "gemm: args is NULL");
+  TSFMX_REQUIRE(a->m > 0 && a->n > 0, "gemm: m (%lld) and n (%d) must be positive", (long long)a->m, a->n);
+  TSFMX_REQUIRE(a->n % 8 == 0, "gemm: n (%d) must be a multiple of 8", a->n);
+  TSFMX_REQUIRE(a->num_segments == 1 || a->num_segments == 2, "gemm: num_segments must be 1 or 2");
+  TSFMX_REQUIRE(a->precision == TSFMX_PREC_BF16 || a->precision == TSFMX_PREC_BF16X3, "gemm: bad precision");
+  TSFMX_REQUIRE(a->d != nullptr, "gemm: d is NULL");
+  TSFMX_REQUIRE(a->d_dtype >= TSFMX_DT_F32 && a->d_dtype <= TSFMX_DT_BF16_SPLIT, "gemm: bad d_dtype");
+  TSFMX_REQUIRE(a->act >= TSFMX_ACT_NONE && a->act <= TSFMX_ACT_RELU, "gemm: bad act");
+  TSFMX_REQUIRE(a->m < (int64_t(1) << 31) - 256, "gemm: m too large");
+  const bool split = a->precision == TSFMX_PREC_BF16X3;
+
+  int cg = g_force_cta_group;
+  if (cg == 0) cg = 2;
+  const int64_t rows_per_tile = BM * cg;
+  const int bn = 256;
+
+  GemmParams p = {};
+  p.m = a->m;
+  p.n = a->n;
+  p.tiles_m = static_cast<int32_t>((a->m + rows_per_tile - 1) / rows_per_tile);
+  p.tiles_n = (a->n + bn - 1) / bn;
+  p.act = a->act;
+  p.d_dtype = a->d_dtype;
+  p.bias = a->bias;
+  p.row_scale = a->row_scale;
+  p.row_shift = a->row_shift;
+  p.residual = a->residual;
+  p.ldr = a->ldr;
+  p.d = a->d;
+  p.ldd = a->ldd;
+  p.n_store = a->n_store > 0 ? a->n_store : a->n;
+  TSFMX_REQUIRE(p.n_store <= a->n, "gemm: n_store (%d) > n (%d)", p.n_store, a->n);
+  p.split_off = a->split_off > 0 ? a->split_off : a->n;
+  TSFMX_REQUIRE(!(a->residual != nullptr) || a->ldr >= p.n_store, "gemm: ldr too small");
+  TSFMX_REQUIRE(a->ldd >= p.n_store, "gemm: ldd too small");
+
+  const int elem = a->d_dtype == TSFMX_DT_F32 ? 4 : 2;
+  bool vec = (reinterpret_cast<uintptr_t>(a->d) % 16 == 0) && ((a->ldd * elem) % 16 == 0);
+  if (a->d_dtype == TSFMX_DT_BF16_SPLIT) vec = vec && (p.split_off % 8 == 0);
+  if (a->residual != nullptr) vec = vec && (reinterpret_cast<uintptr_t>(a->residual) % 16 == 0) && (a->ldr % 4 == 0);
+  if (a->bias != nullptr) vec = vec && (reinterpret_cast<uintptr_t>(a->bias) % 16 == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  int nx = 0;
+  for (int s = 0; s < a->num_segments; ++s) {
+    const tsfmx_gemm_segment& sg = a->seg[s];
+    TSFMX_REQUIRE(sg.a != nullptr && sg.b != nullptr, "gemm: segment %d has NULL operand", s);
+    TSFMX_REQUIRE(sg.k > 0 && sg.k % BK == 0, "gemm: segment %d k (%d) must be a positive multiple of %d", s, sg.k, BK);
+    TSFMX_REQUIRE(sg.lda % 8 == 0 && sg.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
+    TSFMX_REQUIRE(reinterpret_cast<uintptr_t>(sg.a) % 16 == 0 && reinterpret_cast<uintptr_t>(sg.b) % 16 == 0,
+                  "gemm: operands must be 16-byte aligned");
+    const int64_t cols = split ? 2 * static_cast<int64_t>(sg.k) : sg.k;
+    TSFMX_REQUIRE(sg.lda >= cols && sg.ldb >= cols, "gemm: lda/ldb smaller than the stored row length");
+    int rc = make_tmap_bf16(&p.tma_a[s], sg.a, a->m, cols, sg.lda, BM);
+    if (rc != TSFMX_OK) return rc;
+    rc = make_tmap_bf16(&p.tma_b[s], sg.b, a->n, cols, sg.ldb, bn / cg);
+    if (rc != TSFMX_OK) return rc;
+    const int nkb = sg.k / BK;
+    if (!split) {
+      p.xseg[nx++] = XSeg{s, s, 0, 0, nkb};
+    } else {
+      p.xseg[nx++] = XSeg{s, s, sg.k, 0, nkb};  // lo * hi   (small terms first)
+      p.xseg[nx++] = XSeg{s, s, 0, sg.k, nkb};  // hi * lo
+      p.xseg[nx++] = XSeg{s, s, 0, 0, nkb};     // hi * hi
+    }
+  }
+  p.num_xseg = nx;
+
+  if (cg == 2) return launch_gemm<256, 2>(p, stream);
+  return launch_gemm<256, 1>(p, stream);
+}

@@ -1,0 +1,250 @@
+"""Thin tensor-level wrappers over the C ABI: one function per entry point of ``include/tsfmx_b200.h``.
+
+PyTorch is only the allocator / stream provider here; all arithmetic happens in the CUDA library.
+Storage conventions: ``DT_BF16`` -> ``torch.bfloat16 [R, K]``; ``DT_BF16_SPLIT`` -> ``torch.bfloat16 [R, 2K]``
+(hi | lo); ``DT_F32`` -> ``torch.float32 [R, K]``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from collections.abc import Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, DT_BF16, DT_BF16_SPLIT, DT_F32, PREC_BF16, PREC_BF16X3, GemmArgs, check, ptr, stream
+
+
+def act_dtype(precision: int) -> int:
+    """Storage of a GEMM input activation for a precision mode."""
+    return DT_BF16_SPLIT if precision == PREC_BF16X3 else DT_BF16
+
+
+def alloc(rows: int, cols: int, dtype: int, device: torch.device) -> torch.Tensor:
+    if dtype == DT_F32:
+        return torch.empty(rows, cols, dtype=torch.float32, device=device)
+    if dtype == DT_BF16:
+        return torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
+    return torch.empty(rows, 2 * cols, dtype=torch.bfloat16, device=device)
+
+
+def _as_u8(mask: torch.Tensor) -> torch.Tensor:
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    if mask.dtype == torch.uint8:
+        return mask.contiguous()
+    return (mask != 0).contiguous().view(torch.uint8)
+
+
+def timesfm_patchify_norm(
+    x: torch.Tensor, mask: torch.Tensor, patch_len: int = 32, tokens_dtype: int = DT_F32
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> tokens [B*N, 2P], mu [B, N], sigma [B, N], patch_mask [B, N] (bool), num_masked [B] (int32)."""
+    _lib.require_cuda(x, mask)
+    lib = _lib.load()
+    x = x.contiguous().float()
+    m8 = _as_u8(mask)
+    b, c = x.shape
+    n = c // patch_len
+    tokens = alloc(b * n, 2 * patch_len, tokens_dtype, x.device)
+    mu = torch.empty(b, n, dtype=torch.float32, device=x.device)
+    sigma = torch.empty(b, n, dtype=torch.float32, device=x.device)
+    pm = torch.empty(b, n, dtype=torch.uint8, device=x.device)
+    nm = torch.empty(b, dtype=torch.int32, device=x.device)
+    check(
+        lib.tsfmx_timesfm_patchify_norm(
+            ptr(x), ptr(m8), b, c, patch_len, tokens_dtype, ptr(tokens), ptr(mu), ptr(sigma), ptr(pm), ptr(nm), stream()
+        )
+    )
+    return tokens, mu, sigma, pm.view(torch.bool), nm
+
+
+def chronos2_patchify_norm(
+    x: torch.Tensor,
+    mask: torch.Tensor,
+    patch: int = 16,
+    use_arcsinh: bool = True,
+    time_encoding_scale: float = 8192.0,
+    out_dtype: int = DT_F32,
+    out_cols: int | None = None,
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> patched [B*N, out_cols], attn_mask [B, N] (bool, True = observed), loc [B], scale [B]."""
+    _lib.require_cuda(x, mask)
+    lib = _lib.load()
+    x = x.contiguous().float()
+    m8 = _as_u8(mask)
+    b, c = x.shape
+    n = (c + patch - 1) // patch
+    out_cols = 3 * patch if out_cols is None else out_cols
+    patched = alloc(b * n, out_cols, out_dtype, x.device)
+    am = torch.empty(b, n, dtype=torch.uint8, device=x.device)
+    loc = torch.empty(b, dtype=torch.float32, device=x.device)
+    scale = torch.empty(b, dtype=torch.float32, device=x.device)
+    check(
+        lib.tsfmx_chronos2_patchify_norm(
+            ptr(x), ptr(m8), b, c, patch, int(use_arcsinh), float(time_encoding_scale), out_dtype, out_cols,
+            ptr(patched), ptr(am), ptr(loc), ptr(scale), stream(),
+        )
+    )
+    return patched, am.view(torch.bool), loc, scale
+
+
+def chronos_t5_tokenize(
+    x: torch.Tensor,
+    boundaries: torch.Tensor,
+    n_special: int = 2,
+    n_tokens: int = 4096,
+    pad_id: int = 0,
+    eos_id: int = 1,
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> ids [B, C+1] int64, attention_mask [B, C+1] bool, scale [B] fp32."""
+    _lib.require_cuda(x, boundaries)
+    lib = _lib.load()
+    x = x.contiguous().float()
+    boundaries = boundaries.contiguous().float()
+    b, c = x.shape
+    ids = torch.empty(b, c + 1, dtype=torch.int64, device=x.device)
+    am = torch.empty(b, c + 1, dtype=torch.uint8, device=x.device)
+    scale = torch.empty(b, dtype=torch.float32, device=x.device)
+    check(
+        lib.tsfmx_chronos_t5_tokenize(
+            ptr(x), b, c, ptr(boundaries), boundaries.numel(), n_special, n_tokens, pad_id, eos_id, ptr(ids), ptr(am),
+            ptr(scale), stream(),
+        )
+    )
+    return ids, am.view(torch.bool), scale
+
+
+def chronos_t5_dequantize(ids: torch.Tensor, centers: torch.Tensor, scale: torch.Tensor, n_special: int = 2) -> torch.Tensor:
+    _lib.require_cuda(ids, centers, scale)
+    lib = _lib.load()
+    ids = ids.contiguous()
+    centers = centers.contiguous().float()
+    scale = scale.contiguous().float()
+    b, length = ids.shape
+    out = torch.empty(b, length, dtype=torch.float32, device=ids.device)
+    check(
+        lib.tsfmx_chronos_t5_dequantize(
+            ptr(ids), b, length, ptr(centers), centers.numel(), n_special, ptr(scale), ptr(out), stream()
+        )
+    )
+    return out
+
+
+def cast_rows(x: torch.Tensor, out_dtype: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 [R, K] (row stride allowed) -> bf16 [R, K] or split bf16 [R, 2K]."""
+    _lib.require_cuda(x)
+    lib = _lib.load()
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = alloc(rows, cols, out_dtype, x.device)
+    check(lib.tsfmx_cast_rows(ptr(x), rows, cols, x.stride(0), out_dtype, ptr(out), stream()))
+    return out
+
+
+def gemm(
+    segments: Sequence[tuple[torch.Tensor, torch.Tensor, int]],
+    m: int,
+    n: int,
+    out: torch.Tensor,
+    d_dtype: int,
+    precision: int = PREC_BF16,
+    act: int = ACT_NONE,
+    bias: torch.Tensor | None = None,
+    row_scale: torch.Tensor | None = None,
+    row_shift: torch.Tensor | None = None,
+    residual: torch.Tensor | None = None,
+    n_store: int = 0,
+    ldd: int | None = None,
+    split_off: int = 0,
+) -> torch.Tensor:
+    """``out = epilogue(sum_s A_s @ B_s^T)``; each segment is (A [m, k or 2k], B [n, k or 2k], k)."""
+    lib = _lib.load()
+    args = GemmArgs()
+    args.m, args.n, args.num_segments = m, n, len(segments)
+    for i, (a, b, k) in enumerate(segments):
+        _lib.require_cuda(a, b)
+        assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+        assert a.stride(-1) == 1 and b.stride(-1) == 1
+        args.seg[i].a, args.seg[i].lda = a.data_ptr(), a.stride(0)
+        args.seg[i].b, args.seg[i].ldb = b.data_ptr(), b.stride(0)
+        args.seg[i].k = k
+    args.precision, args.act = precision, act
+    args.bias, args.row_scale, args.row_shift = ptr(bias), ptr(row_scale), ptr(row_shift)
+    args.residual = ptr(residual)
+    args.ldr = residual.stride(0) if residual is not None else 0
+    args.d = out.data_ptr()
+    args.ldd = out.stride(0) if ldd is None else ldd
+    args.d_dtype, args.n_store, args.split_off = d_dtype, n_store, split_off
+    check(lib.tsfmx_gemm(ctypes.byref(args), stream()))
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out_dtype: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    _lib.require_cuda(x, w)
+    lib = _lib.load()
+    rows, cols = x.shape
+    if out is None:
+        out = alloc(rows, cols, out_dtype, x.device)
+    check(lib.tsfmx_rmsnorm(ptr(x), rows, cols, ptr(w), eps, out_dtype, ptr(out), stream()))
+    return out
+
+
+def norm_residual_norm(
+    a: torch.Tensor,
+    x: torch.Tensor,
+    w_post: torch.Tensor | None,
+    w_next: torch.Tensor | None,
+    eps: float,
+    y: torch.Tensor | None,
+    yn_dtype: int,
+    yn: torch.Tensor | None,
+) -> None:
+    _lib.require_cuda(a, x)
+    lib = _lib.load()
+    rows, cols = x.shape
+    a_dtype = DT_BF16 if a.dtype == torch.bfloat16 else DT_F32
+    check(
+        lib.tsfmx_norm_residual_norm(
+            ptr(a), a_dtype, ptr(x), rows, cols, ptr(w_post), ptr(w_next), eps, ptr(y), yn_dtype, ptr(yn), stream()
+        )
+    )
+
+
+def timesfm_attention(
+    qkv: torch.Tensor,
+    batch: int,
+    num_patches: int,
+    num_heads: int,
+    head_dim: int,
+    patch_mask: torch.Tensor | None,
+    num_masked: torch.Tensor | None,
+    inv_freq: torch.Tensor,
+    q_ln_w: torch.Tensor,
+    k_ln_w: torch.Tensor,
+    q_scale: torch.Tensor,
+    eps: float,
+    out_dtype: int,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    _lib.require_cuda(qkv)
+    lib = _lib.load()
+    qkv_dtype = DT_BF16 if qkv.dtype == torch.bfloat16 else DT_F32
+    if out is None:
+        out = alloc(batch * num_patches, num_heads * head_dim, out_dtype, qkv.device)
+    pm = None if patch_mask is None else _as_u8(patch_mask)
+    check(
+        lib.tsfmx_timesfm_attention(
+            ptr(qkv), qkv_dtype, batch, num_patches, num_heads, head_dim, ptr(pm), ptr(num_masked), ptr(inv_freq),
+            ptr(q_ln_w), ptr(k_ln_w), ptr(q_scale), eps, out_dtype, ptr(out), stream(),
+        )
+    )
+    return out
+
+
+def split_to_float(t: torch.Tensor) -> torch.Tensor:
+    """Debug helper: split bf16 [R, 2K] -> fp32 [R, K] (hi + lo)."""
+    k = t.shape[1] // 2
+    return t[:, :k].float() + t[:, k:].float()
