@@ -1,0 +1,319 @@
+"""TimesFM 2.5 adapter (reference tsfmx/tsfm/timesfm.py:17-166), B200-native.
+
+The reference wraps the third-party ``timesfm`` torch module; here the parameters live in a plain
+container with the upstream state-dict key names (so ``google/timesfm-2.5-200m-pytorch`` safetensors
+load with ``strict=True``) and every stage runs through the C ABI:
+
+  preprocess  : fused patchify + running RevIN stats + mask-concat kernel, then the tokenizer
+                ResidualBlock as two tcgen05 GEMMs (bias + SiLU epilogue; hidden and residual paths
+                accumulated into one TMEM tile)
+  forward     : per layer  QKV GEMM -> attention kernel -> out-proj GEMM -> fused post-norm +
+                residual + pre-norm -> ff0 GEMM (SiLU epilogue) -> ff1 GEMM -> fused norms
+  postprocess : point head on the LAST patch only (the reference projects all N patches and keeps
+                ``[:, -1]``, timesfm.py:125-129) with inverse RevIN + horizon slice in the epilogue
+"""
+
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import ACT_SILU, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
+from .base import PreprocessResult, TsfmAdapter
+
+
+# --------------------------------------------------------------------------- parameter containers
+class _ResidualBlock(nn.Module):
+    """output_layer(act(hidden_layer(x))) + residual_layer(x); parameters only."""
+
+    def __init__(self, d_in: int, d_hidden: int, d_out: int, bias: bool) -> None:
+        super().__init__()
+        self.hidden_layer = nn.Linear(d_in, d_hidden, bias=bias)
+        self.output_layer = nn.Linear(d_hidden, d_out, bias=bias)
+        self.residual_layer = nn.Linear(d_in, d_out, bias=bias)
+
+
+class _RMSNorm(nn.Module):
+    def __init__(self, dims: int) -> None:
+        super().__init__()
+        self.scale = nn.Parameter(torch.ones(dims))
+
+
+class _PerDimScale(nn.Module):
+    def __init__(self, dims: int) -> None:
+        super().__init__()
+        self.per_dim_scale = nn.Parameter(torch.zeros(dims))
+
+
+class _Attention(nn.Module):
+    def __init__(self, md: int, heads: int, hd: int) -> None:
+        super().__init__()
+        self.qkv_proj = nn.Linear(md, 3 * heads * hd, bias=False)  # rows: [q | k | v], head-major inside
+        self.out = nn.Linear(heads * hd, md, bias=False)
+        self.query_ln = _RMSNorm(hd)
+        self.key_ln = _RMSNorm(hd)
+        self.per_dim_scale = _PerDimScale(hd)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, md: int, heads: int, hd: int, ff: int) -> None:
+        super().__init__()
+        self.pre_attn_ln = _RMSNorm(md)
+        self.post_attn_ln = _RMSNorm(md)
+        self.attn = _Attention(md, heads, hd)
+        self.pre_ff_ln = _RMSNorm(md)
+        self.post_ff_ln = _RMSNorm(md)
+        self.ff0 = nn.Linear(md, ff, bias=False)
+        self.ff1 = nn.Linear(ff, md, bias=False)
+
+
+class TimesFM2p5Module(nn.Module):
+    """Parameters of TimesFM 2.5 with upstream attribute / key names (p, o, os, q, md, x, ...)."""
+
+    def __init__(self, num_layers: int = 20, with_quantile_head: bool = True) -> None:
+        super().__init__()
+        self.p, self.o, self.os, self.q = 32, 128, 1024, 10
+        self.md, self.h, self.hd, self.ff, self.x = 1280, 16, 80, 1280, num_layers
+        self.eps = 1e-6
+        self.config = SimpleNamespace(decode_index=5, context_limit=16384)
+        self.tokenizer = _ResidualBlock(2 * self.p, self.md, self.md, bias=True)
+        self.stacked_xf = nn.ModuleList(_Transformer(self.md, self.h, self.hd, self.ff) for _ in range(num_layers))
+        self.output_projection_point = _ResidualBlock(self.md, self.md, self.o * self.q, bias=False)
+        if with_quantile_head:  # unused by tsfmx; kept so upstream checkpoints load strictly
+            self.output_projection_quantiles = _ResidualBlock(self.md, self.md, self.os * self.q, bias=False)
+
+
+def init_random_(model: nn.Module, seed: int = 0) -> None:
+    """Deterministic random init of EVERY tensor: Linear ~ N(0, 0.02), biases ~ N(0, 0.01),
+    RMSNorm scales 1 + 0.1 N(0, 1), per-dim scale ~ N(0, 0.5).  Generated on the CPU so the values do not
+    depend on the device."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("per_dim_scale"):
+                v = 0.5 * torch.randn(p.shape, generator=gen)
+            elif name.endswith(".scale"):
+                v = 1.0 + 0.1 * torch.randn(p.shape, generator=gen)
+            elif name.endswith(".bias"):
+                v = 0.01 * torch.randn(p.shape, generator=gen)
+            else:
+                v = 0.02 * torch.randn(p.shape, generator=gen)
+            p.copy_(v.to(p.device))
+
+
+# --------------------------------------------------------------------------- adapter
+class TimesFM2p5Adapter(TsfmAdapter):
+    """Adapter for TimesFM 2.5 (200 M layout; ``num_layers=50`` gives the "500 M" shape of BASELINE.json)."""
+
+    def __init__(self, num_layers: int = 20, precision: str = "bf16", with_quantile_head: bool = True) -> None:
+        super().__init__()
+        self._model = TimesFM2p5Module(num_layers, with_quantile_head)
+        self.set_precision(precision)
+        self._packed: dict[object, dict[str, object]] = {}
+
+    def set_precision(self, precision: str) -> None:
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        self.precision = precision
+
+    @property
+    def model_dims(self) -> int:
+        return int(self._model.md)
+
+    @property
+    def patch_len(self) -> int:
+        return int(self._model.p)
+
+    @property
+    def point_forecast_index(self) -> int:
+        return int(self._model.config.decode_index)
+
+    # ------------------------------------------------------------------ packed weights
+    def _weights(self) -> dict[str, object]:
+        """bf16 (or split-bf16) copies of the Linear weights + derived per-layer vectors, cached until a
+        parameter changes."""
+        prec = PRECISIONS[self.precision]
+        params = list(self._model.parameters())
+        key = (prec, tuple((p.data_ptr(), p._version) for p in params))
+        if key in self._packed:
+            return self._packed[key]
+        self._packed.clear()
+        m = self._model
+        adt = ops.act_dtype(prec)
+
+        def pack(lin: nn.Linear) -> torch.Tensor:
+            return ops.cast_rows(lin.weight.detach().float().contiguous(), adt)
+
+        def f32(t: torch.Tensor) -> torch.Tensor:
+            return t.detach().float().contiguous()
+
+        dev = params[0].device
+        hd = m.hd
+        w: dict[str, object] = {
+            "tok_hidden": pack(m.tokenizer.hidden_layer),
+            "tok_hidden_b": f32(m.tokenizer.hidden_layer.bias),
+            "tok_out": pack(m.tokenizer.output_layer),
+            "tok_res": pack(m.tokenizer.residual_layer),
+            "tok_out_b": f32(m.tokenizer.output_layer.bias + m.tokenizer.residual_layer.bias),
+            "head_hidden": pack(m.output_projection_point.hidden_layer),
+            "head_out": pack(m.output_projection_point.output_layer),
+            "head_res": pack(m.output_projection_point.residual_layer),
+            "inv_freq": (1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev),
+            "layers": [],
+        }
+        for xf in m.stacked_xf:
+            w["layers"].append(
+                {
+                    "pre_attn": f32(xf.pre_attn_ln.scale),
+                    "post_attn": f32(xf.post_attn_ln.scale),
+                    "pre_ff": f32(xf.pre_ff_ln.scale),
+                    "post_ff": f32(xf.post_ff_ln.scale),
+                    "qkv": pack(xf.attn.qkv_proj),
+                    "out": pack(xf.attn.out),
+                    "q_ln": f32(xf.attn.query_ln.scale),
+                    "k_ln": f32(xf.attn.key_ln.scale),
+                    "q_scale": f32(
+                        torch.nn.functional.softplus(xf.attn.per_dim_scale.per_dim_scale.detach().float())
+                        * (1.442695041 / math.sqrt(hd))
+                    ),
+                    "ff0": pack(xf.ff0),
+                    "ff1": pack(xf.ff1),
+                }
+            )
+        self._packed[key] = w
+        return w
+
+    # ------------------------------------------------------------------ stages
+    def preprocess(self, inputs: torch.Tensor, masks: torch.Tensor) -> PreprocessResult:
+        """Patch, normalise (running RevIN) and tokenize (reference timesfm.py:36-83).
+
+        Raises ValueError if the context is not a multiple of the patch length or the mask shape differs.
+        """
+        m = self._model
+        batch_size, context = inputs.shape[0], inputs.shape[1]
+        if context % m.p != 0:
+            raise ValueError(f"context length ({context}) must be divisible by patch length ({m.p})")
+        if masks.shape != inputs.shape:
+            raise ValueError(f"masks shape {masks.shape} must match inputs shape {inputs.shape}")
+        if not inputs.is_cuda:
+            raise TsfmxError("TimesFM2p5Adapter runs on B200 only; there is no CPU fallback")
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        n = context // m.p
+        rows = batch_size * n
+        masks = masks.bool()
+        tokens, mu, sigma, _pm, _nm = ops.timesfm_patchify_norm(inputs, masks, m.p, adt)
+        hidden = ops.alloc(rows, m.md, adt, inputs.device)
+        ops.gemm([(tokens, w["tok_hidden"], 2 * m.p)], rows, m.md, hidden, adt, precision=prec, act=ACT_SILU,
+                 bias=w["tok_hidden_b"])
+        emb = torch.empty(rows, m.md, dtype=torch.float32, device=inputs.device)
+        ops.gemm([(hidden, w["tok_out"], m.md), (tokens, w["tok_res"], 2 * m.p)], rows, m.md, emb, DT_F32,
+                 precision=prec, bias=w["tok_out_b"])
+        return PreprocessResult(
+            input_embeddings=emb.view(batch_size, n, m.md),
+            masks=masks.reshape(batch_size, n, m.p),
+            normalization_stats={"context_mu": mu, "context_sigma": sigma},
+        )
+
+    def forward(self, input_embeddings: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        """Run the stacked transformer layers (reference timesfm.py:85-98) -> (batch, patches, model_dims)."""
+        m = self._model
+        if not input_embeddings.is_cuda:
+            raise TsfmxError("TimesFM2p5Adapter runs on B200 only; there is no CPU fallback")
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        fast = prec == PREC_BF16
+        mid_dt = DT_BF16 if fast else DT_F32  # GEMM outputs consumed by the norm / attention kernels
+        w = self._weights()
+        b, n, d = input_embeddings.shape
+        rows = b * n
+        dev = input_embeddings.device
+        x = input_embeddings.reshape(rows, d).float().contiguous()
+        patch_mask = masks[..., -1].contiguous()  # a patch is padded iff its last step is (timesfm.py:97)
+        num_masked = patch_mask.sum(-1, dtype=torch.int32)
+        y = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        layers = w["layers"]
+        if not layers:
+            return x.view(b, n, d).clone()
+        xn = ops.rmsnorm(x, layers[0]["pre_attn"], m.eps, adt)
+        qkv = ops.alloc(rows, 3 * d, mid_dt, dev)
+        attn = ops.alloc(rows, d, adt, dev)
+        a = ops.alloc(rows, d, mid_dt, dev)
+        hbuf = ops.alloc(rows, m.ff, adt, dev)
+        for i, lw in enumerate(layers):
+            ops.gemm([(xn, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
+            ops.timesfm_attention(qkv, b, n, m.h, m.hd, patch_mask, num_masked, w["inv_freq"], lw["q_ln"], lw["k_ln"],
+                                  lw["q_scale"], m.eps, adt, out=attn)
+            ops.gemm([(attn, lw["out"], d)], rows, d, a, mid_dt, precision=prec)
+            ops.norm_residual_norm(a, x if i == 0 else y, lw["post_attn"], lw["pre_ff"], m.eps, y, adt, xn)
+            ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU)
+            ops.gemm([(hbuf, lw["ff1"], m.ff)], rows, d, a, mid_dt, precision=prec)
+            last = i == len(layers) - 1
+            ops.norm_residual_norm(a, y, lw["post_ff"], None if last else layers[i + 1]["pre_attn"], m.eps, y, adt,
+                                   None if last else xn)
+        return y.view(b, n, d)
+
+    def postprocess(
+        self,
+        horizon: int,
+        output_embeddings: torch.Tensor,
+        normalization_stats: dict[str, torch.Tensor],
+    ) -> torch.Tensor:
+        """Point/quantile head + inverse RevIN (reference timesfm.py:100-129) -> (batch, horizon, 10).
+
+        Raises ValueError if ``horizon`` exceeds the output patch length (no AR decode).
+        """
+        m = self._model
+        if horizon > m.o:
+            raise ValueError(
+                f"horizon must be <= output_patch_len ({m.o}), got {horizon}. AR decode is not supported."
+            )
+        if not output_embeddings.is_cuda:
+            raise TsfmxError("TimesFM2p5Adapter runs on B200 only; there is no CPU fallback")
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        b, n, d = output_embeddings.shape
+        emb = output_embeddings.float()
+        if emb.stride(-1) != 1 or emb.stride(1) != d:
+            emb = emb.contiguous()
+        last = emb[:, -1, :]  # only the last patch reaches the output (timesfm.py:129)
+        mu_last = normalization_stats["context_mu"][:, -1].contiguous()
+        sigma_last = normalization_stats["context_sigma"][:, -1].contiguous()
+        a = ops.cast_rows(last, adt)
+        hid = ops.alloc(b, m.md, adt, emb.device)
+        ops.gemm([(a, w["head_hidden"], d)], b, m.md, hid, adt, precision=prec, act=ACT_SILU)
+        out = torch.empty(b, horizon * m.q, dtype=torch.float32, device=emb.device)
+        ops.gemm([(hid, w["head_out"], m.md), (a, w["head_res"], d)], b, m.o * m.q, out, DT_F32, precision=prec,
+                 row_scale=sigma_last, row_shift=mu_last, n_store=horizon * m.q)
+        return out.view(b, horizon, m.q)
+
+    # ------------------------------------------------------------------ checkpoints / freezing
+    def load_checkpoint(self, path: str) -> None:
+        """Load upstream TimesFM 2.5 safetensors (strict), reference timesfm.py:131-134."""
+        from safetensors.torch import load_file
+
+        self._model.load_state_dict(load_file(path), strict=True)
+
+    @classmethod
+    def from_pretrained(cls, device: torch.device, repo_id: str = "google/timesfm-2.5-200m-pytorch") -> "TimesFM2p5Adapter":
+        """Download + load pretrained weights (reference timesfm.py:136-158); needs network access."""
+        from huggingface_hub import hf_hub_download
+
+        instance = cls()
+        instance.to(device)
+        instance.load_checkpoint(hf_hub_download(repo_id=repo_id, filename="model.safetensors"))
+        return instance
+
+    def freeze_parameters(self) -> None:
+        for param in self.parameters():
+            param.requires_grad = False
+
+    def unfreeze_parameters(self) -> None:
+        for param in self.parameters():
+            param.requires_grad = True
