@@ -171,6 +171,8 @@ typedef struct {
 } tsfmx_gemm_args;
 
 int tsfmx_gemm(const tsfmx_gemm_args* args, void* stream);
+/* test / tuning hook: 0 = automatic, 1 = one CTA per tile (UMMA 128xN), 2 = CTA pairs (cta_group::2, UMMA 256xN) */
+int tsfmx_gemm_set_cta_group(int cta_group);
 
 /* y = x * rsqrt(mean(x^2) + eps) * w, rows of `cols` fp32 -> bf16 / split / f32. */
 int tsfmx_rmsnorm(const float* x, int64_t rows, int32_t cols, const float* w, float eps, int32_t out_dtype,
@@ -206,6 +208,9 @@ int tsfmx_timesfm_attention(const void* qkv, int32_t qkv_dtype, int64_t batch, i
                             const int32_t* num_masked, const float* inv_freq, const float* q_ln_w,
                             const float* k_ln_w, const float* q_scale, float eps, int32_t out_dtype, void* out,
                             void* stream);
+
+/* test hook: non-zero forces the fp32 SIMT attention kernel even where the tensor-core kernel applies */
+int tsfmx_attention_force_simt(int on);
 
 #ifdef __cplusplus
 }

@@ -175,6 +175,330 @@ __global__ void timesfm_attention_kernel(const void* __restrict__ qkv, int64_t b
   }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Tensor-core version for the throughput mode (bf16 qkv in, bf16 out).
+//
+// One warp owns one (series, head).  Its q/k/v rows (N x 80 bf16 each, 160-byte row segments of the
+// [B*N, 3*H*hd] qkv matrix) are fetched with 16-byte cp.async into padded shared-memory tiles, q and k
+// are conditioned in place in fp32 (RoPE from a per-block cos/sin table, RMSNorm over head_dim,
+// per-dim query scale; two lanes per row), and the products S = Q K^T and O = P V run on
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32) with ldmatrix-fed fragments.  Sequences here have at most
+// 64 patches, so a whole score row block lives in registers: no online-softmax rescaling is needed.
+// tcgen05 is deliberately not used: its minimum tile is 64 rows and a head has 16 (ctx 512).
+// ----------------------------------------------------------------------------------------
+constexpr int MMA_HD = 80;
+constexpr int MMA_LD = 88;  // padded row (176 B): ldmatrix rows land in distinct bank groups
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NT>  // number of 16-row tiles: N <= 16 * NT
+__global__ void __launch_bounds__(256) timesfm_attention_mma_kernel(
+    const __nv_bfloat16* __restrict__ qkv, int64_t batch, int num_patches, int num_heads,
+    const uint8_t* __restrict__ patch_mask, const int32_t* __restrict__ num_masked,
+    const float* __restrict__ inv_freq, const float* __restrict__ q_ln_w, const float* __restrict__ k_ln_w,
+    const float* __restrict__ q_scale, float eps, __nv_bfloat16* __restrict__ out) {
+  constexpr int ROWS = 16 * NT;
+  constexpr int HALF = MMA_HD / 2;          // 40 rotary pairs
+  constexpr int TILE = ROWS * MMA_LD;       // elements per q / k / v tile
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  float2* s_rope = reinterpret_cast<float2*>(smem_attn);                  // [2 * ROWS][40] (cos, sin)
+  float* s_wq = reinterpret_cast<float*>(s_rope + 2 * ROWS * HALF);       // [80] q_ln_w * q_scale
+  float* s_wk = s_wq + MMA_HD;                                            // [80] k_ln_w
+  __nv_bfloat16* s_tiles = reinterpret_cast<__nv_bfloat16*>(s_wk + MMA_HD);
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = num_patches;
+  __nv_bfloat16* sQ = s_tiles + warp * 3 * TILE;
+  __nv_bfloat16* sK = sQ + TILE;
+  __nv_bfloat16* sV = sK + TILE;
+
+  // ---- per-block tables: cos/sin of (pos * inv_freq) for pos in [-N, N), and the folded norm weights
+  for (int i = threadIdx.x; i < 2 * N * HALF; i += blockDim.x) {
+    const int p = i / HALF, f = i - p * HALF;
+    float sn, cs;
+    sincosf(static_cast<float>(p - N) * __ldg(inv_freq + f), &sn, &cs);
+    s_rope[i] = make_float2(cs, sn);
+  }
+  for (int i = threadIdx.x; i < MMA_HD; i += blockDim.x) {
+    s_wq[i] = __ldg(q_ln_w + i) * __ldg(q_scale + i);
+    s_wk[i] = __ldg(k_ln_w + i);
+  }
+  __syncthreads();
+
+  const int width = num_heads * MMA_HD;
+  const int64_t qkv_ld = 3 * static_cast<int64_t>(width);
+  const int64_t total = batch * num_heads;
+  const int g = lane >> 2, t = lane & 3;
+  const int ntk = (N + 15) >> 4;  // 16-row tiles actually populated
+
+  for (int64_t unit = static_cast<int64_t>(blockIdx.x) * warps_per_block + warp; unit < total;
+       unit += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+    const int64_t b = unit / num_heads;
+    const int h = static_cast<int>(unit - b * num_heads);
+    const int nm = num_masked != nullptr ? num_masked[b] : 0;
+
+    // ---- async fetch of the raw q / k / v rows (10 x 16 B per row)
+    const __nv_bfloat16* gbase = qkv + b * N * qkv_ld + h * MMA_HD;
+    for (int c = lane; c < 3 * N * 10; c += 32) {
+      const int which = c / (N * 10);
+      const int rem = c - which * (N * 10);
+      const int row = rem / 10, ch = rem - row * 10;
+      cp_async_16(sQ + which * TILE + row * MMA_LD + ch * 8, gbase + row * qkv_ld + which * width + ch * 8);
+    }
+    // rows beyond N (only when N is not a multiple of 16): zero so the MMAs see finite data
+    for (int c = lane; c < 3 * (ntk * 16 - N) * 10; c += 32) {
+      const int which = c / ((ntk * 16 - N) * 10);
+      const int rem = c - which * ((ntk * 16 - N) * 10);
+      const int row = N + rem / 10, ch = rem % 10;
+      *reinterpret_cast<uint4*>(sQ + which * TILE + row * MMA_LD + ch * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // valid-key bitmask (bit j: key j exists and is not padded)
+    uint64_t kmask = 0;
+    {
+      const bool v0 = lane < N && (patch_mask == nullptr || patch_mask[b * N + lane] == 0);
+      const bool v1 = lane + 32 < N && (patch_mask == nullptr || patch_mask[b * N + lane + 32] == 0);
+      kmask = static_cast<uint64_t>(__ballot_sync(0xffffffffu, v0)) |
+              (static_cast<uint64_t>(__ballot_sync(0xffffffffu, v1)) << 32);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    // ---- condition q and k in place: lane pair (2r, 2r+1) owns row r; each lane 20 rotary pairs
+#pragma unroll
+    for (int rt = 0; rt < NT; ++rt) {
+      const int r = rt * 16 + (lane >> 1);
+      if (rt < ntk) {
+        const int hf = lane & 1;
+        const bool live = r < N;
+        const float2* rope = s_rope + (live ? (r - nm + N) : 0) * HALF + 20 * hf;
+        __nv_bfloat16* qrow = sQ + r * MMA_LD + 20 * hf;
+        __nv_bfloat16* krow = sK + r * MMA_LD + 20 * hf;
+        float q1[20], q2[20], k1[20], k2[20];
+        float qss = 0.f, kss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const uint2 a1 = *reinterpret_cast<const uint2*>(qrow + 4 * i);
+          const uint2 a2 = *reinterpret_cast<const uint2*>(qrow + HALF + 4 * i);
+          const uint2 c1 = *reinterpret_cast<const uint2*>(krow + 4 * i);
+          const uint2 c2 = *reinterpret_cast<const uint2*>(krow + HALF + 4 * i);
+          const uint32_t aw1[2] = {a1.x, a1.y}, aw2[2] = {a2.x, a2.y}, cw1[2] = {c1.x, c1.y}, cw2[2] = {c2.x, c2.y};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int idx = 4 * i + e;
+            const float2 cssn = rope[idx];
+            auto pick = [&](const uint32_t(&w)[2]) {
+              const uint32_t word = w[e >> 1];
+              return __uint_as_float((e & 1) ? (word & 0xffff0000u) : (word << 16));
+            };
+            const float x1 = pick(aw1), x2 = pick(aw2), y1 = pick(cw1), y2 = pick(cw2);
+            q1[idx] = x1 * cssn.x - x2 * cssn.y;
+            q2[idx] = x2 * cssn.x + x1 * cssn.y;
+            k1[idx] = y1 * cssn.x - y2 * cssn.y;
+            k2[idx] = y2 * cssn.x + y1 * cssn.y;
+            qss += q1[idx] * q1[idx] + q2[idx] * q2[idx];
+            kss += k1[idx] * k1[idx] + k2[idx] * k2[idx];
+          }
+        }
+        qss += __shfl_xor_sync(0xffffffffu, qss, 1);
+        kss += __shfl_xor_sync(0xffffffffu, kss, 1);
+        const float qrs = rsqrtf(qss * (1.0f / MMA_HD) + eps);
+        const float krs = rsqrtf(kss * (1.0f / MMA_HD) + eps);
+        const float* wq1 = s_wq + 20 * hf;
+        const float* wk1 = s_wk + 20 * hf;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          uint2 o1, o2, p1, p2;
+          o1.x = pack_bf16x2(q1[4 * i] * qrs * wq1[4 * i], q1[4 * i + 1] * qrs * wq1[4 * i + 1]);
+          o1.y = pack_bf16x2(q1[4 * i + 2] * qrs * wq1[4 * i + 2], q1[4 * i + 3] * qrs * wq1[4 * i + 3]);
+          o2.x = pack_bf16x2(q2[4 * i] * qrs * wq1[HALF + 4 * i], q2[4 * i + 1] * qrs * wq1[HALF + 4 * i + 1]);
+          o2.y = pack_bf16x2(q2[4 * i + 2] * qrs * wq1[HALF + 4 * i + 2], q2[4 * i + 3] * qrs * wq1[HALF + 4 * i + 3]);
+          p1.x = pack_bf16x2(k1[4 * i] * krs * wk1[4 * i], k1[4 * i + 1] * krs * wk1[4 * i + 1]);
+          p1.y = pack_bf16x2(k1[4 * i + 2] * krs * wk1[4 * i + 2], k1[4 * i + 3] * krs * wk1[4 * i + 3]);
+          p2.x = pack_bf16x2(k2[4 * i] * krs * wk1[HALF + 4 * i], k2[4 * i + 1] * krs * wk1[HALF + 4 * i + 1]);
+          p2.y = pack_bf16x2(k2[4 * i + 2] * krs * wk1[HALF + 4 * i + 2], k2[4 * i + 3] * krs * wk1[HALF + 4 * i + 3]);
+          if (live) {
+            *reinterpret_cast<uint2*>(qrow + 4 * i) = o1;
+            *reinterpret_cast<uint2*>(qrow + HALF + 4 * i) = o2;
+            *reinterpret_cast<uint2*>(krow + 4 * i) = p1;
+            *reinterpret_cast<uint2*>(krow + HALF + 4 * i) = p2;
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- per 16-query tile: S = Q K^T (tensor cores) -> masked softmax (registers) -> O = P V
+    const uint32_t sq_addr = smem_u32(sQ), sk_addr = smem_u32(sK), sv_addr = smem_u32(sV);
+#pragma unroll
+    for (int qi = 0; qi < NT; ++qi) {
+      if (qi < ntk) {
+        uint32_t qa[5][4];
+        {
+          const int row = qi * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+          const int col = 8 * (lane >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks) ldmatrix_x4(sq_addr + (row * MMA_LD + col + 16 * ks) * 2, qa[ks]);
+        }
+        const int row0 = qi * 16 + g, row1 = row0 + 8;
+        // a row whose keys are all masked attends uniformly to ALL N keys (additive finfo.min mask)
+        const bool dead0 = (kmask & ((2ull << row0) - 1ull)) == 0ull;
+        const bool dead1 = (kmask & ((2ull << row1) - 1ull)) == 0ull;
+        const bool any_dead = __any_sync(0xffffffffu, (dead0 && row0 < N) || (dead1 && row1 < N));
+        const int kj_end = any_dead ? ntk : qi + 1;
+
+        float s[NT][2][4];
+#pragma unroll
+        for (int kj = 0; kj < NT; ++kj) {
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[kj][nt][e] = 0.f;
+          if (kj <= qi) {
+            const int key = kj * 16 + (lane & 7) + 8 * (lane >> 4);
+            const int col = 8 * ((lane >> 3) & 1);
+#pragma unroll
+            for (int ks = 0; ks < 5; ++ks) {
+              uint32_t kb[4];
+              ldmatrix_x4(sk_addr + (key * MMA_LD + col + 16 * ks) * 2, kb);
+              mma_bf16_16816(s[kj][0], qa[ks], kb[0], kb[1]);
+              mma_bf16_16816(s[kj][1], qa[ks], kb[2], kb[3]);
+            }
+          }
+        }
+        // mask + row max
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int kj = 0; kj < NT; ++kj)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int key = kj * 16 + nt * 8 + 2 * t + (e & 1);
+              const int row = (e & 2) ? row1 : row0;
+              const bool ok = kj <= qi && key <= row && ((kmask >> key) & 1ull);
+              const float v = ok ? s[kj][nt][e] : -INFINITY;
+              s[kj][nt][e] = v;
+              if (e & 2) mx1 = fmaxf(mx1, v); else mx0 = fmaxf(mx0, v);
+            }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int kj = 0; kj < NT; ++kj)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int key = kj * 16 + nt * 8 + 2 * t + (e & 1);
+              const bool dead = (e & 2) ? dead1 : dead0;
+              const float mx = (e & 2) ? mx1 : mx0;
+              float p;
+              if (dead) p = key < N ? 1.f : 0.f;
+              else p = s[kj][nt][e] == -INFINITY ? 0.f : __expf(s[kj][nt][e] - mx);
+              s[kj][nt][e] = p;
+              if (e & 2) sum1 += p; else sum0 += p;
+            }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+        float o[10][4];
+#pragma unroll
+        for (int dt = 0; dt < 10; ++dt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
+#pragma unroll
+        for (int kj = 0; kj < NT; ++kj) {
+          if (kj < kj_end) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[kj][0][0], s[kj][0][1]);
+            pa[1] = pack_bf16x2(s[kj][0][2], s[kj][0][3]);
+            pa[2] = pack_bf16x2(s[kj][1][0], s[kj][1][1]);
+            pa[3] = pack_bf16x2(s[kj][1][2], s[kj][1][3]);
+            const int key = kj * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+            const int col = 8 * (lane >> 4);
+#pragma unroll
+            for (int dp = 0; dp < 5; ++dp) {
+              uint32_t vb[4];
+              ldmatrix_x4_trans(sv_addr + (key * MMA_LD + col + 16 * dp) * 2, vb);
+              mma_bf16_16816(o[2 * dp], pa, vb[0], vb[1]);
+              mma_bf16_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+            }
+          }
+        }
+        // the Q rows of this tile are dead now: stage the normalised output there for coalesced stores
+        __syncwarp();
+#pragma unroll
+        for (int dt = 0; dt < 10; ++dt) {
+          *reinterpret_cast<uint32_t*>(sQ + row0 * MMA_LD + dt * 8 + 2 * t) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+          *reinterpret_cast<uint32_t*>(sQ + row1 * MMA_LD + dt * 8 + 2 * t) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+        }
+      }
+    }
+    __syncwarp();
+    __nv_bfloat16* obase = out + b * N * width + h * MMA_HD;
+    for (int c = lane; c < N * 10; c += 32) {
+      const int row = c / 10, ch = c - row * 10;
+      *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * width + ch * 8) =
+          *reinterpret_cast<const uint4*>(sQ + row * MMA_LD + ch * 8);
+    }
+    __syncwarp();
+  }
+}
+
+template <int NT>
+int launch_attention_mma(const void* qkv, int64_t batch, int N, int H, const uint8_t* pm, const int32_t* nm,
+                         const float* inv_freq, const float* qw, const float* kw, const float* qs, float eps, void* out,
+                         cudaStream_t stream) {
+  constexpr int ROWS = 16 * NT;
+  constexpr int per_warp = 3 * ROWS * MMA_LD * 2;
+  constexpr int fixed = 2 * ROWS * 40 * 8 + 2 * MMA_HD * 4;
+  int wpb = (200 * 1024 - fixed) / per_warp;
+  if (wpb > 8) wpb = 8;
+  const int smem = fixed + wpb * per_warp;
+  auto kern = timesfm_attention_mma_kernel<NT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("timesfm_attention: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+      return TSFMX_ERR_CUDA;
+    }
+  }
+  const int64_t total = batch * H;
+  const int64_t blocks = (total + wpb - 1) / wpb;
+  const int per_sm = (220 * 1024) / smem > 0 ? (220 * 1024) / smem : 1;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  kern<<<grid, wpb * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), batch, N, H, pm, nm, inv_freq, qw,
+                                          kw, qs, eps, reinterpret_cast<__nv_bfloat16*>(out));
+  return check_last_launch("timesfm_attention_mma");
+}
+
 template <int HD, int QKV_BF16>
 int launch_attention(const void* qkv, int64_t batch, int N, int H, const uint8_t* pm, const int32_t* nm,
                      const float* inv_freq, const float* qw, const float* kw, const float* qs, float eps, int out_dtype,
@@ -207,10 +531,17 @@ int launch_attention(const void* qkv, int64_t batch, int N, int H, const uint8_t
   return launch(timesfm_attention_kernel<HD, QKV_BF16, TSFMX_DT_BF16_SPLIT>);
 }
 
+int g_force_simt = 0;  // test hook
+
 }  // namespace
 }  // namespace tsfmx
 
 using namespace tsfmx;
+
+extern "C" int tsfmx_attention_force_simt(int on) {
+  g_force_simt = on ? 1 : 0;
+  return TSFMX_OK;
+}
 
 extern "C" int tsfmx_timesfm_attention(const void* qkv, int32_t qkv_dtype, int64_t batch, int32_t num_patches,
                                        int32_t num_heads, int32_t head_dim, const uint8_t* patch_mask,
@@ -229,6 +560,17 @@ extern "C" int tsfmx_timesfm_attention(const void* qkv, int32_t qkv_dtype, int64
     return TSFMX_ERR_UNSUPPORTED;
   }
   if (batch == 0) return TSFMX_OK;
+  const bool aligned = reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  if (qkv_dtype == TSFMX_DT_BF16 && out_dtype == TSFMX_DT_BF16 && aligned && num_patches <= 64 && !g_force_simt) {
+    if (num_patches <= 16)
+      return launch_attention_mma<1>(qkv, batch, num_patches, num_heads, patch_mask, num_masked, inv_freq, q_ln_w,
+                                     k_ln_w, q_scale, eps, out, stream);
+    if (num_patches <= 32)
+      return launch_attention_mma<2>(qkv, batch, num_patches, num_heads, patch_mask, num_masked, inv_freq, q_ln_w,
+                                     k_ln_w, q_scale, eps, out, stream);
+    return launch_attention_mma<4>(qkv, batch, num_patches, num_heads, patch_mask, num_masked, inv_freq, q_ln_w,
+                                   k_ln_w, q_scale, eps, out, stream);
+  }
   if (qkv_dtype == TSFMX_DT_BF16)
     return launch_attention<80, 1>(qkv, batch, num_patches, num_heads, patch_mask, num_masked, inv_freq, q_ln_w, k_ln_w,
                                    q_scale, eps, out_dtype, out, stream);

@@ -65,13 +65,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-// Arrive on the same barrier offset inside CTA `cta` of the cluster.
+// Arrive on the same barrier offset inside CTA `cta` of the cluster.  Default (.release.cta) semantics on
+// purpose: a `.release.cluster` arrive compiles to MEMBAR.ALL.GPU + ERRBAR per call, which throttled the
+// non-leader TMA producer to ~1 k-block/us (ncu source page, profiles/r1_gemm_notes.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 remote;\n\t"
       "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");

@@ -95,6 +95,7 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
         [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p,
          c_void_p],
     ),
+    "tsfmx_attention_force_simt": (c_int32, [c_int32]),
     "tsfmx_timesfm_attention": (
         c_int32,
         [c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,0 +1,84 @@
+"""Generate the golden vectors under tests/golden/ (run in the build container, where /root/reference exists).
+
+    python tests/golden/make_golden.py
+
+The reference ships no fixtures for this path (its tests/ directory is empty), so the vectors are produced by
+running the reference's OWN ``MultimodalDecoder`` + ``MultimodalFusion`` (imported from
+/root/reference/src) around the oracle adapter (oracle/timesfm_oracle.py) on seeded inputs and seeded
+random-init weights.  Weights are not stored: they are regenerated from the seed by
+``tsfmx_b200.tsfm.timesfm.init_random_`` (CPU torch generator) and ``torch.manual_seed`` (fusion Xavier init).
+"""
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT / "multimodal-timesfm_b200"))
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, "/root/reference/src")
+
+from oracle import chronos_t5_oracle as T5  # noqa: E402
+from oracle import timesfm_oracle as O  # noqa: E402
+from tsfmx.decoder import MultimodalDecoder as RefDecoder  # noqa: E402  (the reference's real class)
+from tsfmx.decoder import MultimodalDecoderConfig as RefConfig  # noqa: E402
+from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig  # noqa: E402
+from tsfmx_b200.tsfm.timesfm import TimesFM2p5Adapter, init_random_  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def timesfm_case(name, num_layers, batch, context, horizon, padded, fusion_layers=1, hidden=(), seed=0):
+    adapter = TimesFM2p5Adapter(num_layers=num_layers, with_quantile_head=False)
+    init_random_(adapter, seed=seed)
+    torch.manual_seed(seed + 100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, fusion_layers, list(hidden)))
+    oracle = O.oracle_from_product(dec)
+    ref = RefDecoder(oracle.adapter, RefConfig(384, fusion_layers, list(hidden))).eval()
+    ref.fusion.load_state_dict(oracle.fusion.state_dict())
+    ctx, masks, text, _ = O.synthetic_batch(batch, context, horizon, padded=padded, seed=1234 + seed)
+    text = text.half().float()  # stored as fp16: round first so both sides see identical inputs
+    with torch.no_grad():
+        pre = ref.adapter.preprocess(ctx, masks)
+        full = ref.forward_full(horizon, ctx, masks, text)
+        point = ref(horizon, ctx, masks, text)
+        no_text = ref.forward_full(horizon, ctx, masks, None)
+    np.savez_compressed(
+        OUT / f"{name}.npz",
+        num_layers=num_layers, fusion_layers=fusion_layers, hidden=np.array(hidden, dtype=np.int64), seed=seed,
+        horizon=horizon, context=ctx.numpy(), masks=masks.numpy(), text=text.numpy().astype(np.float16),
+        context_mu=pre.normalization_stats["context_mu"].numpy(),
+        context_sigma=pre.normalization_stats["context_sigma"].numpy(),
+        patch_mask=pre.masks[..., -1].numpy(),
+        emb_checksum=pre.input_embeddings.double().sum(-1).numpy(),
+        forecast=full.numpy(), point=point.numpy(), forecast_no_text=no_text.numpy(),
+    )
+    print(name, full.shape, float(full.abs().max()))
+
+
+def t5_case():
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(16, 512, generator=g) * torch.rand(16, 1, generator=g) * 8
+    x[0, :9] = float("nan")
+    x[1] = float("nan")
+    x[2] = 0.0
+    x[3] *= 1e3
+    x[5] *= 0.01
+    x[5, 100], x[5, 200] = 1e6, -1e6  # outliers -> clamp to the outer bins
+    centers, boundaries = T5.tables()
+    x[4, :500] = boundaries[1800:2300]
+    ids, am, scale = T5.tokenize(x, boundaries)
+    np.savez_compressed(OUT / "chronos_t5_tokens.npz", x=x.numpy(), ids=ids.numpy().astype(np.int16),
+                        attention_mask=am.numpy(), scale=scale.numpy())
+    print("t5", ids.shape, int(ids.min()), int(ids.max()))
+
+
+if __name__ == "__main__":
+    # text embeddings are stored as fp16 to keep the fixtures small; the tests up-cast the stored values, so the
+    # inputs are identical on both sides.
+    timesfm_case("timesfm_l2_b4_c512_h128", 2, 4, 512, 128, padded=True)
+    timesfm_case("timesfm_l20_b2_c512_h128", 20, 2, 512, 128, padded=False, seed=1)
+    timesfm_case("timesfm_l2_b3_c2048_h64_f2", 2, 3, 2048, 64, padded=True, fusion_layers=2, hidden=(512,), seed=2)
+    t5_case()

@@ -228,7 +228,8 @@ def test_chronos_t5_tokenize_bit_exact(context):
     x[0, :5] = float("nan")
     x[1] = float("nan")  # fully missing series -> scale 1, all PAD
     x[2] = 0.0  # scale not > 0 -> 1
-    x[3] *= 1e4  # clamps at the outer bins
+    x[3] *= 0.01
+    x[3, 10], x[3, 20] = 1e6, -1e6  # outliers -> clamp to the outer bins
     centers, boundaries = _t5_tables()
     # exact hits on bin boundaries (right=True tie rule)
     x[4, : min(context, 4094)] = boundaries[: min(context, 4094)].clamp(-1e4, 1e4)
@@ -378,3 +379,36 @@ def test_timesfm_attention(n, qkv_bf16):
     assert _rel(out, ref) < 2e-5
     out_s = ops.timesfm_attention(qkv, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6, DT_BF16_SPLIT)
     assert _rel(ops.split_to_float(out_s), ref) < 5e-5
+
+
+@pytest.mark.parametrize("n", [16, 64, 5, 32, 40, 1])
+def test_timesfm_attention_tensor_core_path(n):
+    """bf16 in / bf16 out goes through the mma.sync kernel; the fp32 SIMT kernel is the yardstick as well."""
+    b, h, hd = 37, 16, 80
+    gen = torch.Generator(device=DEV).manual_seed(100 + n)
+    qkv = torch.randn(b * n, 3 * h * hd, generator=gen, device=DEV).to(torch.bfloat16)
+    pm = torch.zeros(b, n, dtype=torch.bool, device=DEV)
+    pm[1, : n // 2] = True
+    pm[2, :1] = True
+    pm[3, :] = True
+    pm[4, : n - 1] = True
+    nm = pm.sum(-1).int()
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd)).to(DEV)
+    qw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    kw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    per_dim = 0.5 * torch.randn(hd, generator=gen, device=DEV)
+    q_scale = (torch.nn.functional.softplus(per_dim) * (1.442695041 / math.sqrt(hd))).contiguous()
+    ref = _ref_attention(qkv.float(), b, n, h, hd, pm, inv_freq, qw, kw, per_dim)
+    lib = _lib.load()
+    c0 = _lib.launch_count()
+    out = ops.timesfm_attention(qkv, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6, DT_BF16)
+    assert _lib.launch_count() == c0 + 1
+    _lib.check(lib.tsfmx_attention_force_simt(1))
+    try:
+        simt = ops.timesfm_attention(qkv, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6, DT_BF16)
+    finally:
+        _lib.check(lib.tsfmx_attention_force_simt(0))
+    assert not torch.isnan(out.float()).any()
+    assert _rel(simt.float(), ref) < 6e-3
+    assert _rel(out.float(), ref) < 2e-2, _rel(out.float(), ref)
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2

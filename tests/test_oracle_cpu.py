@@ -1,0 +1,137 @@
+"""CPU tests of the oracle: against the committed golden vectors, against the reference's own classes (when
+/root/reference is present, i.e. in the build container) and against the HF TimesFM-2.5 port."""
+
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import chronos_t5_oracle as T5
+from oracle import timesfm_oracle as O
+from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig
+from tsfmx_b200.tsfm.timesfm import TimesFM2p5Adapter, init_random_
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+REF_SRC = Path("/root/reference/src")
+
+
+def build_pair(num_layers, fusion_layers=1, hidden=(), seed=0):
+    adapter = TimesFM2p5Adapter(num_layers=num_layers, with_quantile_head=False)
+    init_random_(adapter, seed=seed)
+    torch.manual_seed(seed + 100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, fusion_layers, list(hidden)))
+    return dec, O.oracle_from_product(dec)
+
+
+def load_case(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize(
+    "name", ["timesfm_l2_b4_c512_h128", "timesfm_l20_b2_c512_h128", "timesfm_l2_b3_c2048_h64_f2"]
+)
+def test_oracle_reproduces_golden(name):
+    g = load_case(name)
+    _, oracle = build_pair(int(g["num_layers"]), int(g["fusion_layers"]), tuple(g["hidden"].tolist()), int(g["seed"]))
+    ctx = torch.from_numpy(g["context"])
+    masks = torch.from_numpy(g["masks"])
+    text = torch.from_numpy(g["text"]).float()
+    h = int(g["horizon"])
+    with torch.no_grad():
+        pre = oracle.adapter.preprocess(ctx, masks)
+        full = oracle.forward_full(h, ctx, masks, text)
+        point = oracle(h, ctx, masks, text)
+        no_text = oracle.forward_full(h, ctx, masks, None)
+    assert np.array_equal(pre.masks[..., -1].numpy(), g["patch_mask"])
+    np.testing.assert_allclose(pre.normalization_stats["context_mu"].numpy(), g["context_mu"], atol=1e-6)
+    np.testing.assert_allclose(pre.normalization_stats["context_sigma"].numpy(), g["context_sigma"], atol=1e-6)
+    scale = float(np.abs(g["forecast"]).max())
+    # different CPU vector widths reorder the fp32 GEMM reductions: allow 2e-5 relative
+    assert np.abs(full.numpy() - g["forecast"]).max() < 2e-5 * scale
+    assert np.abs(point.numpy() - g["point"]).max() < 2e-5 * scale
+    assert np.abs(no_text.numpy() - g["forecast_no_text"]).max() < 2e-5 * scale
+    assert np.array_equal(point.numpy(), full.numpy()[..., 5])  # decode_index 5 = point forecast channel
+
+
+@pytest.mark.skipif(not REF_SRC.exists(), reason="/root/reference is only present in the build container")
+def test_oracle_decoder_equals_reference_decoder():
+    import sys
+
+    sys.path.insert(0, str(REF_SRC))
+    from tsfmx.decoder import MultimodalDecoder as RefDecoder
+    from tsfmx.decoder import MultimodalDecoderConfig as RefConfig
+    from tsfmx.fusion import MultimodalFusion as RefFusion
+
+    for layers, hidden in ((1, []), (2, [96]), (3, [128, 64])):
+        _, oracle = build_pair(1, layers, tuple(hidden), seed=4)
+        ref = RefDecoder(oracle.adapter, RefConfig(384, layers, hidden)).eval()
+        assert isinstance(ref.fusion, RefFusion)
+        ref.fusion.load_state_dict(oracle.fusion.state_dict())  # same state-dict keys projection.{0,2,4}.weight
+        ctx, masks, text, _ = O.synthetic_batch(3, 256, 40, padded=True)
+        with torch.no_grad():
+            assert torch.equal(ref.forward_full(40, ctx, masks, text), oracle.forward_full(40, ctx, masks, text))
+            assert torch.equal(ref(40, ctx, masks, None), oracle(40, ctx, masks, None))
+        with pytest.raises(ValueError):
+            ref.forward_full(40, ctx, masks[:, :5], text)
+        with pytest.raises(ValueError):
+            oracle.forward_full(40, ctx, masks[:, :5], text)
+
+
+def test_oracle_matches_hf_timesfm2_5_model():
+    from transformers.models.timesfm2_5 import modeling_timesfm2_5 as hf
+
+    _, oracle = build_pair(2)
+    model = hf.TimesFm2_5Model(O.make_hf_config(2)).eval()
+    model.input_ff_layer.load_state_dict(oracle.adapter.tokenizer.state_dict())
+    for a, b in zip(model.layers, oracle.adapter.stacked_xf):
+        a.load_state_dict(b.state_dict())
+    ctx, masks, _text, _ = O.synthetic_batch(4, 512, 128, padded=True)
+    with torch.no_grad():
+        out = model(past_values=ctx, past_values_padding=masks.long())
+        pre = oracle.adapter.preprocess(ctx, masks)
+        hidden = oracle.adapter(pre.input_embeddings, pre.masks)
+    assert torch.equal(out.last_hidden_state, hidden)
+    assert torch.equal(out.context_mu, pre.normalization_stats["context_mu"])
+    assert torch.equal(out.context_sigma, pre.normalization_stats["context_sigma"])
+
+
+def test_running_stats_property():
+    # unmasked: stats after patch k == mean / population std of x[: 32 (k + 1)]  
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 256, generator=g) * 2 + 3
+    _, oracle = build_pair(0)
+    pre = oracle.adapter.preprocess(x, torch.zeros_like(x, dtype=torch.bool))
+    for k in range(8):
+        seg = x[:, : 32 * (k + 1)].double()
+        assert torch.allclose(pre.normalization_stats["context_mu"][:, k].double(), seg.mean(-1), atol=1e-5)
+        assert torch.allclose(pre.normalization_stats["context_sigma"][:, k].double(), seg.std(-1, unbiased=False), atol=1e-5)
+
+
+def test_t5_tokenizer_oracle_golden_and_properties():
+    g = load_case("chronos_t5_tokens")
+    centers, boundaries = T5.tables()
+    assert boundaries.numel() == 4094 and centers.numel() == 4093
+    x = torch.from_numpy(g["x"])
+    ids, am, scale = T5.tokenize(x, boundaries)
+    assert np.array_equal(ids.numpy(), g["ids"].astype(np.int64))
+    assert np.array_equal(am.numpy(), g["attention_mask"])
+    assert np.array_equal(scale.numpy(), g["scale"])
+    assert ids[:, -1].eq(T5.EOS_ID).all() and am[:, -1].all()
+    assert ids[1, :-1].eq(T5.PAD_ID).all() and scale[1] == 1.0 and scale[2] == 1.0
+    assert ids.max() == 4095 and ids[ids > 1].min() >= 2
+    # the order-independent scale is within a few ulp of torch's own fp32 nansum (upstream's arithmetic) ...
+    up = torch.nansum(x.abs() * ~torch.isnan(x), -1) / torch.nansum((~torch.isnan(x)).float(), -1)
+    up[~(up > 0)] = 1.0
+    assert ((scale - up).abs() <= 8 * torch.finfo(torch.float32).eps * up.abs()).all()
+    # ... and upstream's ids agree everywhere except (possibly) exact bin-edge ties
+    up_ids = torch.bucketize(x / up[:, None], boundaries, right=True) + 2
+    up_ids.clamp_(0, 4095)
+    up_ids[torch.isnan(x)] = 0
+    assert (up_ids != ids[:, :-1]).float().mean() < 1e-3
+    # dequantise(tokenise(x)) is within half a bin of x (in scaled units) inside the bin range
+    vals = T5.dequantize(ids[:, :-1], centers, scale)
+    ok = ~torch.isnan(x) & ((x / scale[:, None]).abs() < 14.9)
+    half_bin = 30.0 / 4092 / 2
+    assert (((vals - x) / scale[:, None]).abs()[ok] <= half_bin * 1.001).all()
