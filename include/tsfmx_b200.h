@@ -54,9 +54,12 @@ enum { TSFMX_PREC_BF16 = 0, TSFMX_PREC_BF16X3 = 1 };
 /* element storage of an output / input matrix */
 enum { TSFMX_DT_F32 = 0, TSFMX_DT_BF16 = 1, TSFMX_DT_BF16_SPLIT = 2 };
 
-enum { TSFMX_ACT_NONE = 0, TSFMX_ACT_SILU = 1, TSFMX_ACT_RELU = 2 };
+/* *_GRAD: the epilogue multiplies the accumulator (an upstream gradient) by act'(aux) — backward pass */
+enum { TSFMX_ACT_NONE = 0, TSFMX_ACT_SILU = 1, TSFMX_ACT_RELU = 2, TSFMX_ACT_SILU_GRAD = 3, TSFMX_ACT_RELU_GRAD = 4 };
 
 int tsfmx_abi_version(void);
+/* sizeof(tsfmx_gemm_args) as compiled: lets a binding verify its struct layout */
+int tsfmx_sizeof_gemm_args(void);
 const char* tsfmx_last_error(void);
 /* number of kernels this library has launched on the calling process (all threads) */
 uint64_t tsfmx_launch_count(void);
@@ -144,8 +147,8 @@ typedef struct {
 
 /*
  * D = epilogue( sum_s A_s * B_s^T )   with epilogue, in this order:
- *   v = acc + bias[col]; v = act(v); v = v * row_scale[row] + row_shift[row];
- *   v += residual[row, col]; store columns < n_store as d_dtype.
+ *   v = acc + bias[col]; [pre_act[row, col] = v;] v = act(v)  (or v *= act'(aux[row, col]) for *_GRAD);
+ *   v = v * row_scale[row] + row_shift[row]; v += residual[row, col]; store columns < n_store as d_dtype.
  * Used for every Linear on the path: TimesFM tokenizer / transformer / head
  * ResidualBlocks (two segments: hidden path + residual path), MultimodalFusion
  * (reference fusion.py:46-47: relu epilogue + residual add), Chronos-2 blocks.
@@ -167,6 +170,12 @@ typedef struct {
   int32_t d_dtype; /* TSFMX_DT_* */
   int32_t n_store; /* store only columns < n_store (0 = n) */
   int32_t split_off; /* BF16_SPLIT: column offset of the lo half (0 = n) */
+  int32_t aux_dtype;      /* TSFMX_DT_F32 or TSFMX_DT_BF16 */
+  const void* aux;        /* [m, >= n_store]: SILU_GRAD -> saved pre-activation u; RELU_GRAD -> pre- or post-activation */
+  int64_t ld_aux;
+  void* pre_act;          /* optional [m, >= n_store]: acc + bias before the activation (training forward) */
+  int64_t ld_pre;
+  int32_t pre_act_dtype;  /* TSFMX_DT_F32 or TSFMX_DT_BF16 */
   int32_t reserved;
 } tsfmx_gemm_args;
 
@@ -208,6 +217,48 @@ int tsfmx_timesfm_attention(const void* qkv, int32_t qkv_dtype, int64_t batch, i
                             const int32_t* num_masked, const float* inv_freq, const float* q_ln_w,
                             const float* k_ln_w, const float* q_scale, float eps, int32_t out_dtype, void* out,
                             void* stream);
+
+/* ------------------------------------------------------------------------
+ * Backward pass of the fusion fine-tune step (reference tsfmx/trainer.py:200-219; the adapter is frozen,
+ * trainer.py:76-77, so only activation gradients flow through the backbone).  The dgrad GEMMs are
+ * tsfmx_gemm on pre-transposed weights with the *_GRAD epilogues.
+ * ---------------------------------------------------------------------- */
+
+/*
+ * One norm / residual junction of a TimesFM 2.5 layer, backwards:
+ *   g_total = g_res + RMSNorm_bwd(v1, w1, g1)      (either term may be absent: g_res NULL / v1 NULL)
+ *   g2      = RMSNorm_bwd(v2, w2, g_total)         (skipped when v2 is NULL)
+ * with RMSNorm_bwd(v, w, g) = r (w g) - v r^3 mean(v w g), r = (mean(v^2) + eps)^-1/2.
+ * v1 / g1 / v2 are f32 or bf16 [rows, cols]; g_total fp32 (may alias g_res); g2 of g2_dtype.
+ */
+int tsfmx_rmsnorm_bwd_chain(const float* g_res, const void* v1, int32_t v1_dtype, const float* w1, const void* g1,
+                            int32_t g1_dtype, const void* v2, int32_t v2_dtype, const float* w2, int64_t rows,
+                            int32_t cols, float eps, float* g_total, int32_t g2_dtype, void* g2, void* stream);
+
+/*
+ * Gradient of tsfmx_timesfm_attention w.r.t. its qkv input: recomputes the conditioned q / k and the
+ * probabilities, then dV = P^T dO, dS = P (dO V^T - rowsum), dq' = dS k', dk' = dS^T q' and back through
+ * per-dim scale, RMSNorm and RoPE.  d_out [B*N, H*hd] f32 / bf16; dqkv [B*N, 3*H*hd] of dqkv_dtype.
+ */
+int tsfmx_timesfm_attention_bwd(const void* qkv, int32_t qkv_dtype, const void* d_out, int32_t dout_dtype,
+                                int64_t batch, int32_t num_patches, int32_t num_heads, int32_t head_dim,
+                                const uint8_t* patch_mask, const int32_t* num_masked, const float* inv_freq,
+                                const float* q_ln_w, const float* k_ln_w, const float* q_scale, float eps,
+                                int32_t dqkv_dtype, void* dqkv, void* stream);
+
+/*
+ * out[c, r] = (mask == NULL || mask[r, c] > 0) ? in[r, c] : 0 for r < rows, zero for rows <= r < ld_out.
+ * Produces the K-major operands of the fusion weight gradient dW[n, k] = sum_tokens dpre[t, n] text[t, k]
+ * (reference: autograd of fusion.py:46-47) with K = tokens padded to ld_out (a multiple of 64).
+ * in / mask: f32, bf16 or split [rows, cols]; out: bf16 [cols, ld_out] or split [cols, 2*ld_out].
+ */
+int tsfmx_transpose_mask(const void* in, int32_t in_dtype, int64_t rows, int32_t cols, int64_t ld_in, const void* mask,
+                         int32_t mask_dtype, int64_t ld_mask, int32_t out_dtype, void* out, int64_t ld_out,
+                         void* stream);
+
+/* out[r, c] = mask[r, c] > 0 ? in[r, c] : 0; fp32 in -> f32 / bf16 / split out (relu' gate of the fusion dgrad) */
+int tsfmx_mask_cast_rows(const float* in, int64_t rows, int32_t cols, const void* mask, int32_t mask_dtype,
+                         int64_t ld_mask, int32_t out_dtype, void* out, void* stream);
 
 /* test hook: non-zero forces the fp32 SIMT attention kernel even where the tensor-core kernel applies */
 int tsfmx_attention_force_simt(int on);

@@ -26,6 +26,7 @@ SOURCES = [
     "elementwise.cu",
     "attention.cu",
     "gemm.cu",
+    "backward.cu",
     "model.cu",
 ]
 

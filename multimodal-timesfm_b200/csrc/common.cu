@@ -49,6 +49,8 @@ int num_sms() {
 
 extern "C" int tsfmx_abi_version(void) { return TSFMX_ABI_VERSION; }
 
+extern "C" int tsfmx_sizeof_gemm_args(void) { return static_cast<int>(sizeof(tsfmx_gemm_args)); }
+
 extern "C" const char* tsfmx_last_error(void) { return tsfmx::g_error; }
 
 extern "C" uint64_t tsfmx_launch_count(void) { return tsfmx::g_launches.load(std::memory_order_relaxed); }

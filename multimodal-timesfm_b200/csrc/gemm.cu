@@ -16,7 +16,7 @@
 //                           256xBNx16 with cta_group::2), tcgen05.commit frees smem slots
 //   warp 2    TMEM allocator (2 x BN fp32 columns: the epilogue of tile i overlaps the
 //                           MMAs of tile i+1)
-//   warps 4-7 epilogue:     tcgen05.ld 32x32b -> registers -> bias/act/affine/residual ->
+//   warps 4-11 epilogue:    tcgen05.ld 32x32b -> registers -> bias/act/affine/residual ->
 //                           vectorised global stores (f32 / bf16 / split bf16)
 #include <stdarg.h>
 #include <stdio.h>
@@ -31,8 +31,9 @@ constexpr int BM = 128;      // rows per CTA tile (TMEM lanes)
 constexpr int BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;   // K of one tcgen05.mma kind::f16
 constexpr int MAX_XSEG = 6;  // expanded segments (2 logical x 3 split products)
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter, each owning half of the tile's columns
 
 struct XSeg {
   int32_t a_idx, b_idx;    // which tensor map
@@ -58,6 +59,12 @@ struct alignas(64) GemmParams {
   int64_t ldd;
   int32_t n_store, split_off;
   int32_t vec_ok;  // all pointers / leading dims allow 16-byte vector access
+  const void* aux;  // *_GRAD activations: the saved pre-activation (SiLU) / activation output (ReLU)
+  int64_t ld_aux;
+  int32_t aux_dtype;
+  int32_t pre_dtype;
+  void* pre_act;    // optional second output: acc + bias, before the activation (saved for the backward pass)
+  int64_t ld_pre;
 };
 
 template <int BN, int CG>
@@ -73,8 +80,13 @@ struct Cfg {
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
 };
 
+__device__ __forceinline__ float load_aux(const void* base, int dtype, int64_t idx) {
+  return dtype == TSFMX_DT_F32 ? reinterpret_cast<const float*>(base)[idx]
+                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == TSFMX_ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == TSFMX_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));  // MUFU.EX2 + MUFU.RCP: keeps the epilogue off the critical path
   if (act == TSFMX_ACT_RELU) return fmaxf(v, 0.0f);
   return v;
 }
@@ -103,9 +115,35 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         if (col0 + i < n_store) v[i] += __ldg(p.bias + col0 + i);
     }
   }
-  if (p.act != TSFMX_ACT_NONE) {
+  if (p.pre_act != nullptr) {
+    // training forward: keep the pre-activation for the backward pass
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (col0 + i < n_store) {
+        const int64_t o = row * p.ld_pre + col0 + i;
+        if (p.pre_dtype == TSFMX_DT_F32) reinterpret_cast<float*>(p.pre_act)[o] = v[i];
+        else reinterpret_cast<__nv_bfloat16*>(p.pre_act)[o] = __float2bfloat16_rn(v[i]);
+      }
+    }
+  }
+  if (p.act == TSFMX_ACT_SILU || p.act == TSFMX_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+  } else if (p.act == TSFMX_ACT_SILU_GRAD) {
+    // v = dL/d silu(u)  ->  dL/du = v * sigmoid(u) * (1 + u * (1 - sigmoid(u)))
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (col0 + i < n_store) {
+        const float u = load_aux(p.aux, p.aux_dtype, row * p.ld_aux + col0 + i);
+        const float sg = 1.0f / (1.0f + __expf(-u));
+        v[i] *= sg * (1.0f + u * (1.0f - sg));
+      }
+    }
+  } else if (p.act == TSFMX_ACT_RELU_GRAD) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (col0 + i < n_store) v[i] = load_aux(p.aux, p.aux_dtype, row * p.ld_aux + col0 + i) > 0.0f ? v[i] : 0.0f;
+    }
   }
   if (p.row_scale != nullptr) {
     const float s = __ldg(p.row_scale + row);
@@ -215,7 +253,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);        // one tcgen05.commit
-      mbar_init(&tmem_empty_bar[i], 4 * CG);  // one arrive per epilogue warp (of every CTA of the pair)
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS * CG);  // one arrive per epilogue warp (of every CTA of the pair)
     }
     fence_barrier_init();
   }
@@ -295,7 +333,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int chalf = (warp - EPI_WARP0) >> 2;   // which half of the tile's columns this warp drains
     uint32_t iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
@@ -306,7 +345,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
       const int col_base = n_blk * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);  // warp-collective: issued even for out-of-range rows
         tmem_ld_wait();
@@ -436,7 +475,14 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
   TSFMX_REQUIRE(a->precision == TSFMX_PREC_BF16 || a->precision == TSFMX_PREC_BF16X3, "gemm: bad precision");
   TSFMX_REQUIRE(a->d != nullptr, "gemm: d is NULL");
   TSFMX_REQUIRE(a->d_dtype >= TSFMX_DT_F32 && a->d_dtype <= TSFMX_DT_BF16_SPLIT, "gemm: bad d_dtype");
-  TSFMX_REQUIRE(a->act >= TSFMX_ACT_NONE && a->act <= TSFMX_ACT_RELU, "gemm: bad act");
+  TSFMX_REQUIRE(a->act >= TSFMX_ACT_NONE && a->act <= TSFMX_ACT_RELU_GRAD, "gemm: bad act");
+  TSFMX_REQUIRE(!(a->act == TSFMX_ACT_SILU_GRAD || a->act == TSFMX_ACT_RELU_GRAD) ||
+                    (a->aux != nullptr && (a->aux_dtype == TSFMX_DT_F32 || a->aux_dtype == TSFMX_DT_BF16) &&
+                     a->ld_aux >= (a->n_store > 0 ? a->n_store : a->n)),
+                "gemm: *_GRAD activations need aux (f32 or bf16) with ld_aux >= n_store");
+  TSFMX_REQUIRE(a->pre_act == nullptr || ((a->pre_act_dtype == TSFMX_DT_F32 || a->pre_act_dtype == TSFMX_DT_BF16) &&
+                                          a->ld_pre >= (a->n_store > 0 ? a->n_store : a->n)),
+                "gemm: pre_act must be f32 or bf16 with ld_pre >= n_store");
   TSFMX_REQUIRE(a->m < (int64_t(1) << 31) - 256, "gemm: m too large");
   const bool split = a->precision == TSFMX_PREC_BF16X3;
 
@@ -459,6 +505,12 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
   p.ldr = a->ldr;
   p.d = a->d;
   p.ldd = a->ldd;
+  p.aux = a->aux;
+  p.ld_aux = a->ld_aux;
+  p.aux_dtype = a->aux_dtype;
+  p.pre_act = a->pre_act;
+  p.ld_pre = a->ld_pre;
+  p.pre_dtype = a->pre_act_dtype;
   p.n_store = a->n_store > 0 ? a->n_store : a->n;
   TSFMX_REQUIRE(p.n_store <= a->n, "gemm: n_store (%d) > n (%d)", p.n_store, a->n);
   p.split_off = a->split_off > 0 ? a->split_off : a->n;

@@ -19,7 +19,7 @@ LIB_PATH = _CSRC / "libtsfmx_b200.so"
 OK = 0
 PREC_BF16, PREC_BF16X3 = 0, 1
 DT_F32, DT_BF16, DT_BF16_SPLIT = 0, 1, 2
-ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_RELU, ACT_SILU_GRAD, ACT_RELU_GRAD = 0, 1, 2, 3, 4
 
 PRECISIONS = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
@@ -57,6 +57,12 @@ class GemmArgs(Structure):
         ("d_dtype", c_int32),
         ("n_store", c_int32),
         ("split_off", c_int32),
+        ("aux_dtype", c_int32),
+        ("aux", c_void_p),
+        ("ld_aux", c_int64),
+        ("pre_act", c_void_p),
+        ("ld_pre", c_int64),
+        ("pre_act_dtype", c_int32),
         ("reserved", c_int32),
     ]
 
@@ -96,6 +102,26 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
          c_void_p],
     ),
     "tsfmx_attention_force_simt": (c_int32, [c_int32]),
+    "tsfmx_sizeof_gemm_args": (c_int32, []),
+    "tsfmx_rmsnorm_bwd_chain": (
+        c_int32,
+        [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_int32,
+         c_float, c_void_p, c_int32, c_void_p, c_void_p],
+    ),
+    "tsfmx_timesfm_attention_bwd": (
+        c_int32,
+        [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p],
+    ),
+    "tsfmx_transpose_mask": (
+        c_int32,
+        [c_void_p, c_int32, c_int64, c_int32, c_int64, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_int64,
+         c_void_p],
+    ),
+    "tsfmx_mask_cast_rows": (
+        c_int32,
+        [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p],
+    ),
     "tsfmx_timesfm_attention": (
         c_int32,
         [c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -124,6 +150,11 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     if lib.tsfmx_abi_version() != 1:
         raise TsfmxError(f"ABI version mismatch: library reports {lib.tsfmx_abi_version()}, binding expects 1")
+    if lib.tsfmx_sizeof_gemm_args() != ctypes.sizeof(GemmArgs):
+        raise TsfmxError(
+            f"tsfmx_gemm_args layout mismatch: library {lib.tsfmx_sizeof_gemm_args()} bytes, binding "
+            f"{ctypes.sizeof(GemmArgs)} bytes"
+        )
     _lib = lib
     return lib
 

@@ -59,6 +59,8 @@ class MultimodalDecoder(nn.Module):
         if masks.shape != inputs.shape:
             raise ValueError(f"masks shape {masks.shape} must match inputs shape {inputs.shape}")
         masks = masks.bool()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_full_training(horizon, inputs, masks, text_embeddings)
         preprocessed = self.adapter.preprocess(inputs, masks)
         embeddings = (
             self.fusion(preprocessed.input_embeddings, text_embeddings)
@@ -67,6 +69,23 @@ class MultimodalDecoder(nn.Module):
         )
         output_embeddings = self.adapter(embeddings, preprocessed.masks)
         return self.adapter.postprocess(horizon, output_embeddings, preprocessed.normalization_stats)
+
+    def _forward_full_training(self, horizon, inputs, masks, text_embeddings):
+        """Differentiable path of the reference's "multimodal" training mode (trainer.py:76-77,119-123): frozen
+        adapter, trainable fusion.  Full fine-tuning of the adapter ("baseline" mode) is SURVEY.md section 8(f) rank 4."""
+        from .autograd import FusedForecastFunction
+
+        if any(p.requires_grad for p in self.adapter.parameters()):
+            raise NotImplementedError(
+                "baseline mode (adapter.unfreeze_parameters) needs backbone weight gradients, which the B200 path does "
+                "not produce yet; call adapter.freeze_parameters() to train the fusion module (multimodal mode)"
+            )
+        if text_embeddings is None:
+            raise ValueError("training the fusion module needs text_embeddings")
+        if not hasattr(self.adapter, "forward_saving"):
+            raise NotImplementedError(f"{type(self.adapter).__name__} has no training path yet")
+        weights = [lin.weight for lin in self.fusion.linears()]
+        return FusedForecastFunction.apply(self, horizon, inputs, masks, text_embeddings, *weights)
 
     def forward(
         self,

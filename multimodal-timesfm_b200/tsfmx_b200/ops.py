@@ -159,8 +159,13 @@ def gemm(
     n_store: int = 0,
     ldd: int | None = None,
     split_off: int = 0,
+    aux: torch.Tensor | None = None,
+    pre_act: torch.Tensor | None = None,
 ) -> torch.Tensor:
-    """``out = epilogue(sum_s A_s @ B_s^T)``; each segment is (A [m, k or 2k], B [n, k or 2k], k)."""
+    """``out = epilogue(sum_s A_s @ B_s^T)``; each segment is (A [m, k or 2k], B [n, k or 2k], k).
+
+    ``aux``: saved activation input for the ``*_GRAD`` epilogues; ``pre_act``: optional second output receiving
+    ``acc + bias`` before the activation (fp32 or bf16)."""
     lib = _lib.load()
     args = GemmArgs()
     args.m, args.n, args.num_segments = m, n, len(segments)
@@ -178,6 +183,12 @@ def gemm(
     args.d = out.data_ptr()
     args.ldd = out.stride(0) if ldd is None else ldd
     args.d_dtype, args.n_store, args.split_off = d_dtype, n_store, split_off
+    if aux is not None:
+        args.aux, args.ld_aux = aux.data_ptr(), aux.stride(0)
+        args.aux_dtype = DT_BF16 if aux.dtype == torch.bfloat16 else DT_F32
+    if pre_act is not None:
+        args.pre_act, args.ld_pre = pre_act.data_ptr(), pre_act.stride(0)
+        args.pre_act_dtype = DT_BF16 if pre_act.dtype == torch.bfloat16 else DT_F32
     check(lib.tsfmx_gemm(ctypes.byref(args), stream()))
     return out
 
@@ -248,3 +259,102 @@ def split_to_float(t: torch.Tensor) -> torch.Tensor:
     """Debug helper: split bf16 [R, 2K] -> fp32 [R, K] (hi + lo)."""
     k = t.shape[1] // 2
     return t[:, :k].float() + t[:, k:].float()
+
+
+# ----------------------------------------------------------------------------- backward pass
+def _dt(t: torch.Tensor) -> int:
+    return DT_BF16 if t.dtype == torch.bfloat16 else DT_F32
+
+
+def rmsnorm_bwd_chain(
+    g_res: torch.Tensor | None,
+    v1: torch.Tensor | None,
+    w1: torch.Tensor | None,
+    g1: torch.Tensor | None,
+    v2: torch.Tensor | None,
+    w2: torch.Tensor | None,
+    eps: float,
+    g_total: torch.Tensor | None,
+    g2_dtype: int,
+    g2: torch.Tensor | None,
+    rows: int,
+    cols: int,
+) -> None:
+    lib = _lib.load()
+    check(
+        lib.tsfmx_rmsnorm_bwd_chain(
+            ptr(g_res), ptr(v1), _dt(v1) if v1 is not None else 0, ptr(w1), ptr(g1), _dt(g1) if g1 is not None else 0,
+            ptr(v2), _dt(v2) if v2 is not None else 0, ptr(w2), rows, cols, eps, ptr(g_total), g2_dtype, ptr(g2),
+            stream(),
+        )
+    )
+
+
+def timesfm_attention_bwd(
+    qkv: torch.Tensor,
+    d_out: torch.Tensor,
+    batch: int,
+    num_patches: int,
+    num_heads: int,
+    head_dim: int,
+    patch_mask: torch.Tensor | None,
+    num_masked: torch.Tensor | None,
+    inv_freq: torch.Tensor,
+    q_ln_w: torch.Tensor,
+    k_ln_w: torch.Tensor,
+    q_scale: torch.Tensor,
+    eps: float,
+    dqkv_dtype: int,
+    dqkv: torch.Tensor | None = None,
+) -> torch.Tensor:
+    lib = _lib.load()
+    _lib.require_cuda(qkv, d_out)
+    if dqkv is None:
+        dqkv = alloc(batch * num_patches, 3 * num_heads * head_dim, dqkv_dtype, qkv.device)
+    pm = None if patch_mask is None else _as_u8(patch_mask)
+    check(
+        lib.tsfmx_timesfm_attention_bwd(
+            ptr(qkv), _dt(qkv), ptr(d_out), _dt(d_out), batch, num_patches, num_heads, head_dim, ptr(pm),
+            ptr(num_masked), ptr(inv_freq), ptr(q_ln_w), ptr(k_ln_w), ptr(q_scale), eps, dqkv_dtype, ptr(dqkv), stream(),
+        )
+    )
+    return dqkv
+
+
+def _storage_dtype(t: torch.Tensor, logical_cols: int) -> int:
+    if t.dtype == torch.float32:
+        return DT_F32
+    return DT_BF16_SPLIT if t.shape[1] == 2 * logical_cols else DT_BF16
+
+
+def transpose_mask(
+    x: torch.Tensor, rows: int, cols: int, out_dtype: int, mask: torch.Tensor | None = None
+) -> tuple[torch.Tensor, int]:
+    """[rows, cols] (f32 / bf16 / split) -> K-major transposed [cols, kpad] (bf16 / split), kpad = rows rounded up to 64.
+    Returns (out, kpad)."""
+    lib = _lib.load()
+    _lib.require_cuda(x)
+    kpad = (rows + 63) // 64 * 64
+    out = alloc(cols, kpad, out_dtype, x.device)
+    check(
+        lib.tsfmx_transpose_mask(
+            ptr(x), _storage_dtype(x, cols), rows, cols, x.stride(0), ptr(mask),
+            _storage_dtype(mask, cols) if mask is not None else 0, mask.stride(0) if mask is not None else 0,
+            out_dtype, ptr(out), kpad, stream(),
+        )
+    )
+    return out, kpad
+
+
+def mask_cast_rows(x: torch.Tensor, mask: torch.Tensor, out_dtype: int) -> torch.Tensor:
+    """fp32 [R, C] gated by mask[r, c] > 0 -> f32 / bf16 / split [R, C]."""
+    lib = _lib.load()
+    _lib.require_cuda(x, mask)
+    rows, cols = x.shape
+    out = alloc(rows, cols, out_dtype, x.device)
+    check(
+        lib.tsfmx_mask_cast_rows(
+            ptr(x), rows, cols, ptr(mask), _storage_dtype(mask, cols), mask.stride(0), out_dtype, ptr(out), stream()
+        )
+    )
+    return out

@@ -1,0 +1,179 @@
+"""Fine-tune entry point (reference tsfmx/trainer.py:35-399): MSE on the point forecast, gradient accumulation,
+gradient clipping, AdamW, per-step LR schedule.
+
+Kept from the reference: the class name, constructor arguments, "multimodal" = frozen adapter + trainable fusion
+(trainer.py:76-77,119-123), loss / accumulation / clip / step order (trainer.py:200-219), ``RuntimeError`` on empty
+datasets, checkpoint dictionary keys (types.py:42-61).  Added for the B200 box: data parallelism — each rank takes its
+slice of every batch and the fusion gradients are averaged with one NCCL all-reduce per optimizer step, before the
+clip.  Not rebuilt (host-side, out of the hot path): W&B logging, checkpoint rotation, "baseline" full fine-tuning.
+"""
+
+from __future__ import annotations
+
+import math
+from collections.abc import Iterator, Sequence
+from typing import Any
+
+import torch
+from torch import nn
+from torch.optim import AdamW, Optimizer
+from torch.optim.lr_scheduler import LambdaLR, LRScheduler
+from torch.utils.data import DataLoader
+
+from . import distributed as tdist
+from .data.collate import baseline_collate_fn, multimodal_collate_fn
+from .decoder import MultimodalDecoder
+
+
+def linear_schedule_with_warmup(optimizer: Optimizer, warmup_steps: int, total_steps: int) -> LambdaLR:
+    """Linear warm-up then linear decay to zero (reference optimization.py:19-45)."""
+
+    def fn(step: int) -> float:
+        if step < warmup_steps:
+            return step / max(1, warmup_steps)
+        return max(0.0, (total_steps - step) / max(1, total_steps - warmup_steps))
+
+    return LambdaLR(optimizer, fn)
+
+
+def cosine_schedule_with_warmup(optimizer: Optimizer, warmup_steps: int, total_steps: int, cycles: float = 0.5) -> LambdaLR:
+    """Linear warm-up then cosine decay (reference optimization.py:48-79)."""
+
+    def fn(step: int) -> float:
+        if step < warmup_steps:
+            return step / max(1, warmup_steps)
+        progress = (step - warmup_steps) / max(1, total_steps - warmup_steps)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * cycles * 2.0 * progress)))
+
+    return LambdaLR(optimizer, fn)
+
+
+class MultimodalTrainer:
+    """Trainer for the fusion fine-tune ("multimodal" mode) on one or several B200s."""
+
+    def __init__(
+        self,
+        model: MultimodalDecoder,
+        args: Any,
+        train_dataset: Sequence,
+        val_dataset: Sequence,
+        mode: str,
+        device: torch.device,
+        wandb_run: Any | None = None,
+        optimizers: tuple[Optimizer | None, LRScheduler | None] = (None, None),
+    ) -> None:
+        self.model = model
+        self.args = args
+        self.train_dataset = train_dataset
+        self.val_dataset = val_dataset
+        self.mode = mode
+        self.device = device
+        self._wandb_run = wandb_run
+        self.rank, self.world_size, _ = tdist.world_info()
+        self.model.to(self.device)
+        if mode == "multimodal":
+            self.model.adapter.freeze_parameters()
+        else:
+            raise NotImplementedError(
+                "mode='baseline' (full fine-tuning of the adapter) needs backbone weight gradients; the B200 path "
+                "implements the reference's multimodal mode (frozen adapter, trainable fusion)"
+            )
+        collate = multimodal_collate_fn if mode == "multimodal" else baseline_collate_fn
+        pin = self.device.type == "cuda"
+        self.train_loader = DataLoader(train_dataset, batch_size=args.per_device_train_batch_size * self.world_size,
+                                       shuffle=True, num_workers=0, collate_fn=collate, pin_memory=pin,
+                                       generator=torch.Generator().manual_seed(getattr(args, "seed", 0)))
+        self.val_loader = DataLoader(val_dataset, batch_size=args.per_device_eval_batch_size * self.world_size,
+                                     shuffle=False, num_workers=0, collate_fn=collate, pin_memory=pin)
+        self.loss_fn = nn.MSELoss()
+        optimizer, scheduler = optimizers
+        steps_per_epoch = math.ceil(len(self.train_loader) / args.gradient_accumulation_steps)
+        total_steps = args.num_train_epochs * steps_per_epoch
+        self.optimizer = optimizer or AdamW(self._get_trainable_params(), lr=args.learning_rate,
+                                            weight_decay=args.weight_decay)
+        self.lr_scheduler = scheduler or self._create_scheduler(total_steps)
+        self.current_epoch = 0
+        self.global_step = 0
+        self.best_val_loss = float("inf")
+
+    def _get_trainable_params(self) -> Iterator[nn.Parameter]:
+        return self.model.fusion.parameters()
+
+    def _create_scheduler(self, total_steps: int) -> LRScheduler:
+        kind = getattr(self.args, "lr_scheduler_type", "linear")
+        warmup = int(getattr(self.args, "warmup_steps", 0) or round(getattr(self.args, "warmup_ratio", 0.0) * total_steps))
+        if kind == "linear":
+            return linear_schedule_with_warmup(self.optimizer, warmup, total_steps)
+        if kind == "cosine":
+            return cosine_schedule_with_warmup(self.optimizer, warmup, total_steps)
+        raise NotImplementedError(f"Unknown lr_scheduler_type: {kind}")
+
+    # ------------------------------------------------------------------ one micro-batch / one optimizer step
+    def _forward_loss(self, batch: dict) -> torch.Tensor:
+        batch = tdist.shard_batch(batch, self.rank, self.world_size)
+        context = batch["context"].to(self.device, non_blocking=True)
+        horizon = batch["horizon"].to(self.device, non_blocking=True)
+        input_padding = torch.zeros_like(context, dtype=torch.bool)  # reference trainer.py:204
+        text = batch["text_embeddings"].to(self.device, non_blocking=True) if "text_embeddings" in batch else None
+        point = self.model(horizon.shape[-1], context, input_padding, text)
+        return self.loss_fn(point, horizon)
+
+    def optimizer_step(self) -> None:
+        """All-reduce (mean) of the fusion gradients, clip, AdamW, LR schedule (reference trainer.py:213-219)."""
+        params = list(self._get_trainable_params())
+        tdist.allreduce_mean_([p.grad for p in params])
+        if self.args.max_grad_norm > 0:
+            nn.utils.clip_grad_norm_(params, self.args.max_grad_norm)
+        self.optimizer.step()
+        self.optimizer.zero_grad()
+        self.lr_scheduler.step()
+        self.global_step += 1
+
+    def train_epoch(self) -> float:
+        """Average training loss of the epoch (mean over ranks of the per-shard losses).
+
+        Raises RuntimeError if the training dataset is empty (reference trainer.py:196-197)."""
+        self.model.train()
+        num_batches = len(self.train_loader)
+        if num_batches == 0:
+            raise RuntimeError("Training dataset is empty.")
+        accum = self.args.gradient_accumulation_steps
+        losses = []
+        for i, batch in enumerate(self.train_loader):
+            loss = self._forward_loss(batch) / accum
+            loss.backward()
+            losses.append(loss.detach() * accum)  # no per-micro-batch .item() sync (reference trainer.py:211)
+            if (i + 1) % accum == 0 or (i + 1) == num_batches:
+                self.optimizer_step()
+        total = torch.stack(losses).sum()
+        tdist.allreduce_mean_([total])
+        return float(total.item()) / num_batches
+
+    def validate_epoch(self) -> float:
+        """Raises RuntimeError if the validation dataset is empty (reference trainer.py:258-259)."""
+        self.model.eval()
+        num_batches = len(self.val_loader)
+        if num_batches == 0:
+            raise RuntimeError("Validation dataset is empty.")
+        with torch.no_grad():
+            total = torch.stack([self._forward_loss(batch) for batch in self.val_loader]).sum()
+        tdist.allreduce_mean_([total])
+        return float(total.item()) / num_batches
+
+    def train(self) -> None:
+        for epoch in range(self.args.num_train_epochs):
+            self.current_epoch = epoch
+            self.train_epoch()
+            val = self.validate_epoch()
+            self.best_val_loss = min(self.best_val_loss, val)
+
+    def build_checkpoint(self) -> dict[str, Any]:
+        """Same keys as the reference ``MultimodalCheckpoint`` (types.py:42-56, trainer.py:285-303)."""
+        return {
+            "epoch": self.current_epoch,
+            "global_step": self.global_step,
+            "optimizer_state_dict": self.optimizer.state_dict(),
+            "scheduler_state_dict": self.lr_scheduler.state_dict(),
+            "best_val_loss": self.best_val_loss,
+            "fusion_state_dict": self.model.fusion.state_dict(),
+        }

@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .._lib import ACT_SILU, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
+from .._lib import ACT_SILU, ACT_SILU_GRAD, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
 from .base import PreprocessResult, TsfmAdapter
 
 
@@ -148,6 +148,10 @@ class TimesFM2p5Adapter(TsfmAdapter):
         def pack(lin: nn.Linear) -> torch.Tensor:
             return ops.cast_rows(lin.weight.detach().float().contiguous(), adt)
 
+        def pack_t(lin: nn.Linear) -> torch.Tensor:
+            """W^T, K-major: the B operand of the dgrad GEMM dX = dY W (built lazily, only for training)."""
+            return ops.cast_rows(lin.weight.detach().float().t().contiguous(), adt)
+
         def f32(t: torch.Tensor) -> torch.Tensor:
             return t.detach().float().contiguous()
 
@@ -184,8 +188,26 @@ class TimesFM2p5Adapter(TsfmAdapter):
                     "ff1": pack(xf.ff1),
                 }
             )
+        w["_pack_t"] = pack_t
         self._packed[key] = w
         return w
+
+    def _weights_t(self) -> dict[str, object]:
+        """Transposed (dgrad) packs of the frozen backbone weights, cached next to the forward packs."""
+        w = self._weights()
+        if "t" not in w:
+            m, pack_t = self._model, w["_pack_t"]
+            w["t"] = {
+                "head_hidden": pack_t(m.output_projection_point.hidden_layer),
+                "head_out": pack_t(m.output_projection_point.output_layer),
+                "head_res": pack_t(m.output_projection_point.residual_layer),
+                "layers": [
+                    {"qkv": pack_t(xf.attn.qkv_proj), "out": pack_t(xf.attn.out), "ff0": pack_t(xf.ff0),
+                     "ff1": pack_t(xf.ff1)}
+                    for xf in m.stacked_xf
+                ],
+            }
+        return w["t"]
 
     # ------------------------------------------------------------------ stages
     def preprocess(self, inputs: torch.Tensor, masks: torch.Tensor) -> PreprocessResult:
@@ -292,6 +314,135 @@ class TimesFM2p5Adapter(TsfmAdapter):
         ops.gemm([(hid, w["head_out"], m.md), (a, w["head_res"], d)], b, m.o * m.q, out, DT_F32, precision=prec,
                  row_scale=sigma_last, row_shift=mu_last, n_store=horizon * m.q)
         return out.view(b, horizon, m.q)
+
+    # ------------------------------------------------------------------ training path (frozen backbone)
+    def forward_saving(self, input_embeddings: torch.Tensor, masks: torch.Tensor):
+        """``forward`` that also keeps, per layer, what the activation-gradient pass needs: the layer input x,
+        the mid-layer stream y, the raw qkv, the out-proj / ff1 outputs a1 / a2 and the ff0 pre-activation u."""
+        m = self._model
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32
+        w = self._weights()
+        b, n, d = input_embeddings.shape
+        rows = b * n
+        dev = input_embeddings.device
+        x = input_embeddings.reshape(rows, d).float().contiguous()
+        patch_mask = masks[..., -1].contiguous()
+        num_masked = patch_mask.sum(-1, dtype=torch.int32)
+        layers = w["layers"]
+        saved = {"patch_mask": patch_mask, "num_masked": num_masked, "shape": (b, n, d), "layers": []}
+        if not layers:
+            return x.view(b, n, d), saved
+        xn = ops.rmsnorm(x, layers[0]["pre_attn"], m.eps, adt)
+        attn = ops.alloc(rows, d, adt, dev)
+        hbuf = ops.alloc(rows, m.ff, adt, dev)
+        cur = x
+        for i, lw in enumerate(layers):
+            qkv = ops.alloc(rows, 3 * d, mid_dt, dev)
+            a1 = ops.alloc(rows, d, mid_dt, dev)
+            a2 = ops.alloc(rows, d, mid_dt, dev)
+            u = ops.alloc(rows, m.ff, mid_dt, dev)
+            y = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            z = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            ops.gemm([(xn, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
+            ops.timesfm_attention(qkv, b, n, m.h, m.hd, patch_mask, num_masked, w["inv_freq"], lw["q_ln"], lw["k_ln"],
+                                  lw["q_scale"], m.eps, adt, out=attn)
+            ops.gemm([(attn, lw["out"], d)], rows, d, a1, mid_dt, precision=prec)
+            ops.norm_residual_norm(a1, cur, lw["post_attn"], lw["pre_ff"], m.eps, y, adt, xn)
+            ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU, pre_act=u)
+            ops.gemm([(hbuf, lw["ff1"], m.ff)], rows, d, a2, mid_dt, precision=prec)
+            last = i == len(layers) - 1
+            ops.norm_residual_norm(a2, y, lw["post_ff"], None if last else layers[i + 1]["pre_attn"], m.eps, z, adt,
+                                   None if last else xn)
+            saved["layers"].append({"x": cur, "y": y, "qkv": qkv, "a1": a1, "a2": a2, "u": u})
+            cur = z
+        return cur.view(b, n, d), saved
+
+    def forward_backward(self, saved, d_out: torch.Tensor) -> torch.Tensor:
+        """Activation gradient of ``forward``: dL/d(output embeddings) [M, D] fp32 -> dL/d(input embeddings)."""
+        m = self._model
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32
+        w, wt = self._weights(), self._weights_t()
+        b, n, d = saved["shape"]
+        rows = b * n
+        dev = d_out.device
+        layers, tlayers, sl = w["layers"], wt["layers"], saved["layers"]
+        if not layers:
+            return d_out
+        g = d_out.contiguous()  # running dL/dz (fp32), updated in place layer by layer
+        g2 = ops.alloc(rows, d, adt, dev)  # gradient w.r.t. a GEMM output, as the next dgrad's A operand
+        du = ops.alloc(rows, m.ff, adt, dev)
+        gmid = ops.alloc(rows, d, mid_dt, dev)
+        datt = ops.alloc(rows, d, mid_dt, dev)
+        dqkv = ops.alloc(rows, 3 * d, adt, dev)
+        # top of the stack: da2 = RMSNorm_bwd(a2, post_ff, dz)
+        ops.rmsnorm_bwd_chain(g, None, None, None, sl[-1]["a2"], layers[-1]["post_ff"], m.eps, None, adt, g2, rows, d)
+        for i in reversed(range(len(layers))):
+            lw, tw, s = layers[i], tlayers[i], sl[i]
+            # dhff = da2 W1 ; du = dhff * silu'(u)
+            ops.gemm([(g2, tw["ff1"], d)], rows, m.ff, du, adt, precision=prec, act=ACT_SILU_GRAD, aux=s["u"])
+            # dyn = du W0
+            ops.gemm([(du, tw["ff0"], m.ff)], rows, d, gmid, mid_dt, precision=prec)
+            # dy = dz + RMSNorm_bwd(y, pre_ff, dyn) ; da1 = RMSNorm_bwd(a1, post_attn, dy)
+            ops.rmsnorm_bwd_chain(g, s["y"], lw["pre_ff"], gmid, s["a1"], lw["post_attn"], m.eps, g, adt, g2, rows, d)
+            # datt = da1 Wo
+            ops.gemm([(g2, tw["out"], d)], rows, d, datt, mid_dt, precision=prec)
+            ops.timesfm_attention_bwd(s["qkv"], datt, b, n, m.h, m.hd, saved["patch_mask"], saved["num_masked"],
+                                      w["inv_freq"], lw["q_ln"], lw["k_ln"], lw["q_scale"], m.eps, adt, dqkv=dqkv)
+            # dxn = dqkv Wqkv
+            ops.gemm([(dqkv, tw["qkv"], 3 * d)], rows, d, gmid, mid_dt, precision=prec)
+            # dx = dy + RMSNorm_bwd(x, pre_attn, dxn) ; and, for the layer below, da2 = RMSNorm_bwd(a2, post_ff, dx)
+            below = i - 1
+            ops.rmsnorm_bwd_chain(g, s["x"], lw["pre_attn"], gmid, sl[below]["a2"] if below >= 0 else None,
+                                  layers[below]["post_ff"] if below >= 0 else None, m.eps, g, adt,
+                                  g2 if below >= 0 else None, rows, d)
+        return g
+
+    def postprocess_saving(self, horizon: int, output_embeddings: torch.Tensor, normalization_stats):
+        """``postprocess`` that keeps the head's pre-activation and operands for the backward pass."""
+        m = self._model
+        if horizon > m.o:
+            raise ValueError(
+                f"horizon must be <= output_patch_len ({m.o}), got {horizon}. AR decode is not supported."
+            )
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32
+        w = self._weights()
+        b, n, d = output_embeddings.shape
+        last = output_embeddings[:, -1, :]
+        sigma_last = normalization_stats["context_sigma"][:, -1].contiguous()
+        mu_last = normalization_stats["context_mu"][:, -1].contiguous()
+        a = ops.cast_rows(last, adt)
+        hid = ops.alloc(b, m.md, adt, last.device)
+        z = ops.alloc(b, m.md, mid_dt, last.device)
+        ops.gemm([(a, w["head_hidden"], d)], b, m.md, hid, adt, precision=prec, act=ACT_SILU, pre_act=z)
+        out = torch.empty(b, horizon * m.q, dtype=torch.float32, device=last.device)
+        ops.gemm([(hid, w["head_out"], m.md), (a, w["head_res"], d)], b, m.o * m.q, out, DT_F32, precision=prec,
+                 row_scale=sigma_last, row_shift=mu_last, n_store=horizon * m.q)
+        return out.view(b, horizon, m.q), {"z": z, "sigma": sigma_last, "horizon": horizon, "b": b}
+
+    def postprocess_backward(self, saved, grad_forecast: torch.Tensor) -> torch.Tensor:
+        """dL/d(forecast) [B, h, 10] -> dL/d(last-patch embedding) [B, D] fp32."""
+        m = self._model
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        wt = self._weights_t()
+        b, horizon = saved["b"], saved["horizon"]
+        dev = grad_forecast.device
+        # undo the epilogue: out = acc * sigma + mu, only the first horizon*q columns exist
+        dpre32 = torch.zeros(b, m.o * m.q, dtype=torch.float32, device=dev)
+        dpre32[:, : horizon * m.q] = grad_forecast.reshape(b, horizon * m.q) * saved["sigma"][:, None]
+        dpre = ops.cast_rows(dpre32, adt)
+        dz = ops.alloc(b, m.md, adt, dev)
+        ops.gemm([(dpre, wt["head_out"], m.o * m.q)], b, m.md, dz, adt, precision=prec, act=ACT_SILU_GRAD, aux=saved["z"])
+        d_last = torch.empty(b, m.md, dtype=torch.float32, device=dev)
+        ops.gemm([(dz, wt["head_hidden"], m.md), (dpre, wt["head_res"], m.o * m.q)], b, m.md, d_last, DT_F32,
+                 precision=prec)
+        return d_last
 
     # ------------------------------------------------------------------ checkpoints / freezing
     def load_checkpoint(self, path: str) -> None:

@@ -57,4 +57,4 @@ def test_gemm_args_struct_layout():
     import ctypes
 
     assert ctypes.sizeof(_lib.GemmSegment) == 40
-    assert ctypes.sizeof(_lib.GemmArgs) == 8 + 4 + 4 + 80 + 4 + 4 + 8 * 4 + 8 + 8 + 8 + 4 * 4
+    assert ctypes.sizeof(_lib.GemmArgs) == 8 + 4 + 4 + 80 + 4 + 4 + 8 * 4 + 8 + 8 + 8 + 4 * 4 + 8 * 4 + 4 + 4

@@ -1,0 +1,213 @@
+"""Fusion fine-tune step (reference tsfmx/trainer.py:200-219) on the CUDA path: backward kernels against torch
+autograd, and the fusion-weight gradient / loss curve against the CPU oracle's autograd."""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import timesfm_oracle as O  # noqa: E402  (checker only)
+from tsfmx_b200 import _lib, ops  # noqa: E402
+from tsfmx_b200._lib import ACT_RELU_GRAD, ACT_SILU, ACT_SILU_GRAD, DT_BF16, DT_BF16_SPLIT, DT_F32, PREC_BF16X3  # noqa: E402
+from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig  # noqa: E402
+from tsfmx_b200.tsfm.timesfm import TimesFM2p5Adapter, init_random_  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _rms(v, w, eps=1e-6):
+    return w * (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps))
+
+
+# ----------------------------------------------------------------------------- kernels vs torch autograd (fp64)
+@pytest.mark.parametrize("with_v1,with_res,with_v2", [(True, True, True), (False, True, True), (True, True, False), (True, False, True)])
+def test_rmsnorm_bwd_chain(with_v1, with_res, with_v2):
+    rows, cols = 301, 1280
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    r = lambda *s: torch.randn(*s, generator=gen, device=DEV)  # noqa: E731
+    g_res, v1, g1, v2 = r(rows, cols), r(rows, cols), r(rows, cols), r(rows, cols)
+    w1, w2 = 1 + 0.1 * r(cols), 1 + 0.1 * r(cols)
+    v1d = v1.double().requires_grad_(True)
+    v2d = v2.double().requires_grad_(True)
+    total = torch.zeros(rows, cols, dtype=torch.float64, device=DEV)
+    if with_v1:
+        (gv1,) = torch.autograd.grad(_rms(v1d, w1.double()), v1d, g1.double())
+        total = total + gv1
+    if with_res:
+        total = total + g_res.double()
+    g_total = torch.empty(rows, cols, device=DEV)
+    g2 = ops.alloc(rows, cols, DT_BF16_SPLIT, torch.device(DEV))
+    ops.rmsnorm_bwd_chain(g_res if with_res else None, v1 if with_v1 else None, w1 if with_v1 else None,
+                          g1 if with_v1 else None, v2 if with_v2 else None, w2 if with_v2 else None, 1e-6, g_total,
+                          DT_BF16_SPLIT, g2 if with_v2 else None, rows, cols)
+    assert rel_l2(g_total, total.float()) < 1e-5
+    if with_v2:
+        (gv2,) = torch.autograd.grad(_rms(v2d, w2.double()), v2d, total)
+        assert rel_l2(ops.split_to_float(g2), gv2.float()) < 3e-5
+
+
+def _attn_fwd_torch(qkv, b, n, h, hd, pm, inv_freq, qw, kw, per_dim):
+    d = h * hd
+    q, k, v = qkv.reshape(b, n, 3, h, hd).unbind(2)
+    nm = pm.sum(-1)
+    pos = (torch.arange(n, device=qkv.device)[None, :] - nm[:, None]).double()
+    freqs = pos[..., None] * inv_freq.double()[None, None, :]
+    emb = torch.cat([freqs, freqs], -1)
+    cos, sin = emb.cos()[:, :, None, :], emb.sin()[:, :, None, :]
+    rot = lambda t: torch.cat([-t[..., hd // 2 :], t[..., : hd // 2]], -1)  # noqa: E731
+    q = q * cos + rot(q) * sin
+    k = k * cos + rot(k) * sin
+    q = _rms(q, qw.double()) * (torch.nn.functional.softplus(per_dim.double()) * (1.442695041 / math.sqrt(hd)))
+    k = _rms(k, kw.double())
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k)
+    causal = torch.tril(torch.ones(n, n, dtype=torch.bool, device=qkv.device))
+    allowed = causal[None, None] & (~pm)[:, None, None, :]
+    s = s + torch.where(allowed, 0.0, torch.finfo(torch.float32).min).double()
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhqk,bkhd->bqhd", p, v).reshape(b * n, d)
+
+
+@pytest.mark.parametrize("n", [16, 5, 40])
+def test_attention_bwd(n):
+    b, h, hd = 5, 16, 80
+    gen = torch.Generator(device=DEV).manual_seed(n)
+    qkv = torch.randn(b * n, 3 * h * hd, generator=gen, device=DEV)
+    dout = torch.randn(b * n, h * hd, generator=gen, device=DEV)
+    pm = torch.zeros(b, n, dtype=torch.bool, device=DEV)
+    pm[1, : n // 2] = True
+    pm[2, :1] = True
+    nm = pm.sum(-1).int()
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd)).to(DEV)
+    qw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    kw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    per_dim = 0.5 * torch.randn(hd, generator=gen, device=DEV)
+    q_scale = (torch.nn.functional.softplus(per_dim) * (1.442695041 / math.sqrt(hd))).contiguous()
+    qd = qkv.double().requires_grad_(True)
+    out = _attn_fwd_torch(qd, b, n, h, hd, pm, inv_freq, qw, kw, per_dim)
+    (ref,) = torch.autograd.grad(out, qd, dout.double())
+    # all-masked (uniform) rows pass gradient through the additive mask exactly like torch autograd does
+    got = ops.timesfm_attention_bwd(qkv, dout, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6, DT_F32)
+    assert rel_l2(got, ref.float()) < 2e-5
+    got_s = ops.timesfm_attention_bwd(qkv, dout, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6, DT_BF16_SPLIT)
+    assert rel_l2(ops.split_to_float(got_s), ref.float()) < 5e-5
+
+
+def test_gemm_grad_epilogues_and_pre_act():
+    m, n, k = 200, 1280, 1280
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    a32 = torch.randn(m, k, generator=gen, device=DEV)
+    b32 = torch.randn(n, k, generator=gen, device=DEV) / math.sqrt(k)
+    a, b = ops.cast_rows(a32, DT_BF16_SPLIT), ops.cast_rows(b32, DT_BF16_SPLIT)
+    u = torch.randn(m, n, generator=gen, device=DEV)
+    acc = a32.double() @ b32.double().t()
+    out = torch.empty(m, n, device=DEV)
+    ops.gemm([(a, b, k)], m, n, out, DT_F32, precision=PREC_BF16X3, act=ACT_SILU_GRAD, aux=u)
+    ud = u.double()
+    sg = torch.sigmoid(ud)
+    assert rel_l2(out, (acc * sg * (1 + ud * (1 - sg))).float()) < 3e-5
+    ops.gemm([(a, b, k)], m, n, out, DT_F32, precision=PREC_BF16X3, act=ACT_RELU_GRAD, aux=u.to(torch.bfloat16))
+    assert rel_l2(out, (acc * (u.to(torch.bfloat16).double() > 0)).float()) < 3e-5
+    pre = torch.empty(m, n, device=DEV)
+    ops.gemm([(a, b, k)], m, n, out, DT_F32, precision=PREC_BF16X3, act=ACT_SILU, pre_act=pre)
+    assert rel_l2(pre, acc.float()) < 3e-5
+    assert rel_l2(out, (acc * torch.sigmoid(acc)).float()) < 3e-5
+
+
+@pytest.mark.parametrize("in_kind", ["f32", "bf16", "split"])
+def test_transpose_mask_and_mask_cast(in_kind):
+    rows, cols = 333, 384
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x32 = torch.randn(rows, cols, generator=gen, device=DEV)
+    mask = torch.randn(rows, cols, generator=gen, device=DEV)
+    if in_kind == "f32":
+        x, xf = x32, x32
+    elif in_kind == "bf16":
+        x = x32.to(torch.bfloat16)
+        xf = x.float()
+    else:
+        x = ops.cast_rows(x32, DT_BF16_SPLIT)
+        xf = ops.split_to_float(x)
+    out, kpad = ops.transpose_mask(x, rows, cols, DT_BF16_SPLIT, mask=mask)
+    assert kpad == 384 and out.shape == (cols, 2 * kpad)
+    got = ops.split_to_float(out)
+    ref = (xf * (mask > 0)).t()
+    assert rel_l2(got[:, :rows], ref) < 1e-5
+    assert got[:, rows:].abs().max().item() == 0.0
+    out_b, _ = ops.transpose_mask(x, rows, cols, DT_BF16)
+    assert torch.equal(out_b[:, :rows], xf.t().to(torch.bfloat16))
+    if in_kind == "f32":
+        mc = ops.mask_cast_rows(x32, mask, DT_BF16_SPLIT)
+        assert rel_l2(ops.split_to_float(mc), x32 * (mask > 0)) < 1e-5
+
+
+# ----------------------------------------------------------------------------- end to end vs the oracle's autograd
+def build(num_layers, fusion_layers=1, hidden=(), seed=0):
+    adapter = TimesFM2p5Adapter(num_layers=num_layers, with_quantile_head=False)
+    init_random_(adapter, seed=seed)
+    torch.manual_seed(seed + 100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, fusion_layers, list(hidden)))
+    oracle = O.oracle_from_product(dec)
+    return dec.to(DEV), oracle
+
+
+def oracle_grads(oracle, horizon, ctx, masks, text, target):
+    oracle.adapter.freeze_parameters()
+    for p in oracle.fusion.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    loss = torch.nn.functional.mse_loss(oracle(horizon, ctx, masks, text), target)
+    loss.backward()
+    return loss.item(), [p.grad.clone() for p in oracle.fusion.parameters()]
+
+
+@pytest.mark.parametrize("layers,fusion_layers,hidden,padded", [(2, 1, (), False), (3, 1, (), True), (2, 2, (512,), False), (2, 3, (256, 128), False)])
+def test_fusion_gradient_matches_oracle(layers, fusion_layers, hidden, padded):
+    dec, oracle = build(layers, fusion_layers, hidden)
+    dec.set_precision("bf16x3")
+    dec.adapter.freeze_parameters()
+    dec.train()
+    ctx, masks, text, target = O.synthetic_batch(6, 512, 64, padded=padded, seed=21)
+    ref_loss, ref_grads = oracle_grads(oracle, 64, ctx, masks, text, target)
+    point = dec(64, ctx.to(DEV), masks.to(DEV), text.to(DEV))
+    loss = torch.nn.functional.mse_loss(point, target.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    for lin, ref in zip(dec.fusion.linears(), ref_grads):
+        assert lin.weight.grad is not None and lin.weight.grad.shape == ref.shape
+        err = rel_l2(lin.weight.grad.cpu(), ref)
+        assert err < 1e-3, err  # relative L2 <= 1e-3 in the fp32-accumulate mode
+    assert all(p.grad is None for p in dec.adapter.parameters())
+
+
+def test_gradient_accumulation_and_bf16_mode():
+    dec, oracle = build(2)
+    dec.adapter.freeze_parameters()
+    ctx, masks, text, target = O.synthetic_batch(8, 512, 128, seed=5)
+    _, ref_grads = oracle_grads(oracle, 128, ctx, masks, text, target)
+    # two micro-batches of 4 with loss / 2 == one batch of 8 (trainer.py:208-209)
+    dec.set_precision("bf16x3")
+    for sl in (slice(0, 4), slice(4, 8)):
+        point = dec(128, ctx[sl].to(DEV), masks[sl].to(DEV), text[sl].to(DEV))
+        (torch.nn.functional.mse_loss(point, target[sl].to(DEV)) / 2).backward()
+    assert rel_l2(dec.fusion.linears()[0].weight.grad.cpu(), ref_grads[0]) < 1e-3
+    dec.zero_grad()
+    dec.set_precision("bf16")
+    point = dec(128, ctx.to(DEV), masks.to(DEV), text.to(DEV))
+    torch.nn.functional.mse_loss(point, target.to(DEV)).backward()
+    err = rel_l2(dec.fusion.linears()[0].weight.grad.cpu(), ref_grads[0])
+    print(f"bf16-mode fusion gradient rel L2 = {err:.3e}")
+    assert err < 6e-2
+
+
+def test_baseline_mode_is_refused_loudly():
+    dec, _ = build(1)
+    dec.adapter.unfreeze_parameters()
+    ctx, masks, text, _ = O.synthetic_batch(2, 512, 16)
+    with pytest.raises(NotImplementedError, match="baseline mode"):
+        dec(16, ctx.to(DEV), masks.to(DEV), text.to(DEV))
