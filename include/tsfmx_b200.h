@@ -218,6 +218,27 @@ int tsfmx_timesfm_attention(const void* qkv, int32_t qkv_dtype, int64_t batch, i
                             const float* k_ln_w, const float* q_scale, float eps, int32_t out_dtype, void* out,
                             void* stream);
 
+/*
+ * Chronos-2 time self-attention core of one encoder block (upstream Chronos2Model.encoder, driven by
+ * Chronos2Adapter.forward, reference tsfmx/tsfm/chronos.py:119-123): RoPE(q, k) with positions arange(T),
+ * no 1/sqrt(d) scaling, bidirectional, additive key mask, fp32 softmax.
+ *   qkv [B*T, 3*H*hd] f32 / bf16 = [q | k | v];  key_mask [B, T] u8, non-zero = attendable;  inv_freq [hd/2]
+ *   out [B*T, H*hd] of out_dtype.  A row whose keys are all masked gets uniform weights (finfo.min semantics).
+ * The block's group self-attention needs no kernel: with group_ids = arange(B) (chronos.py:117) it equals
+ * h + (W_o W_v) RMSNorm(h), one tsfmx_gemm.
+ */
+int tsfmx_encoder_attention(const void* qkv, int32_t qkv_dtype, int64_t batch, int32_t seq, int32_t num_heads,
+                            int32_t head_dim, const uint8_t* key_mask, const float* inv_freq, int32_t out_dtype,
+                            void* out, void* stream);
+
+/*
+ * Chronos-2 output epilogue (reference chronos.py:159-169): preds [B*np, Q*patch] (patch-major rows of the
+ * output ResidualBlock, np = ceil(horizon / patch)) -> out [B, horizon, Q] = sinh(x) * scale[b] + loc[b].
+ */
+int tsfmx_chronos2_finalize(const float* preds, int64_t batch, int32_t num_patches_used, int32_t num_quantiles,
+                            int32_t patch, int32_t horizon, int32_t use_arcsinh, const float* loc, const float* scale,
+                            float* out, void* stream);
+
 /* ------------------------------------------------------------------------
  * Backward pass of the fusion fine-tune step (reference tsfmx/trainer.py:200-219; the adapter is frozen,
  * trainer.py:76-77, so only activation gradients flow through the backbone).  The dgrad GEMMs are

@@ -27,6 +27,7 @@ SOURCES = [
     "attention.cu",
     "gemm.cu",
     "backward.cu",
+    "chronos.cu",
     "model.cu",
 ]
 

@@ -102,6 +102,14 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
          c_void_p],
     ),
     "tsfmx_attention_force_simt": (c_int32, [c_int32]),
+    "tsfmx_encoder_attention": (
+        c_int32,
+        [c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p],
+    ),
+    "tsfmx_chronos2_finalize": (
+        c_int32,
+        [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "tsfmx_sizeof_gemm_args": (c_int32, []),
     "tsfmx_rmsnorm_bwd_chain": (
         c_int32,

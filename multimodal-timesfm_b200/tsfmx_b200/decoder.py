@@ -59,7 +59,8 @@ class MultimodalDecoder(nn.Module):
         if masks.shape != inputs.shape:
             raise ValueError(f"masks shape {masks.shape} must match inputs shape {inputs.shape}")
         masks = masks.bool()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        # train() mode with autograd on = the reference's fine-tune step; eval() / no_grad = plain forecasting
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_full_training(horizon, inputs, masks, text_embeddings)
         preprocessed = self.adapter.preprocess(inputs, masks)
         embeddings = (

@@ -66,7 +66,7 @@ class MultimodalFusion(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, ts_embeddings: torch.Tensor, text_embeddings: torch.Tensor) -> torch.Tensor:
         """``ts_embeddings + relu(W_k ... relu(W_1 text))`` (reference fusion.py:44-47)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .autograd import fusion_forward_with_grad
 
             return fusion_forward_with_grad(self, ts_embeddings, text_embeddings)

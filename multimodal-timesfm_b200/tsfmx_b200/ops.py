@@ -358,3 +358,44 @@ def mask_cast_rows(x: torch.Tensor, mask: torch.Tensor, out_dtype: int) -> torch
         )
     )
     return out
+
+
+# ----------------------------------------------------------------------------- Chronos-2
+def encoder_attention(
+    qkv: torch.Tensor,
+    batch: int,
+    seq: int,
+    num_heads: int,
+    head_dim: int,
+    key_mask: torch.Tensor | None,
+    inv_freq: torch.Tensor,
+    out_dtype: int,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    lib = _lib.load()
+    _lib.require_cuda(qkv)
+    if out is None:
+        out = alloc(batch * seq, num_heads * head_dim, out_dtype, qkv.device)
+    km = None if key_mask is None else _as_u8(key_mask)
+    check(
+        lib.tsfmx_encoder_attention(
+            ptr(qkv), _dt(qkv), batch, seq, num_heads, head_dim, ptr(km), ptr(inv_freq), out_dtype, ptr(out), stream()
+        )
+    )
+    return out
+
+
+def chronos2_finalize(
+    preds: torch.Tensor, batch: int, patches_used: int, num_quantiles: int, patch: int, horizon: int,
+    use_arcsinh: bool, loc: torch.Tensor, scale: torch.Tensor,
+) -> torch.Tensor:
+    lib = _lib.load()
+    _lib.require_cuda(preds, loc, scale)
+    out = torch.empty(batch, horizon, num_quantiles, dtype=torch.float32, device=preds.device)
+    check(
+        lib.tsfmx_chronos2_finalize(
+            ptr(preds), batch, patches_used, num_quantiles, patch, horizon, int(use_arcsinh),
+            ptr(loc.reshape(-1).contiguous()), ptr(scale.reshape(-1).contiguous()), ptr(out), stream(),
+        )
+    )
+    return out

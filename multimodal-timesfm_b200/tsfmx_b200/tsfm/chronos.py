@@ -1,0 +1,363 @@
+"""Chronos-2 adapter (reference tsfmx/tsfm/chronos.py:16-207), B200-native.
+
+The reference wraps ``chronos.Chronos2Model`` (chronos-forecasting 2.2.2); here ``Chronos2Module`` is a plain
+parameter container with the upstream state-dict key names and every stage runs through the C ABI:
+
+  preprocess  : fused instance-norm + arcsinh + patch(16) + time-encoding kernel, then the input ResidualBlock
+                (48 -> 3072 -> 768, bias, ReLU) as two tcgen05 GEMMs
+  forward     : [context | REG | 64 future patches] assembled once (the future-patch embeddings are batch
+                invariant: zeros + fixed time encoding, so they are computed once and broadcast); per block
+                QKV GEMM -> attention kernel (RoPE, no scaling, key mask) -> out GEMM -> fused residual + norm ->
+                group attention as ONE GEMM on the pre-multiplied W_o W_v (group_ids = arange(B), reference
+                chronos.py:117, makes it per-series) -> fused residual + norm -> ReLU MLP (2 GEMMs)
+  postprocess : output ResidualBlock on the ceil(horizon / 16) patches that are needed, sinh / scale / loc and the
+                (B, horizon, 21) reorder in one epilogue kernel
+"""
+
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import ACT_RELU, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
+from ..fusion import _pad_k
+from .base import PreprocessResult, TsfmAdapter
+
+QUANTILES = [0.01, 0.05] + [round(0.1 + 0.05 * i, 2) for i in range(17)] + [0.95, 0.99]
+
+
+class _ResidualBlock(nn.Module):
+    def __init__(self, d_in: int, d_hidden: int, d_out: int) -> None:
+        super().__init__()
+        self.hidden_layer = nn.Linear(d_in, d_hidden)
+        self.output_layer = nn.Linear(d_hidden, d_out)
+        self.residual_layer = nn.Linear(d_in, d_out)
+
+
+class _LayerNorm(nn.Module):
+    def __init__(self, dims: int) -> None:
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dims))
+
+
+class _MHA(nn.Module):
+    def __init__(self, d_model: int, inner: int) -> None:
+        super().__init__()
+        self.q = nn.Linear(d_model, inner, bias=False)
+        self.k = nn.Linear(d_model, inner, bias=False)
+        self.v = nn.Linear(d_model, inner, bias=False)
+        self.o = nn.Linear(inner, d_model, bias=False)
+
+
+class _AttnLayer(nn.Module):
+    def __init__(self, d_model: int, inner: int) -> None:
+        super().__init__()
+        self.self_attention = _MHA(d_model, inner)
+        self.layer_norm = _LayerNorm(d_model)
+
+
+class _MLP(nn.Module):
+    def __init__(self, d_model: int, d_ff: int) -> None:
+        super().__init__()
+        self.wi = nn.Linear(d_model, d_ff, bias=False)
+        self.wo = nn.Linear(d_ff, d_model, bias=False)
+
+
+class _FFLayer(nn.Module):
+    def __init__(self, d_model: int, d_ff: int) -> None:
+        super().__init__()
+        self.mlp = _MLP(d_model, d_ff)
+        self.layer_norm = _LayerNorm(d_model)
+
+
+class _Block(nn.Module):
+    def __init__(self, d_model: int, inner: int, d_ff: int) -> None:
+        super().__init__()
+        # layer.0 = time self-attention, layer.1 = group self-attention, layer.2 = feed forward
+        self.layer = nn.ModuleList([_AttnLayer(d_model, inner), _AttnLayer(d_model, inner), _FFLayer(d_model, d_ff)])
+
+
+class _Encoder(nn.Module):
+    def __init__(self, num_layers: int, d_model: int, inner: int, d_ff: int) -> None:
+        super().__init__()
+        self.block = nn.ModuleList(_Block(d_model, inner, d_ff) for _ in range(num_layers))
+        self.final_layer_norm = _LayerNorm(d_model)
+
+
+class Chronos2Module(nn.Module):
+    """Parameters of Chronos-2 (amazon/chronos-2 layout) with upstream key names."""
+
+    def __init__(self, num_layers: int = 12) -> None:
+        super().__init__()
+        self.model_dim, self.num_heads, self.d_kv, self.d_ff = 768, 12, 64, 3072
+        self.eps = 1e-6
+        self.rope_theta = 10000.0
+        self.chronos_config = SimpleNamespace(
+            context_length=8192, input_patch_size=16, input_patch_stride=16, output_patch_size=16,
+            quantiles=list(QUANTILES), use_reg_token=True, use_arcsinh=True, max_output_patches=64,
+            time_encoding_scale=8192,
+        )
+        self.config = SimpleNamespace(reg_token_id=1, pad_token_id=0, vocab_size=2)
+        self.num_quantiles = len(QUANTILES)
+        inner = self.num_heads * self.d_kv
+        self.shared = nn.Embedding(2, self.model_dim)
+        self.input_patch_embedding = _ResidualBlock(3 * 16, self.d_ff, self.model_dim)
+        self.encoder = _Encoder(num_layers, self.model_dim, inner, self.d_ff)
+        self.output_patch_embedding = _ResidualBlock(self.model_dim, self.d_ff, self.num_quantiles * 16)
+
+
+def init_random_(model: nn.Module, seed: int = 0) -> None:
+    """Deterministic init of every tensor: matrices ~ N(0, 0.03), biases ~ N(0, 0.01), norm weights 1 + 0.1 N."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "layer_norm.weight" in name:
+                v = 1.0 + 0.1 * torch.randn(p.shape, generator=gen)
+            elif name.endswith(".bias"):
+                v = 0.01 * torch.randn(p.shape, generator=gen)
+            else:
+                v = 0.03 * torch.randn(p.shape, generator=gen)
+            p.copy_(v.to(p.device))
+
+
+class Chronos2Adapter(TsfmAdapter):
+    """Adapter for Amazon Chronos-2 (120 M encoder-only model)."""
+
+    def __init__(self, model: Chronos2Module | None = None, precision: str = "bf16") -> None:
+        super().__init__()
+        self._model = model if model is not None else Chronos2Module()
+        self.set_precision(precision)
+        self._packed: dict[object, dict[str, object]] = {}
+
+    def set_precision(self, precision: str) -> None:
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        self.precision = precision
+
+    @property
+    def model_dims(self) -> int:
+        return int(self._model.model_dim)
+
+    @property
+    def patch_len(self) -> int:
+        return int(self._model.chronos_config.input_patch_size)
+
+    @property
+    def point_forecast_index(self) -> int:
+        return list(self._model.chronos_config.quantiles).index(0.5)
+
+    # ------------------------------------------------------------------ packed weights
+    def _weights(self) -> dict[str, object]:
+        prec = PRECISIONS[self.precision]
+        params = list(self._model.parameters())
+        key = (prec, tuple((p.data_ptr(), p._version) for p in params))
+        if key in self._packed:
+            return self._packed[key]
+        self._packed.clear()
+        m = self._model
+        adt = ops.act_dtype(prec)
+        dev = params[0].device
+
+        def pack(wt: torch.Tensor) -> torch.Tensor:
+            return ops.cast_rows(_pad_k(wt.detach().float()), adt)
+
+        def f32(t: torch.Tensor) -> torch.Tensor:
+            return t.detach().float().contiguous()
+
+        ipe, ope = m.input_patch_embedding, m.output_patch_embedding
+        w: dict[str, object] = {
+            "in_hidden": pack(ipe.hidden_layer.weight), "in_hidden_b": f32(ipe.hidden_layer.bias),
+            "in_out": pack(ipe.output_layer.weight), "in_res": pack(ipe.residual_layer.weight),
+            "in_out_b": f32(ipe.output_layer.bias + ipe.residual_layer.bias),
+            "out_hidden": pack(ope.hidden_layer.weight), "out_hidden_b": f32(ope.hidden_layer.bias),
+            "out_out": pack(ope.output_layer.weight), "out_res": pack(ope.residual_layer.weight),
+            "out_out_b": f32(ope.output_layer.bias + ope.residual_layer.bias),
+            "final_ln": f32(m.encoder.final_layer_norm.weight),
+            "reg": f32(m.shared.weight[m.config.reg_token_id]),
+            "inv_freq": (1.0 / (m.rope_theta ** (torch.arange(0, m.d_kv, 2, dtype=torch.int64).float() / m.d_kv))).to(dev),
+            "blocks": [],
+        }
+        for blk in m.encoder.block:
+            t_att, g_att, ff = blk.layer[0], blk.layer[1], blk.layer[2]
+            ta, ga = t_att.self_attention, g_att.self_attention
+            # group attention with group_ids = arange(B): h + W_o W_v LN(h)  (product formed in fp64)
+            w_ov = (ga.o.weight.detach().double() @ ga.v.weight.detach().double()).float()
+            w["blocks"].append(
+                {
+                    "ln_t": f32(t_att.layer_norm.weight),
+                    "qkv": pack(torch.cat([ta.q.weight, ta.k.weight, ta.v.weight], dim=0)),
+                    "o": pack(ta.o.weight),
+                    "ln_g": f32(g_att.layer_norm.weight),
+                    "ov": pack(w_ov),
+                    "ln_f": f32(ff.layer_norm.weight),
+                    "wi": pack(ff.mlp.wi.weight),
+                    "wo": pack(ff.mlp.wo.weight),
+                }
+            )
+        self._packed[key] = w
+        return w
+
+    def _embed_patches(self, patched: torch.Tensor, rows: int, w: dict, prec: int) -> torch.Tensor:
+        """input_patch_embedding: ResidualBlock 48(->64 padded) -> 3072 -> 768, bias, ReLU -> fp32 [rows, 768]."""
+        m = self._model
+        adt = ops.act_dtype(prec)
+        hidden = ops.alloc(rows, m.d_ff, adt, patched.device)
+        ops.gemm([(patched, w["in_hidden"], 64)], rows, m.d_ff, hidden, adt, precision=prec, act=ACT_RELU,
+                 bias=w["in_hidden_b"])
+        emb = torch.empty(rows, m.model_dim, dtype=torch.float32, device=patched.device)
+        ops.gemm([(hidden, w["in_out"], m.d_ff), (patched, w["in_res"], 64)], rows, m.model_dim, emb, DT_F32,
+                 precision=prec, bias=w["in_out_b"])
+        return emb
+
+    # ------------------------------------------------------------------ stages
+    def preprocess(self, inputs: torch.Tensor, masks: torch.Tensor) -> PreprocessResult:
+        """Normalise, patch, time-encode and embed (reference chronos.py:35-60).
+
+        masks: True = padded.  Returns embeddings (B, ceil(C/16), 768), patch masks (True = no observed point in
+        the patch) and ``loc`` / ``scale`` of shape (B, 1)."""
+        if not inputs.is_cuda:
+            raise TsfmxError("Chronos2Adapter runs on B200 only; there is no CPU fallback")
+        m, cc = self._model, self._model.chronos_config
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        if inputs.shape[-1] > cc.context_length:  # upstream truncates to the last context_length steps
+            inputs, masks = inputs[..., -cc.context_length :], masks[..., -cc.context_length :]
+        b = inputs.shape[0]
+        patched, attn_mask, loc, scale = ops.chronos2_patchify_norm(
+            inputs, masks.bool(), cc.input_patch_size, cc.use_arcsinh, float(cc.time_encoding_scale), adt, out_cols=64
+        )
+        n = attn_mask.shape[1]
+        emb = self._embed_patches(patched, b * n, w, prec)
+        return PreprocessResult(
+            input_embeddings=emb.view(b, n, m.model_dim),
+            masks=~attn_mask,
+            normalization_stats={"loc": loc.view(b, 1), "scale": scale.view(b, 1)},
+        )
+
+    def _future_embeds(self, w: dict, prec: int, dev: torch.device) -> torch.Tensor:
+        """Embeddings of the 64 all-zero future patches: only the fixed time encoding is non-zero, so they are the
+        same for every series (reference chronos.py:82-100 recomputes them B times)."""
+        key = ("future", prec)
+        if key not in w:
+            cc = self._model.chronos_config
+            nop, ps = cc.max_output_patches, cc.output_patch_size
+            x = torch.zeros(nop, 64, dtype=torch.float32, device=dev)
+            x[:, :ps] = (torch.arange(0, nop * ps, dtype=torch.float32, device=dev) / cc.time_encoding_scale).view(nop, ps)
+            w[key] = self._embed_patches(ops.cast_rows(x, ops.act_dtype(prec)), nop, w, prec)
+        return w[key]
+
+    def forward(self, input_embeddings: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        """Run the encoder on [context | REG | future] and return the 64 forecast positions
+        (reference chronos.py:62-126) -> (batch, 64, 768)."""
+        if not input_embeddings.is_cuda:
+            raise TsfmxError("Chronos2Adapter runs on B200 only; there is no CPU fallback")
+        m, cc = self._model, self._model.chronos_config
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32
+        w = self._weights()
+        dev = input_embeddings.device
+        b, n, d = input_embeddings.shape
+        nop = cc.max_output_patches
+        extra = 1 if cc.use_reg_token else 0
+        t = n + extra + nop
+        h = torch.empty(b, t, d, dtype=torch.float32, device=dev)
+        h[:, :n] = input_embeddings
+        if extra:
+            h[:, n] = w["reg"]
+        h[:, n + extra :] = self._future_embeds(w, prec, dev)
+        key_mask = torch.ones(b, t, dtype=torch.bool, device=dev)
+        key_mask[:, :n] = ~masks.bool()
+        rows = b * t
+        h2 = h.view(rows, d)
+        blocks = w["blocks"]
+        inner = m.num_heads * m.d_kv
+        if not blocks:
+            out = ops.rmsnorm(h2, w["final_ln"], m.eps, DT_F32)
+            return out.view(b, t, d)[:, -nop:].contiguous()
+        xn = ops.rmsnorm(h2, blocks[0]["ln_t"], m.eps, adt)
+        qkv = ops.alloc(rows, 3 * inner, mid_dt, dev)
+        attn = ops.alloc(rows, inner, adt, dev)
+        a = ops.alloc(rows, d, mid_dt, dev)
+        u = ops.alloc(rows, m.d_ff, adt, dev)
+        final = None
+        for i, bw in enumerate(blocks):
+            ops.gemm([(xn, bw["qkv"], d)], rows, 3 * inner, qkv, mid_dt, precision=prec)
+            ops.encoder_attention(qkv, b, t, m.num_heads, m.d_kv, key_mask, w["inv_freq"], adt, out=attn)
+            ops.gemm([(attn, bw["o"], inner)], rows, d, a, mid_dt, precision=prec)
+            ops.norm_residual_norm(a, h2, None, bw["ln_g"], m.eps, h2, adt, xn)
+            ops.gemm([(xn, bw["ov"], d)], rows, d, a, mid_dt, precision=prec)
+            ops.norm_residual_norm(a, h2, None, bw["ln_f"], m.eps, h2, adt, xn)
+            ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
+            ops.gemm([(u, bw["wo"], m.d_ff)], rows, d, a, mid_dt, precision=prec)
+            if i + 1 < len(blocks):
+                ops.norm_residual_norm(a, h2, None, blocks[i + 1]["ln_t"], m.eps, h2, adt, xn)
+            else:
+                final = torch.empty(rows, d, dtype=torch.float32, device=dev)
+                ops.norm_residual_norm(a, h2, None, w["final_ln"], m.eps, h2, DT_F32, final)
+        return final.view(b, t, d)[:, -nop:].contiguous()
+
+    def postprocess(
+        self,
+        horizon: int,
+        output_embeddings: torch.Tensor,
+        normalization_stats: dict[str, torch.Tensor],
+    ) -> torch.Tensor:
+        """Quantile head + inverse instance norm (reference chronos.py:128-169) -> (batch, horizon, 21).
+
+        Raises ValueError if ``horizon`` exceeds 64 patches * 16 steps."""
+        m, cc = self._model, self._model.chronos_config
+        nop, ps = cc.max_output_patches, cc.output_patch_size
+        max_horizon = nop * ps
+        if horizon > max_horizon:
+            raise ValueError(
+                f"horizon ({horizon}) exceeds the maximum prediction length "
+                f"({max_horizon} = {nop} patches * {ps} steps)."
+            )
+        if not output_embeddings.is_cuda:
+            raise TsfmxError("Chronos2Adapter runs on B200 only; there is no CPU fallback")
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        b, _, d = output_embeddings.shape
+        used = (horizon + ps - 1) // ps  # only these output patches reach the forecast
+        x = output_embeddings[:, :used].float().reshape(b * used, d).contiguous()
+        xa = ops.cast_rows(x, adt)
+        rows = b * used
+        hid = ops.alloc(rows, m.d_ff, adt, x.device)
+        ops.gemm([(xa, w["out_hidden"], d)], rows, m.d_ff, hid, adt, precision=prec, act=ACT_RELU, bias=w["out_hidden_b"])
+        nq = m.num_quantiles
+        preds = torch.empty(rows, nq * ps, dtype=torch.float32, device=x.device)
+        ops.gemm([(hid, w["out_out"], m.d_ff), (xa, w["out_res"], d)], rows, nq * ps, preds, DT_F32, precision=prec,
+                 bias=w["out_out_b"])
+        return ops.chronos2_finalize(preds, b, used, nq, ps, horizon, cc.use_arcsinh, normalization_stats["loc"],
+                                     normalization_stats["scale"])
+
+    # ------------------------------------------------------------------ checkpoints / freezing
+    def load_checkpoint(self, path: str) -> None:
+        """Load an upstream Chronos-2 safetensors checkpoint (strict), reference chronos.py:171-174."""
+        from safetensors.torch import load_file
+
+        self._model.load_state_dict(load_file(path), strict=True)
+
+    @classmethod
+    def from_pretrained(cls, device: torch.device, repo_id: str = "amazon/chronos-2") -> "Chronos2Adapter":
+        """Download + load pretrained weights (reference chronos.py:176-199); needs network access."""
+        from huggingface_hub import hf_hub_download
+
+        instance = cls(Chronos2Module())
+        instance.to(device)
+        instance.load_checkpoint(hf_hub_download(repo_id=repo_id, filename="model.safetensors"))
+        return instance
+
+    def freeze_parameters(self) -> None:
+        for param in self.parameters():
+            param.requires_grad = False
+
+    def unfreeze_parameters(self) -> None:
+        for param in self.parameters():
+            param.requires_grad = True

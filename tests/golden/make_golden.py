@@ -75,6 +75,35 @@ def t5_case():
     print("t5", ids.shape, int(ids.min()), int(ids.max()))
 
 
+def chronos2_case():
+    from oracle import chronos2_oracle as C
+    from tsfmx_b200.tsfm.chronos import Chronos2Module
+    from tsfmx_b200.tsfm.chronos import init_random_ as c2_init
+
+    module = Chronos2Module(2)
+    c2_init(module, 0)
+    o_adapter = C.OracleChronos2Adapter(C.Chronos2Model(C.Chronos2Config(num_layers=2)))
+    o_adapter.load_upstream_state_dict(module.state_dict())
+    ref = RefDecoder(o_adapter, RefConfig(384, 1, [])).eval()  # the reference's real decoder + fusion classes
+    torch.manual_seed(100)
+    torch.nn.init.xavier_uniform_(ref.fusion.projection[0].weight)
+    ctx, masks, _t, _ = O.synthetic_batch(3, 500, 40, padded=True, seed=9, patch_len=16)
+    ctx = ctx * 2 + 0.5
+    g = torch.Generator().manual_seed(9)
+    text = torch.randn(3, 32, 384, generator=g)
+    text = (text / text.norm(dim=-1, keepdim=True)).half().float()
+    with torch.no_grad():
+        pre = ref.adapter.preprocess(ctx, masks)
+        full = ref.forward_full(40, ctx, masks, text)
+    np.savez_compressed(
+        OUT / "chronos2_l2_b3_c500_h40.npz", context=ctx.numpy(), masks=masks.numpy(), text=text.numpy().astype(np.float16),
+        fusion_weight=ref.fusion.projection[0].weight.detach().numpy().astype(np.float32),
+        patch_mask=pre.masks.numpy(), loc=pre.normalization_stats["loc"].numpy(),
+        scale=pre.normalization_stats["scale"].numpy(), forecast=full.numpy(),
+    )
+    print("chronos2", full.shape, float(full.abs().max()))
+
+
 if __name__ == "__main__":
     # text embeddings are stored as fp16 to keep the fixtures small; the tests up-cast the stored values, so the
     # inputs are identical on both sides.
@@ -82,3 +111,4 @@ if __name__ == "__main__":
     timesfm_case("timesfm_l20_b2_c512_h128", 20, 2, 512, 128, padded=False, seed=1)
     timesfm_case("timesfm_l2_b3_c2048_h64_f2", 2, 3, 2048, 64, padded=True, fusion_layers=2, hidden=(512,), seed=2)
     t5_case()
+    chronos2_case()

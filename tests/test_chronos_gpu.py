@@ -1,0 +1,123 @@
+"""Chronos-2 adapter path (reference tsfmx/tsfm/chronos.py) on the CUDA path against the restated CPU oracle."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import chronos2_oracle as C  # noqa: E402  (checker only)
+from oracle import timesfm_oracle as O  # noqa: E402
+from tsfmx_b200 import ops  # noqa: E402
+from tsfmx_b200._lib import DT_BF16_SPLIT, DT_F32  # noqa: E402
+from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig  # noqa: E402
+from tsfmx_b200.tsfm.chronos import Chronos2Adapter, Chronos2Module, init_random_  # noqa: E402
+
+DEV = "cuda"
+FP32_TOL = 1e-3
+BF16_TOL = 5e-2
+
+
+def rel_max(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def build(num_layers, seed=0):
+    module = Chronos2Module(num_layers)
+    init_random_(module, seed)
+    adapter = Chronos2Adapter(module)
+    torch.manual_seed(seed + 100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, []))
+    o_model = C.Chronos2Model(C.Chronos2Config(num_layers=num_layers))
+    o_adapter = C.OracleChronos2Adapter(o_model)
+    o_adapter.load_upstream_state_dict(module.state_dict())
+    oracle = O.OracleDecoder(o_adapter, 384, 1, [])
+    with torch.no_grad():
+        oracle.fusion.projection[0].weight.copy_(dec.fusion.linears()[0].weight)
+    return dec.to(DEV).eval(), oracle.eval()
+
+
+def batch(b, context, horizon, padded, seed=3):
+    ctx, masks, _t, _ = O.synthetic_batch(b, context, horizon, padded=padded, seed=seed, patch_len=16)
+    g = torch.Generator().manual_seed(seed)
+    n = (context + 15) // 16
+    text = torch.randn(b, n, 384, generator=g)
+    text = text / text.norm(dim=-1, keepdim=True)
+    return ctx * 3 + 1, masks, text
+
+
+def test_encoder_attention_kernel():
+    b, t, h, hd = 3, 97, 12, 64
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    qkv = torch.randn(b * t, 3 * h * hd, generator=gen, device=DEV)
+    km = torch.ones(b, t, dtype=torch.bool, device=DEV)
+    km[1, :20] = False
+    km[2, :] = False  # all keys masked -> uniform
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(DEV)
+    q, k, v = qkv.double().reshape(b, t, 3, h, hd).permute(2, 0, 3, 1, 4)
+    freqs = torch.arange(t, device=DEV).float()[:, None] * inv_freq[None, :]
+    emb = torch.cat([freqs, freqs], -1)
+    cos, sin = emb.cos().double(), emb.sin().double()
+    q = q * cos + C.rotate_half(q) * sin
+    k = k * cos + C.rotate_half(k) * sin
+    s = q @ k.transpose(-1, -2) + ((~km)[:, None, None, :] * torch.finfo(torch.float32).min).double()
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, h * hd).float()
+    got = ops.encoder_attention(qkv, b, t, h, hd, km, inv_freq, DT_F32)
+    assert rel_max(got, ref) < 2e-5
+    got = ops.encoder_attention(qkv.to(torch.bfloat16), b, t, h, hd, km, inv_freq, DT_BF16_SPLIT)
+    assert rel_max(ops.split_to_float(got), ref) < 2e-2
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_preprocess_stage(padded):
+    dec, oracle = build(1)
+    dec.set_precision("bf16x3")
+    ctx, masks, _ = batch(6, 512, 64, padded)
+    with torch.no_grad():
+        ref = oracle.adapter.preprocess(ctx, masks)
+        got = dec.adapter.preprocess(ctx.to(DEV), masks.to(DEV))
+    assert torch.equal(got.masks.cpu(), ref.masks)  # bit-exact patch mask
+    assert got.normalization_stats["loc"].shape == (6, 1)
+    assert (got.normalization_stats["loc"].cpu() - ref.normalization_stats["loc"]).abs().max().item() < 1e-5
+    assert rel_max(got.normalization_stats["scale"].cpu(), ref.normalization_stats["scale"]) < 1e-5
+    assert rel_max(got.input_embeddings.cpu(), ref.input_embeddings) < 1e-4
+
+
+@pytest.mark.parametrize("layers,context,horizon,padded", [(2, 512, 128, False), (12, 512, 128, True), (2, 2048, 256, True), (2, 500, 17, False)])
+def test_forward_full_parity_fp32_mode(layers, context, horizon, padded):
+    dec, oracle = build(layers)
+    dec.set_precision("bf16x3")
+    ctx, masks, text = batch(5, context, horizon, padded)
+    with torch.no_grad():
+        ref = oracle.forward_full(horizon, ctx, masks, text)
+        got = dec.forward_full(horizon, ctx.to(DEV), masks.to(DEV), text.to(DEV)).cpu()
+        ref_pt = oracle(horizon, ctx, masks, text)
+        got_pt = dec(horizon, ctx.to(DEV), masks.to(DEV), text.to(DEV)).cpu()
+    assert got.shape == ref.shape == (5, horizon, 21)
+    assert rel_max(got, ref) < FP32_TOL, rel_max(got, ref)
+    assert rel_max(got_pt, ref_pt) < FP32_TOL
+    assert dec.adapter.point_forecast_index == 10
+
+
+def test_forward_full_bf16_mode_and_no_text():
+    dec, oracle = build(12)
+    ctx, masks, text = batch(5, 512, 128, False)
+    with torch.no_grad():
+        ref = oracle.forward_full(128, ctx, masks, text)
+        dec.set_precision("bf16")
+        got = dec.forward_full(128, ctx.to(DEV), masks.to(DEV), text.to(DEV)).cpu()
+        err = rel_max(got, ref)
+        print(f"chronos-2 bf16 mode rel_max = {err:.3e}")
+        assert err < BF16_TOL
+        dec.set_precision("bf16x3")
+        ref2 = oracle.forward_full(128, ctx, masks, None)
+        got2 = dec.forward_full(128, ctx.to(DEV), masks.to(DEV), None).cpu()
+    assert rel_max(got2, ref2) < FP32_TOL
+
+
+def test_horizon_limit_error():
+    dec, oracle = build(1)
+    ctx, masks, _ = batch(2, 512, 16, False)
+    with pytest.raises(ValueError, match="exceeds the maximum prediction length"):
+        dec.forward_full(1025, ctx.to(DEV), masks.to(DEV), None)
+    with pytest.raises(ValueError, match="exceeds the maximum prediction length"):
+        oracle.forward_full(1025, ctx, masks, None)

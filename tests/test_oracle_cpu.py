@@ -135,3 +135,42 @@ def test_t5_tokenizer_oracle_golden_and_properties():
     ok = ~torch.isnan(x) & ((x / scale[:, None]).abs() < 14.9)
     half_bin = 30.0 / 4092 / 2
     assert (((vals - x) / scale[:, None]).abs()[ok] <= half_bin * 1.001).all()
+
+
+def test_chronos2_oracle_properties_and_golden():
+    from oracle import chronos2_oracle as C
+    from tsfmx_b200.tsfm.chronos import Chronos2Module
+    from tsfmx_b200.tsfm.chronos import init_random_ as c2_init
+
+    module = Chronos2Module(2)
+    c2_init(module, 0)
+    adapter = C.OracleChronos2Adapter(C.Chronos2Model(C.Chronos2Config(num_layers=2)))
+    adapter.load_upstream_state_dict(module.state_dict())
+    assert adapter.point_forecast_index == 10 and adapter.patch_len == 16 and adapter.model_dims == 768
+    g = load_case("chronos2_l2_b3_c500_h40")
+    oracle = O.OracleDecoder(adapter, 384, 1, [])
+    with torch.no_grad():
+        oracle.fusion.projection[0].weight.copy_(torch.from_numpy(g["fusion_weight"]))
+        ctx, masks = torch.from_numpy(g["context"]), torch.from_numpy(g["masks"])
+        pre = adapter.preprocess(ctx, masks)
+        full = oracle.forward_full(40, ctx, masks, torch.from_numpy(g["text"]).float())
+    assert np.array_equal(pre.masks.numpy(), g["patch_mask"])
+    assert pre.input_embeddings.shape == (3, 32, 768)  # 500 steps are left-padded to 32 patches of 16
+    np.testing.assert_allclose(pre.normalization_stats["loc"].numpy(), g["loc"], rtol=1e-6)
+    assert np.abs(full.numpy() - g["forecast"]).max() < 2e-5 * np.abs(g["forecast"]).max()
+    # degenerate group attention (group_ids = arange(B)) == h + W_o W_v LN(h) on unmasked tokens
+    blk = adapter._model.blocks[0]
+    h = torch.randn(4, 7, 768)
+    fmin = torch.finfo(torch.float32).min
+    gtm = (1.0 - torch.einsum("qb,bt->qbt", torch.eye(4), torch.ones(4, 7)).permute(2, 0, 1)[:, None]) * fmin
+    ht = h.transpose(0, 1)
+    with torch.no_grad():
+        full_attn = ht + blk.group_attn(blk.group_ln(ht), gtm)
+        assert torch.allclose(full_attn, C.degenerate_group_attention(blk, ht), atol=1e-6)
+    # inverse instance norm round trip
+    x = torch.randn(3, 64) * 5 + 2
+    patched, _am, (loc, scale) = adapter._model._prepare_patched_context(x, torch.ones_like(x))
+    back = adapter._model.instance_norm_inverse(patched[..., 16:32].reshape(3, 64), (loc, scale))
+    assert torch.allclose(back, x, atol=1e-4)
+    with pytest.raises(ValueError, match="exceeds the maximum prediction length"):
+        adapter.postprocess(1025, torch.zeros(1, 64, 768), {"loc": loc[:1], "scale": scale[:1]})
