@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--context", type=int, default=CONTEXT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-norm", action="store_true", help="A/B: norm/residual junctions in the GEMM epilogue")
     return ap.parse_args()
 
 
@@ -197,9 +198,19 @@ class GemmTimer:
             return r
 
         ops.gemm = timed_gemm
-        import tsfmx_b200.tsfm.timesfm as tm
+        orig_rn = ops.gemm_rownorm
 
-        tm.ops.gemm = timed_gemm
+        def timed_rownorm(a, b, k, m, n, *rest, **kw):
+            if not timer.enabled or m < 8192 or k != 1280:
+                return orig_rn(a, b, k, m, n, *rest, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig_rn(a, b, k, m, n, *rest, **kw)
+            e1.record()
+            timer.pairs.append((e0, e1, 2.0 * m * n * k))
+            return r
+
+        ops.gemm_rownorm = timed_rownorm
 
     def result(self) -> tuple[float, float, int]:
         ms = sum(a.elapsed_time(b) for a, b, _ in self.pairs)
@@ -230,6 +241,7 @@ def run_b200_arm(args) -> None:
     torch.manual_seed(100)
     dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(TEXT_DIMS, 1, [])).to(dev).eval()
     dec.set_precision("bf16")
+    adapter.fused_norm = args.fused_norm
 
     # each rank owns its shard of series: distinct seeds, same shapes (weak scaling, no collective)
     B = args.batch
@@ -300,7 +312,9 @@ def run_b200_arm(args) -> None:
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "traffic": None,
-        "kernel": "gemm_bf16_tcgen05_kernel<256,2> (decoder-layer GEMMs: qkv / attn-out / ff0 / ff1)",
+        "kernel": "gemm_bf16_tcgen05_kernel<256,2> (qkv, ff0) + gemm_rownorm_tcgen05_kernel (attn-out, ff1 with the "
+                  "norm/residual junction in the epilogue)" if adapter.fused_norm else
+                  "gemm_bf16_tcgen05_kernel<256,2> (decoder-layer GEMMs: qkv / attn-out / ff0 / ff1)",
         "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1),
         "algorithmic_flops_per_launch": flops / max(n_gemm, 1),
         "share_of_step": gemm_ms / ms_resident, "peak_source": f"{peaks['source']} bf16_tflops_sustained",

@@ -183,6 +183,20 @@ int tsfmx_gemm(const tsfmx_gemm_args* args, void* stream);
 /* test / tuning hook: 0 = automatic, 1 = one CTA per tile (UMMA 128xN), 2 = CTA pairs (cta_group::2, UMMA 256xN) */
 int tsfmx_gemm_set_cta_group(int cta_group);
 
+/*
+ * GEMM with the norm / residual junction of a transformer layer fused into its epilogue (one launch instead
+ * of tsfmx_gemm + tsfmx_norm_residual_norm; the GEMM result never goes to HBM):
+ *   a = A W^T;  y = RMSNorm(a) * w_post + x  (w_post NULL: y = a + x);  yn = RMSNorm(y) * w_next  (w_next NULL: yn = y)
+ * Replaces attn.out / ff1 + post_ln + residual + next pre_ln of upstream timesfm Transformer.forward (called at
+ * reference tsfmx/tsfm/timesfm.py:97; HF twin modeling_timesfm2_5.py:378-388).  n / 256 CTAs form a cluster that owns
+ * a full 128-row x n panel; row statistics are exchanged through distributed shared memory.
+ *   seg: one K-segment (split operands when precision = BF16X3); n in {512, 768, 1024, 1280}
+ *   x, y fp32 [m, n] (y may alias x); yn [m, n] of yn_dtype or NULL.
+ */
+int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int32_t n, int32_t precision, const float* w_post,
+                       const float* w_next, const float* x, float* y, int32_t yn_dtype, void* yn, float eps,
+                       void* stream);
+
 /* y = x * rsqrt(mean(x^2) + eps) * w, rows of `cols` fp32 -> bf16 / split / f32. */
 int tsfmx_rmsnorm(const float* x, int64_t rows, int32_t cols, const float* w, float eps, int32_t out_dtype,
                   void* out, void* stream);
@@ -280,6 +294,9 @@ int tsfmx_transpose_mask(const void* in, int32_t in_dtype, int64_t rows, int32_t
 /* out[r, c] = mask[r, c] > 0 ? in[r, c] : 0; fp32 in -> f32 / bf16 / split out (relu' gate of the fusion dgrad) */
 int tsfmx_mask_cast_rows(const float* in, int64_t rows, int32_t cols, const void* mask, int32_t mask_dtype,
                          int64_t ld_mask, int32_t out_dtype, void* out, void* stream);
+
+/* tuning hook: key 0 = series per warp of timesfm_patchify_norm, key 1 = its warps per block (0 = default) */
+int tsfmx_tune(int32_t key, int32_t value);
 
 /* test hook: non-zero forces the fp32 SIMT attention kernel even where the tensor-core kernel applies */
 int tsfmx_attention_force_simt(int on);

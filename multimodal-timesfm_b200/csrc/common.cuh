@@ -305,6 +305,11 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
                : "l"(p));
   return v;
 }
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
   uint32_t v;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));

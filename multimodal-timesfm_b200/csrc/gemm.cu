@@ -369,6 +369,328 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
   }
 }
 
+
+// =====================================================================================================
+// GEMM with the row-norm / residual junction of a transformer layer fused into its epilogue:
+//
+//     a  = A W^T                               (K-loop as above; a never leaves the chip)
+//     y  = RMSNorm(a) * w_post + x             (w_post NULL: y = a + x, the pre-norm form of Chronos-2)
+//     yn = RMSNorm(y) * w_next                 (w_next NULL: yn = y)
+//
+// i.e. out-proj / ff1 of a TimesFM 2.5 layer together with `post_ln(.) + x` and the next `pre_ln`
+// (HF twin modeling_timesfm2_5.py:378-388) — the work of norm_residual_norm_kernel without the HBM
+// round trip of `a` and without a separate launch.  RMSNorm needs statistics over the whole row
+// (N = 1280) while one CTA's TMEM holds 256 columns, so C = N / 256 CTAs form a thread-block cluster
+// that owns a full 128-row x N output panel: every CTA runs its own 128x256 tcgen05 tile, the A tile is
+// fetched ONCE per cluster (each issuer CTA multicasts a row slice to all C CTAs) and the per-row sums of
+// squares are exchanged through distributed shared memory with st.async + mbarrier complete_tx (no cluster
+// barrier, no fence).  y is written back into the accumulator's TMEM columns between the two passes.
+// =====================================================================================================
+constexpr int RN_BN = 256;
+constexpr int RN_MAXC = 5;
+constexpr int RN_STAGES = 4;
+
+struct alignas(64) RownormParams {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  XSeg xseg[3];
+  int32_t num_xseg;
+  int32_t n;
+  int64_t m;
+  int32_t tiles_m;
+  int32_t cluster;      // C = n / 256
+  int32_t a_issuers;    // CTAs that fetch a slice of the A tile (4 when C >= 4, else 2)
+  int32_t yn_dtype;
+  const float* w_post;
+  const float* w_next;
+  const float* x;
+  float* y;
+  void* yn;
+  float eps;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0,
+                                                  int32_t c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(const __grid_constant__ RownormParams p) {
+  constexpr int STAGES = RN_STAGES;
+  constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+  constexpr int B_BYTES = RN_BN * BK * 2;     // 32 KB
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int RED_FLOATS = 2 * 2 * RN_MAXC * 2 * BM;  // [acc stage][round][src CTA][column half][row]
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + RED_FLOATS);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* red_bar = tmem_empty_bar + 2;  // [acc stage][round]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.cluster;
+  const uint32_t rank = cluster_ctarank();
+  const uint16_t all_mask = static_cast<uint16_t>((1u << C) - 1u);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);                          // own arrive(+expect_tx); bytes come from C issuers
+      mbar_init(&empty_bar[i], static_cast<uint32_t>(C));  // every CTA's MMA must be done with the stage
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&red_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int first_tile = blockIdx.x / C;
+  const int tile_step = gridDim.x / C;
+  const int rows_per_issuer = BM / p.a_issuers;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = first_tile; tile < p.tiles_m; tile += tile_step) {
+        const int32_t a_row = tile * BM + static_cast<int>(rank) * rows_per_issuer;
+        const int32_t b_row = static_cast<int>(rank) * RN_BN;
+        for (int s = 0; s < p.num_xseg; ++s) {
+          const XSeg sg = p.xseg[s];
+          for (int kb = 0; kb < sg.nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(smem_b + stage * B_BYTES, &p.tma_b, &full_bar[stage], sg.b_koff + kb * BK, b_row);
+            if (static_cast<int>(rank) < p.a_issuers)
+              tma_load_2d_mcast(smem_a + stage * A_BYTES + static_cast<int>(rank) * rows_per_issuer * BK * 2, &p.tma_a,
+                                &full_bar[stage], sg.a_koff + kb * BK, a_row, all_mask);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (every CTA: cta_group::1)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, RN_BN);
+      uint32_t stage = 0, phase = 0, iter = 0;
+      for (int tile = first_tile; tile < p.tiles_m; tile += tile_step, ++iter) {
+        const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * RN_BN;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.num_xseg; ++s) {
+          const int nkb = p.xseg[s].nkb;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_umma_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
+            const uint64_t db = make_umma_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_bf16<1>(tmem_d, da + 2 * k, db + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit_mcast(&empty_bar[stage], all_mask);  // the A slice we multicast lives in every CTA
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full_bar[as]);
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue: norm / residual / norm
+    const int q = warp & 3;
+    const int chalf = (warp - EPI_WARP0) >> 2;
+    const int row_in_tile = q * 32 + lane;
+    const bool two_norms = p.w_post != nullptr;  // pass 1 (statistics of a) only exists in the post-norm form
+    const bool norm_out = p.w_next != nullptr && p.yn != nullptr;
+    const float inv_n = 1.0f / static_cast<float>(p.n);
+    const uint32_t red_bytes = static_cast<uint32_t>(C) * 2 * BM * 4;
+    uint32_t iter = 0;
+    for (int tile = first_tile; tile < p.tiles_m; tile += tile_step, ++iter) {
+      const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+      const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
+      const bool row_ok = row < p.m;
+      const uint32_t taddr = tmem_base + as * RN_BN + (static_cast<uint32_t>(q * 32) << 16) + chalf * 128;
+      const int col_base = static_cast<int>(rank) * RN_BN + chalf * 128;
+      float* red_stage = red + as * (2 * RN_MAXC * 2 * BM);
+      // arm this tile's two exchange rounds (one arming thread per CTA)
+      if (warp == EPI_WARP0 && lane == 0) {
+        if (two_norms) mbar_arrive_expect_tx(&red_bar[as * 2 + 0], red_bytes);
+        if (norm_out) mbar_arrive_expect_tx(&red_bar[as * 2 + 1], red_bytes);
+      }
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+
+      auto exchange = [&](int round, float partial) -> float {
+        // push my partial sum of squares to every CTA of the cluster (incl. myself), then gather all of them
+        float* slot = red_stage + round * (RN_MAXC * 2 * BM) + (static_cast<int>(rank) * 2 + chalf) * BM + row_in_tile;
+        const uint32_t slot_addr = smem_u32(slot), bar_addr = smem_u32(&red_bar[as * 2 + round]);
+        for (int dst = 0; dst < C; ++dst)
+          st_async_f32(mapa_u32(slot_addr, dst), partial, mapa_u32(bar_addr, dst));
+        mbar_wait(&red_bar[as * 2 + round], aphase);
+        const float* base = red_stage + round * (RN_MAXC * 2 * BM) + row_in_tile;
+        float total = 0.f;
+        for (int src = 0; src < 2 * C; ++src) total += base[src * BM];  // same order in every CTA
+        return total;
+      };
+
+      float rs_a = 1.0f;
+      if (two_norms) {
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(r[i]);
+            ss = fmaf(v, v, ss);
+          }
+        }
+        const float tot = exchange(0, row_ok ? ss : 0.f);
+        rs_a = 1.0f / sqrtf(tot * inv_n + p.eps);
+      }
+      // pass 2: y = a * rs_a * w_post + x  (or a + x); write y; keep y in TMEM; statistics of y
+      float ssy = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = col_base + c * 32;
+        if (two_norms) {
+          const float4* w4 = reinterpret_cast<const float4*>(p.w_post + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 w = __ldg(w4 + i);
+            r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) * rs_a * w.x);
+            r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) * rs_a * w.y);
+            r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) * rs_a * w.z);
+            r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) * rs_a * w.w);
+          }
+        }
+        if (row_ok) {
+          const float* xp = p.x + row * p.n + col0;
+          float* yp = p.y + row * p.n + col0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(xp + 4 * i);
+            const float y0 = __uint_as_float(r[4 * i + 0]) + xv.x, y1 = __uint_as_float(r[4 * i + 1]) + xv.y;
+            const float y2 = __uint_as_float(r[4 * i + 2]) + xv.z, y3 = __uint_as_float(r[4 * i + 3]) + xv.w;
+            *reinterpret_cast<float4*>(yp + 4 * i) = make_float4(y0, y1, y2, y3);
+            r[4 * i + 0] = __float_as_uint(y0), r[4 * i + 1] = __float_as_uint(y1);
+            r[4 * i + 2] = __float_as_uint(y2), r[4 * i + 3] = __float_as_uint(y3);
+            ssy += y0 * y0 + y1 * y1 + y2 * y2 + y3 * y3;
+          }
+        }
+        if (p.yn != nullptr) {
+          if (norm_out) {
+            tmem_st_32x32(taddr + c * 32, r);  // y replaces a in the accumulator columns for pass 3
+          } else if (row_ok) {
+            // yn = y (no second norm): emit directly
+            GemmParams gp = {};
+            gp.d = p.yn, gp.ldd = (p.yn_dtype == TSFMX_DT_BF16_SPLIT ? 2 : 1) * static_cast<int64_t>(p.n);
+            gp.d_dtype = p.yn_dtype, gp.n_store = p.n, gp.split_off = p.n, gp.vec_ok = 1;
+            epilogue_chunk(gp, r, row, col0);
+          }
+        }
+      }
+      if (norm_out) {
+        tmem_st_wait();
+        const float tot = exchange(1, row_ok ? ssy : 0.f);
+        const float rs_y = 1.0f / sqrtf(tot * inv_n + p.eps);
+        GemmParams gp = {};
+        gp.d = p.yn, gp.ldd = (p.yn_dtype == TSFMX_DT_BF16_SPLIT ? 2 : 1) * static_cast<int64_t>(p.n);
+        gp.d_dtype = p.yn_dtype, gp.n_store = p.n, gp.split_off = p.n, gp.vec_ok = 1;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = col_base + c * 32;
+          const float4* w4 = reinterpret_cast<const float4*>(p.w_next + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 w = __ldg(w4 + i);
+            r[4 * i + 0] = __float_as_uint(w.x * (__uint_as_float(r[4 * i + 0]) * rs_y));
+            r[4 * i + 1] = __float_as_uint(w.y * (__uint_as_float(r[4 * i + 1]) * rs_y));
+            r[4 * i + 2] = __float_as_uint(w.z * (__uint_as_float(r[4 * i + 2]) * rs_y));
+            r[4 * i + 3] = __float_as_uint(w.w * (__uint_as_float(r[4 * i + 3]) * rs_y));
+          }
+          if (row_ok) epilogue_chunk(gp, r, row, col0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -551,4 +873,98 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
 
   if (cg == 2) return launch_gemm<256, 2>(p, stream);
   return launch_gemm<256, 1>(p, stream);
+}
+
+extern "C" int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int32_t n, int32_t precision,
+                                  const float* w_post, const float* w_next, const float* x, float* y,
+                                  int32_t yn_dtype, void* yn, float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(seg != nullptr && seg->a != nullptr && seg->b != nullptr, "gemm_rownorm: NULL operand");
+  TSFMX_REQUIRE(m > 0 && m < (int64_t(1) << 31) - 256, "gemm_rownorm: bad m");
+  TSFMX_REQUIRE(n > 0 && n % RN_BN == 0 && n / RN_BN >= 2 && n / RN_BN <= RN_MAXC,
+                "gemm_rownorm: n (%d) must be 512, 768, 1024 or 1280", n);
+  TSFMX_REQUIRE(precision == TSFMX_PREC_BF16 || precision == TSFMX_PREC_BF16X3, "gemm_rownorm: bad precision");
+  TSFMX_REQUIRE(x != nullptr && y != nullptr, "gemm_rownorm: x and y are required");
+  TSFMX_REQUIRE(yn == nullptr || (yn_dtype >= TSFMX_DT_F32 && yn_dtype <= TSFMX_DT_BF16_SPLIT), "gemm_rownorm: bad yn_dtype");
+  TSFMX_REQUIRE(seg->k > 0 && seg->k % BK == 0, "gemm_rownorm: k (%d) must be a positive multiple of %d", seg->k, BK);
+  TSFMX_REQUIRE(seg->lda % 8 == 0 && seg->ldb % 8 == 0, "gemm_rownorm: lda/ldb must be multiples of 8 elements");
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  TSFMX_REQUIRE(al16(seg->a) && al16(seg->b) && al16(x) && al16(y) && al16(yn) && al16(w_post) && al16(w_next),
+                "gemm_rownorm: pointers must be 16-byte aligned");
+  const bool split = precision == TSFMX_PREC_BF16X3;
+  const int64_t cols = split ? 2 * static_cast<int64_t>(seg->k) : seg->k;
+  TSFMX_REQUIRE(seg->lda >= cols && seg->ldb >= cols, "gemm_rownorm: lda/ldb smaller than the stored row length");
+
+  RownormParams p = {};
+  p.m = m;
+  p.n = n;
+  p.tiles_m = static_cast<int32_t>((m + BM - 1) / BM);
+  p.cluster = n / RN_BN;
+  p.a_issuers = p.cluster >= 4 ? 4 : 2;
+  p.yn_dtype = yn_dtype;
+  p.w_post = w_post;
+  p.w_next = w_next;
+  p.x = x;
+  p.y = y;
+  p.yn = yn;
+  p.eps = eps;
+  int rc = make_tmap_bf16(&p.tma_a, seg->a, m, cols, seg->lda, BM / p.a_issuers);
+  if (rc != TSFMX_OK) return rc;
+  rc = make_tmap_bf16(&p.tma_b, seg->b, n, cols, seg->ldb, RN_BN);
+  if (rc != TSFMX_OK) return rc;
+  const int nkb = seg->k / BK;
+  int nx = 0;
+  if (!split) {
+    p.xseg[nx++] = XSeg{0, 0, 0, 0, nkb};
+  } else {
+    p.xseg[nx++] = XSeg{0, 0, seg->k, 0, nkb};
+    p.xseg[nx++] = XSeg{0, 0, 0, seg->k, nkb};
+    p.xseg[nx++] = XSeg{0, 0, 0, 0, nkb};
+  }
+  p.num_xseg = nx;
+
+  constexpr int SMEM = RN_STAGES * (BM * BK * 2 + RN_BN * BK * 2) + 2 * 2 * RN_MAXC * 2 * BM * 4 + 1024 + 256;
+  auto kern = gemm_rownorm_tcgen05_kernel;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) {
+      set_error("gemm_rownorm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return TSFMX_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent: as many clusters as the device can hold at once
+  static int max_clusters[RN_MAXC + 1] = {0};
+  if (max_clusters[p.cluster] == 0) {
+    cfg.gridDim = dim3(p.cluster * 64);
+    int nc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    if (e != cudaSuccess || nc <= 0) {
+      (void)cudaGetLastError();
+      nc = num_sms() / p.cluster;
+    }
+    max_clusters[p.cluster] = nc;
+  }
+  int clusters = max_clusters[p.cluster];
+  if (clusters > p.tiles_m) clusters = p.tiles_m;
+  cfg.gridDim = dim3(clusters * p.cluster);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_rownorm launch failed: %s", cudaGetErrorString(e));
+    return TSFMX_ERR_CUDA;
+  }
+  return check_last_launch("gemm_rownorm_tcgen05");
 }

@@ -52,7 +52,7 @@ __device__ __forceinline__ float group8_sum(float v) {
 }
 
 template <int OUT>
-__global__ void __launch_bounds__(WARPS * 32) timesfm_patchify_norm_kernel(
+__global__ void __launch_bounds__(WARPS * 32) timesfm_patchify_norm_generic_kernel(
     const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, void* tokens,
     float* __restrict__ mu_out, float* __restrict__ sigma_out, uint8_t* __restrict__ patch_mask_out,
     int32_t* __restrict__ num_masked_out) {
@@ -186,6 +186,165 @@ __global__ void __launch_bounds__(WARPS * 32) timesfm_patchify_norm_kernel(
 }
 
 // ----------------------------------------------------------------------------------------
+// Staged variant (the one that runs for context <= 4096): a warp stages G consecutive series in shared
+// memory with 16-byte cp.async (one bulk of loads in flight, nothing is read twice from HBM), computes the
+// per-patch statistics cooperatively (8 lanes per patch, 4 patches in flight per lane group), then lane s
+// runs the sequential merge of series s — so the dependent chain of divisions / square roots is paid once
+// per G series instead of once per series — and finally the warp normalises from shared memory and streams
+// the tokens out.  Slot layout per series: (3 N + 1) floats (odd stride: conflict-free lane-per-series scan).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_groups() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int OUT>
+__global__ void __launch_bounds__(256) timesfm_patchify_norm_kernel(
+    const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, int group_size,
+    void* tokens, float* __restrict__ mu_out, float* __restrict__ sigma_out, uint8_t* __restrict__ patch_mask_out,
+    int32_t* __restrict__ num_masked_out) {
+  extern __shared__ __align__(16) uint8_t smem_tf[];
+  const int warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, q = lane & 7;
+  const int N = context >> 5;
+  const int G = group_size;
+  const int slot_stride = 3 * N + 1;
+  const int per_warp = ((G * context * 5 + G * slot_stride * 4) + 15) & ~15;
+  uint8_t* base = smem_tf + warp * per_warp;
+  float* sx = reinterpret_cast<float*>(base);
+  uint8_t* sm = base + G * context * 4;
+  float* slots = reinterpret_cast<float*>(sm + G * context);
+  const float inv_n = 1.0f / static_cast<float>(N);
+  const int64_t num_groups = (batch + G - 1) / G;
+
+  for (int64_t gi = static_cast<int64_t>(blockIdx.x) * warps + warp; gi < num_groups;
+       gi += static_cast<int64_t>(gridDim.x) * warps) {
+    const int64_t b0 = gi * G;
+    const int cnt = static_cast<int>(batch - b0 < G ? batch - b0 : G);
+    const int P = cnt * N;  // patches staged by this warp
+    // ---- stage x (fp32) and mask (u8) of `cnt` consecutive series
+    {
+      const float* gx = x + b0 * context;
+      const uint8_t* gm = mask + b0 * context;
+      const int nx = cnt * context / 4, nmk = cnt * context / 16;
+      for (int i = lane; i < nx; i += 32) cp_async16(sx + 4 * i, gx + 4 * i);
+      for (int i = lane; i < nmk; i += 32) cp_async16(sm + 16 * i, gm + 16 * i);
+      cp_async_wait_all_groups();
+      __syncwarp();
+    }
+    // ---- per-patch statistics: 8 lanes per patch, 4 independent patches per lane group and iteration
+    for (int p0 = 0; p0 < P; p0 += 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = p0 + grp + 4 * j;
+        const bool live = p < P;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t mk = 0x01010101u;
+        if (live) {
+          v = *reinterpret_cast<const float4*>(sx + p * 32 + 4 * q);
+          mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
+        }
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        float valid[4];
+        float c = 0.f, sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          valid[k] = ((mk >> (8 * k)) & 0xffu) ? 0.f : 1.f;
+          c += valid[k];
+          sum += xv[k] * valid[k];
+        }
+        c = group8_sum(c);
+        sum = group8_sum(sum);
+        const float c_safe = c == 0.f ? 1.f : c;
+        const float inc_mu = c == 0.f ? 0.f : __fdiv_rn(sum, c_safe);
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float d = (xv[k] - inc_mu) * valid[k];
+          sq += d * d;
+        }
+        sq = group8_sum(sq);
+        if (live && q == 0) {
+          const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
+          const int k = p - s * N;
+          float* slot = slots + s * slot_stride + 3 * k;
+          slot[0] = c;
+          slot[1] = inc_mu;
+          slot[2] = c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f));
+        }
+        // the patch counts as padded iff its LAST element is padded (timesfm.py:97)
+        if (live && q == 7 && patch_mask_out != nullptr) patch_mask_out[b0 * N + p] = (mk >> 24) ? 1 : 0;
+      }
+    }
+    __syncwarp();
+    // ---- sequential merge (reference order and formula; HF twin modeling_timesfm2_5.py:528-568): lane s = series s
+    if (lane < cnt) {
+      float* slot = slots + lane * slot_stride;
+      const uint8_t* mrow = sm + lane * context;
+      float run_n = 0.f, run_mu = 0.f, run_sigma = 0.f;
+      int masked = 0;
+      for (int i = 0; i < N; ++i) {
+        const float inc_n = slot[3 * i], inc_mu = slot[3 * i + 1], inc_sigma = slot[3 * i + 2];
+        const float new_n = __fadd_rn(run_n, inc_n);
+        const float new_n_safe = new_n == 0.f ? 1.f : new_n;
+        float new_mu = __fdiv_rn(__fadd_rn(__fmul_rn(run_n, run_mu), __fmul_rn(inc_mu, inc_n)), new_n_safe);
+        if (new_n == 0.f) new_mu = 0.f;
+        const float d1 = __fsub_rn(run_mu, new_mu), d2 = __fsub_rn(inc_mu, new_mu);
+        const float t1 = __fmul_rn(run_n, __fmul_rn(run_sigma, run_sigma));
+        const float t2 = __fmul_rn(inc_n, __fmul_rn(inc_sigma, inc_sigma));
+        const float t3 = __fmul_rn(run_n, __fmul_rn(d1, d1));
+        const float t4 = __fmul_rn(inc_n, __fmul_rn(d2, d2));
+        float new_var = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4), new_n_safe);
+        if (new_n == 0.f) new_var = 0.f;
+        run_n = new_n;
+        run_mu = new_mu;
+        run_sigma = sqrtf(fmaxf(new_var, 0.f));
+        slot[3 * i] = run_mu;  // the slot now holds the cumulative stats of this patch
+        slot[3 * i + 1] = run_sigma;
+        masked += mrow[32 * i + 31] ? 1 : 0;
+      }
+      if (num_masked_out != nullptr) num_masked_out[b0 + lane] = masked;
+    }
+    __syncwarp();
+    // ---- mu / sigma out, coalesced (the group's [cnt, N] block is contiguous in [B, N])
+    for (int i = lane; i < P; i += 32) {
+      const int s = static_cast<int>((static_cast<float>(i) + 0.5f) * inv_n);
+      const int k = i - s * N;
+      const float* slot = slots + s * slot_stride + 3 * k;
+      if (mu_out != nullptr) mu_out[b0 * N + i] = slot[0];
+      if (sigma_out != nullptr) sigma_out[b0 * N + i] = slot[1];
+    }
+    // ---- RevIN with the cumulative stats of the own patch, zero the padded points, emit tokens
+    for (int p0 = 0; p0 < P; p0 += 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = p0 + grp + 4 * j;
+        if (p < P) {
+          const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
+          const int k = p - s * N;
+          const float* slot = slots + s * slot_stride + 3 * k;
+          const float mu_p = slot[0], sigma_p = slot[1];
+          const float inv_sig = __fdiv_rn(1.0f, sigma_p < 1e-6f ? 1.f : sigma_p);
+          const float4 v = *reinterpret_cast<const float4*>(sx + p * 32 + 4 * q);
+          const uint32_t mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
+          const float xv[4] = {v.x, v.y, v.z, v.w};
+          float val[4], msk[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const bool padded = ((mk >> (8 * kk)) & 0xffu) != 0;
+            msk[kk] = padded ? 1.f : 0.f;
+            val[kk] = padded ? 0.f : (xv[kk] - mu_p) * inv_sig;
+          }
+          store_token_quad<OUT>(tokens, b0 * N + p, q, val, msk);
+        }
+      }
+    }
+    __syncwarp();  // the next group's cp.async must not overwrite tiles still being read
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // Chronos-2 context preparation.
 // ----------------------------------------------------------------------------------------
 template <int OUT>
@@ -276,6 +435,141 @@ __global__ void __launch_bounds__(WARPS * 32) chronos2_patchify_norm_kernel(
   }
 }
 
+// asinh(x) = sign(x) log(|x| + sqrt(x^2 + 1)); odd Taylor series below 1/8 where the log form cancels.
+// Relative error < 3e-7 over the whole range (libdevice asinhf costs ~2x the instructions).
+__device__ __forceinline__ float fast_asinh(float x) {
+  const float t = fabsf(x);
+  float r;
+  if (t < 0.125f) {
+    const float t2 = t * t;
+    r = t * fmaf(t2, fmaf(t2, fmaf(t2, -0.044642857f, 0.075f), -0.16666667f), 1.0f);
+  } else {
+    r = logf(t + sqrtf(fmaf(t, t, 1.0f)));
+  }
+  return copysignf(r, x);
+}
+
+// Fast path (context % 16 == 0, no left padding): one warp per series, lane l owns float4 #(l + 32 j) — four
+// consecutive lanes own one 16-step patch — the row stays in registers across the three passes (mean, variance,
+// emit) and every global access is a 16-byte streaming load / store.
+template <int NV, int OUT>  // NV float4 per lane cached (context <= 128 * NV)
+__global__ void __launch_bounds__(WARPS * 32) chronos2_patchify_norm_fast_kernel(
+    const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, int use_arcsinh,
+    float time_scale, int out_cols, void* out, uint8_t* __restrict__ attn_mask, float* __restrict__ loc_out,
+    float* __restrict__ scale_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = context >> 2;
+  const int num_patches = context >> 4;
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * WARPS + warp; b < batch;
+       b += static_cast<int64_t>(gridDim.x) * WARPS) {
+    const float* xr = x + b * context;
+    const uint8_t* mr = mask + b * context;
+    float4 v[NV];
+    uint32_t mk[NV];
+    float sum = 0.f, cnt = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int f = lane + 32 * j;
+      if (f < nvec) {
+        v[j] = ld_stream_f4(xr + 4 * f);
+        mk[j] = ld_stream_u32(mr + 4 * f);
+      } else {
+        v[j] = make_float4(NAN, NAN, NAN, NAN);
+        mk[j] = 0x01010101u;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (!isnan(xv[k])) { sum += xv[k]; cnt += 1.f; }
+    }
+    sum = warp_sum(sum);
+    cnt = warp_sum(cnt);
+    const float loc = cnt > 0.f ? __fdiv_rn(sum, cnt) : 0.f;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (!isnan(xv[k])) { const float d = xv[k] - loc; sq += d * d; }
+    }
+    sq = warp_sum(sq);
+    float scale = cnt > 0.f ? sqrtf(__fdiv_rn(sq, cnt)) : 1.f;
+    if (scale == 0.f) scale = 1e-5f;
+    if (lane == 0) {
+      if (loc_out != nullptr) loc_out[b] = loc;
+      if (scale_out != nullptr) scale_out[b] = scale;
+    }
+    const int row_mul = OUT == TSFMX_DT_BF16_SPLIT ? 2 * out_cols : out_cols;
+    const float inv_scale = __fdiv_rn(1.0f, scale);
+    const float inv_time_scale = __fdiv_rn(1.0f, time_scale);
+    // a power-of-two time scale (8192 for Chronos-2) makes the reciprocal multiply exact
+    const bool tenc_exact = (__float_as_uint(time_scale) & 0x007fffffu) == 0u;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int f = lane + 32 * j;
+      const bool live = f < nvec;
+      const int patch = f >> 2, qd = f & 3;
+      const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      float tenc[4], val[4], msk[4];
+      int any = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = 4 * f + k;
+        tenc[k] = tenc_exact ? static_cast<float>(e - context) * inv_time_scale
+                             : __fdiv_rn(static_cast<float>(e - context), time_scale);
+        const bool obs = ((mk[j] >> (8 * k)) & 0xffu) == 0;
+        msk[k] = obs ? 1.f : 0.f;
+        any |= obs ? 1 : 0;
+        float sv = (xv[k] - loc) * inv_scale;
+        if (use_arcsinh) sv = fast_asinh(sv);
+        val[k] = obs ? sv : 0.f;
+      }
+      // attention mask of the patch = any observed point among its 16 steps (4 consecutive lanes)
+      any |= __shfl_xor_sync(0xffffffffu, any, 1);
+      any |= __shfl_xor_sync(0xffffffffu, any, 2);
+      if (live) {
+        if (attn_mask != nullptr && qd == 0) attn_mask[b * num_patches + patch] = static_cast<uint8_t>(any);
+        const int64_t row = (b * num_patches + patch) * row_mul;
+        if constexpr (OUT == TSFMX_DT_F32) {
+          float* o = reinterpret_cast<float*>(out) + row;
+          st_stream_f4(o + 4 * qd, make_float4(tenc[0], tenc[1], tenc[2], tenc[3]));
+          st_stream_f4(o + 16 + 4 * qd, make_float4(val[0], val[1], val[2], val[3]));
+          st_stream_f4(o + 32 + 4 * qd, make_float4(msk[0], msk[1], msk[2], msk[3]));
+          if (out_cols >= 64) st_stream_f4(o + 48 + 4 * qd, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + row;
+          if constexpr (OUT == TSFMX_DT_BF16) {
+            st_stream_u2(o + 4 * qd, make_uint2(pack_bf16x2(tenc[0], tenc[1]), pack_bf16x2(tenc[2], tenc[3])));
+            st_stream_u2(o + 16 + 4 * qd, make_uint2(pack_bf16x2(val[0], val[1]), pack_bf16x2(val[2], val[3])));
+            st_stream_u2(o + 32 + 4 * qd, make_uint2(pack_bf16x2(msk[0], msk[1]), pack_bf16x2(msk[2], msk[3])));
+            if (out_cols >= 64) st_stream_u2(o + 48 + 4 * qd, make_uint2(0u, 0u));
+          } else {
+            uint2 h, l;
+            split_bf16x2(tenc[0], tenc[1], h.x, l.x);
+            split_bf16x2(tenc[2], tenc[3], h.y, l.y);
+            st_stream_u2(o + 4 * qd, h);
+            st_stream_u2(o + out_cols + 4 * qd, l);
+            split_bf16x2(val[0], val[1], h.x, l.x);
+            split_bf16x2(val[2], val[3], h.y, l.y);
+            st_stream_u2(o + 16 + 4 * qd, h);
+            st_stream_u2(o + out_cols + 16 + 4 * qd, l);
+            st_stream_u2(o + 32 + 4 * qd, make_uint2(pack_bf16x2(msk[0], msk[1]), pack_bf16x2(msk[2], msk[3])));
+            st_stream_u2(o + out_cols + 32 + 4 * qd, make_uint2(0u, 0u));
+            if (out_cols >= 64) {
+              st_stream_u2(o + 48 + 4 * qd, make_uint2(0u, 0u));
+              st_stream_u2(o + out_cols + 48 + 4 * qd, make_uint2(0u, 0u));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------
 // Chronos-T5 mean-scale + uniform-bin tokeniser.  Bit-exact ids: fp32 IEEE division x / scale,
 // then count(boundaries <= v) looked up in the caller's boundary table (torch.bucketize right=True).
@@ -295,7 +589,7 @@ __device__ __forceinline__ int bucketize_right(const float* __restrict__ sb, int
   return i;
 }
 
-template <int NV>  // float4 per lane cached in registers (context <= 128 * NV); NV == 0: re-read
+template <int NE>  // elements cached per lane (context <= 32 * NE); NE == 0: re-read the row
 __global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_kernel(
     const float* __restrict__ x, int64_t batch, int context, const float* __restrict__ boundaries, int nb,
     int n_special, int n_tokens, int pad_id, int eos_id, int64_t* __restrict__ ids,
@@ -306,32 +600,27 @@ __global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_kernel(
   const float b1 = nb > 2 ? sb[1] : 0.f;
   const float inv_step = nb > 3 ? static_cast<float>(nb - 3) / (sb[nb - 2] - sb[1]) : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool vec = (context % 4) == 0;
-  const int nvec = context >> 2;
 
+  // lane l owns elements l, l + 32, ...: 128-byte coalesced loads, 256-byte coalesced int64 id stores
   for (int64_t b = static_cast<int64_t>(blockIdx.x) * WARPS + warp; b < batch;
        b += static_cast<int64_t>(gridDim.x) * WARPS) {
     const float* xr = x + b * context;
     int64_t* idr = ids + b * (context + 1);
     uint8_t* amr = attn_mask + b * (context + 1);
-    float4 cache[NV > 0 ? NV : 1];
+    float cache[NE > 0 ? NE : 1];
     // sum(|x|) is accumulated in fp64 and rounded to fp32 once, so the scale (and hence every id)
     // does not depend on the reduction order.
     double sum = 0.0;
     float cnt = 0.f;
-    if (NV > 0 && vec) {
+    if (NE > 0) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int f = lane + 32 * j;
-        cache[j] = f < nvec ? ld_stream_f4(xr + 4 * f) : make_float4(NAN, NAN, NAN, NAN);
+      for (int k = 0; k < NE; ++k) {
+        const int e = lane + 32 * k;
+        cache[k] = e < context ? ld_stream_f32(xr + e) : NAN;
       }
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float xv[4] = {cache[j].x, cache[j].y, cache[j].z, cache[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (!isnan(xv[k])) { sum += static_cast<double>(fabsf(xv[k])); cnt += 1.f; }
-      }
+      for (int k = 0; k < NE; ++k)
+        if (!isnan(cache[k])) { sum += static_cast<double>(fabsf(cache[k])); cnt += 1.f; }
     } else {
       for (int e = lane; e < context; e += 32) {
         const float v = __ldg(xr + e);
@@ -354,21 +643,13 @@ __global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_kernel(
       t = max(0, min(n_tokens - 1, t));
       return t;
     };
-    if (NV > 0 && vec) {
+    if (NE > 0) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int f = lane + 32 * j;
-        if (f < nvec) {
-          const float xv[4] = {cache[j].x, cache[j].y, cache[j].z, cache[j].w};
-          uint32_t am = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            idr[4 * f + k] = tok(xv[k]);
-            am |= (isnan(xv[k]) ? 0u : 1u) << (8 * k);
-          }
-          // row base is only byte-aligned (row length C+1): byte stores
-#pragma unroll
-          for (int k = 0; k < 4; ++k) amr[4 * f + k] = static_cast<uint8_t>((am >> (8 * k)) & 0xffu);
+      for (int k = 0; k < NE; ++k) {
+        const int e = lane + 32 * k;
+        if (e < context) {
+          idr[e] = tok(cache[k]);
+          amr[e] = isnan(cache[k]) ? 0 : 1;
         }
       }
     } else {
@@ -422,10 +703,51 @@ int grid_for_series(int64_t batch) {
   return static_cast<int>(blocks < cap ? blocks : cap);
 }
 
+int g_tf_group = 0, g_tf_warps = 0, g_t5_variant = 0;  // tuning hooks (0 = default)
+
+template <int OUT>
+int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, int context, void* tokens, float* mu,
+                          float* sigma, uint8_t* patch_mask, int32_t* num_masked, cudaStream_t stream) {
+  const int N = context >> 5;
+  int G = g_tf_group > 0 ? g_tf_group : 2048 / context;  // ~10 KB of series per warp keeps 20 warps / SM resident
+  if (G > 4) G = 4;
+  if (G < 1) G = 1;
+  const int per_warp = ((G * context * 5 + G * (3 * N + 1) * 4) + 15) & ~15;
+  int warps = g_tf_warps > 0 ? g_tf_warps : 4;
+  while (warps > 1 && warps * per_warp > 100 * 1024) --warps;
+  const int smem = warps * per_warp;
+  auto kern = timesfm_patchify_norm_kernel<OUT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("timesfm_patchify_norm: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+      return TSFMX_ERR_CUDA;
+    }
+  }
+  const int64_t groups = (batch + G - 1) / G;
+  const int64_t blocks = (groups + warps - 1) / warps;
+  const int per_sm = (220 * 1024) / smem > 0 ? (220 * 1024) / smem : 1;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm * 2;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  kern<<<grid, warps * 32, smem, stream>>>(x, mask, batch, context, G, tokens, mu, sigma, patch_mask, num_masked);
+  return check_last_launch("timesfm_patchify_norm");
+}
+
 }  // namespace
 }  // namespace tsfmx
 
 using namespace tsfmx;
+
+extern "C" int tsfmx_tune(int32_t key, int32_t value) {
+  switch (key) {
+    case 0: g_tf_group = value; return TSFMX_OK;
+    case 1: g_tf_warps = value; return TSFMX_OK;
+    case 2: g_t5_variant = value; return TSFMX_OK;
+    default:
+      set_error("tune: unknown key %d", key);
+      return TSFMX_ERR_INVALID_ARGUMENT;
+  }
+}
 
 extern "C" int tsfmx_timesfm_patchify_norm(const float* x, const uint8_t* mask, int64_t batch, int32_t context,
                                            int32_t patch_len, int32_t tokens_dtype, void* tokens, float* mu,
@@ -442,25 +764,34 @@ extern "C" int tsfmx_timesfm_patchify_norm(const float* x, const uint8_t* mask, 
   TSFMX_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(mask) % 4 == 0 &&
                     reinterpret_cast<uintptr_t>(tokens) % 16 == 0,
                 "timesfm_patchify_norm: x/tokens must be 16-byte and mask 4-byte aligned");
+  TSFMX_REQUIRE(tokens_dtype >= TSFMX_DT_F32 && tokens_dtype <= TSFMX_DT_BF16_SPLIT,
+                "timesfm_patchify_norm: bad tokens_dtype %d", tokens_dtype);
   if (batch == 0) return TSFMX_OK;
+  if (context <= 4096 && reinterpret_cast<uintptr_t>(mask) % 16 == 0) {
+    switch (tokens_dtype) {
+      case TSFMX_DT_F32:
+        return launch_timesfm_staged<TSFMX_DT_F32>(x, mask, batch, context, tokens, mu, sigma, patch_mask, num_masked, stream);
+      case TSFMX_DT_BF16:
+        return launch_timesfm_staged<TSFMX_DT_BF16>(x, mask, batch, context, tokens, mu, sigma, patch_mask, num_masked, stream);
+      default:
+        return launch_timesfm_staged<TSFMX_DT_BF16_SPLIT>(x, mask, batch, context, tokens, mu, sigma, patch_mask, num_masked, stream);
+    }
+  }
   const int grid = grid_for_series(batch);
   const dim3 block(WARPS * 32);
   switch (tokens_dtype) {
     case TSFMX_DT_F32:
-      timesfm_patchify_norm_kernel<TSFMX_DT_F32><<<grid, block, 0, stream>>>(x, mask, batch, context, tokens, mu, sigma,
-                                                                            patch_mask, num_masked);
+      timesfm_patchify_norm_generic_kernel<TSFMX_DT_F32><<<grid, block, 0, stream>>>(x, mask, batch, context, tokens, mu,
+                                                                                    sigma, patch_mask, num_masked);
       break;
     case TSFMX_DT_BF16:
-      timesfm_patchify_norm_kernel<TSFMX_DT_BF16><<<grid, block, 0, stream>>>(x, mask, batch, context, tokens, mu,
-                                                                             sigma, patch_mask, num_masked);
-      break;
-    case TSFMX_DT_BF16_SPLIT:
-      timesfm_patchify_norm_kernel<TSFMX_DT_BF16_SPLIT><<<grid, block, 0, stream>>>(x, mask, batch, context, tokens, mu,
-                                                                                   sigma, patch_mask, num_masked);
+      timesfm_patchify_norm_generic_kernel<TSFMX_DT_BF16><<<grid, block, 0, stream>>>(x, mask, batch, context, tokens, mu,
+                                                                                     sigma, patch_mask, num_masked);
       break;
     default:
-      set_error("timesfm_patchify_norm: bad tokens_dtype %d", tokens_dtype);
-      return TSFMX_ERR_INVALID_ARGUMENT;
+      timesfm_patchify_norm_generic_kernel<TSFMX_DT_BF16_SPLIT><<<grid, block, 0, stream>>>(
+          x, mask, batch, context, tokens, mu, sigma, patch_mask, num_masked);
+      break;
   }
   return check_last_launch("timesfm_patchify_norm");
 }
@@ -476,6 +807,28 @@ extern "C" int tsfmx_chronos2_patchify_norm(const float* x, const uint8_t* mask,
   if (batch == 0) return TSFMX_OK;
   const int grid = grid_for_series(batch);
   const dim3 block(WARPS * 32);
+  TSFMX_REQUIRE(out_dtype >= TSFMX_DT_F32 && out_dtype <= TSFMX_DT_BF16_SPLIT, "chronos2_patchify_norm: bad out_dtype %d",
+                out_dtype);
+  const bool fast = patch == 16 && context % 16 == 0 && context <= 2048 && (out_cols == 48 || out_cols == 64) &&
+                    reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(mask) % 4 == 0 &&
+                    reinterpret_cast<uintptr_t>(patched) % 16 == 0;
+  if (fast) {
+#define TSFMX_C2_LAUNCH(NVV, DT)                                                                              \
+  chronos2_patchify_norm_fast_kernel<NVV, DT><<<grid, block, 0, stream>>>(x, mask, batch, context, use_arcsinh, \
+                                                                          time_encoding_scale, out_cols, patched, \
+                                                                          attn_mask, loc, scale)
+    if (context <= 512) {
+      if (out_dtype == TSFMX_DT_F32) TSFMX_C2_LAUNCH(4, TSFMX_DT_F32);
+      else if (out_dtype == TSFMX_DT_BF16) TSFMX_C2_LAUNCH(4, TSFMX_DT_BF16);
+      else TSFMX_C2_LAUNCH(4, TSFMX_DT_BF16_SPLIT);
+    } else {
+      if (out_dtype == TSFMX_DT_F32) TSFMX_C2_LAUNCH(16, TSFMX_DT_F32);
+      else if (out_dtype == TSFMX_DT_BF16) TSFMX_C2_LAUNCH(16, TSFMX_DT_BF16);
+      else TSFMX_C2_LAUNCH(16, TSFMX_DT_BF16_SPLIT);
+    }
+#undef TSFMX_C2_LAUNCH
+    return check_last_launch("chronos2_patchify_norm");
+  }
   switch (out_dtype) {
     case TSFMX_DT_F32:
       chronos2_patchify_norm_kernel<TSFMX_DT_F32><<<grid, block, 0, stream>>>(
@@ -509,12 +862,12 @@ extern "C" int tsfmx_chronos_t5_tokenize(const float* x, int64_t batch, int32_t 
   const int grid = grid_for_series(batch);
   const dim3 block(WARPS * 32);
   const size_t smem = static_cast<size_t>(n_boundaries) * sizeof(float);
-  const bool aligned = reinterpret_cast<uintptr_t>(x) % 16 == 0 && context % 4 == 0;
-  if (aligned && context <= 512) {
-    chronos_t5_tokenize_kernel<4><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries, n_special,
+  const int variant = g_t5_variant > 0 ? g_t5_variant : (context <= 512 ? 1 : (context <= 2048 ? 2 : 3));
+  if (variant == 1 && context <= 512) {
+    chronos_t5_tokenize_kernel<16><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries, n_special,
                                                                  n_tokens, pad_id, eos_id, ids, attn_mask, scale);
-  } else if (aligned && context <= 2048) {
-    chronos_t5_tokenize_kernel<16><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries,
+  } else if (variant == 2 && context <= 2048) {
+    chronos_t5_tokenize_kernel<64><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries,
                                                                   n_special, n_tokens, pad_id, eos_id, ids, attn_mask,
                                                                   scale);
   } else {

@@ -95,6 +95,11 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "tsfmx_cast_rows": (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
     "tsfmx_gemm": (c_int32, [POINTER(GemmArgs), c_void_p]),
     "tsfmx_gemm_set_cta_group": (c_int32, [c_int32]),
+    "tsfmx_gemm_rownorm": (
+        c_int32,
+        [POINTER(GemmSegment), c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+         c_float, c_void_p],
+    ),
     "tsfmx_rmsnorm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_float, c_int32, c_void_p, c_void_p]),
     "tsfmx_norm_residual_norm": (
         c_int32,
@@ -102,6 +107,7 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
          c_void_p],
     ),
     "tsfmx_attention_force_simt": (c_int32, [c_int32]),
+    "tsfmx_tune": (c_int32, [c_int32, c_int32]),
     "tsfmx_encoder_attention": (
         c_int32,
         [c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p],

@@ -193,6 +193,33 @@ def gemm(
     return out
 
 
+def gemm_rownorm(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    k: int,
+    m: int,
+    n: int,
+    precision: int,
+    w_post: torch.Tensor | None,
+    w_next: torch.Tensor | None,
+    x: torch.Tensor,
+    y: torch.Tensor,
+    yn_dtype: int,
+    yn: torch.Tensor | None,
+    eps: float,
+) -> None:
+    """``y = rmsnorm(a @ b^T) * w_post + x`` (or ``a @ b^T + x``) and ``yn = rmsnorm(y) * w_next`` (or ``y``) in one launch."""
+    lib = _lib.load()
+    _lib.require_cuda(a, b, x, y)
+    seg = _lib.GemmSegment()
+    seg.a, seg.lda, seg.b, seg.ldb, seg.k = a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), k
+    check(
+        lib.tsfmx_gemm_rownorm(
+            ctypes.byref(seg), m, n, precision, ptr(w_post), ptr(w_next), ptr(x), ptr(y), yn_dtype, ptr(yn), eps, stream()
+        )
+    )
+
+
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out_dtype: int, out: torch.Tensor | None = None) -> torch.Tensor:
     _lib.require_cuda(x, w)
     lib = _lib.load()

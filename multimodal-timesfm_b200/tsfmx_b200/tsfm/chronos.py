@@ -129,6 +129,7 @@ class Chronos2Adapter(TsfmAdapter):
     def __init__(self, model: Chronos2Module | None = None, precision: str = "bf16") -> None:
         super().__init__()
         self._model = model if model is not None else Chronos2Module()
+        self.fused_norm = False  # True: residual + RMS LayerNorm junctions in the GEMM epilogue (measured slower, kept for A/B)
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
 
@@ -288,17 +289,29 @@ class Chronos2Adapter(TsfmAdapter):
         for i, bw in enumerate(blocks):
             ops.gemm([(xn, bw["qkv"], d)], rows, 3 * inner, qkv, mid_dt, precision=prec)
             ops.encoder_attention(qkv, b, t, m.num_heads, m.d_kv, key_mask, w["inv_freq"], adt, out=attn)
-            ops.gemm([(attn, bw["o"], inner)], rows, d, a, mid_dt, precision=prec)
-            ops.norm_residual_norm(a, h2, None, bw["ln_g"], m.eps, h2, adt, xn)
-            ops.gemm([(xn, bw["ov"], d)], rows, d, a, mid_dt, precision=prec)
-            ops.norm_residual_norm(a, h2, None, bw["ln_f"], m.eps, h2, adt, xn)
-            ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
-            ops.gemm([(u, bw["wo"], m.d_ff)], rows, d, a, mid_dt, precision=prec)
-            if i + 1 < len(blocks):
-                ops.norm_residual_norm(a, h2, None, blocks[i + 1]["ln_t"], m.eps, h2, adt, xn)
-            else:
+            has_next = i + 1 < len(blocks)
+            if not has_next:
                 final = torch.empty(rows, d, dtype=torch.float32, device=dev)
-                ops.norm_residual_norm(a, h2, None, w["final_ln"], m.eps, h2, DT_F32, final)
+            if self.fused_norm:
+                # residual add + next RMS LayerNorm in the GEMM epilogue (3-CTA clusters own a 768-wide row panel)
+                ops.gemm_rownorm(attn, bw["o"], inner, rows, d, prec, None, bw["ln_g"], h2, h2, adt, xn, m.eps)
+                ops.gemm_rownorm(xn, bw["ov"], d, rows, d, prec, None, bw["ln_f"], h2, h2, adt, xn, m.eps)
+                ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
+                if has_next:
+                    ops.gemm_rownorm(u, bw["wo"], m.d_ff, rows, d, prec, None, blocks[i + 1]["ln_t"], h2, h2, adt, xn, m.eps)
+                else:
+                    ops.gemm_rownorm(u, bw["wo"], m.d_ff, rows, d, prec, None, w["final_ln"], h2, h2, DT_F32, final, m.eps)
+            else:
+                ops.gemm([(attn, bw["o"], inner)], rows, d, a, mid_dt, precision=prec)
+                ops.norm_residual_norm(a, h2, None, bw["ln_g"], m.eps, h2, adt, xn)
+                ops.gemm([(xn, bw["ov"], d)], rows, d, a, mid_dt, precision=prec)
+                ops.norm_residual_norm(a, h2, None, bw["ln_f"], m.eps, h2, adt, xn)
+                ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
+                ops.gemm([(u, bw["wo"], m.d_ff)], rows, d, a, mid_dt, precision=prec)
+                if has_next:
+                    ops.norm_residual_norm(a, h2, None, blocks[i + 1]["ln_t"], m.eps, h2, adt, xn)
+                else:
+                    ops.norm_residual_norm(a, h2, None, w["final_ln"], m.eps, h2, DT_F32, final)
         return final.view(b, t, d)[:, -nop:].contiguous()
 
     def postprocess(

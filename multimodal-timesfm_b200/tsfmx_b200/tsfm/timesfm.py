@@ -112,6 +112,7 @@ class TimesFM2p5Adapter(TsfmAdapter):
     def __init__(self, num_layers: int = 20, precision: str = "bf16", with_quantile_head: bool = True) -> None:
         super().__init__()
         self._model = TimesFM2p5Module(num_layers, with_quantile_head)
+        self.fused_norm = False  # True: norm/residual junctions in the GEMM epilogue (5-CTA clusters; measured slower, kept for A/B)
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
 
@@ -268,16 +269,24 @@ class TimesFM2p5Adapter(TsfmAdapter):
         a = ops.alloc(rows, d, mid_dt, dev)
         hbuf = ops.alloc(rows, m.ff, adt, dev)
         for i, lw in enumerate(layers):
+            last = i == len(layers) - 1
+            nxt = None if last else layers[i + 1]["pre_attn"]
             ops.gemm([(xn, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
             ops.timesfm_attention(qkv, b, n, m.h, m.hd, patch_mask, num_masked, w["inv_freq"], lw["q_ln"], lw["k_ln"],
                                   lw["q_scale"], m.eps, adt, out=attn)
-            ops.gemm([(attn, lw["out"], d)], rows, d, a, mid_dt, precision=prec)
-            ops.norm_residual_norm(a, x if i == 0 else y, lw["post_attn"], lw["pre_ff"], m.eps, y, adt, xn)
-            ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU)
-            ops.gemm([(hbuf, lw["ff1"], m.ff)], rows, d, a, mid_dt, precision=prec)
-            last = i == len(layers) - 1
-            ops.norm_residual_norm(a, y, lw["post_ff"], None if last else layers[i + 1]["pre_attn"], m.eps, y, adt,
-                                   None if last else xn)
+            if self.fused_norm:
+                # out-proj / ff1 with post-norm + residual + next pre-norm in the GEMM epilogue (5-CTA clusters)
+                ops.gemm_rownorm(attn, lw["out"], d, rows, d, prec, lw["post_attn"], lw["pre_ff"], x if i == 0 else y, y,
+                                 adt, xn, m.eps)
+                ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU)
+                ops.gemm_rownorm(hbuf, lw["ff1"], m.ff, rows, d, prec, lw["post_ff"], nxt, y, y, adt,
+                                 None if last else xn, m.eps)
+            else:
+                ops.gemm([(attn, lw["out"], d)], rows, d, a, mid_dt, precision=prec)
+                ops.norm_residual_norm(a, x if i == 0 else y, lw["post_attn"], lw["pre_ff"], m.eps, y, adt, xn)
+                ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU)
+                ops.gemm([(hbuf, lw["ff1"], m.ff)], rows, d, a, mid_dt, precision=prec)
+                ops.norm_residual_norm(a, y, lw["post_ff"], nxt, m.eps, y, adt, None if last else xn)
         return y.view(b, n, d)
 
     def postprocess(

@@ -412,3 +412,36 @@ def test_timesfm_attention_tensor_core_path(n):
     assert _rel(simt.float(), ref) < 6e-3
     assert _rel(out.float(), ref) < 2e-2, _rel(out.float(), ref)
     assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2
+
+
+# ----------------------------------------------------------------------------- cluster-fused GEMM + row norm
+@pytest.mark.parametrize("precision", [PREC_BF16, PREC_BF16X3])
+@pytest.mark.parametrize("n,k,m", [(1280, 1280, 1000), (768, 3072, 300), (1280, 1280, 128 * 40 + 5), (768, 768, 64)])
+@pytest.mark.parametrize("post,nxt", [(True, True), (False, True), (True, False)])
+def test_gemm_rownorm(precision, n, k, m, post, nxt):
+    gen = torch.Generator(device=DEV).manual_seed(n + k + m)
+    a, af = _make_operand(m, k, precision, gen)
+    b32 = torch.randn(n, k, generator=gen, device=DEV) / math.sqrt(k)
+    if precision == PREC_BF16:
+        b = b32.to(torch.bfloat16)
+        bf = b.float()
+    else:
+        b, bf = ops.cast_rows(b32, DT_BF16_SPLIT), b32
+    x = torch.randn(m, n, generator=gen, device=DEV)
+    w1 = 1 + 0.1 * torch.randn(n, generator=gen, device=DEV)
+    w2 = 1 + 0.1 * torch.randn(n, generator=gen, device=DEV)
+    adt = DT_BF16_SPLIT if precision == PREC_BF16X3 else DT_BF16
+    y = torch.full((m, n), float("nan"), device=DEV)
+    yn = ops.alloc(m, n, adt, torch.device(DEV))
+    ops.gemm_rownorm(a, b, k, m, n, precision, w1 if post else None, w2 if nxt else None, x, y, adt, yn, 1e-6)
+    acc = af.double() @ bf.double().t()
+    if post:
+        acc = w1.double() * (acc * torch.rsqrt(acc.pow(2).mean(-1, keepdim=True) + 1e-6))
+    ry = acc + x.double()
+    ryn = w2.double() * (ry * torch.rsqrt(ry.pow(2).mean(-1, keepdim=True) + 1e-6)) if nxt else ry
+    assert _rel(y, ry.float()) < 3e-5
+    assert _rel(_to_float(yn, adt), ryn.float()) < (6e-3 if adt == DT_BF16 else 5e-5)
+    # in place (y aliases x), the way the layer loop uses it
+    x2 = x.clone()
+    ops.gemm_rownorm(a, b, k, m, n, precision, w1 if post else None, w2 if nxt else None, x2, x2, adt, yn, 1e-6)
+    assert torch.equal(x2, y)
