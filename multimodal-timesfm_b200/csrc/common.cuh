@@ -108,7 +108,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
-    if ((++spins & 0xfffu) == 0 && clock64() - t0 > TSFMX_MBAR_TIMEOUT_CYCLES) {
+    if ((++spins & 0xfu) == 0 && clock64() - t0 > TSFMX_MBAR_TIMEOUT_CYCLES) {
       printf("tsfmx: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              addr, parity);
       __trap();
@@ -128,6 +128,24 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // ---- TMA
+// 1-D bulk copy global -> shared (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned;
+// completion is credited to `bar` as transaction bytes.  Read-once data: evict-first L2 policy.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], pol;\n\t"
+      "}\n" ::"r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
 }

@@ -345,6 +345,169 @@ __global__ void __launch_bounds__(256) timesfm_patchify_norm_kernel(
 }
 
 // ----------------------------------------------------------------------------------------
+// TMA-pipelined variant (the default for context <= 4096): a persistent block walks over tiles of G consecutive
+// series.  One thread keeps a ring of STAGES tiles in flight with 1-D bulk copies (cp.async.bulk, completion on an
+// mbarrier), so the HBM reads of the next tiles overlap the arithmetic of the current one and cost no load
+// instructions; the block computes the per-patch statistics (8 lanes per patch), thread s runs the sequential merge
+// of series s (reference order: one dependent chain of divisions / square roots per series, paid once per tile for up
+// to 32 series side by side), and the block normalises from shared memory and streams the tokens out with full-line
+// 16-byte stores.  Slot layout: patch k of series s at (k * G + s) * 3 floats (stride 3: conflict-free merge scan).
+// ----------------------------------------------------------------------------------------
+constexpr int TF_THREADS = 256;
+
+template <int OUT>
+__global__ void __launch_bounds__(TF_THREADS) timesfm_patchify_norm_tma_kernel(
+    const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, int group_size,
+    int stages, void* tokens, float* __restrict__ mu_out, float* __restrict__ sigma_out,
+    uint8_t* __restrict__ patch_mask_out, int32_t* __restrict__ num_masked_out) {
+  extern __shared__ __align__(128) uint8_t smem_tma[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int pg = tid >> 3, q = tid & 7;  // phase C: patch group (32 per block) and quad inside the patch
+  const int N = context >> 5;
+  const int G = group_size;
+  const int stage_bytes = (G * context * 5 + 127) & ~127;
+  // slot of patch k of series s: 4 floats at (k * G + s) * 4 -> the merge thread of series s reads/writes 16 bytes,
+  // consecutive threads consecutive slots (conflict-free)
+  float4* slots = reinterpret_cast<float4*>(smem_tma + stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slots + G * N);
+  const float inv_n = 1.0f / static_cast<float>(N);
+  const int64_t num_tiles = (batch + G - 1) / G;
+
+  auto issue = [&](int64_t tile, int stage) {
+    const int64_t b0 = tile * G;
+    const uint32_t cnt = static_cast<uint32_t>(batch - b0 < G ? batch - b0 : G);
+    uint8_t* dst = smem_tma + stage * stage_bytes;
+    mbar_arrive_expect_tx(&full_bar[stage], cnt * context * 5u);
+    bulk_load_1d(dst, x + b0 * context, cnt * context * 4u, &full_bar[stage]);
+    bulk_load_1d(dst + G * context * 4, mask + b0 * context, cnt * context, &full_bar[stage]);
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&full_bar[i], 1);
+    fence_barrier_init();
+    for (int i = 0; i < stages; ++i) {
+      const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+      if (tile < num_tiles) issue(tile, i);
+    }
+  }
+  __syncthreads();
+
+  // chunk rotation of phase A: lane l reads 16-byte chunk (j + rot) & 7 of its patch at step j, so that the 8 lanes
+  // of a quarter warp hit 8 different bank groups (patches are 128 bytes apart) and the 4-byte mask reads of the
+  // whole warp hit 32 different banks
+  const int rot = lane + (lane >> 3);
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t b0 = tile * G;
+    const int cnt = static_cast<int>(batch - b0 < G ? batch - b0 : G);
+    const int P = cnt * N;
+    const float* sx = reinterpret_cast<const float*>(smem_tma + stage * stage_bytes);
+    const uint8_t* sm = smem_tma + stage * stage_bytes + G * context * 4;
+    mbar_wait(&full_bar[stage], parity);
+
+    // ---- phase A: statistics of every patch, one thread per patch (no shuffles)
+    for (int p = tid; p < P; p += TF_THREADS) {
+      const float4* xp = reinterpret_cast<const float4*>(sx + p * 32);
+      const uint32_t* mp = reinterpret_cast<const uint32_t*>(sm + p * 32);
+      float xv[32];
+      uint32_t mbits = 0;  // bit e = element e of the patch is padded
+      float c = 0.f, sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = (j + rot) & 7;
+        const float4 v = xp[ch];
+        const uint32_t mk = mp[ch];
+        xv[4 * j + 0] = v.x, xv[4 * j + 1] = v.y, xv[4 * j + 2] = v.z, xv[4 * j + 3] = v.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool padded = ((mk >> (8 * k)) & 0xffu) != 0;
+          mbits |= (padded ? 1u : 0u) << (4 * j + k);
+          c += padded ? 0.f : 1.f;
+          sum += padded ? 0.f : xv[4 * j + k];
+        }
+      }
+      const float c_safe = c == 0.f ? 1.f : c;
+      const float inc_mu = c == 0.f ? 0.f : __fdiv_rn(sum, c_safe);
+      float sq = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float d = ((mbits >> e) & 1u) ? 0.f : xv[e] - inc_mu;
+        sq = fmaf(d, d, sq);
+      }
+      const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
+      const int k = p - s * N;
+      // the patch counts as padded iff its LAST element is padded (timesfm.py:97)
+      const float flag = sm[p * 32 + 31] ? 1.f : 0.f;
+      slots[k * G + s] = make_float4(c, inc_mu, c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f)), flag);
+    }
+    __syncthreads();
+    // ---- phase B: sequential merge (reference order and formula; HF twin modeling_timesfm2_5.py:528-568),
+    //      thread s = series s; the slot becomes {cumulative mu, cumulative sigma, 1 / safe sigma, padded flag}
+    if (tid < cnt) {
+      float run_n = 0.f, run_mu = 0.f, run_sigma = 0.f;
+      int masked = 0;
+      for (int i = 0; i < N; ++i) {
+        const float4 inc = slots[i * G + tid];
+        const float inc_n = inc.x, inc_mu = inc.y, inc_sigma = inc.z;
+        const float new_n = __fadd_rn(run_n, inc_n);
+        const float new_n_safe = new_n == 0.f ? 1.f : new_n;
+        float new_mu = __fdiv_rn(__fadd_rn(__fmul_rn(run_n, run_mu), __fmul_rn(inc_mu, inc_n)), new_n_safe);
+        if (new_n == 0.f) new_mu = 0.f;
+        const float d1 = __fsub_rn(run_mu, new_mu), d2 = __fsub_rn(inc_mu, new_mu);
+        const float t1 = __fmul_rn(run_n, __fmul_rn(run_sigma, run_sigma));
+        const float t2 = __fmul_rn(inc_n, __fmul_rn(inc_sigma, inc_sigma));
+        const float t3 = __fmul_rn(run_n, __fmul_rn(d1, d1));
+        const float t4 = __fmul_rn(inc_n, __fmul_rn(d2, d2));
+        float new_var = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4), new_n_safe);
+        if (new_n == 0.f) new_var = 0.f;
+        run_n = new_n;
+        run_mu = new_mu;
+        run_sigma = sqrtf(fmaxf(new_var, 0.f));
+        slots[i * G + tid] =
+            make_float4(run_mu, run_sigma, __fdiv_rn(1.0f, run_sigma < 1e-6f ? 1.f : run_sigma), inc.w);
+        masked += inc.w != 0.f ? 1 : 0;
+      }
+      if (num_masked_out != nullptr) num_masked_out[b0 + tid] = masked;
+    }
+    __syncthreads();
+    // ---- mu / sigma / patch mask out, coalesced (the tile's [cnt, N] block is contiguous in [B, N])
+    for (int i = tid; i < P; i += TF_THREADS) {
+      const int s = static_cast<int>((static_cast<float>(i) + 0.5f) * inv_n);
+      const int k = i - s * N;
+      const float4 st = slots[k * G + s];
+      if (mu_out != nullptr) mu_out[b0 * N + i] = st.x;
+      if (sigma_out != nullptr) sigma_out[b0 * N + i] = st.y;
+      if (patch_mask_out != nullptr) patch_mask_out[b0 * N + i] = st.w != 0.f ? 1 : 0;
+    }
+    // ---- phase C: RevIN with the cumulative stats of the own patch, zero the padded points, emit tokens
+    //      (8 lanes per patch: every store instruction writes whole 128-byte lines)
+    for (int p = pg; p < P; p += TF_THREADS / 8) {
+      const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
+      const int k = p - s * N;
+      const float4 st = slots[k * G + s];
+      const float4 v = *reinterpret_cast<const float4*>(sx + p * 32 + 4 * q);
+      const uint32_t mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+      float val[4], msk[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const bool padded = ((mk >> (8 * kk)) & 0xffu) != 0;
+        msk[kk] = padded ? 1.f : 0.f;
+        val[kk] = padded ? 0.f : (xv[kk] - st.x) * st.z;
+      }
+      store_token_quad<OUT>(tokens, b0 * N + p, q, val, msk);
+    }
+    __syncthreads();  // every thread is done with this stage and with the slots
+    if (tid == 0) {
+      const int64_t next = tile + static_cast<int64_t>(stages) * gridDim.x;
+      if (next < num_tiles) issue(next, stage);
+    }
+    if (++stage == stages) { stage = 0; parity ^= 1; }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // Chronos-2 context preparation.
 // ----------------------------------------------------------------------------------------
 template <int OUT>
@@ -703,33 +866,66 @@ int grid_for_series(int64_t batch) {
   return static_cast<int>(blocks < cap ? blocks : cap);
 }
 
-int g_tf_group = 0, g_tf_warps = 0, g_t5_variant = 0;  // tuning hooks (0 = default)
+int g_tf_group = 0, g_tf_warps = 0, g_t5_variant = 0, g_tf_variant = 0;  // tuning hooks (0 = default)
 
 template <int OUT>
 int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, int context, void* tokens, float* mu,
                           float* sigma, uint8_t* patch_mask, int32_t* num_masked, cudaStream_t stream) {
   const int N = context >> 5;
-  int G = g_tf_group > 0 ? g_tf_group : 2048 / context;  // ~10 KB of series per warp keeps 20 warps / SM resident
-  if (G > 4) G = 4;
+  if (g_tf_variant == 1) {  // A/B: warp-staged cp.async kernel
+    int G = g_tf_group > 0 ? g_tf_group : 2048 / context;
+    if (G > 4) G = 4;
+    if (G < 1) G = 1;
+    const int per_warp = ((G * context * 5 + G * (3 * N + 1) * 4) + 15) & ~15;
+    int warps = g_tf_warps > 0 ? g_tf_warps : 4;
+    while (warps > 1 && warps * per_warp > 100 * 1024) --warps;
+    const int smem = warps * per_warp;
+    auto kern = timesfm_patchify_norm_kernel<OUT>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) {
+        set_error("timesfm_patchify_norm: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+        return TSFMX_ERR_CUDA;
+      }
+    }
+    const int64_t groups = (batch + G - 1) / G;
+    const int64_t blocks = (groups + warps - 1) / warps;
+    const int per_sm = (220 * 1024) / smem > 0 ? (220 * 1024) / smem : 1;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm * 2;
+    const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+    kern<<<grid, warps * 32, smem, stream>>>(x, mask, batch, context, G, tokens, mu, sigma, patch_mask, num_masked);
+    return check_last_launch("timesfm_patchify_norm");
+  }
+  // TMA-pipelined kernel: tiles of G series (<= 32: one merge thread per series), `stages` tiles in flight per block
+  int G = g_tf_group > 0 ? g_tf_group : (40 * 1024) / (context * 5);
+  if (G > 32) G = 32;
   if (G < 1) G = 1;
-  const int per_warp = ((G * context * 5 + G * (3 * N + 1) * 4) + 15) & ~15;
-  int warps = g_tf_warps > 0 ? g_tf_warps : 4;
-  while (warps > 1 && warps * per_warp > 100 * 1024) --warps;
-  const int smem = warps * per_warp;
-  auto kern = timesfm_patchify_norm_kernel<OUT>;
-  if (smem > 48 * 1024) {
+  int stages = g_tf_warps > 0 ? g_tf_warps : 2;
+  auto smem_for = [&](int g, int st) {
+    return st * ((g * context * 5 + 127) & ~127) + g * N * 16 + st * 8 + 128;
+  };
+  while (stages > 1 && smem_for(G, stages) > 220 * 1024) --stages;
+  while (G > 1 && smem_for(G, stages) > 220 * 1024) --G;
+  const int smem = smem_for(G, stages);
+  TSFMX_REQUIRE(smem <= 227 * 1024, "timesfm_patchify_norm: context %d does not fit the staged kernel", context);
+  auto kern = timesfm_patchify_norm_tma_kernel<OUT>;
+  static int smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("timesfm_patchify_norm: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
       return TSFMX_ERR_CUDA;
     }
+    smem_set = smem;
   }
-  const int64_t groups = (batch + G - 1) / G;
-  const int64_t blocks = (groups + warps - 1) / warps;
-  const int per_sm = (220 * 1024) / smem > 0 ? (220 * 1024) / smem : 1;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm * 2;
-  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
-  kern<<<grid, warps * 32, smem, stream>>>(x, mask, batch, context, G, tokens, mu, sigma, patch_mask, num_masked);
+  const int64_t tiles = (batch + G - 1) / G;
+  int per_sm = (224 * 1024) / (smem + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2048 / TF_THREADS) per_sm = 2048 / TF_THREADS;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+  const int grid = static_cast<int>(tiles < cap ? tiles : cap);
+  kern<<<grid, TF_THREADS, smem, stream>>>(x, mask, batch, context, G, stages, tokens, mu, sigma, patch_mask,
+                                           num_masked);
   return check_last_launch("timesfm_patchify_norm");
 }
 
@@ -743,6 +939,7 @@ extern "C" int tsfmx_tune(int32_t key, int32_t value) {
     case 0: g_tf_group = value; return TSFMX_OK;
     case 1: g_tf_warps = value; return TSFMX_OK;
     case 2: g_t5_variant = value; return TSFMX_OK;
+    case 3: g_tf_variant = value; return TSFMX_OK;
     default:
       set_error("tune: unknown key %d", key);
       return TSFMX_ERR_INVALID_ARGUMENT;

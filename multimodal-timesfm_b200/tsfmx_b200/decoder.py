@@ -12,6 +12,7 @@ from dataclasses import dataclass, field
 import torch
 from torch import nn
 
+from . import lanes
 from .fusion import MultimodalFusion
 from .tsfm.base import TsfmAdapter
 
@@ -39,6 +40,8 @@ class MultimodalDecoder(nn.Module):
             hidden_dims=config.fusion_hidden_dims,
         )
         self.fusion.precision = getattr(adapter, "precision", "bf16")
+        # series lanes for forecasting (tsfmx_b200.lanes): 2 = overlap one lane's GEMMs with the other's HBM-bound kernels
+        self.lanes = 2
 
     def set_precision(self, precision: str) -> None:
         """"bf16" (throughput) or "bf16x3" (parity: <= 1e-3 relative against the fp32 reference)."""
@@ -62,14 +65,50 @@ class MultimodalDecoder(nn.Module):
         # train() mode with autograd on = the reference's fine-tune step; eval() / no_grad = plain forecasting
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_full_training(horizon, inputs, masks, text_embeddings)
-        preprocessed = self.adapter.preprocess(inputs, masks)
-        embeddings = (
-            self.fusion(preprocessed.input_embeddings, text_embeddings)
-            if text_embeddings is not None
-            else preprocessed.input_embeddings
+        count = self._lane_count(inputs)
+        if count > 1:
+            if text_embeddings is not None and text_embeddings.shape[0] != inputs.shape[0]:
+                raise ValueError(
+                    f"text_embeddings batch ({text_embeddings.shape[0]}) does not match inputs batch ({inputs.shape[0]})"
+                )
+            cuts = lanes.split_points(inputs.shape[0], count, multiple=8)
+            parts = lanes.run_lanes(
+                lambda i: self._forecast_steps(
+                    horizon,
+                    inputs[cuts[i][0] : cuts[i][1]],
+                    masks[cuts[i][0] : cuts[i][1]],
+                    None if text_embeddings is None else text_embeddings[cuts[i][0] : cuts[i][1]],
+                ),
+                len(cuts),
+                inputs.device,
+            )
+            return torch.cat(parts, dim=0)
+        return lanes.drain(self._forecast_steps(horizon, inputs, masks, text_embeddings))
+
+    def _forecast_steps(self, horizon, inputs, masks, text_embeddings):
+        """preprocess -> fusion -> forward -> postprocess (reference decoder.py:65-72) as one step generator."""
+        preprocessed = yield from lanes.steps(self.adapter, "preprocess", inputs, masks)
+        if text_embeddings is not None:
+            if hasattr(self.fusion, "forward_device_steps") and not self.fusion.training:
+                embeddings = yield from self.fusion.forward_device_steps(preprocessed.input_embeddings, text_embeddings)
+            else:
+                embeddings = self.fusion(preprocessed.input_embeddings, text_embeddings)
+                yield
+        else:
+            embeddings = preprocessed.input_embeddings
+        output_embeddings = yield from lanes.steps(self.adapter, "forward", embeddings, preprocessed.masks)
+        return (
+            yield from lanes.steps(self.adapter, "postprocess", horizon, output_embeddings, preprocessed.normalization_stats)
         )
-        output_embeddings = self.adapter(embeddings, preprocessed.masks)
-        return self.adapter.postprocess(horizon, output_embeddings, preprocessed.normalization_stats)
+
+    def _lane_count(self, inputs: torch.Tensor) -> int:
+        """Lanes to cut a forecast batch into: ``self.lanes`` when every lane still fills the GPU (>= 8192 patch
+        tokens, i.e. >= 64 GEMM row tiles of 128), else 1."""
+        want = int(getattr(self, "lanes", 1))
+        if want <= 1 or not inputs.is_cuda or inputs.dim() != 2:
+            return 1
+        tokens = inputs.shape[0] * max(1, inputs.shape[1] // max(1, self.adapter.patch_len))
+        return max(1, min(want, tokens // 8192))
 
     def _forward_full_training(self, horizon, inputs, masks, text_embeddings):
         """Differentiable path of the reference's "multimodal" training mode (trainer.py:76-77,119-123): frozen

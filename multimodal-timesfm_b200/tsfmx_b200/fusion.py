@@ -14,6 +14,7 @@ from torch import nn
 
 from . import ops
 from ._lib import ACT_RELU, DT_F32, PRECISIONS, TsfmxError
+from .lanes import drain
 
 
 class MultimodalFusion(nn.Module):
@@ -73,6 +74,10 @@ class MultimodalFusion(nn.Module):
         return self.forward_device(ts_embeddings, text_embeddings)
 
     def forward_device(self, ts_embeddings: torch.Tensor, text_embeddings: torch.Tensor) -> torch.Tensor:
+        return drain(self.forward_device_steps(ts_embeddings, text_embeddings))
+
+    def forward_device_steps(self, ts_embeddings: torch.Tensor, text_embeddings: torch.Tensor):
+        """The fusion as a step generator (one ``yield`` per kernel launch, see ``tsfmx_b200.lanes``)."""
         if not ts_embeddings.is_cuda:
             raise TsfmxError("MultimodalFusion runs on B200 only; there is no CPU fallback")
         precision = PRECISIONS[self.precision]
@@ -88,6 +93,7 @@ class MultimodalFusion(nn.Module):
         m = ts2.shape[0]
         weights = self._packed_weights(precision)
         h = ops.cast_rows(_pad_k(tx2), adt)
+        yield
         for i, w in enumerate(weights):
             n = self.dims[i + 1]
             k = _round64(self.dims[i])
@@ -95,12 +101,14 @@ class MultimodalFusion(nn.Module):
             if last:
                 out = torch.empty(m, n, dtype=torch.float32, device=ts2.device)
                 ops.gemm([(h, w, k)], m, n, out, DT_F32, precision=precision, act=ACT_RELU, residual=ts2)
+                yield
                 return out.reshape(*lead, n)
             n_pad = _round64(n)
             nxt = ops.alloc(m, n_pad, adt, ts2.device)
             if n_pad != n:
                 nxt.zero_()
             ops.gemm([(h, w, k)], m, n, nxt, adt, precision=precision, act=ACT_RELU, split_off=n_pad)
+            yield
             h = nxt
         raise AssertionError("unreachable")
 

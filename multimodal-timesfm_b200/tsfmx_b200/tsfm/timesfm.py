@@ -23,6 +23,7 @@ from torch import nn
 
 from .. import ops
 from .._lib import ACT_SILU, ACT_SILU_GRAD, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
+from ..lanes import drain
 from .base import PreprocessResult, TsfmAdapter
 
 
@@ -216,6 +217,10 @@ class TimesFM2p5Adapter(TsfmAdapter):
 
         Raises ValueError if the context is not a multiple of the patch length or the mask shape differs.
         """
+        return drain(self.preprocess_steps(inputs, masks))
+
+    def preprocess_steps(self, inputs: torch.Tensor, masks: torch.Tensor):
+        """``preprocess`` as a step generator (one ``yield`` per kernel launch, see ``tsfmx_b200.lanes``)."""
         m = self._model
         batch_size, context = inputs.shape[0], inputs.shape[1]
         if context % m.p != 0:
@@ -231,12 +236,15 @@ class TimesFM2p5Adapter(TsfmAdapter):
         rows = batch_size * n
         masks = masks.bool()
         tokens, mu, sigma, _pm, _nm = ops.timesfm_patchify_norm(inputs, masks, m.p, adt)
+        yield
         hidden = ops.alloc(rows, m.md, adt, inputs.device)
         ops.gemm([(tokens, w["tok_hidden"], 2 * m.p)], rows, m.md, hidden, adt, precision=prec, act=ACT_SILU,
                  bias=w["tok_hidden_b"])
+        yield
         emb = torch.empty(rows, m.md, dtype=torch.float32, device=inputs.device)
         ops.gemm([(hidden, w["tok_out"], m.md), (tokens, w["tok_res"], 2 * m.p)], rows, m.md, emb, DT_F32,
                  precision=prec, bias=w["tok_out_b"])
+        yield
         return PreprocessResult(
             input_embeddings=emb.view(batch_size, n, m.md),
             masks=masks.reshape(batch_size, n, m.p),
@@ -245,6 +253,10 @@ class TimesFM2p5Adapter(TsfmAdapter):
 
     def forward(self, input_embeddings: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         """Run the stacked transformer layers (reference timesfm.py:85-98) -> (batch, patches, model_dims)."""
+        return drain(self.forward_steps(input_embeddings, masks))
+
+    def forward_steps(self, input_embeddings: torch.Tensor, masks: torch.Tensor):
+        """``forward`` as a step generator (one ``yield`` per kernel launch, see ``tsfmx_b200.lanes``)."""
         m = self._model
         if not input_embeddings.is_cuda:
             raise TsfmxError("TimesFM2p5Adapter runs on B200 only; there is no CPU fallback")
@@ -264,6 +276,7 @@ class TimesFM2p5Adapter(TsfmAdapter):
         if not layers:
             return x.view(b, n, d).clone()
         xn = ops.rmsnorm(x, layers[0]["pre_attn"], m.eps, adt)
+        yield
         qkv = ops.alloc(rows, 3 * d, mid_dt, dev)
         attn = ops.alloc(rows, d, adt, dev)
         a = ops.alloc(rows, d, mid_dt, dev)
@@ -272,21 +285,31 @@ class TimesFM2p5Adapter(TsfmAdapter):
             last = i == len(layers) - 1
             nxt = None if last else layers[i + 1]["pre_attn"]
             ops.gemm([(xn, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
+            yield
             ops.timesfm_attention(qkv, b, n, m.h, m.hd, patch_mask, num_masked, w["inv_freq"], lw["q_ln"], lw["k_ln"],
                                   lw["q_scale"], m.eps, adt, out=attn)
+            yield
             if self.fused_norm:
                 # out-proj / ff1 with post-norm + residual + next pre-norm in the GEMM epilogue (5-CTA clusters)
                 ops.gemm_rownorm(attn, lw["out"], d, rows, d, prec, lw["post_attn"], lw["pre_ff"], x if i == 0 else y, y,
                                  adt, xn, m.eps)
+                yield
                 ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU)
+                yield
                 ops.gemm_rownorm(hbuf, lw["ff1"], m.ff, rows, d, prec, lw["post_ff"], nxt, y, y, adt,
                                  None if last else xn, m.eps)
+                yield
             else:
                 ops.gemm([(attn, lw["out"], d)], rows, d, a, mid_dt, precision=prec)
+                yield
                 ops.norm_residual_norm(a, x if i == 0 else y, lw["post_attn"], lw["pre_ff"], m.eps, y, adt, xn)
+                yield
                 ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU)
+                yield
                 ops.gemm([(hbuf, lw["ff1"], m.ff)], rows, d, a, mid_dt, precision=prec)
+                yield
                 ops.norm_residual_norm(a, y, lw["post_ff"], nxt, m.eps, y, adt, None if last else xn)
+                yield
         return y.view(b, n, d)
 
     def postprocess(
@@ -299,6 +322,11 @@ class TimesFM2p5Adapter(TsfmAdapter):
 
         Raises ValueError if ``horizon`` exceeds the output patch length (no AR decode).
         """
+        return drain(self.postprocess_steps(horizon, output_embeddings, normalization_stats))
+
+    def postprocess_steps(self, horizon: int, output_embeddings: torch.Tensor,
+                          normalization_stats: dict[str, torch.Tensor]):
+        """``postprocess`` as a step generator (see ``tsfmx_b200.lanes``)."""
         m = self._model
         if horizon > m.o:
             raise ValueError(
@@ -317,11 +345,14 @@ class TimesFM2p5Adapter(TsfmAdapter):
         mu_last = normalization_stats["context_mu"][:, -1].contiguous()
         sigma_last = normalization_stats["context_sigma"][:, -1].contiguous()
         a = ops.cast_rows(last, adt)
+        yield
         hid = ops.alloc(b, m.md, adt, emb.device)
         ops.gemm([(a, w["head_hidden"], d)], b, m.md, hid, adt, precision=prec, act=ACT_SILU)
+        yield
         out = torch.empty(b, horizon * m.q, dtype=torch.float32, device=emb.device)
         ops.gemm([(hid, w["head_out"], m.md), (a, w["head_res"], d)], b, m.o * m.q, out, DT_F32, precision=prec,
                  row_scale=sigma_last, row_shift=mu_last, n_store=horizon * m.q)
+        yield
         return out.view(b, horizon, m.q)
 
     # ------------------------------------------------------------------ training path (frozen backbone)

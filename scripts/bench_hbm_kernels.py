@@ -40,8 +40,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--contexts", default="", help="comma-separated context lengths (default 512,2048)")
     ap.add_argument("--tf-group", type=int, default=0, help="series per warp of timesfm_patchify_norm (0 = default)")
     ap.add_argument("--tf-warps", type=int, default=0, help="warps per block of timesfm_patchify_norm (0 = default)")
+    ap.add_argument("--tf-variant", type=int, default=0, help="0 = TMA-pipelined kernel (tf-group = series per tile, "
+                    "tf-warps = stages), 1 = warp-staged cp.async kernel")
     ap.add_argument("--t5-variant", type=int, default=0, help="1/2 = register-cached row (<=512 / <=2048), 3 = re-read")
     args = ap.parse_args()
     from tsfmx_b200 import _lib
@@ -49,10 +52,13 @@ def main():
     _lib.check(_lib.load().tsfmx_tune(0, args.tf_group))
     _lib.check(_lib.load().tsfmx_tune(1, args.tf_warps))
     _lib.check(_lib.load().tsfmx_tune(2, args.t5_variant))
+    _lib.check(_lib.load().tsfmx_tune(3, args.tf_variant))
     dev = torch.device("cuda")
     peak = peak_gbs()
     cases = []
-    for ctx_len, batch in ((512, 262144), (2048, 65536)):
+    ap_ctx = [(512, 262144), (2048, 65536)] if not args.contexts else [
+        (int(c), max(8192, 262144 * 512 // int(c))) for c in args.contexts.split(",")]
+    for ctx_len, batch in ap_ctx:
         g = torch.Generator(device=dev).manual_seed(ctx_len)
         x = torch.randn(batch, ctx_len, generator=g, device=dev)
         mask = torch.zeros(batch, ctx_len, dtype=torch.bool, device=dev)
@@ -77,7 +83,7 @@ def main():
         print(json.dumps({
             "kernel": name, "series": batch, "algorithmic_bytes_per_series": bytes_per_series, "ms": round(ms, 4),
             "series_per_s": batch / (ms * 1e-3), "achieved_GBps": round(gbs, 1), "peak_GBps": peak,
-            "frac_of_measured_hbm_peak": round(gbs / peak, 3), "tf_group": args.tf_group, "tf_warps": args.tf_warps,
+            "frac_of_measured_hbm_peak": round(gbs / peak, 3), "tf_group": args.tf_group, "tf_warps": args.tf_warps, "tf_variant": args.tf_variant,
             "note": "time includes torch.empty of the outputs; working set >> 126 MB L2",
         }), flush=True)
 

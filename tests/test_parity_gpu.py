@@ -158,3 +158,26 @@ def test_error_behaviour_matches_reference(model2):
         dec.forward_full(129, x, m, None)
     with pytest.raises(ValueError, match="AR decode is not supported"):
         oracle.forward_full(129, x.cpu(), m.cpu(), None)
+
+
+@pytest.mark.parametrize("lanes_n,batch", [(2, 512), (3, 771), (4, 1024)])
+def test_series_lanes_bit_identical(model2, lanes_n, batch):
+    """Cutting the batch into series lanes on separate streams (tsfmx_b200.lanes) must not change a single bit:
+    every series is independent on the whole path, so the lanes only change which kernels overlap in time."""
+    dec, _ = model2
+    dec.set_precision("bf16")
+    ctx, masks, text, _ = O.synthetic_batch(batch, 512, 128, padded=True)
+    ctx, masks, text = ctx.to(DEV), masks.to(DEV), text.to(DEV)
+    saved = dec.lanes
+    try:
+        with torch.no_grad():
+            dec.lanes = 1
+            one = dec.forward_full(128, ctx, masks, text)
+            dec.lanes = lanes_n
+            assert dec._lane_count(ctx) == min(lanes_n, batch * 16 // 8192)
+            many = dec.forward_full(128, ctx, masks, text)
+            again = dec.forward_full(128, ctx, masks, text)
+        torch.cuda.synchronize()
+    finally:
+        dec.lanes = saved
+    assert torch.equal(one, many) and torch.equal(many, again)
