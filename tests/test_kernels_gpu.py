@@ -250,6 +250,33 @@ def test_chronos_t5_tokenize_bit_exact(context):
     assert torch.equal(vals.cpu(), ref_vals)
 
 
+def test_chronos_t5_tokenize_division_stress():
+    """The kernel divides by the per-series scale with a hoisted reciprocal + two FMA refinements; every id must still
+    equal torch's IEEE division + bucketize, including values parked on / next to bin boundaries and series whose
+    scale spans 80 binades."""
+    b, context = 4096, 512
+    gen = torch.Generator().manual_seed(7)
+    expo = torch.randint(-40, 40, (b, 1), generator=gen).float()
+    x = torch.randn(b, context, generator=gen) * torch.exp2(expo)
+    centers, boundaries = _t5_tables()
+    # rows 0..1023: every element sits exactly on / one ulp around (boundary * scale) of a first-pass scale
+    inner = boundaries[1:-1]
+    am = torch.ones_like(x, dtype=torch.bool)
+    scale0 = (x.abs().double().sum(-1).float() / context)
+    pick = inner[torch.randint(0, inner.numel(), (1024, context), generator=gen)]
+    edge = pick * scale0[:1024, None]
+    nudged = torch.nextafter(edge, torch.where(torch.rand(1024, context, generator=gen) < 0.5, -1.0, 1.0) * torch.inf)
+    x[:1024] = torch.where(torch.rand(1024, context, generator=gen) < 0.5, edge, nudged)
+    scale = (x.abs().double().sum(-1).float() / context)
+    scale[~(scale > 0)] = 1.0
+    ref = torch.bucketize(x / scale[:, None], boundaries, right=True) + 2
+    ref.clamp_(0, 4095)
+    ids, gam, gscale = ops.chronos_t5_tokenize(x.to(DEV), boundaries.to(DEV))
+    assert torch.equal(gscale.cpu(), scale)
+    assert torch.equal(ids.cpu()[:, :context], ref)
+    assert bool(gam.all())
+
+
 # ----------------------------------------------------------------------------- Chronos-2 context preparation
 @pytest.mark.parametrize("context", [512, 2048, 500])
 @pytest.mark.parametrize("out_cols", [48, 64])
