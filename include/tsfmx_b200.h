@@ -246,6 +246,16 @@ int tsfmx_encoder_attention(const void* qkv, int32_t qkv_dtype, int64_t batch, i
                             void* out, void* stream);
 
 /*
+ * Tensor-core variant of tsfmx_encoder_attention for the throughput mode: qkv and out bf16, head_dim 64, seq <= 208
+ * (Chronos-2: T = ctx/16 + 65 = 97 at ctx 512, 193 at ctx 2048).  Same semantics (positions arange(T), no 1/sqrt(d),
+ * bidirectional, key mask, all-masked rows -> uniform weights); rope_table [seq, head_dim/2, 2] fp32 = (cos, sin) of
+ * position * inv_freq, filled once by tsfmx_rope_table and reused by every block and every call.
+ */
+int tsfmx_rope_table(const float* inv_freq, int32_t half_dim, int32_t seq, float* table, void* stream);
+int tsfmx_encoder_attention_mma(const void* qkv, int64_t batch, int32_t seq, int32_t num_heads, int32_t head_dim,
+                                const uint8_t* key_mask, const float* rope_table, void* out, void* stream);
+
+/*
  * Chronos-2 output epilogue (reference chronos.py:159-169): preds [B*np, Q*patch] (patch-major rows of the
  * output ResidualBlock, np = ceil(horizon / patch)) -> out [B, horizon, Q] = sinh(x) * scale[b] + loc[b].
  */

@@ -117,6 +117,253 @@ __global__ void __launch_bounds__(128) encoder_attention_kernel(const void* __re
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Tensor-core version for the throughput mode (bf16 qkv in, bf16 out), T <= 16 * NT tokens.
+//
+// One CTA of 7 warps per (series, head).  The head's q / k rows are fetched with 16-byte loads, rotated in fp32 with
+// a precomputed (cos, sin) table and parked as bf16 in padded shared-memory tiles; v rows go there with cp.async.
+// Every warp then owns 16-query tiles: S = Q K^T on mma.sync.m16n8k16 (bf16 x bf16 -> fp32) with the whole score row
+// block (T <= 208 keys) in registers - no online-softmax rescaling - key mask and softmax in registers, O = P V on
+// the tensor cores again, and the result leaves through the tile's own (dead) Q rows as 16-byte coalesced stores.
+// tcgen05 is deliberately not used: per (series, head) the problem is 97..193 x 64, far below its 128-row tiles.
+// ----------------------------------------------------------------------------------------
+constexpr int ENC_HD = 64;
+constexpr int ENC_LD = 72;  // padded row (144 B): ldmatrix rows land in distinct bank groups
+constexpr int ENC_WARPS = 7;
+
+__device__ __forceinline__ void enc_cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void enc_ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void enc_ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void enc_mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__global__ void rope_table_kernel(const float* __restrict__ inv_freq, int half, int seq, float2* __restrict__ table) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < seq * half; i += gridDim.x * blockDim.x) {
+    const int t = i / half, d = i - t * half;
+    float sn, cs;
+    sincosf(static_cast<float>(t) * __ldg(inv_freq + d), &sn, &cs);
+    table[i] = make_float2(cs, sn);
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(ENC_WARPS * 32, (NT <= 9 ? 2 : 1)) encoder_attention_mma_kernel(
+    const __nv_bfloat16* __restrict__ qkv, int seq, int num_heads, const uint8_t* __restrict__ key_mask,
+    const float2* __restrict__ rope, __nv_bfloat16* __restrict__ out) {
+  constexpr int ROWS = 16 * NT;
+  constexpr int HALF = ENC_HD / 2;
+  constexpr int TILE = ROWS * ENC_LD;
+  extern __shared__ __align__(16) uint8_t smem_enc[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_enc);
+  __nv_bfloat16* sK = sQ + TILE;
+  __nv_bfloat16* sV = sK + TILE;
+  uint8_t* s_valid = reinterpret_cast<uint8_t*>(sV + TILE);  // [ROWS] 1 = key exists and may be attended
+  __shared__ int s_any;
+  const int T = seq;
+  const int b = blockIdx.x / num_heads, h = blockIdx.x - b * num_heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int width = num_heads * ENC_HD;
+  const int64_t ld = 3 * static_cast<int64_t>(width);
+  const __nv_bfloat16* gbase = qkv + static_cast<int64_t>(b) * T * ld + h * ENC_HD;
+
+  if (threadIdx.x == 0) s_any = 0;
+  // ---- v rows: raw 16-byte async copies (8 per row); rows >= T zero-filled for all three tiles
+  for (int c = threadIdx.x; c < T * 8; c += blockDim.x) {
+    const int row = c >> 3, ch = c & 7;
+    enc_cp_async_16(sV + row * ENC_LD + ch * 8, gbase + row * ld + 2 * width + ch * 8);
+  }
+  for (int c = threadIdx.x; c < (ROWS - T) * 8 * 3; c += blockDim.x) {
+    const int which = c / ((ROWS - T) * 8), rem = c - which * ((ROWS - T) * 8);
+    const int row = T + (rem >> 3), ch = rem & 7;
+    *reinterpret_cast<uint4*>(sQ + which * TILE + row * ENC_LD + ch * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();  // s_any = 0 visible before the ORs below
+  {
+    int any = 0;
+    for (int j = threadIdx.x; j < ROWS; j += blockDim.x) {
+      const uint8_t v = j < T && (key_mask == nullptr || key_mask[static_cast<int64_t>(b) * T + j] != 0) ? 1 : 0;
+      s_valid[j] = v;
+      any |= v;
+    }
+    if (any) s_any = 1;  // benign race: every writer stores 1
+  }
+  // ---- q / k rows with the rotary embedding (rotate-half, position = token index): one thread per (row, 8 dims of
+  //      the first half + the matching 8 dims of the second half)
+  for (int c = threadIdx.x; c < T * 4; c += blockDim.x) {
+    const int row = c >> 2, ch = c & 3;
+    const __nv_bfloat16* g = gbase + row * ld + ch * 8;
+    const uint4 qa = *reinterpret_cast<const uint4*>(g), qb = *reinterpret_cast<const uint4*>(g + HALF);
+    const uint4 ka = *reinterpret_cast<const uint4*>(g + width), kb = *reinterpret_cast<const uint4*>(g + width + HALF);
+    const float4* rp = reinterpret_cast<const float4*>(rope + row * HALF + ch * 8);
+    const uint32_t qaw[4] = {qa.x, qa.y, qa.z, qa.w}, qbw[4] = {qb.x, qb.y, qb.z, qb.w};
+    const uint32_t kaw[4] = {ka.x, ka.y, ka.z, ka.w}, kbw[4] = {kb.x, kb.y, kb.z, kb.w};
+    uint32_t oq1[4], oq2[4], ok1[4], ok2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 cs = __ldg(rp + i);  // (cos, sin) of dims 2i, 2i + 1
+      const float q1a = bf16_lo(qaw[i]), q1b = bf16_hi(qaw[i]), q2a = bf16_lo(qbw[i]), q2b = bf16_hi(qbw[i]);
+      const float k1a = bf16_lo(kaw[i]), k1b = bf16_hi(kaw[i]), k2a = bf16_lo(kbw[i]), k2b = bf16_hi(kbw[i]);
+      oq1[i] = pack_bf16x2(q1a * cs.x - q2a * cs.y, q1b * cs.z - q2b * cs.w);
+      oq2[i] = pack_bf16x2(q2a * cs.x + q1a * cs.y, q2b * cs.z + q1b * cs.w);
+      ok1[i] = pack_bf16x2(k1a * cs.x - k2a * cs.y, k1b * cs.z - k2b * cs.w);
+      ok2[i] = pack_bf16x2(k2a * cs.x + k1a * cs.y, k2b * cs.z + k1b * cs.w);
+    }
+    *reinterpret_cast<uint4*>(sQ + row * ENC_LD + ch * 8) = make_uint4(oq1[0], oq1[1], oq1[2], oq1[3]);
+    *reinterpret_cast<uint4*>(sQ + row * ENC_LD + HALF + ch * 8) = make_uint4(oq2[0], oq2[1], oq2[2], oq2[3]);
+    *reinterpret_cast<uint4*>(sK + row * ENC_LD + ch * 8) = make_uint4(ok1[0], ok1[1], ok1[2], ok1[3]);
+    *reinterpret_cast<uint4*>(sK + row * ENC_LD + HALF + ch * 8) = make_uint4(ok2[0], ok2[1], ok2[2], ok2[3]);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  const bool has_key = s_any != 0;  // every key masked: uniform weights over all T keys (finfo.min semantics)
+  const int g = lane >> 2, t = lane & 3;
+  const int ntk = (T + 15) >> 4;
+  const uint32_t sq_addr = smem_u32(sQ), sk_addr = smem_u32(sK), sv_addr = smem_u32(sV);
+  for (int qi = warp; qi < ntk; qi += ENC_WARPS) {
+    uint32_t qf[4][4];
+    {
+      const int row = qi * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+      const int col = 8 * (lane >> 4);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) enc_ldmatrix_x4(sq_addr + (row * ENC_LD + col + 16 * ks) * 2, qf[ks]);
+    }
+    float s[NT][2][4];
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[kj][nt][e] = 0.f;
+      if (kj < ntk) {
+        const int key = kj * 16 + (lane & 7) + 8 * (lane >> 4);
+        const int col = 8 * ((lane >> 3) & 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t kb[4];
+          enc_ldmatrix_x4(sk_addr + (key * ENC_LD + col + 16 * ks) * 2, kb);
+          enc_mma_16816(s[kj][0], qf[ks], kb[0], kb[1]);
+          enc_mma_16816(s[kj][1], qf[ks], kb[2], kb[3]);
+        }
+      }
+    }
+    // mask + row max (rows g and g + 8 of the tile; this thread holds keys 2t, 2t + 1 of every 8-key group)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int key = kj * 16 + nt * 8 + 2 * t;
+        const uint32_t vv = *reinterpret_cast<const uint16_t*>(s_valid + key);
+        const bool ok0 = has_key ? (vv & 0xffu) != 0 : key < T;
+        const bool ok1 = has_key ? (vv >> 8) != 0 : key + 1 < T;
+        s[kj][nt][0] = ok0 ? (has_key ? s[kj][nt][0] : 0.f) : -INFINITY;
+        s[kj][nt][1] = ok1 ? (has_key ? s[kj][nt][1] : 0.f) : -INFINITY;
+        s[kj][nt][2] = ok0 ? (has_key ? s[kj][nt][2] : 0.f) : -INFINITY;
+        s[kj][nt][3] = ok1 ? (has_key ? s[kj][nt][3] : 0.f) : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[kj][nt][0], s[kj][nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[kj][nt][2], s[kj][nt][3]));
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float mx = (e & 2) ? mx1 : mx0;
+          const float p = s[kj][nt][e] == -INFINITY ? 0.f : __expf(s[kj][nt][e] - mx);
+          s[kj][nt][e] = p;
+          if (e & 2) sum1 += p; else sum0 += p;
+        }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj) {
+      if (kj < ntk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[kj][0][0], s[kj][0][1]);
+        pa[1] = pack_bf16x2(s[kj][0][2], s[kj][0][3]);
+        pa[2] = pack_bf16x2(s[kj][1][0], s[kj][1][1]);
+        pa[3] = pack_bf16x2(s[kj][1][2], s[kj][1][3]);
+        const int key = kj * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int col = 8 * (lane >> 4);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t vb[4];
+          enc_ldmatrix_x4_trans(sv_addr + (key * ENC_LD + col + 16 * dp) * 2, vb);
+          enc_mma_16816(o[2 * dp], pa, vb[0], vb[1]);
+          enc_mma_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    // the Q rows of this tile are dead now (only this warp read them): stage the output there
+    __syncwarp();
+    const int row0 = qi * 16 + g, row1 = row0 + 8;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      *reinterpret_cast<uint32_t*>(sQ + row0 * ENC_LD + dt * 8 + 2 * t) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sQ + row1 * ENC_LD + dt * 8 + 2 * t) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+    }
+    __syncwarp();
+    __nv_bfloat16* obase = out + static_cast<int64_t>(b) * T * width + h * ENC_HD;
+    for (int c = lane; c < 16 * 8; c += 32) {
+      const int row = qi * 16 + (c >> 3), ch = c & 7;
+      if (row < T)
+        *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * width + ch * 8) =
+            *reinterpret_cast<const uint4*>(sQ + row * ENC_LD + ch * 8);
+    }
+  }
+}
+
+template <int NT>
+int launch_encoder_attention_mma(const void* qkv, int64_t batch, int seq, int num_heads, const uint8_t* key_mask,
+                                 const float* rope, void* out, cudaStream_t stream) {
+  constexpr int smem = 3 * 16 * NT * ENC_LD * 2 + 16 * NT;
+  auto kern = encoder_attention_mma_kernel<NT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("encoder_attention_mma: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+      return TSFMX_ERR_CUDA;
+    }
+  }
+  kern<<<static_cast<int>(batch * num_heads), ENC_WARPS * 32, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), seq, num_heads, key_mask, reinterpret_cast<const float2*>(rope),
+      reinterpret_cast<__nv_bfloat16*>(out));
+  return check_last_launch("encoder_attention_mma");
+}
+
 __global__ void chronos2_finalize_kernel(const float* __restrict__ preds, int64_t batch, int num_patches_used,
                                          int num_quantiles, int patch, int horizon, int use_arcsinh,
                                          const float* __restrict__ loc, const float* __restrict__ scale,
@@ -174,6 +421,36 @@ extern "C" int tsfmx_encoder_attention(const void* qkv, int32_t qkv_dtype, int64
   if (out_dtype == TSFMX_DT_F32) return launch(encoder_attention_kernel<64, TSFMX_DT_F32>);
   if (out_dtype == TSFMX_DT_BF16) return launch(encoder_attention_kernel<64, TSFMX_DT_BF16>);
   return launch(encoder_attention_kernel<64, TSFMX_DT_BF16_SPLIT>);
+}
+
+extern "C" int tsfmx_rope_table(const float* inv_freq, int32_t half_dim, int32_t seq, float* table, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(inv_freq != nullptr && table != nullptr, "rope_table: NULL pointer");
+  TSFMX_REQUIRE(half_dim > 0 && seq > 0, "rope_table: bad sizes");
+  const int total = half_dim * seq;
+  rope_table_kernel<<<(total + 255) / 256, 256, 0, stream>>>(inv_freq, half_dim, seq, reinterpret_cast<float2*>(table));
+  return check_last_launch("rope_table");
+}
+
+extern "C" int tsfmx_encoder_attention_mma(const void* qkv, int64_t batch, int32_t seq, int32_t num_heads,
+                                           int32_t head_dim, const uint8_t* key_mask, const float* rope_table,
+                                           void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(qkv != nullptr && out != nullptr && rope_table != nullptr, "encoder_attention_mma: NULL pointer");
+  TSFMX_REQUIRE(batch >= 0 && seq > 0 && num_heads > 0, "encoder_attention_mma: bad sizes");
+  TSFMX_REQUIRE(batch * num_heads < (int64_t(1) << 31), "encoder_attention_mma: too many (series, head) pairs");
+  TSFMX_REQUIRE(reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(rope_table) % 16 == 0,
+                "encoder_attention_mma: pointers must be 16-byte aligned");
+  if (head_dim != ENC_HD || seq > 208) {
+    set_error("encoder_attention_mma: head_dim %d / seq %d unsupported (head_dim 64, seq <= 208)", head_dim, seq);
+    return TSFMX_ERR_UNSUPPORTED;
+  }
+  if (batch == 0) return TSFMX_OK;
+  if (seq <= 64) return launch_encoder_attention_mma<4>(qkv, batch, seq, num_heads, key_mask, rope_table, out, stream);
+  if (seq <= 112) return launch_encoder_attention_mma<7>(qkv, batch, seq, num_heads, key_mask, rope_table, out, stream);
+  if (seq <= 144) return launch_encoder_attention_mma<9>(qkv, batch, seq, num_heads, key_mask, rope_table, out, stream);
+  return launch_encoder_attention_mma<13>(qkv, batch, seq, num_heads, key_mask, rope_table, out, stream);
 }
 
 extern "C" int tsfmx_chronos2_finalize(const float* preds, int64_t batch, int32_t num_patches_used,

@@ -108,6 +108,11 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     ),
     "tsfmx_attention_force_simt": (c_int32, [c_int32]),
     "tsfmx_tune": (c_int32, [c_int32, c_int32]),
+    "tsfmx_rope_table": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "tsfmx_encoder_attention_mma": (
+        c_int32,
+        [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "tsfmx_encoder_attention": (
         c_int32,
         [c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p],

@@ -388,6 +388,23 @@ def mask_cast_rows(x: torch.Tensor, mask: torch.Tensor, out_dtype: int) -> torch
 
 
 # ----------------------------------------------------------------------------- Chronos-2
+_force_simt_encoder_attention = False  # test hook: run the fp32 SIMT kernel where the tensor-core one applies
+_rope_tables: dict[tuple, torch.Tensor] = {}
+
+
+def rope_table(inv_freq: torch.Tensor, seq: int) -> torch.Tensor:
+    """(cos, sin) of position * inv_freq for positions [0, seq): fp32 [seq, half, 2], cached per inv_freq tensor."""
+    key = (inv_freq.data_ptr(), inv_freq._version, inv_freq.device, seq)
+    table = _rope_tables.get(key)
+    if table is None:
+        if len(_rope_tables) > 64:
+            _rope_tables.clear()
+        table = torch.empty(seq, inv_freq.numel(), 2, dtype=torch.float32, device=inv_freq.device)
+        check(_lib.load().tsfmx_rope_table(ptr(inv_freq), inv_freq.numel(), seq, ptr(table), stream()))
+        _rope_tables[key] = table
+    return table
+
+
 def encoder_attention(
     qkv: torch.Tensor,
     batch: int,
@@ -404,6 +421,12 @@ def encoder_attention(
     if out is None:
         out = alloc(batch * seq, num_heads * head_dim, out_dtype, qkv.device)
     km = None if key_mask is None else _as_u8(key_mask)
+    if (qkv.dtype == torch.bfloat16 and out_dtype == DT_BF16 and head_dim == 64 and seq <= 208
+            and not _force_simt_encoder_attention):
+        table = rope_table(inv_freq, seq)
+        check(lib.tsfmx_encoder_attention_mma(ptr(qkv), batch, seq, num_heads, head_dim, ptr(km), ptr(table), ptr(out),
+                                              stream()))
+        return out
     check(
         lib.tsfmx_encoder_attention(
             ptr(qkv), _dt(qkv), batch, seq, num_heads, head_dim, ptr(km), ptr(inv_freq), out_dtype, ptr(out), stream()

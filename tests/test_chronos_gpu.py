@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 from oracle import chronos2_oracle as C  # noqa: E402  (checker only)
 from oracle import timesfm_oracle as O  # noqa: E402
 from tsfmx_b200 import ops  # noqa: E402
-from tsfmx_b200._lib import DT_BF16_SPLIT, DT_F32  # noqa: E402
+from tsfmx_b200._lib import DT_BF16, DT_BF16_SPLIT, DT_F32  # noqa: E402
 from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig  # noqa: E402
 from tsfmx_b200.tsfm.chronos import Chronos2Adapter, Chronos2Module, init_random_  # noqa: E402
 
@@ -65,6 +65,42 @@ def test_encoder_attention_kernel():
     assert rel_max(got, ref) < 2e-5
     got = ops.encoder_attention(qkv.to(torch.bfloat16), b, t, h, hd, km, inv_freq, DT_BF16_SPLIT)
     assert rel_max(ops.split_to_float(got), ref) < 2e-2
+
+
+@pytest.mark.parametrize("t", [97, 193, 33, 129, 208, 100])
+def test_encoder_attention_tensor_core_path(t):
+    """bf16 in / bf16 out runs the mma.sync kernel (one CTA per (series, head)); check it against fp64 torch on the
+    same bf16-rounded inputs, including a partly masked and a fully masked series."""
+    b, h, hd = 5, 12, 64
+    gen = torch.Generator(device=DEV).manual_seed(t)
+    qkv = torch.randn(b * t, 3 * h * hd, generator=gen, device=DEV)
+    qkv[:, : 2 * h * hd] *= 0.35  # there is no 1/sqrt(d) in this attention: keep the logits O(1) like the model's
+    qkv = qkv.to(torch.bfloat16)
+    km = torch.ones(b, t, dtype=torch.bool, device=DEV)
+    km[1, : t // 3] = False
+    km[2, :] = False  # all keys masked -> uniform over all t keys
+    km[3, 5::2] = False
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(DEV)
+    q, k, v = qkv.double().reshape(b, t, 3, h, hd).permute(2, 0, 3, 1, 4)
+    freqs = torch.arange(t, device=DEV).float()[:, None] * inv_freq[None, :]
+    emb = torch.cat([freqs, freqs], -1)
+    cos, sin = emb.cos().double(), emb.sin().double()
+    q = q * cos + C.rotate_half(q) * sin
+    k = k * cos + C.rotate_half(k) * sin
+    s = q @ k.transpose(-1, -2) + ((~km)[:, None, None, :] * torch.finfo(torch.float32).min).double()
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, h * hd).float()
+    launches = ops._lib.launch_count()
+    got = ops.encoder_attention(qkv, b, t, h, hd, km, inv_freq, DT_BF16)
+    assert ops._lib.launch_count() - launches <= 2  # rope table (first call) + the attention kernel
+    ops._force_simt_encoder_attention = True
+    try:
+        simt = ops.encoder_attention(qkv, b, t, h, hd, km, inv_freq, DT_BF16)
+    finally:
+        ops._force_simt_encoder_attention = False
+    assert got.dtype == torch.bfloat16 and got.shape == (b * t, h * hd)
+    err, err_simt = rel_max(got.float(), ref), rel_max(got.float(), simt.float())
+    assert err < 1e-2, (err, err_simt)  # bf16 q/k after RoPE, bf16 probabilities, bf16 output
+    assert err_simt < 1e-2, (err, err_simt)
 
 
 @pytest.mark.parametrize("padded", [False, True])
