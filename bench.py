@@ -321,7 +321,13 @@ def run_b200_arm(args) -> None:
     n_tokens = B * (args.context // PATCH)
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["tflops"], "traffic": None,
+        "frac": achieved / peaks["tflops"],
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of the four decoder-layer
+        # GEMMs at M = 65536 (profiles/r1_ncu_gemm_decoder_layer.md): qkv 631.5 MB, attn-out 297.9, ff0 295.3, ff1 299.2
+        "traffic": 381.0e6 if B == BATCH_PER_GPU and args.context == CONTEXT else None,
+        "traffic_unit": "bytes per launch (mean over qkv / attn-out / ff0 / ff1)",
+        "algorithmic_bytes_per_launch": (2 * n_tokens * 1280 * 4 + 2 * n_tokens * (3840 + 3 * 1280)
+                                         + 2 * 1280 * (3840 + 3 * 1280)) / 4,
         "kernel": "gemm_bf16_tcgen05_kernel<256,2> (qkv, ff0) + gemm_rownorm_tcgen05_kernel (attn-out, ff1 with the "
                   "norm/residual junction in the epilogue)" if adapter.fused_norm else
                   "gemm_bf16_tcgen05_kernel<256,2> (decoder-layer GEMMs: qkv / attn-out / ff0 / ff1)",

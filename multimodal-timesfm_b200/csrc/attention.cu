@@ -531,7 +531,6 @@ int launch_attention(const void* qkv, int64_t batch, int N, int H, const uint8_t
   return launch(timesfm_attention_kernel<HD, QKV_BF16, TSFMX_DT_BF16_SPLIT>);
 }
 
-int g_force_simt = 0;  // test hook
 
 }  // namespace
 }  // namespace tsfmx
@@ -539,7 +538,7 @@ int g_force_simt = 0;  // test hook
 using namespace tsfmx;
 
 extern "C" int tsfmx_attention_force_simt(int on) {
-  g_force_simt = on ? 1 : 0;
+  g_force_simt_attention = on ? 1 : 0;
   return TSFMX_OK;
 }
 
@@ -561,7 +560,7 @@ extern "C" int tsfmx_timesfm_attention(const void* qkv, int32_t qkv_dtype, int64
   }
   if (batch == 0) return TSFMX_OK;
   const bool aligned = reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
-  if (qkv_dtype == TSFMX_DT_BF16 && out_dtype == TSFMX_DT_BF16 && aligned && num_patches <= 64 && !g_force_simt) {
+  if (qkv_dtype == TSFMX_DT_BF16 && out_dtype == TSFMX_DT_BF16 && aligned && num_patches <= 64 && !g_force_simt_attention) {
     if (num_patches <= 16)
       return launch_attention_mma<1>(qkv, batch, num_patches, num_heads, patch_mask, num_masked, inv_freq, q_ln_w,
                                      k_ln_w, q_scale, eps, out, stream);

@@ -498,6 +498,12 @@ extern "C" int tsfmx_timesfm_attention_bwd(const void* qkv, int32_t qkv_dtype, c
   }
   if (batch == 0) return TSFMX_OK;
   const int N = num_patches;
+  const bool aligned = reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0 &&
+                       reinterpret_cast<uintptr_t>(dqkv) % 16 == 0;
+  if (qkv_dtype == TSFMX_DT_BF16 && dout_dtype == TSFMX_DT_BF16 && dqkv_dtype == TSFMX_DT_BF16 && aligned && N <= 64 &&
+      !g_force_simt_attention)
+    return launch_timesfm_attention_bwd_mma(qkv, d_out, batch, N, num_heads, patch_mask, num_masked, inv_freq, q_ln_w,
+                                            k_ln_w, q_scale, eps, dqkv, stream);
   const int per_warp_bytes = (9 * N * 81 + 4 * N) * 4;
   int wpb = (200 * 1024) / per_warp_bytes;
   if (wpb > 4) wpb = 4;

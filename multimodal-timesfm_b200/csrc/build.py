@@ -27,6 +27,7 @@ SOURCES = [
     "attention.cu",
     "gemm.cu",
     "backward.cu",
+    "attention_bwd.cu",
     "chronos.cu",
     "model.cu",
 ]

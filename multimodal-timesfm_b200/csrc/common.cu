@@ -14,6 +14,8 @@ thread_local char g_error[1024] = "";
 std::atomic<uint64_t> g_launches{0};
 }  // namespace
 
+int g_force_simt_attention = 0;
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

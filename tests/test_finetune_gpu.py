@@ -98,6 +98,40 @@ def test_attention_bwd(n):
     assert rel_l2(ops.split_to_float(got_s), ref.float()) < 5e-5
 
 
+@pytest.mark.parametrize("n", [16, 5, 40, 64, 32])
+def test_attention_bwd_tensor_core_path(n):
+    """bf16 qkv / dO / dqkv run the mma.sync backward kernel (one warp per (series, head), P and dS transposed in
+    registers); check against fp64 torch autograd on the same bf16-rounded inputs and against the fp32 SIMT kernel."""
+    b, h, hd = 6, 16, 80
+    gen = torch.Generator(device=DEV).manual_seed(100 + n)
+    qkv = torch.randn(b * n, 3 * h * hd, generator=gen, device=DEV).to(torch.bfloat16)
+    dout = torch.randn(b * n, h * hd, generator=gen, device=DEV).to(torch.bfloat16)
+    pm = torch.zeros(b, n, dtype=torch.bool, device=DEV)
+    pm[1, : n // 2] = True
+    pm[2, :1] = True
+    pm[3, : n - 1] = True
+    nm = pm.sum(-1).int()
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd)).to(DEV)
+    qw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    kw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    per_dim = 0.5 * torch.randn(hd, generator=gen, device=DEV)
+    q_scale = (torch.nn.functional.softplus(per_dim) * (1.442695041 / math.sqrt(hd))).contiguous()
+    qd = qkv.double().requires_grad_(True)
+    out = _attn_fwd_torch(qd, b, n, h, hd, pm, inv_freq, qw, kw, per_dim)
+    (ref,) = torch.autograd.grad(out, qd, dout.double())
+    got = ops.timesfm_attention_bwd(qkv, dout, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6, DT_BF16)
+    _lib.check(_lib.load().tsfmx_attention_force_simt(1))
+    try:
+        simt = ops.timesfm_attention_bwd(qkv, dout, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6, DT_BF16)
+    finally:
+        _lib.check(_lib.load().tsfmx_attention_force_simt(0))
+    assert got.dtype == torch.bfloat16 and got.shape == (b * n, 3 * h * hd)
+    e_ref, e_simt = rel_l2(got.float(), ref.float()), rel_l2(got.float(), simt.float())
+    for part, name in ((slice(0, h * hd), "dq"), (slice(h * hd, 2 * h * hd), "dk"), (slice(2 * h * hd, None), "dv")):
+        assert rel_l2(got.float()[:, part], ref.float()[:, part]) < 2e-2, (name, e_ref, e_simt)
+    assert e_simt < 2e-2, (e_ref, e_simt)
+
+
 def test_gemm_grad_epilogues_and_pre_act():
     m, n, k = 200, 1280, 1280
     gen = torch.Generator(device=DEV).manual_seed(2)
