@@ -256,6 +256,34 @@ int tsfmx_encoder_attention_mma(const void* qkv, int64_t batch, int32_t seq, int
                                 const uint8_t* key_mask, const float* rope_table, void* out, void* stream);
 
 /*
+ * Chronos-T5 backbone stages (BASELINE.json configs[2]; upstream chronos.ChronosModel -> transformers T5ForConditionalGeneration,
+ * HF twin transformers/models/t5/modeling_t5.py; not part of the reference, which only wraps Chronos-2).
+ *
+ * tsfmx_embed_rows: out[r, :] = table[ids[r], :] (fp32 table [vocab, dims], dims % 4 == 0).
+ *
+ * tsfmx_t5_attention: general T5 attention core, fp32 SIMT (parity mode, single-query decoding over the KV cache,
+ *   teacher forcing).  For series b, query row i (position q_pos0 + i) and key j (position j):
+ *     score = q . k  (no 1/sqrt(d))  + bias[h, (j - q_pos) + bias_zero]   if bias != NULL (index clamped to the table)
+ *     key j takes part iff (key_mask == NULL or key_mask[b, j] != 0) and (not causal or j <= q_pos);
+ *     a query whose admissible keys are all masked attends uniformly to them (finfo.min semantics).
+ *   q [B, tq] rows of stride ldq (series stride q_batch_stride, both in elements), k / v likewise with tk rows;
+ *   head h owns columns [64 h, 64 h + 64) of every row; out rows of stride ldo, width num_heads * 64.
+ *
+ * tsfmx_t5_encoder_attention_mma: throughput mode of the encoder self-attention (bidirectional, key mask, bias table
+ *   [num_heads, 2 seq - 1] indexed by (key - query) + seq - 1): qkv bf16 [B*seq, 3*H*64] = [q | k | v], out bf16
+ *   [B*seq, H*64]; K and V of one (series, head) stay in shared memory, online softmax over 64-key chunks; seq <= 704.
+ */
+int tsfmx_embed_rows(const int64_t* ids, int64_t rows, int32_t dims, int32_t vocab, const float* table, float* out,
+                     void* stream);
+int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, int64_t q_batch_stride, const void* k, const void* v,
+                       int32_t kv_dtype, int64_t ldk, int64_t ldv, int64_t kv_batch_stride, int64_t batch, int32_t tq,
+                       int32_t tk, int32_t num_heads, int32_t head_dim, int32_t q_pos0, int32_t causal,
+                       const uint8_t* key_mask, const float* bias, int32_t bias_len, int32_t bias_zero,
+                       int32_t out_dtype, void* out, int64_t ldo, int64_t o_batch_stride, void* stream);
+int tsfmx_t5_encoder_attention_mma(const void* qkv, int64_t batch, int32_t seq, int32_t num_heads, int32_t head_dim,
+                                   const uint8_t* key_mask, const float* bias, void* out, void* stream);
+
+/*
  * Chronos-2 output epilogue (reference chronos.py:159-169): preds [B*np, Q*patch] (patch-major rows of the
  * output ResidualBlock, np = ceil(horizon / patch)) -> out [B, horizon, Q] = sinh(x) * scale[b] + loc[b].
  */

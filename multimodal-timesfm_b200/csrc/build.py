@@ -29,6 +29,7 @@ SOURCES = [
     "backward.cu",
     "attention_bwd.cu",
     "chronos.cu",
+    "t5.cu",
     "model.cu",
 ]
 

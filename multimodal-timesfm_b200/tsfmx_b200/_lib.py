@@ -108,6 +108,17 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     ),
     "tsfmx_attention_force_simt": (c_int32, [c_int32]),
     "tsfmx_tune": (c_int32, [c_int32, c_int32]),
+    "tsfmx_embed_rows": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "tsfmx_t5_attention": (
+        c_int32,
+        [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32,
+         c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64,
+         c_int64, c_void_p],
+    ),
+    "tsfmx_t5_encoder_attention_mma": (
+        c_int32,
+        [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "tsfmx_rope_table": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "tsfmx_encoder_attention_mma": (
         c_int32,

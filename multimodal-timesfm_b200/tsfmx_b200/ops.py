@@ -449,3 +449,73 @@ def chronos2_finalize(
         )
     )
     return out
+
+
+# ----------------------------------------------------------------------------- Chronos-T5
+def embed_rows(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """ids (any shape, int64) -> fp32 [ids.numel(), dims] rows of the fp32 ``table`` [vocab, dims]."""
+    lib = _lib.load()
+    _lib.require_cuda(ids, table)
+    ids = ids.reshape(-1).contiguous().to(torch.int64)
+    table = table.contiguous().float()
+    out = torch.empty(ids.numel(), table.shape[1], dtype=torch.float32, device=table.device)
+    check(lib.tsfmx_embed_rows(ptr(ids), ids.numel(), table.shape[1], table.shape[0], ptr(table), ptr(out), stream()))
+    return out
+
+
+def t5_attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    batch: int,
+    tq: int,
+    tk: int,
+    num_heads: int,
+    out_dtype: int,
+    out: torch.Tensor,
+    *,
+    q_rows: tuple[int, int],
+    kv_rows: tuple[int, int],
+    out_rows: tuple[int, int],
+    ldv: int | None = None,
+    q_pos0: int = 0,
+    causal: bool = False,
+    key_mask: torch.Tensor | None = None,
+    bias: torch.Tensor | None = None,
+    bias_zero: int = 0,
+) -> torch.Tensor:
+    """General T5 attention core (fp32 SIMT).  ``*_rows`` = (row stride, series stride) in elements of the q / k,v /
+    out buffers; ``q``, ``k``, ``v`` may be views into one buffer (e.g. a [B, L, 3W] cache)."""
+    lib = _lib.load()
+    _lib.require_cuda(q, k, v, out)
+    km = None if key_mask is None else _as_u8(key_mask)
+    check(
+        lib.tsfmx_t5_attention(
+            ptr(q), _dt(q), q_rows[0], q_rows[1], ptr(k), ptr(v), _dt(k), kv_rows[0], kv_rows[0] if ldv is None else ldv,
+            kv_rows[1], batch, tq, tk, num_heads, 64, q_pos0, int(causal), ptr(km), ptr(bias),
+            0 if bias is None else bias.shape[-1], bias_zero, out_dtype, ptr(out), out_rows[0], out_rows[1], stream(),
+        )
+    )
+    return out
+
+
+def t5_encoder_attention(
+    qkv: torch.Tensor, batch: int, seq: int, num_heads: int, key_mask: torch.Tensor | None, bias: torch.Tensor | None,
+    out_dtype: int, out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """Encoder self-attention over qkv [B*seq, 3*H*64]; ``bias`` fp32 [H, 2 seq - 1] indexed by (key - query) + seq - 1.
+    bf16 in / bf16 out takes the tensor-core kernel, everything else the fp32 SIMT core."""
+    lib = _lib.load()
+    _lib.require_cuda(qkv)
+    width = num_heads * 64
+    if out is None:
+        out = alloc(batch * seq, width, out_dtype, qkv.device)
+    km = None if key_mask is None else _as_u8(key_mask)
+    if qkv.dtype == torch.bfloat16 and out_dtype == DT_BF16 and seq <= 704 and not _force_simt_encoder_attention:
+        check(lib.tsfmx_t5_encoder_attention_mma(ptr(qkv), batch, seq, num_heads, 64, ptr(km), ptr(bias), ptr(out), stream()))
+        return out
+    ld = 3 * width
+    t5_attention(qkv, qkv[:, width:], qkv[:, 2 * width:], batch, seq, seq, num_heads, out_dtype, out,
+                 q_rows=(ld, seq * ld), kv_rows=(ld, seq * ld), out_rows=(width, seq * width), key_mask=km, bias=bias,
+                 bias_zero=seq - 1)
+    return out
