@@ -53,34 +53,66 @@ struct T5AttnParams {
   void* out; int out_dtype; int64_t ldo; int64_t o_batch_stride;
 };
 
+// 64 consecutive elements of a row as floats (16-byte loads; bf16 rows are 128 B, fp32 rows 256 B)
+__device__ __forceinline__ void t5_load_row64(const void* base, int dtype, int64_t off, float (&r)[T5_HD]) {
+  if (dtype == TSFMX_DT_F32) {
+    const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 v = __ldg(p4 + i);
+      r[4 * i] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
+    }
+  } else {
+    const uint4* p4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 v = __ldg(p4 + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        r[8 * i + 2 * e] = __uint_as_float(w[e] << 16);
+        r[8 * i + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+      }
+    }
+  }
+}
+
+// One warp per (series, query row, head).  Scores: lane l owns keys l, l + 32, ... and reads each key row whole
+// (eight independent 16-byte loads in flight per lane, no per-key reduction); P V: lane l owns dims 2l, 2l + 1 and
+// streams the value rows (coalesced), four keys per iteration.
 template <int OUT>
 __global__ void __launch_bounds__(128) t5_attention_kernel(const T5AttnParams p) {
   extern __shared__ float s_scores[];  // [4 warps][tk]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sc = s_scores + warp * p.tk;
   const int64_t units = static_cast<int64_t>(p.tq) * p.num_heads;
-  const int64_t total = units * gridDim.y;  // gridDim.y = batch chunk handled through blockIdx.y
-  (void)total;
   const int b = blockIdx.y;
   for (int64_t u = static_cast<int64_t>(blockIdx.x) * 4 + warp; u < units; u += static_cast<int64_t>(gridDim.x) * 4) {
     const int i = static_cast<int>(u / p.num_heads), h = static_cast<int>(u - static_cast<int64_t>(i) * p.num_heads);
     const int qpos = p.q_pos0 + i;
     const int64_t qoff = b * p.q_batch_stride + i * p.ldq + h * T5_HD;
-    const float q0 = t5_ld(p.q, p.q_dtype, qoff + lane), q1 = t5_ld(p.q, p.q_dtype, qoff + lane + 32);
+    float q[T5_HD];
+    t5_load_row64(p.q, p.q_dtype, qoff, q);
     const uint8_t* km = p.key_mask != nullptr ? p.key_mask + static_cast<int64_t>(b) * p.tk : nullptr;
     const float* bias = p.bias != nullptr ? p.bias + static_cast<int64_t>(h) * p.bias_len : nullptr;
     const int jend = p.causal ? min(p.tk, qpos + 1) : p.tk;
-    // scores: the warp walks the keys, every lane holds two of the 64 dims (coalesced 128 / 256-byte key rows)
+    const int64_t kbase = b * p.kv_batch_stride + h * T5_HD;
     float mx = -INFINITY;
     bool any = false;
-    for (int j = 0; j < jend; ++j) {
-      const int64_t koff = b * p.kv_batch_stride + j * p.ldk + h * T5_HD;
-      float acc = q0 * t5_ld(p.k, p.kv_dtype, koff + lane) + q1 * t5_ld(p.k, p.kv_dtype, koff + lane + 32);
-      acc = warp_sum(acc);
-      const bool ok = km == nullptr || km[j] != 0;
+    for (int j = lane; j < jend; j += 32) {
       float s = -INFINITY;
-      if (ok) {
-        s = acc;
+      if (km == nullptr || km[j] != 0) {
+        float kr[T5_HD];
+        t5_load_row64(p.k, p.kv_dtype, kbase + j * p.ldk, kr);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int d = 0; d < T5_HD; d += 4) {
+          a0 = fmaf(q[d], kr[d], a0);
+          a1 = fmaf(q[d + 1], kr[d + 1], a1);
+          a2 = fmaf(q[d + 2], kr[d + 2], a2);
+          a3 = fmaf(q[d + 3], kr[d + 3], a3);
+        }
+        s = (a0 + a1) + (a2 + a3);
         if (bias != nullptr) {
           int idx = j - qpos + p.bias_zero;
           idx = idx < 0 ? 0 : (idx >= p.bias_len ? p.bias_len - 1 : idx);
@@ -88,10 +120,11 @@ __global__ void __launch_bounds__(128) t5_attention_kernel(const T5AttnParams p)
         }
         any = true;
       }
-      if (lane == 0) sc[j] = s;
+      sc[j] = s;
       mx = fmaxf(mx, s);
     }
-    __syncwarp();
+    mx = warp_max(mx);
+    any = __any_sync(0xffffffffu, any);
     // every admissible key masked: the additive finfo.min mask of the reference yields uniform weights over them all
     float sum = 0.f;
     for (int j = lane; j < jend; j += 32) {
@@ -102,27 +135,49 @@ __global__ void __launch_bounds__(128) t5_attention_kernel(const T5AttnParams p)
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < jend; ++j) {
+    // P V: lane l accumulates its own keys l, l + 32, ... over all 64 dims (whole value rows, eight independent
+    // 16-byte loads in flight), then a butterfly reduce-scatter leaves dims 2l, 2l + 1 of the sum in lane l
+    float acc[T5_HD];
+#pragma unroll
+    for (int d = 0; d < T5_HD; ++d) acc[d] = 0.f;
+    for (int j = lane; j < jend; j += 32) {
       const float pj = sc[j];
-      const int64_t voff = b * p.kv_batch_stride + j * p.ldv + h * T5_HD;
-      o0 = fmaf(pj, t5_ld(p.v, p.kv_dtype, voff + lane), o0);
-      o1 = fmaf(pj, t5_ld(p.v, p.kv_dtype, voff + lane + 32), o1);
+      if (pj != 0.f) {
+        float vr[T5_HD];
+        t5_load_row64(p.v, p.kv_dtype, kbase + j * p.ldv, vr);
+#pragma unroll
+        for (int d = 0; d < T5_HD; ++d) acc[d] = fmaf(pj, vr[d], acc[d]);
+      }
     }
+    // reduce-scatter over the 32 lanes: after the step with mask m a lane keeps the half of its values that matches
+    // its bit m and adds the partner's copy of that half
+#pragma unroll
+    for (int half = 32, m = 16; m >= 1; half >>= 1, m >>= 1) {
+      const bool upper = (lane & m) != 0;
+#pragma unroll
+      for (int d = 0; d < half; ++d) {
+        const float mine = upper ? acc[d + half] : acc[d];
+        const float theirs = upper ? acc[d] : acc[d + half];
+        acc[d] = mine + __shfl_xor_sync(0xffffffffu, theirs, m);
+      }
+    }
+    // the half kept at mask m = bit log2(m) of the lane picks the 2m-wide block: lane l ends with dims 2l, 2l + 1
+    float o0 = acc[0], o1 = acc[1];
+    const int pair = lane;
     o0 *= inv, o1 *= inv;
     const int64_t ooff = b * p.o_batch_stride + i * p.ldo;
-    const int c = h * T5_HD + lane;
+    const int c = h * T5_HD + 2 * pair;
     const int width = p.num_heads * T5_HD;
     if constexpr (OUT == TSFMX_DT_F32) {
-      float* o = reinterpret_cast<float*>(p.out) + ooff;
-      o[c] = o0, o[c + 32] = o1;
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + ooff + c) = make_float2(o0, o1);
     } else if constexpr (OUT == TSFMX_DT_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff;
-      o[c] = __float2bfloat16_rn(o0), o[c + 32] = __float2bfloat16_rn(o1);
+      *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c) = pack_bf16x2(o0, o1);
     } else {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + 2 * ooff;  // split rows: [hi(width) | lo(width)]
-      split_bf16(o0, o[c], o[width + c]);
-      split_bf16(o1, o[c + 32], o[width + c + 32]);
+      uint32_t hi, lo;
+      split_bf16x2(o0, o1, hi, lo);
+      *reinterpret_cast<uint32_t*>(o + c) = hi;
+      *reinterpret_cast<uint32_t*>(o + width + c) = lo;
     }
     __syncwarp();
   }
@@ -371,6 +426,14 @@ extern "C" int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, i
     return TSFMX_ERR_UNSUPPORTED;
   }
   TSFMX_REQUIRE(batch < 65536, "t5_attention: batch (%lld) must be below 65536 per call", static_cast<long long>(batch));
+  {
+    auto al16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
+    const int qa = q_dtype == TSFMX_DT_F32 ? 4 : 8, ka = kv_dtype == TSFMX_DT_F32 ? 4 : 8;  // elements per 16 bytes
+    TSFMX_REQUIRE(al16(q) && al16(k) && al16(v) && reinterpret_cast<uintptr_t>(out) % 8 == 0 && ldq % qa == 0 &&
+                      q_batch_stride % qa == 0 && ldk % ka == 0 && ldv % 2 == 0 && kv_batch_stride % ka == 0 &&
+                      ldo % 2 == 0 && o_batch_stride % 2 == 0,
+                  "t5_attention: rows must start on 16-byte boundaries");
+  }
   if (batch == 0) return TSFMX_OK;
   T5AttnParams p = {};
   p.q = q, p.k = k, p.v = v, p.q_dtype = q_dtype, p.kv_dtype = kv_dtype;

@@ -100,9 +100,26 @@ def hf_model_from_product(adapter):
     hf = T5ForConditionalGeneration(cfg).eval()
     state = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
     missing, unexpected = hf.load_state_dict(state, strict=False)
-    allowed = {"encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "lm_head.weight"}
+    allowed = {"encoder.embed_tokens.weight", "decoder.embed_tokens.weight"}
+    if m.tie_word_embeddings:
+        allowed.add("lm_head.weight")
     assert not unexpected and set(missing) <= allowed, (missing, unexpected)
-    hf.tie_weights()
+    if m.tie_word_embeddings:
+        hf.tie_weights()
+    else:
+        # transformers 5.x builds T5ForConditionalGeneration with lm_head.weight aliasing shared.weight even when
+        # config.tie_word_embeddings is False (its forward then skips the d_model ** -0.5 rescale, as it should):
+        # give the head its own parameter and restore the embedding the load just overwrote.
+        hf.lm_head.weight = nn.Parameter(state["lm_head.weight"].clone())
+        with torch.no_grad():
+            hf.shared.weight.copy_(state["shared.weight"])
+            if hf.encoder.embed_tokens.weight.data_ptr() != hf.shared.weight.data_ptr():
+                hf.encoder.embed_tokens.weight.copy_(state["shared.weight"])
+            if hf.decoder.embed_tokens.weight.data_ptr() != hf.shared.weight.data_ptr():
+                hf.decoder.embed_tokens.weight.copy_(state["shared.weight"])
+        assert torch.equal(hf.lm_head.weight, state["lm_head.weight"])
+    assert torch.equal(hf.shared.weight, state["shared.weight"])
+    assert torch.equal(hf.decoder.embed_tokens.weight, state["shared.weight"])
     return hf
 
 

@@ -1,11 +1,13 @@
 """BASELINE.json configs 3-5 next to the headline bench (bench.py = configs[1]); one JSON line per config.
 
-    python scripts/bench_configs.py [--only chronos2|finetune|longctx] [--steps 5] [--warmup 3]
+    python scripts/bench_configs.py [--only chronos2|chronos_t5|finetune|longctx] [--steps 5] [--warmup 3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         scripts/bench_configs.py ...
 
   chronos2  cfg-3: Chronos-2 (12 blocks x 768, the adapter the reference wraps) + 1-layer fusion, ctx 512 / h 128,
             2048 series per GPU, series-sharded, no collective
+  chronos_t5  cfg-3 as BASELINE.json words it: Chronos-T5-base tokenise + encoder + greedy decoding of 64 tokens,
+            per-token text fusion, 1024 series per GPU
   finetune  cfg-4: TimesFM "500M shape" (50 layers) multimodal fine-tune step = forward + activation-gradient pass +
             fusion weight gradient + NCCL all-reduce of the fusion gradients + clip + AdamW, 1024 series per GPU
   longctx   cfg-5: ctx 2048; TimesFM 50 layers at h 128 (the adapter API raises above 128) and Chronos-2 at h 256,
@@ -110,6 +112,33 @@ def main():
         emit(rank, "cfg3-chronos2", f"Chronos-2 (12 x 768) + 1-layer fusion, ctx 512 / h 128, {B} series per GPU, forecast",
              B, ms, args.steps, args.warmup, world, n)
         del dec, data
+        torch.cuda.empty_cache()
+
+    if want("chronos_t5"):
+        from tsfmx_b200.tsfm import chronos_t5 as CT5
+
+        tb, horizon = min(B, 1024), 64
+        adapter = CT5.ChronosT5Adapter(CT5.ChronosT5Module(), precision="bf16")
+        CT5.init_random_(adapter._model, seed=0)
+        torch.manual_seed(100)
+        dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, [])).to(dev).eval()
+        data = []
+        for i in range(2):
+            ctx, masks, text, _ = O.synthetic_batch(tb, 512, horizon, seed=777 + 17 * rank + i, patch_len=32)
+            data.append((ctx.to(dev), masks.to(dev), adapter.expand_text_embeddings(text, 512).to(dev)))
+        with torch.no_grad():
+            ms, n = timed(lambda i: dec(horizon, *data[i % 2]), max(1, args.steps // 2), 1, world, dev)
+            # encoder-only share of the step (tokenise + embed + fusion + 12 encoder blocks)
+            def enc_only(i):
+                c, m, t = data[i % 2]
+                pre = adapter.preprocess(c, m)
+                adapter(dec.fusion(pre.input_embeddings, t), pre.masks)
+            ms_enc, _ = timed(enc_only, max(1, args.steps // 2), 1, world, dev)
+        steps = max(1, args.steps // 2)
+        emit(rank, "cfg3-chronos-t5", f"Chronos-T5-base (12 + 12 layers x 768, vocab 4096) + per-token text fusion, ctx 512 "
+             f"(513 tokens) / greedy decoding of {horizon} tokens, {tb} series per GPU", tb, ms, steps, 1, world, n,
+             {"encoder_ms_per_step": ms_enc / steps})
+        del dec, data, adapter
         torch.cuda.empty_cache()
 
     if want("finetune"):

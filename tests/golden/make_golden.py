@@ -104,6 +104,38 @@ def chronos2_case():
     print("chronos2", full.shape, float(full.abs().max()))
 
 
+def chronos_t5_model_case():
+    """Chronos-T5 forecast (2 + 2 layers of the t5-base shape): the reference's real decoder / fusion classes around
+    the oracle adapter, i.e. transformers' T5ForConditionalGeneration with the seeded weights of the product module."""
+    from oracle import chronos_t5_model_oracle as TM
+    from tsfmx_b200.tsfm.chronos_t5 import ChronosT5Adapter, ChronosT5Module
+    from tsfmx_b200.tsfm.chronos_t5 import init_random_ as t5_init
+
+    adapter = ChronosT5Adapter(ChronosT5Module(num_layers=2, tie_word_embeddings=False))  # untied head: varied tokens
+    t5_init(adapter._model, 0)
+    o_adapter = TM.OracleChronosT5Adapter(TM.hf_model_from_product(adapter))
+    ref = RefDecoder(o_adapter, RefConfig(384, 1, [])).eval()
+    torch.manual_seed(100)
+    torch.nn.init.xavier_uniform_(ref.fusion.projection[0].weight)
+    ctx, masks, text, _ = O.synthetic_batch(4, 96, 16, padded=True, seed=21, patch_len=32)
+    ctx = ctx * 2 + 0.5
+    patch_text = text.half().float()  # stored per patch (fp16); the tests expand it the same way
+    text = adapter.expand_text_embeddings(patch_text, 96)  # per-token text rows (context + EOS)
+    horizon = 16
+    with torch.no_grad():
+        pre = ref.adapter.preprocess(ctx, masks)
+        enc = ref.adapter(ref.fusion(pre.input_embeddings, text), pre.masks)
+        tokens = ref.adapter.decode(enc, pre.normalization_stats["token_ids"] != 0, horizon)
+        full = ref.forward_full(horizon, ctx, masks, text)
+    np.savez_compressed(
+        OUT / "chronos_t5_model_l2_b4_c96_h16.npz", context=ctx.numpy(), masks=masks.numpy(),
+        text=patch_text.numpy().astype(np.float16),
+        token_ids=pre.normalization_stats["token_ids"].numpy().astype(np.int16), scale=pre.normalization_stats["scale"].numpy(),
+        encoder_checksum=enc.double().sum(-1).numpy(), generated=tokens.numpy().astype(np.int16), forecast=full.numpy(),
+    )
+    print("chronos_t5_model", full.shape, tokens[0, :8].tolist())
+
+
 if __name__ == "__main__":
     # text embeddings are stored as fp16 to keep the fixtures small; the tests up-cast the stored values, so the
     # inputs are identical on both sides.
@@ -112,3 +144,4 @@ if __name__ == "__main__":
     timesfm_case("timesfm_l2_b3_c2048_h64_f2", 2, 3, 2048, 64, padded=True, fusion_layers=2, hidden=(512,), seed=2)
     t5_case()
     chronos2_case()
+    chronos_t5_model_case()

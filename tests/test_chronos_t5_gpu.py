@@ -27,8 +27,8 @@ def rel_max(a, b):
     return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
 
 
-def build(layers, seed=0):
-    adapter = ChronosT5Adapter(ChronosT5Module(num_layers=layers))
+def build(layers, seed=0, tied=True):
+    adapter = ChronosT5Adapter(ChronosT5Module(num_layers=layers, tie_word_embeddings=tied))
     init_random_(adapter._model, seed=seed)
     torch.manual_seed(seed + 100)
     dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, []))
@@ -97,9 +97,9 @@ def test_preprocess_and_encoder_parity(padded):
     assert rel_max(enc16.cpu(), enc_ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("layers,context,horizon,padded", [(2, 128, 12, True), (3, 64, 24, False)])
-def test_decoder_parity_and_greedy_ids(layers, context, horizon, padded):
-    dec, oracle = build(layers, seed=3)
+@pytest.mark.parametrize("layers,context,horizon,padded,tied", [(2, 128, 12, True, True), (3, 64, 24, False, False)])
+def test_decoder_parity_and_greedy_ids(layers, context, horizon, padded, tied):
+    dec, oracle = build(layers, seed=3, tied=tied)
     dec.set_precision("bf16x3")
     ctx, masks, text = batch(5, context, padded, seed=9)
     text_tok = dec.adapter.expand_text_embeddings(text, context)
@@ -115,6 +115,11 @@ def test_decoder_parity_and_greedy_ids(layers, context, horizon, padded):
         assert rel_max(logits.cpu(), ref_logits) < FP32_TOL
         tokens, _ = dec.adapter.decode(enc_ref.to(DEV), am.to(DEV), horizon)
         assert torch.equal(tokens.cpu(), ref_tokens)  # greedy ids identical to HF generate
+        # random teacher-forced tokens: every cache slot holds a different key / value
+        rnd = torch.randint(2, 4096, (5, horizon), generator=torch.Generator().manual_seed(1))
+        rnd_logits = oracle.adapter.teacher_forced_logits(enc_ref, am, rnd)
+        _, got_rnd = dec.adapter.decode(enc_ref.to(DEV), am.to(DEV), horizon, forced_ids=rnd.to(DEV), return_logits=True)
+        assert rel_max(got_rnd.cpu(), rnd_logits) < FP32_TOL
         # whole path through the public API
         ref_full = oracle.forward_full(horizon, ctx, masks, text_tok)
         got_full = dec.forward_full(horizon, ctx.to(DEV), masks.to(DEV), text_tok.to(DEV)).cpu()

@@ -85,3 +85,31 @@ def test_chronos2_golden():
     np.testing.assert_allclose(pre.normalization_stats["loc"].cpu().numpy(), g["loc"], rtol=1e-5, atol=1e-6)
     assert np.abs(full - g["forecast"]).max() < 1e-3 * np.abs(g["forecast"]).max()
 
+
+
+def test_chronos_t5_model_golden():
+    """Chronos-T5 forecast against the fixture made by the reference's decoder class around transformers' T5."""
+    from tsfmx_b200.tsfm.chronos_t5 import ChronosT5Adapter, ChronosT5Module
+    from tsfmx_b200.tsfm.chronos_t5 import init_random_ as t5_init
+
+    g = load_case("chronos_t5_model_l2_b4_c96_h16")
+    adapter = ChronosT5Adapter(ChronosT5Module(num_layers=2, tie_word_embeddings=False))
+    t5_init(adapter._model, 0)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, []))
+    torch.manual_seed(100)
+    torch.nn.init.xavier_uniform_(dec.fusion.linears()[0].weight)  # same seeded CPU init as make_golden.py
+    dec = dec.to(DEV).eval()
+    dec.set_precision("bf16x3")
+    ctx, masks = torch.from_numpy(g["context"]).to(DEV), torch.from_numpy(g["masks"]).to(DEV)
+    text = dec.adapter.expand_text_embeddings(torch.from_numpy(g["text"]).float(), 96).to(DEV)
+    with torch.no_grad():
+        pre = dec.adapter.preprocess(ctx, masks)
+        enc = dec.adapter(dec.fusion(pre.input_embeddings, text), pre.masks)
+        tokens, _ = dec.adapter.decode(enc, pre.normalization_stats["token_ids"] != 0, 16)
+        full = dec.forward_full(16, ctx, masks, text).cpu().numpy()
+    assert np.array_equal(pre.normalization_stats["token_ids"].cpu().numpy(), g["token_ids"].astype(np.int64))  # bit-exact
+    assert np.array_equal(pre.normalization_stats["scale"].cpu().numpy(), g["scale"])
+    chk = enc.double().sum(-1).cpu().numpy()
+    assert np.abs(chk - g["encoder_checksum"]).max() < 1e-3 * max(1.0, np.abs(g["encoder_checksum"]).max())
+    assert np.array_equal(tokens.cpu().numpy(), g["generated"].astype(np.int64))  # greedy ids identical
+    assert np.array_equal(full, g["forecast"])  # same ids, same centers, same scale -> identical values

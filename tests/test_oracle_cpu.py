@@ -174,3 +174,38 @@ def test_chronos2_oracle_properties_and_golden():
     assert torch.allclose(back, x, atol=1e-4)
     with pytest.raises(ValueError, match="exceeds the maximum prediction length"):
         adapter.postprocess(1025, torch.zeros(1, 64, 768), {"loc": loc[:1], "scale": scale[:1]})
+
+
+def test_chronos_t5_model_oracle_golden_and_bucket_table():
+    """The Chronos-T5 model oracle (transformers T5 + tokeniser oracle) reproduces its committed fixture, and the
+    product's restated relative-position bucketing equals transformers' own."""
+    import numpy as np
+    from transformers.models.t5.modeling_t5 import T5Attention
+
+    from oracle import chronos_t5_model_oracle as TM
+    from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig
+    from tsfmx_b200.tsfm.chronos_t5 import ChronosT5Adapter, ChronosT5Module, relative_position_bucket
+    from tsfmx_b200.tsfm.chronos_t5 import init_random_ as t5_init
+
+    delta = torch.arange(-700, 701)
+    for bidir in (True, False):
+        ref = T5Attention._relative_position_bucket(delta, bidirectional=bidir, num_buckets=32, max_distance=128)
+        assert torch.equal(relative_position_bucket(delta, bidir, 32, 128), ref)
+
+    z = np.load(GOLDEN / "chronos_t5_model_l2_b4_c96_h16.npz")
+    adapter = ChronosT5Adapter(ChronosT5Module(num_layers=2, tie_word_embeddings=False))
+    t5_init(adapter._model, 0)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, []))
+    torch.manual_seed(100)
+    torch.nn.init.xavier_uniform_(dec.fusion.linears()[0].weight)
+    oracle = TM.oracle_from_product(dec)
+    ctx, masks = torch.from_numpy(z["context"]), torch.from_numpy(z["masks"])
+    text = adapter.expand_text_embeddings(torch.from_numpy(z["text"]).float(), 96)
+    assert text.shape == (4, 97, 384) and float(text[:, -1].abs().max()) == 0.0  # EOS row carries no text
+    with torch.no_grad():
+        pre = oracle.adapter.preprocess(ctx, masks)
+        full = oracle.forward_full(16, ctx, masks, text)
+    assert np.array_equal(pre.normalization_stats["token_ids"].numpy(), z["token_ids"].astype(np.int64))
+    assert np.array_equal(full.numpy(), z["forecast"])
+    with pytest.raises(ValueError):
+        adapter.expand_text_embeddings(torch.zeros(2, 2, 384), 96)
