@@ -388,11 +388,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
 // =====================================================================================================
 constexpr int RN_BN = 256;
 constexpr int RN_MAXC = 5;
-constexpr int RN_STAGES = 4;
+constexpr int RN_STAGES = 3;
+constexpr int RN_XCHUNK = 32;                         // fp32 columns per staged x / y chunk (128 B: one swizzle row)
+constexpr int RN_XBUF_BYTES = BM * RN_XCHUNK * 4;     // 16 KB
+constexpr int RN_XSLOTS = 2;                          // chunk buffers per column half
 
 struct alignas(64) RownormParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
+  CUtensorMap tma_x;    // fp32 [m, n], box 32 x 128, 128B swizzle (load)
+  CUtensorMap tma_y;    // same geometry over y (store); y may alias x
   XSeg xseg[3];
   int32_t num_xseg;
   int32_t n;
@@ -403,8 +408,6 @@ struct alignas(64) RownormParams {
   int32_t yn_dtype;
   const float* w_post;
   const float* w_next;
-  const float* x;
-  float* y;
   void* yn;
   float eps;
 };
@@ -448,26 +451,43 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
+// Second design of the epilogue data path (the first one read x and wrote y with one global row segment per
+// thread and was latency bound, 2x slower than GEMM + norm kernel): x arrives and y leaves through 128-row x
+// 32-column fp32 chunks in 128B-swizzled shared memory, moved by TMA - loads issued one chunk ahead by an otherwise
+// idle control warp, stores asynchronous (bulk groups) - so the epilogue warps only touch TMEM and shared memory
+// (conflict-free 16-byte accesses) and the HBM traffic of the junction overlaps the MMAs of the next tile.
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(const __grid_constant__ RownormParams p) {
   constexpr int STAGES = RN_STAGES;
   constexpr int A_BYTES = BM * BK * 2;        // 16 KB
   constexpr int B_BYTES = RN_BN * BK * 2;     // 32 KB
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int RED_FLOATS = 2 * 2 * RN_MAXC * 2 * BM;  // [acc stage][round][src CTA][column half][row]
+  constexpr int RED_FLOATS = 2 * 2 * RN_MAXC * BM;  // [acc stage][round][src CTA][row]
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
-  float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + RED_FLOATS);
+  uint8_t* xbuf = smem + STAGES * STAGE_BYTES;                       // [2 halves][RN_XSLOTS][16 KB], 1024-aligned
+  float* red = reinterpret_cast<float*>(xbuf + 2 * RN_XSLOTS * RN_XBUF_BYTES);
+  float* pairbuf = red + RED_FLOATS;                                 // [2 rounds][BM]: column half 1 -> half 0
+  float* wbuf = pairbuf + 2 * BM;                                    // [2][RN_BN]: this CTA's w_post / w_next slices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + 2 * RN_BN);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full_bar = bars + 2 * STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* red_bar = tmem_empty_bar + 2;  // [acc stage][round]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 4);
+  uint64_t* red_bar = tmem_empty_bar + 2;   // [acc stage][round]
+  uint64_t* xfull_bar = red_bar + 4;        // [half][slot]
+  uint64_t* xempty_bar = xfull_bar + 2 * RN_XSLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty_bar + 2 * RN_XSLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.cluster;
@@ -477,6 +497,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
+    tma_prefetch_desc(&p.tma_x);
+    tma_prefetch_desc(&p.tma_y);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -488,9 +510,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
       mbar_init(&tmem_empty_bar[i], EPI_WARPS);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&red_bar[i], 1);
+    for (int i = 0; i < 2 * RN_XSLOTS; ++i) {
+      mbar_init(&xfull_bar[i], 1);
+      mbar_init(&xempty_bar[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+  // norm weights of this CTA's 256 columns: read once, then broadcast from shared memory (the L1 left next to
+  // ~225 KB of shared memory does not keep them, and an L2 round trip per chunk stalled the epilogue)
+  for (int i = threadIdx.x; i < 2 * RN_BN; i += blockDim.x) {
+    const float* src = i < RN_BN ? p.w_post : p.w_next;
+    wbuf[i] = src != nullptr ? __ldg(src + cluster_ctarank() * RN_BN + (i % RN_BN)) : 1.0f;
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -501,7 +533,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
   const int rows_per_issuer = BM / p.a_issuers;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (A multicast slices, own B tile)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = first_tile; tile < p.tiles_m; tile += tile_step) {
@@ -551,6 +583,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
         umma_commit(&tmem_full_bar[as]);
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ x producer: residual chunks one step ahead
+    if (lane == 0) {
+      uint32_t n = 0;  // chunk counter (same sequence in both column halves)
+      for (int tile = first_tile; tile < p.tiles_m; tile += tile_step) {
+        for (int c = 0; c < 4; ++c, ++n) {
+          const uint32_t slot = n % RN_XSLOTS, phase = (n / RN_XSLOTS) & 1;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int bi = hh * RN_XSLOTS + static_cast<int>(slot);
+            mbar_wait(&xempty_bar[bi], phase ^ 1);
+            mbar_arrive_expect_tx(&xfull_bar[bi], RN_XBUF_BYTES);
+            tma_load_2d(xbuf + bi * RN_XBUF_BYTES, &p.tma_x, &xfull_bar[bi],
+                        static_cast<int>(rank) * RN_BN + hh * 128 + c * RN_XCHUNK, tile * BM);
+          }
+        }
+      }
+    }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ epilogue: norm / residual / norm
     const int q = warp & 3;
@@ -559,15 +609,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
     const bool two_norms = p.w_post != nullptr;  // pass 1 (statistics of a) only exists in the post-norm form
     const bool norm_out = p.w_next != nullptr && p.yn != nullptr;
     const float inv_n = 1.0f / static_cast<float>(p.n);
-    const uint32_t red_bytes = static_cast<uint32_t>(C) * 2 * BM * 4;
-    uint32_t iter = 0;
+    const uint32_t red_bytes = static_cast<uint32_t>(C) * BM * 4;
+    const bool store_issuer = q == 0 && lane == 0;  // one thread per column half issues the y stores
+    // 16-byte unit u of this thread's row sits at unit (u ^ (row & 7)) of the 128-byte swizzled line
+    const uint32_t xrow_off = static_cast<uint32_t>(row_in_tile) * 128u;
+    const uint32_t xsw = static_cast<uint32_t>(row_in_tile & 7);
+    uint32_t iter = 0, nchunk = 0;
     for (int tile = first_tile; tile < p.tiles_m; tile += tile_step, ++iter) {
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
       const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
       const bool row_ok = row < p.m;
       const uint32_t taddr = tmem_base + as * RN_BN + (static_cast<uint32_t>(q * 32) << 16) + chalf * 128;
       const int col_base = static_cast<int>(rank) * RN_BN + chalf * 128;
-      float* red_stage = red + as * (2 * RN_MAXC * 2 * BM);
+      float* red_stage = red + as * (2 * RN_MAXC * BM);
       // arm this tile's two exchange rounds (one arming thread per CTA)
       if (warp == EPI_WARP0 && lane == 0) {
         if (two_norms) mbar_arrive_expect_tx(&red_bar[as * 2 + 0], red_bytes);
@@ -577,15 +631,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
       tc_fence_after();
 
       auto exchange = [&](int round, float partial) -> float {
-        // push my partial sum of squares to every CTA of the cluster (incl. myself), then gather all of them
-        float* slot = red_stage + round * (RN_MAXC * 2 * BM) + (static_cast<int>(rank) * 2 + chalf) * BM + row_in_tile;
-        const uint32_t slot_addr = smem_u32(slot), bar_addr = smem_u32(&red_bar[as * 2 + round]);
-        for (int dst = 0; dst < C; ++dst)
-          st_async_f32(mapa_u32(slot_addr, dst), partial, mapa_u32(bar_addr, dst));
+        // column half 1 hands its partial to half 0 through shared memory; half 0 pushes the CTA's sum of squares to
+        // every CTA of the cluster (incl. itself); everybody then gathers the C partials in a fixed order
+        if (chalf == 1) pairbuf[round * BM + row_in_tile] = partial;
+        named_bar_sync(3, EPI_WARPS * 32);
+        if (chalf == 0) {
+          const float mine = partial + pairbuf[round * BM + row_in_tile];
+          float* slot = red_stage + round * (RN_MAXC * BM) + static_cast<int>(rank) * BM + row_in_tile;
+          const uint32_t slot_addr = smem_u32(slot), bar_addr = smem_u32(&red_bar[as * 2 + round]);
+          for (int dst = 0; dst < C; ++dst) st_async_f32(mapa_u32(slot_addr, dst), mine, mapa_u32(bar_addr, dst));
+        }
         mbar_wait(&red_bar[as * 2 + round], aphase);
-        const float* base = red_stage + round * (RN_MAXC * 2 * BM) + row_in_tile;
+        const float* base = red_stage + round * (RN_MAXC * BM) + row_in_tile;
         float total = 0.f;
-        for (int src = 0; src < 2 * C; ++src) total += base[src * BM];  // same order in every CTA
+        for (int src = 0; src < C; ++src) total += base[src * BM];  // same order in every CTA
         return total;
       };
 
@@ -606,44 +665,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
         const float tot = exchange(0, row_ok ? ss : 0.f);
         rs_a = 1.0f / sqrtf(tot * inv_n + p.eps);
       }
-      // pass 2: y = a * rs_a * w_post + x  (or a + x); write y; keep y in TMEM; statistics of y
+      // pass 2: y = a * rs_a * w_post + x (or a + x) chunk by chunk through the staged x tiles; y replaces x in the
+      // chunk buffer and leaves with a TMA store; y also replaces a in TMEM for pass 3; statistics of y
       float ssy = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 4; ++c, ++nchunk) {
+        const uint32_t slot = nchunk % RN_XSLOTS, xphase = (nchunk / RN_XSLOTS) & 1;
+        const int bi = chalf * RN_XSLOTS + static_cast<int>(slot);
+        uint8_t* buf = xbuf + bi * RN_XBUF_BYTES;
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
         const int col0 = col_base + c * 32;
         if (two_norms) {
-          const float4* w4 = reinterpret_cast<const float4*>(p.w_post + col0);
+          const float4* w4 = reinterpret_cast<const float4*>(wbuf + chalf * 128 + c * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 w = __ldg(w4 + i);
+            const float4 w = w4[i];
             r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) * rs_a * w.x);
             r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) * rs_a * w.y);
             r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) * rs_a * w.z);
             r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) * rs_a * w.w);
           }
         }
-        if (row_ok) {
-          const float* xp = p.x + row * p.n + col0;
-          float* yp = p.y + row * p.n + col0;
+        mbar_wait(&xfull_bar[bi], xphase);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 xv = *reinterpret_cast<const float4*>(xp + 4 * i);
-            const float y0 = __uint_as_float(r[4 * i + 0]) + xv.x, y1 = __uint_as_float(r[4 * i + 1]) + xv.y;
-            const float y2 = __uint_as_float(r[4 * i + 2]) + xv.z, y3 = __uint_as_float(r[4 * i + 3]) + xv.w;
-            *reinterpret_cast<float4*>(yp + 4 * i) = make_float4(y0, y1, y2, y3);
-            r[4 * i + 0] = __float_as_uint(y0), r[4 * i + 1] = __float_as_uint(y1);
-            r[4 * i + 2] = __float_as_uint(y2), r[4 * i + 3] = __float_as_uint(y3);
-            ssy += y0 * y0 + y1 * y1 + y2 * y2 + y3 * y3;
+        for (int i = 0; i < 8; ++i) {
+          float4* xp = reinterpret_cast<float4*>(buf + xrow_off + ((static_cast<uint32_t>(i) ^ xsw) << 4));
+          const float4 xv = *xp;
+          const float y0 = __uint_as_float(r[4 * i + 0]) + xv.x, y1 = __uint_as_float(r[4 * i + 1]) + xv.y;
+          const float y2 = __uint_as_float(r[4 * i + 2]) + xv.z, y3 = __uint_as_float(r[4 * i + 3]) + xv.w;
+          *xp = make_float4(y0, y1, y2, y3);
+          r[4 * i + 0] = __float_as_uint(y0), r[4 * i + 1] = __float_as_uint(y1);
+          r[4 * i + 2] = __float_as_uint(y2), r[4 * i + 3] = __float_as_uint(y3);
+          if (row_ok) ssy += y0 * y0 + y1 * y1 + y2 * y2 + y3 * y3;
+        }
+        fence_proxy_async_smem();                     // generic-proxy writes of y -> visible to the TMA store
+        named_bar_sync(1 + chalf, 4 * 32);            // the four warps of this column half finished the chunk
+        if (store_issuer) {
+          tma_store_2d(&p.tma_y, buf, col0, tile * BM);  // rows beyond m are clipped by the tensor map
+          tma_store_commit();
+          if (c > 0) {  // the previous chunk's buffer has been read by its store: hand it back to the x producer
+            bulk_wait_read<1>();
+            mbar_arrive(&xempty_bar[chalf * RN_XSLOTS + static_cast<int>((nchunk - 1) % RN_XSLOTS)]);
+          }
+          if (c == 3) {
+            bulk_wait_read<0>();
+            mbar_arrive(&xempty_bar[bi]);
           }
         }
         if (p.yn != nullptr) {
           if (norm_out) {
             tmem_st_32x32(taddr + c * 32, r);  // y replaces a in the accumulator columns for pass 3
           } else if (row_ok) {
-            // yn = y (no second norm): emit directly
             GemmParams gp = {};
             gp.d = p.yn, gp.ldd = (p.yn_dtype == TSFMX_DT_BF16_SPLIT ? 2 : 1) * static_cast<int64_t>(p.n);
             gp.d_dtype = p.yn_dtype, gp.n_store = p.n, gp.split_off = p.n, gp.vec_ok = 1;
@@ -664,10 +738,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
           const int col0 = col_base + c * 32;
-          const float4* w4 = reinterpret_cast<const float4*>(p.w_next + col0);
+          const float4* w4 = reinterpret_cast<const float4*>(wbuf + RN_BN + chalf * 128 + c * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 w = __ldg(w4 + i);
+            const float4 w = w4[i];
             r[4 * i + 0] = __float_as_uint(w.x * (__uint_as_float(r[4 * i + 0]) * rs_y));
             r[4 * i + 1] = __float_as_uint(w.y * (__uint_as_float(r[4 * i + 1]) * rs_y));
             r[4 * i + 2] = __float_as_uint(w.z * (__uint_as_float(r[4 * i + 2]) * rs_y));
@@ -680,6 +754,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
+    if (store_issuer) tma_store_wait<0>();  // all y stores complete before the CTA may exit
   }
 
   // ---------------------------------------------------------------- teardown
@@ -727,6 +802,29 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t col
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) base=%p rows=%lld cols=%lld ld=%lld", (int)r, base,
               (long long)rows, (long long)cols, (long long)ld);
+    return TSFMX_ERR_CUDA;
+  }
+  return TSFMX_OK;
+}
+
+// fp32 [rows, cols] contiguous rows; box = 32 columns (128 B) x 128 rows, 128B swizzle: the x / y chunks of
+// gemm_rownorm.  Rows beyond `rows` read as zero and are clipped on store.
+int make_tmap_f32_chunk(CUtensorMap* map, const void* base, int64_t rows, int64_t cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return TSFMX_ERR_NO_DEVICE;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 4};
+  cuuint32_t box[2] = {RN_XCHUNK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f32 chunk) failed (CUresult %d) base=%p rows=%lld cols=%lld", (int)r, base,
+              (long long)rows, (long long)cols);
     return TSFMX_ERR_CUDA;
   }
   return TSFMX_OK;
@@ -904,10 +1002,14 @@ extern "C" int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int3
   p.yn_dtype = yn_dtype;
   p.w_post = w_post;
   p.w_next = w_next;
-  p.x = x;
-  p.y = y;
   p.yn = yn;
   p.eps = eps;
+  {
+    int rcx = make_tmap_f32_chunk(&p.tma_x, x, m, n);
+    if (rcx != TSFMX_OK) return rcx;
+    rcx = make_tmap_f32_chunk(&p.tma_y, y, m, n);
+    if (rcx != TSFMX_OK) return rcx;
+  }
   int rc = make_tmap_bf16(&p.tma_a, seg->a, m, cols, seg->lda, BM / p.a_issuers);
   if (rc != TSFMX_OK) return rc;
   rc = make_tmap_bf16(&p.tma_b, seg->b, n, cols, seg->ldb, RN_BN);
@@ -923,7 +1025,9 @@ extern "C" int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int3
   }
   p.num_xseg = nx;
 
-  constexpr int SMEM = RN_STAGES * (BM * BK * 2 + RN_BN * BK * 2) + 2 * 2 * RN_MAXC * 2 * BM * 4 + 1024 + 256;
+  constexpr int SMEM = RN_STAGES * (BM * BK * 2 + RN_BN * BK * 2) + 2 * RN_XSLOTS * RN_XBUF_BYTES +
+                       (2 * 2 * RN_MAXC * BM + 2 * BM + 2 * RN_BN) * 4 + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "gemm_rownorm: shared memory budget");
   auto kern = gemm_rownorm_tcgen05_kernel;
   static bool attr_set = false;
   if (!attr_set) {

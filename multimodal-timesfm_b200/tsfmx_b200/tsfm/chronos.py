@@ -16,6 +16,7 @@ parameter container with the upstream state-dict key names and every stage runs 
 
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 
 import torch
@@ -129,7 +130,7 @@ class Chronos2Adapter(TsfmAdapter):
     def __init__(self, model: Chronos2Module | None = None, precision: str = "bf16") -> None:
         super().__init__()
         self._model = model if model is not None else Chronos2Module()
-        self.fused_norm = False  # True: residual + RMS LayerNorm junctions in the GEMM epilogue (measured slower, kept for A/B)
+        self.fused_norm = os.environ.get("TSFMX_FUSED_NORM", "0") == "1"  # True: residual + RMS LayerNorm junctions in the GEMM epilogue (measured slower, kept for A/B)
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
 

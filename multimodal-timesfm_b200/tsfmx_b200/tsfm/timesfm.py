@@ -15,6 +15,7 @@ load with ``strict=True``) and every stage runs through the C ABI:
 
 from __future__ import annotations
 
+import os
 import math
 from types import SimpleNamespace
 
@@ -113,7 +114,7 @@ class TimesFM2p5Adapter(TsfmAdapter):
     def __init__(self, num_layers: int = 20, precision: str = "bf16", with_quantile_head: bool = True) -> None:
         super().__init__()
         self._model = TimesFM2p5Module(num_layers, with_quantile_head)
-        self.fused_norm = False  # True: norm/residual junctions in the GEMM epilogue (5-CTA clusters; measured slower, kept for A/B)
+        self.fused_norm = os.environ.get("TSFMX_FUSED_NORM", "0") == "1"  # True: norm/residual junctions in the GEMM epilogue (5-CTA clusters; measured slower, kept for A/B)
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
 
