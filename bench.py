@@ -8,8 +8,8 @@ weights, synthetic Time-MMD-shaped inputs.  A "step" is one forecast pass over o
 processes its own shard of series (no collective), so scaling is weak and `value` is the whole-job series/s.
 
 One JSON line is printed by rank 0 (contract in the task statement): `value` = device-resident throughput,
-`e2e` = the same metric through the public `MultimodalDecoder.forward` API with pinned host inputs (H2D + D2H
-inside the timed region), `roofline` for the dominant kernel (the decoder-layer tcgen05 GEMMs), and
+`e2e` = the same metric through the public `MultimodalEvaluator.evaluate` API over pinned host batches (H2D of
+every input + D2H of the metrics inside the timed region), `roofline` for the dominant kernel (the decoder-layer tcgen05 GEMMs), and
 `cpu_baseline` = the CPU oracle on the box's host cores on a bounded sample.
 """
 
@@ -70,22 +70,77 @@ def measured_peaks() -> dict:
     return {"tflops": 1400.0, "source": "fallback"}
 
 
+_JSON_FD = 1
+
+
+def emit_json(line: dict) -> None:
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    """Samples SM clocks and throttle reasons of one GPU while the timed region runs.
+
+    In-process NVML (``pynvml``) when it is importable: a poll costs microseconds.  Spawning ``nvidia-smi`` every 200 ms
+    (the fallback) re-initialises the driver each time and was measured to stall the CUDA calls of the host-bound
+    ``e2e`` leg (2 GPUs: 67 k series/s with the subprocess poller, 96 k without)."""
 
     FIELDS = (
         "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     )
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index = index
-        self.samples: list[list[str]] = []
+        self.enabled = enabled and os.environ.get("TSFMX_NO_CLOCKS") != "1"
+        self.samples: list[tuple[int, int, list[str]]] = []  # (sm MHz, max sm MHz, active reasons)
+        self.source = "none"
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
 
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            masks = {
+                "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            }
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        self.source = "nvml"
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                bits = int(get_reasons(h))
+                self.samples.append((int(sm), int(mx), [n for n, m in masks.items() if bits & m]))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+        return True
+
     def _run(self):
+        if not self.enabled:
+            return
+        if self._run_nvml():
+            return
+        self.source = "nvidia-smi"
         while not self._stop.is_set():
             try:
                 out = subprocess.run(
@@ -93,10 +148,13 @@ class ClockSampler:
                     capture_output=True, text=True, timeout=5,
                 ).stdout.strip()
                 if out:
-                    self.samples.append([s.strip() for s in out.splitlines()[0].split(",")])
+                    f = [x.strip() for x in out.splitlines()[0].split(",")]
+                    if f[0].isdigit() and f[1].isdigit():
+                        self.samples.append((int(f[0]), int(f[1]),
+                                             [n for n, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active")]))
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.5)
 
     def __enter__(self):
         self._thread.start()
@@ -107,15 +165,15 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self) -> dict:
-        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({r for s in self.samples for r in s[2]})
         return {
             "sm_mhz": int(statistics.median(sm)) if sm else None,
             "sm_max_mhz": max(mx) if mx else None,
             "reasons": reasons,
             "samples": len(sm),
+            "source": self.source,
         }
 
 
@@ -170,7 +228,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -250,12 +308,18 @@ def run_b200_arm(args) -> None:
     n_host_batches = 2
     host = []
     for i in range(n_host_batches):
-        ctx, masks, text, _ = O.synthetic_batch(B, args.context, HORIZON, seed=1234 + 17 * rank + i)
-        host.append((ctx.pin_memory(), masks.pin_memory(), text.pin_memory()))
-    resident = [(c.to(dev), m.to(dev), t.to(dev)) for c, m, t in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
-    out_host = torch.empty(B, HORIZON, dtype=torch.float32).pin_memory()
-    d2h_bytes = out_host.numel() * out_host.element_size()
+        ctx, masks, text, hor = O.synthetic_batch(B, args.context, HORIZON, seed=1234 + 17 * rank + i)
+        host.append((ctx.pin_memory(), masks.pin_memory(), text.pin_memory(), hor.pin_memory()))
+    resident = [(c.to(dev), m.to(dev), t.to(dev)) for c, m, t, _h in host]
+    # e2e: the reference's forecast entry point, MultimodalEvaluator.evaluate(loader) (reference tsfmx/evaluator.py:29-71),
+    # over pinned host batches: context + horizon target + text embeddings go host -> device every step (the padding
+    # mask is created on the device, evaluator.py:52), the step's metrics (mse, mae) come back as 16 bytes
+    from tsfmx_b200.evaluator import MultimodalEvaluator
+
+    evaluator = MultimodalEvaluator(dec, dev)
+    host_batches = [{"context": c, "horizon": h, "text_embeddings": t} for c, _m, t, h in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+    d2h_bytes = 16
 
     timer = GemmTimer()
     timer.install()
@@ -264,11 +328,8 @@ def run_b200_arm(args) -> None:
         c, m, t = resident[i % n_host_batches]
         return dec(HORIZON, c, m, t)
 
-    def step_e2e(i):
-        c, m, t = host[i % n_host_batches]
-        y = dec(HORIZON, c.to(dev, non_blocking=True), m.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
-        out_host.copy_(y, non_blocking=True)
-        return y
+    def run_e2e(steps):
+        return evaluator.evaluate(host_batches[i % n_host_batches] for i in range(steps))
 
     def barrier():
         if world > 1:
@@ -293,14 +354,13 @@ def run_b200_arm(args) -> None:
     with torch.no_grad():
         for i in range(args.warmup):
             step_resident(i)
-        for i in range(max(1, args.warmup // 2)):
-            step_e2e(i)
+        run_e2e(max(2, args.warmup // 2))
         torch.cuda.synchronize()
         launches0 = _lib.launch_count()
-        with ClockSampler(local_rank) as clocks:
+        with ClockSampler(local_rank, enabled=rank == 0) as clocks:
             ms_resident = timed(step_resident, args.steps)
             launches = _lib.launch_count() - launches0
-            ms_e2e = timed(step_e2e, args.steps)
+            ms_e2e = timed(lambda i: run_e2e(args.steps) if i == 0 else None, 1)
             # roofline pass: the same steps with one lane, so that every kernel runs alone on one stream and the CUDA
             # events around a GEMM launch measure that launch (with lanes the events would also count the time a
             # GEMM queues behind the other lane's GEMM for the SMs)
@@ -354,7 +414,8 @@ def run_b200_arm(args) -> None:
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps,
-                "api": "MultimodalDecoder.forward(horizon, inputs, masks, text_embeddings) from pinned host tensors"},
+                "api": "MultimodalEvaluator.evaluate(loader of pinned host batches): H2D of context, horizon target and text "
+                       "embeddings staged one batch ahead on a copy stream, per-batch (mse, mae) read back (16 B)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks.summary(),
@@ -371,12 +432,18 @@ def run_b200_arm(args) -> None:
                       f"on the HF TimesFM-2.5 port), best of 3 after 1 warm-up, {cores} threads",
         }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL prints its version banner there
+    # whenever NCCL_DEBUG is set) is sent to stderr, and the JSON line goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,37 @@
+"""Forecast entry loop on the GPU: staged (copy-stream) batches give the same metrics as the oracle's forecasts."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import timesfm_oracle as O  # noqa: E402  (checker only)
+from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig  # noqa: E402
+from tsfmx_b200.evaluator import MultimodalEvaluator  # noqa: E402
+from tsfmx_b200.tsfm.timesfm import TimesFM2p5Adapter, init_random_  # noqa: E402
+
+
+def test_evaluator_matches_oracle_metrics():
+    adapter = TimesFM2p5Adapter(num_layers=2, with_quantile_head=False)
+    init_random_(adapter, seed=0)
+    torch.manual_seed(100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, []))
+    oracle = O.oracle_from_product(dec)
+    dec = dec.to("cuda").eval()
+    dec.set_precision("bf16x3")
+    batches, se, ae, n = [], 0.0, 0.0, 0
+    for i, b in enumerate((6, 3, 9, 1)):
+        ctx, _m, text, hor = O.synthetic_batch(b, 512, 64, seed=50 + i)
+        batches.append({"context": ctx.pin_memory(), "horizon": hor.pin_memory(), "text_embeddings": text.pin_memory(),
+                        "metadata": [{}] * b})
+        with torch.no_grad():
+            p = oracle(64, ctx, torch.zeros_like(ctx, dtype=torch.bool), text)
+        se += ((p - hor) ** 2).mean().item() * b
+        ae += (p - hor).abs().mean().item() * b
+        n += b
+    ev = MultimodalEvaluator(dec, torch.device("cuda"))
+    got = ev.evaluate(batches)
+    assert got["mse"] == pytest.approx(se / n, rel=2e-3) and got["mae"] == pytest.approx(ae / n, rel=2e-3)
+    assert ev.evaluate(iter(batches)) == got  # generators work too, and the result is reproducible
+    with pytest.raises(RuntimeError, match="empty"):
+        ev.evaluate([])
