@@ -506,6 +506,7 @@ int launch_attention(const void* qkv, int64_t batch, int N, int H, const uint8_t
   const int per_warp_bytes = (3 * N * (HD + 1) + N) * 4;
   int wpb = (96 * 1024) / per_warp_bytes;
   if (wpb > 4) wpb = 4;
+  if (wpb < 1 && per_warp_bytes <= 224 * 1024) wpb = 1;  // long contexts (up to 224 patches): one warp per block
   if (wpb < 1) {
     set_error("timesfm_attention: %d patches need %d bytes of shared memory per warp; unsupported", N, per_warp_bytes);
     return TSFMX_ERR_UNSUPPORTED;

@@ -35,6 +35,12 @@ int check_last_launch(const char* what) {
   return TSFMX_OK;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

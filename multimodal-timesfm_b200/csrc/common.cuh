@@ -28,6 +28,7 @@ int check_last_launch(const char* what);
   } while (0)
 
 int num_sms();
+int current_device();  // index of the calling thread's CUDA device, clamped to [0, 63] (per-device caches)
 // attention_bwd.cu: tensor-core attention backward (bf16 qkv / dO / dqkv, N <= 64)
 int launch_timesfm_attention_bwd_mma(const void* qkv, const void* dout, int64_t batch, int N, int H, const uint8_t* pm,
                                      const int32_t* nm, const float* inv_freq, const float* qw, const float* kw,

@@ -834,7 +834,8 @@ template <int BN, int CG>
 int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, CG>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};  // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -1029,7 +1030,8 @@ extern "C" int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int3
                        (2 * 2 * RN_MAXC * BM + 2 * BM + 2 * RN_BN) * 4 + 1024 + 256;
   static_assert(SMEM <= 227 * 1024, "gemm_rownorm: shared memory budget");
   auto kern = gemm_rownorm_tcgen05_kernel;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};  // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -1051,7 +1053,8 @@ extern "C" int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int3
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent: as many clusters as the device can hold at once
-  static int max_clusters[RN_MAXC + 1] = {0};
+  static int max_clusters_dev[64][RN_MAXC + 1] = {{0}};
+  int* max_clusters = max_clusters_dev[current_device()];
   if (max_clusters[p.cluster] == 0) {
     cfg.gridDim = dim3(p.cluster * 64);
     int nc = 0;

@@ -1065,7 +1065,8 @@ int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, in
   const int smem = smem_for(G, stages);
   TSFMX_REQUIRE(smem <= 227 * 1024, "timesfm_patchify_norm: context %d does not fit the staged kernel", context);
   auto kern = timesfm_patchify_norm_tma_kernel<OUT>;
-  static int smem_set = 0;
+  static int smem_set_dev[64] = {0};  // cudaFuncSetAttribute is per device
+  int& smem_set = smem_set_dev[current_device()];
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {

@@ -484,7 +484,8 @@ extern "C" int tsfmx_t5_encoder_attention_mma(const void* qkv, int64_t batch, in
   }
   if (batch == 0) return TSFMX_OK;
   auto kern = t5_encoder_attention_mma_kernel;
-  static int smem_set = 0;
+  static int smem_set_dev[64] = {0};  // cudaFuncSetAttribute is per device
+  int& smem_set = smem_set_dev[current_device()];
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {

@@ -62,6 +62,11 @@ class MultimodalDecoder(nn.Module):
         if masks.shape != inputs.shape:
             raise ValueError(f"masks shape {masks.shape} must match inputs shape {inputs.shape}")
         masks = masks.bool()
+        if inputs.shape[0] == 0:  # empty batch: the reference's eager ops return an empty forecast
+            outputs = getattr(self.adapter, "num_outputs", None)
+            if outputs is None:
+                raise ValueError("empty batch and the adapter does not declare num_outputs")
+            return torch.empty(0, horizon, outputs, dtype=torch.float32, device=inputs.device)
         # train() mode with autograd on = the reference's fine-tune step; eval() / no_grad = plain forecasting
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_full_training(horizon, inputs, masks, text_embeddings)

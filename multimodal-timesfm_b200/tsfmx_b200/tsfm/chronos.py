@@ -148,6 +148,11 @@ class Chronos2Adapter(TsfmAdapter):
         return int(self._model.chronos_config.input_patch_size)
 
     @property
+    def num_outputs(self) -> int:
+        """Channels of the ``postprocess`` output (not part of the reference contract; used for empty batches)."""
+        return int(self._model.num_quantiles)
+
+    @property
     def point_forecast_index(self) -> int:
         return list(self._model.chronos_config.quantiles).index(0.5)
 

@@ -209,6 +209,11 @@ class ChronosT5Adapter(TsfmAdapter):
         return 1  # one embedding per time step (plus the EOS position)
 
     @property
+    def num_outputs(self) -> int:
+        """Channels of the ``postprocess`` output (not part of the reference contract; used for empty batches)."""
+        return 1
+
+    @property
     def point_forecast_index(self) -> int:
         return 0
 

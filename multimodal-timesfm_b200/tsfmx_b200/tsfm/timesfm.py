@@ -132,6 +132,11 @@ class TimesFM2p5Adapter(TsfmAdapter):
         return int(self._model.p)
 
     @property
+    def num_outputs(self) -> int:
+        """Channels of the ``postprocess`` output (not part of the reference contract; used for empty batches)."""
+        return int(self._model.q)
+
+    @property
     def point_forecast_index(self) -> int:
         return int(self._model.config.decode_index)
 
