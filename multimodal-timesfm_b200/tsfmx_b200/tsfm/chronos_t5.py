@@ -194,6 +194,8 @@ class ChronosT5Adapter(TsfmAdapter):
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
         self._bias_tables: dict[tuple, torch.Tensor] = {}
+        self._graphs: dict[tuple, tuple] = {}
+        self.use_cuda_graphs = True  # replay the greedy decoding loop from a captured graph
 
     def set_precision(self, precision: str) -> None:
         if precision not in PRECISIONS:
@@ -368,12 +370,45 @@ class ChronosT5Adapter(TsfmAdapter):
     def decode(self, encoder_states: torch.Tensor, attention_mask: torch.Tensor, horizon: int,
                forced_ids: torch.Tensor | None = None, return_logits: bool = False):
         """Autoregressive decoding over the encoder states.  Greedy by default; ``forced_ids`` (batch, horizon) teacher
-        forces the inputs of steps 1.. (tests).  Returns (token ids (batch, horizon) int64, logits or None)."""
-        m = self._model
+        forces the inputs of steps 1.. (tests).  Returns (token ids (batch, horizon) int64, logits or None).
+
+        Plain greedy decoding is launch bound (135 kernels per generated token), so the whole loop is captured once
+        per (batch, tokens, horizon, precision) in a CUDA graph and replayed on later calls (``use_cuda_graphs``)."""
         if horizon < 1:
             raise ValueError(f"horizon must be >= 1, got {horizon}")
         if not encoder_states.is_cuda:
             raise TsfmxError("ChronosT5Adapter runs on B200 only; there is no CPU fallback")
+        if forced_ids is not None or return_logits or not self.use_cuda_graphs or horizon < 4 or torch.cuda.is_current_stream_capturing():
+            return self._decode_eager(encoder_states, attention_mask, horizon, forced_ids, return_logits)
+        self._weights()  # pack (if needed) outside the capture
+        params = tuple((q.data_ptr(), q._version) for q in self._model.parameters())
+        key = (tuple(encoder_states.shape), horizon, self.precision, encoder_states.device.index, params)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 2:  # each graph pins its KV caches: keep two shapes at most
+                self._graphs.clear()
+            static_enc = encoder_states.float().contiguous().clone()
+            static_mask = attention_mask.bool().contiguous().clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up run: sets function attributes, fills every lazy cache
+                self._decode_eager(static_enc, static_mask, horizon, None, False)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                tokens, _ = self._decode_eager(static_enc, static_mask, horizon, None, False)
+            entry = (graph, static_enc, static_mask, tokens)
+            self._graphs[key] = entry
+        graph, static_enc, static_mask, tokens = entry
+        static_enc.copy_(encoder_states)
+        static_mask.copy_(attention_mask.bool())
+        graph.replay()
+        return tokens.clone(), None
+
+    def _decode_eager(self, encoder_states: torch.Tensor, attention_mask: torch.Tensor, horizon: int,
+                      forced_ids: torch.Tensor | None, return_logits: bool):
+        m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
         mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32

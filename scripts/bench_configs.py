@@ -7,7 +7,7 @@
   chronos2  cfg-3: Chronos-2 (12 blocks x 768, the adapter the reference wraps) + 1-layer fusion, ctx 512 / h 128,
             2048 series per GPU, series-sharded, no collective
   chronos_t5  cfg-3 as BASELINE.json words it: Chronos-T5-base tokenise + encoder + greedy decoding of 64 tokens,
-            per-token text fusion, 1024 series per GPU
+            per-token text fusion, 2048 series per GPU
   finetune  cfg-4: TimesFM "500M shape" (50 layers) multimodal fine-tune step = forward + activation-gradient pass +
             fusion weight gradient + NCCL all-reduce of the fusion gradients + clip + AdamW, 1024 series per GPU
   longctx   cfg-5: ctx 2048; TimesFM 50 layers at h 128 (the adapter API raises above 128) and Chronos-2 at h 256,
@@ -117,7 +117,7 @@ def main():
     if want("chronos_t5"):
         from tsfmx_b200.tsfm import chronos_t5 as CT5
 
-        tb, horizon = min(B, 1024), 64
+        tb, horizon = min(B, 2048), 64
         adapter = CT5.ChronosT5Adapter(CT5.ChronosT5Module(), precision="bf16")
         CT5.init_random_(adapter._model, seed=0)
         torch.manual_seed(100)
