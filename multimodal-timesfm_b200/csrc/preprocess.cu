@@ -354,6 +354,27 @@ __global__ void __launch_bounds__(256) timesfm_patchify_norm_kernel(
 // 16-byte stores.  Slot layout: patch k of series s at (k * G + s) * 3 floats (stride 3: conflict-free merge scan).
 // ----------------------------------------------------------------------------------------
 constexpr int TF_THREADS = 256;
+constexpr int TF_BLOCKED_MIN_PATCHES = 16;  // contexts above 512 use the blocked fold of the running statistics
+
+struct RunStats {
+  float n, mu, sigma;
+};
+
+// One step of the reference's update_running_stats: (n, mu, sigma) of the union of the running set and one patch.
+__device__ __forceinline__ RunStats merge_stats(RunStats run, float inc_n, float inc_mu, float inc_sigma) {
+  const float new_n = __fadd_rn(run.n, inc_n);
+  const float new_n_safe = new_n == 0.f ? 1.f : new_n;
+  float new_mu = __fdiv_rn(__fadd_rn(__fmul_rn(run.n, run.mu), __fmul_rn(inc_mu, inc_n)), new_n_safe);
+  if (new_n == 0.f) new_mu = 0.f;
+  const float d1 = __fsub_rn(run.mu, new_mu), d2 = __fsub_rn(inc_mu, new_mu);
+  const float t1 = __fmul_rn(run.n, __fmul_rn(run.sigma, run.sigma));
+  const float t2 = __fmul_rn(inc_n, __fmul_rn(inc_sigma, inc_sigma));
+  const float t3 = __fmul_rn(run.n, __fmul_rn(d1, d1));
+  const float t4 = __fmul_rn(inc_n, __fmul_rn(d2, d2));
+  float new_var = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4), new_n_safe);
+  if (new_n == 0.f) new_var = 0.f;
+  return RunStats{new_n, new_mu, sqrtf(fmaxf(new_var, 0.f))};
+}
 
 template <int OUT>
 __global__ void __launch_bounds__(TF_THREADS) timesfm_patchify_norm_tma_kernel(
@@ -369,7 +390,8 @@ __global__ void __launch_bounds__(TF_THREADS) timesfm_patchify_norm_tma_kernel(
   // slot of patch k of series s: 4 floats at (k * G + s) * 4 -> the merge thread of series s reads/writes 16 bytes,
   // consecutive threads consecutive slots (conflict-free)
   float4* slots = reinterpret_cast<float4*>(smem_tma + stages * stage_bytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slots + G * N);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slots + G * N + G * ((N + 7) >> 3));
+  __shared__ int s_masked[32];
   const float inv_n = 1.0f / static_cast<float>(N);
   const int64_t num_tiles = (batch + G - 1) / G;
 
@@ -442,33 +464,66 @@ __global__ void __launch_bounds__(TF_THREADS) timesfm_patchify_norm_tma_kernel(
       slots[k * G + s] = make_float4(c, inc_mu, c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f)), flag);
     }
     __syncthreads();
-    // ---- phase B: sequential merge (reference order and formula; HF twin modeling_timesfm2_5.py:528-568),
-    //      thread s = series s; the slot becomes {cumulative mu, cumulative sigma, 1 / safe sigma, padded flag}
-    if (tid < cnt) {
-      float run_n = 0.f, run_mu = 0.f, run_sigma = 0.f;
-      int masked = 0;
-      for (int i = 0; i < N; ++i) {
-        const float4 inc = slots[i * G + tid];
-        const float inc_n = inc.x, inc_mu = inc.y, inc_sigma = inc.z;
-        const float new_n = __fadd_rn(run_n, inc_n);
-        const float new_n_safe = new_n == 0.f ? 1.f : new_n;
-        float new_mu = __fdiv_rn(__fadd_rn(__fmul_rn(run_n, run_mu), __fmul_rn(inc_mu, inc_n)), new_n_safe);
-        if (new_n == 0.f) new_mu = 0.f;
-        const float d1 = __fsub_rn(run_mu, new_mu), d2 = __fsub_rn(inc_mu, new_mu);
-        const float t1 = __fmul_rn(run_n, __fmul_rn(run_sigma, run_sigma));
-        const float t2 = __fmul_rn(inc_n, __fmul_rn(inc_sigma, inc_sigma));
-        const float t3 = __fmul_rn(run_n, __fmul_rn(d1, d1));
-        const float t4 = __fmul_rn(inc_n, __fmul_rn(d2, d2));
-        float new_var = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4), new_n_safe);
-        if (new_n == 0.f) new_var = 0.f;
-        run_n = new_n;
-        run_mu = new_mu;
-        run_sigma = sqrtf(fmaxf(new_var, 0.f));
-        slots[i * G + tid] =
-            make_float4(run_mu, run_sigma, __fdiv_rn(1.0f, run_sigma < 1e-6f ? 1.f : run_sigma), inc.w);
-        masked += inc.w != 0.f ? 1 : 0;
+    // ---- phase B: merge of the running statistics (reference formula; HF twin modeling_timesfm2_5.py:528-568); the
+    //      slot becomes {cumulative mu, cumulative sigma, 1 / safe sigma, padded flag}
+    if (N <= TF_BLOCKED_MIN_PATCHES) {
+      // reference order exactly: thread s folds the N patches of series s one after the other
+      if (tid < cnt) {
+        RunStats st = {0.f, 0.f, 0.f};
+        int masked = 0;
+        for (int i = 0; i < N; ++i) {
+          const float4 inc = slots[i * G + tid];
+          st = merge_stats(st, inc.x, inc.y, inc.z);
+          slots[i * G + tid] = make_float4(st.mu, st.sigma, __fdiv_rn(1.0f, st.sigma < 1e-6f ? 1.f : st.sigma), inc.w);
+          masked += inc.w != 0.f ? 1 : 0;
+        }
+        if (num_masked_out != nullptr) num_masked_out[b0 + tid] = masked;
       }
-      if (num_masked_out != nullptr) num_masked_out[b0 + tid] = masked;
+    } else {
+      // long contexts: the N-step chain (two IEEE divisions and a square root per step) would leave the block idle, so
+      // the fold is cut into blocks of 8 patches: (1) every (series, block) thread folds its block from the empty
+      // state, (2) one thread per series folds the block summaries into the state BEFORE each block, (3) every
+      // (series, block) thread folds its patches again from that state.  Same merge formula at every step; the result
+      // differs from the strictly sequential fold only by fp32 rounding (a few 1e-7 relative).
+      const int NB = (N + 7) >> 3;
+      float4* blk = slots + G * N;  // [NB][G] block summaries, then the state before each block
+      for (int u = tid; u < cnt * NB; u += TF_THREADS) {
+        const int b = u / cnt, sr = u - b * cnt;
+        const int k1 = min(N, 8 * b + 8);
+        RunStats st = {0.f, 0.f, 0.f};
+        for (int i = 8 * b; i < k1; ++i) {
+          const float4 inc = slots[i * G + sr];
+          st = merge_stats(st, inc.x, inc.y, inc.z);
+        }
+        blk[b * G + sr] = make_float4(st.n, st.mu, st.sigma, 0.f);
+      }
+      __syncthreads();
+      if (tid < cnt) {
+        RunStats st = {0.f, 0.f, 0.f};
+        for (int b = 0; b < NB; ++b) {
+          const float4 inc = blk[b * G + tid];
+          blk[b * G + tid] = make_float4(st.n, st.mu, st.sigma, 0.f);  // exclusive prefix
+          st = merge_stats(st, inc.x, inc.y, inc.z);
+        }
+        s_masked[tid] = 0;
+      }
+      __syncthreads();
+      for (int u = tid; u < cnt * NB; u += TF_THREADS) {
+        const int b = u / cnt, sr = u - b * cnt;
+        const int k1 = min(N, 8 * b + 8);
+        const float4 pre = blk[b * G + sr];
+        RunStats st = {pre.x, pre.y, pre.z};
+        int masked = 0;
+        for (int i = 8 * b; i < k1; ++i) {
+          const float4 inc = slots[i * G + sr];
+          st = merge_stats(st, inc.x, inc.y, inc.z);
+          slots[i * G + sr] = make_float4(st.mu, st.sigma, __fdiv_rn(1.0f, st.sigma < 1e-6f ? 1.f : st.sigma), inc.w);
+          masked += inc.w != 0.f ? 1 : 0;
+        }
+        if (masked) atomicAdd(&s_masked[sr], masked);
+      }
+      __syncthreads();
+      if (tid < cnt && num_masked_out != nullptr) num_masked_out[b0 + tid] = s_masked[tid];
     }
     __syncthreads();
     // ---- mu / sigma / patch mask out, coalesced (the tile's [cnt, N] block is contiguous in [B, N])
@@ -1058,7 +1113,7 @@ int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, in
   if (G < 1) G = 1;
   int stages = g_tf_warps > 0 ? g_tf_warps : 2;
   auto smem_for = [&](int g, int st) {
-    return st * ((g * context * 5 + 127) & ~127) + g * N * 16 + st * 8 + 128;
+    return st * ((g * context * 5 + 127) & ~127) + g * (N + ((N + 7) >> 3)) * 16 + st * 8 + 128;
   };
   while (stages > 1 && smem_for(G, stages) > 220 * 1024) --stages;
   while (G > 1 && smem_for(G, stages) > 220 * 1024) --G;
