@@ -1,0 +1,86 @@
+"""Host-side logic that needs no GPU: series-lane helpers, the decoder's error behaviour before any device work
+(same ``ValueError``s as the reference, reference tsfmx/decoder.py:62-63, fusion.py:36-42, timesfm.py:48-51,116-119),
+and the loud failure of every adapter on CPU tensors (there is no CPU fallback)."""
+
+import pytest
+import torch
+
+from tsfmx_b200 import lanes
+from tsfmx_b200._lib import TsfmxError
+from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig
+from tsfmx_b200.fusion import MultimodalFusion
+from tsfmx_b200.tsfm.chronos import Chronos2Adapter, Chronos2Module
+from tsfmx_b200.tsfm.chronos_t5 import ChronosT5Adapter, ChronosT5Module
+from tsfmx_b200.tsfm.timesfm import TimesFM2p5Adapter
+
+
+def test_split_points_cover_the_batch_once():
+    for batch, count, mult in [(4096, 2, 8), (1031, 2, 8), (10, 4, 1), (3, 8, 8), (1, 2, 8)]:
+        cuts = lanes.split_points(batch, count, mult)
+        assert cuts[0][0] == 0 and cuts[-1][1] == batch
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        assert all(hi > lo for lo, hi in cuts) and len(cuts) <= max(1, min(count, batch))
+
+
+def test_step_generators_drain_and_fall_back():
+    class Stage:
+        def plain(self, x):
+            return x + 1
+
+        def fancy_steps(self, x):
+            yield
+            yield
+            return x * 2
+
+    s = Stage()
+    assert lanes.drain(lanes.steps(s, "plain", 3)) == 4      # no *_steps variant: one step
+    assert lanes.drain(lanes.steps(s, "fancy", 3)) == 6      # generator's return value comes through
+    assert len(list(lanes.steps(s, "fancy", 3))) == 2
+
+
+def test_lane_count_needs_enough_tokens_per_lane():
+    dec = MultimodalDecoder(TimesFM2p5Adapter(num_layers=1, with_quantile_head=False), MultimodalDecoderConfig())
+    assert dec._lane_count(torch.zeros(4096, 512)) == 1          # CPU tensors never split
+    dec.lanes = 1
+    assert dec._lane_count(torch.zeros(4096, 512)) == 1
+
+
+def test_reference_error_behaviour_before_device_work():
+    dec = MultimodalDecoder(TimesFM2p5Adapter(num_layers=1, with_quantile_head=False), MultimodalDecoderConfig())
+    with pytest.raises(ValueError, match="must match inputs shape"):
+        dec.forward_full(128, torch.zeros(2, 512), torch.zeros(2, 256, dtype=torch.bool))
+    with pytest.raises(ValueError, match="divisible by patch length"):
+        dec.adapter.preprocess(torch.zeros(2, 500), torch.zeros(2, 500, dtype=torch.bool))
+    with pytest.raises(ValueError, match="horizon must be <= output_patch_len"):
+        dec.adapter.postprocess(129, torch.zeros(2, 16, 1280), {})
+    with pytest.raises(ValueError, match="between 1 and 3"):
+        MultimodalFusion(1280, 384, num_layers=4, hidden_dims=[8, 8, 8])
+    with pytest.raises(ValueError, match="hidden_dims must have"):
+        MultimodalFusion(1280, 384, num_layers=2, hidden_dims=[])
+    with pytest.raises(ValueError, match="exceeds the maximum prediction length"):
+        Chronos2Adapter(Chronos2Module(1)).postprocess(1025, torch.zeros(1, 64, 768), {})
+
+
+def test_adapters_refuse_cpu_tensors():
+    x, m = torch.zeros(2, 512), torch.zeros(2, 512, dtype=torch.bool)
+    for adapter in (TimesFM2p5Adapter(num_layers=1, with_quantile_head=False), Chronos2Adapter(Chronos2Module(1)),
+                    ChronosT5Adapter(ChronosT5Module(num_layers=1))):
+        with pytest.raises(TsfmxError, match="no CPU fallback"):
+            adapter.preprocess(x, m)
+    with pytest.raises(TsfmxError, match="no CPU fallback"):
+        MultimodalFusion(1280, 384).forward_device(torch.zeros(2, 16, 1280), torch.zeros(2, 16, 384))
+
+
+def test_state_dict_keys_follow_upstream_names():
+    tf = TimesFM2p5Adapter(num_layers=2, with_quantile_head=True)._model.state_dict()
+    for k in ("tokenizer.hidden_layer.weight", "stacked_xf.1.attn.qkv_proj.weight", "stacked_xf.0.attn.per_dim_scale.per_dim_scale",
+              "stacked_xf.0.pre_attn_ln.scale", "output_projection_point.residual_layer.weight",
+              "output_projection_quantiles.output_layer.weight"):
+        assert k in tf, k
+    t5 = ChronosT5Adapter(ChronosT5Module(num_layers=1))._model.state_dict()
+    for k in ("shared.weight", "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
+              "decoder.block.0.layer.1.EncDecAttention.k.weight", "decoder.block.0.layer.2.DenseReluDense.wo.weight",
+              "encoder.final_layer_norm.weight"):
+        assert k in t5, k
+    dec = MultimodalDecoder(TimesFM2p5Adapter(num_layers=1, with_quantile_head=False), MultimodalDecoderConfig(384, 3, [512, 256]))
+    assert [k for k in dec.fusion.state_dict()] == ["projection.0.weight", "projection.2.weight", "projection.4.weight"]
