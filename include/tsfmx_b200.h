@@ -189,9 +189,11 @@ int tsfmx_gemm_set_cta_group(int cta_group);
  *   a = A W^T;  y = RMSNorm(a) * w_post + x  (w_post NULL: y = a + x);  yn = RMSNorm(y) * w_next  (w_next NULL: yn = y)
  * Replaces attn.out / ff1 + post_ln + residual + next pre_ln of upstream timesfm Transformer.forward (called at
  * reference tsfmx/tsfm/timesfm.py:97; HF twin modeling_timesfm2_5.py:378-388).  n / 256 CTAs form a cluster that owns
- * a full 128-row x n panel; row statistics are exchanged through distributed shared memory.
+ * a full 128-row x n panel; row statistics are exchanged through distributed shared memory; x is read and y written
+ * through TMA-staged 128 x 32 chunks.  Opt-in (the adapters' fused_norm flag): measured at par with tsfmx_gemm +
+ * tsfmx_norm_residual_norm, not faster.
  *   seg: one K-segment (split operands when precision = BF16X3); n in {512, 768, 1024, 1280}
- *   x, y fp32 [m, n] (y may alias x); yn [m, n] of yn_dtype or NULL.
+ *   x, y fp32 [m, n] with contiguous rows of n floats, 16-byte aligned (y may alias x); yn [m, n] of yn_dtype or NULL.
  */
 int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int32_t n, int32_t precision, const float* w_post,
                        const float* w_next, const float* x, float* y, int32_t yn_dtype, void* yn, float eps,

@@ -25,6 +25,7 @@ from torch import nn
 from .. import ops
 from .._lib import ACT_RELU, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
 from ..fusion import _pad_k
+from ..lanes import drain
 from .base import PreprocessResult, TsfmAdapter
 
 QUANTILES = [0.01, 0.05] + [round(0.1 + 0.05 * i, 2) for i in range(17)] + [0.95, 0.99]
@@ -260,6 +261,10 @@ class Chronos2Adapter(TsfmAdapter):
     def forward(self, input_embeddings: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         """Run the encoder on [context | REG | future] and return the 64 forecast positions
         (reference chronos.py:62-126) -> (batch, 64, 768)."""
+        return drain(self.forward_steps(input_embeddings, masks))
+
+    def forward_steps(self, input_embeddings: torch.Tensor, masks: torch.Tensor):
+        """``forward`` as a step generator (one ``yield`` per kernel launch, see ``tsfmx_b200.lanes``)."""
         if not input_embeddings.is_cuda:
             raise TsfmxError("Chronos2Adapter runs on B200 only; there is no CPU fallback")
         m, cc = self._model, self._model.chronos_config
@@ -287,6 +292,7 @@ class Chronos2Adapter(TsfmAdapter):
             out = ops.rmsnorm(h2, w["final_ln"], m.eps, DT_F32)
             return out.view(b, t, d)[:, -nop:].contiguous()
         xn = ops.rmsnorm(h2, blocks[0]["ln_t"], m.eps, adt)
+        yield
         qkv = ops.alloc(rows, 3 * inner, mid_dt, dev)
         attn = ops.alloc(rows, inner, adt, dev)
         a = ops.alloc(rows, d, mid_dt, dev)
@@ -294,30 +300,45 @@ class Chronos2Adapter(TsfmAdapter):
         final = None
         for i, bw in enumerate(blocks):
             ops.gemm([(xn, bw["qkv"], d)], rows, 3 * inner, qkv, mid_dt, precision=prec)
+            yield
             ops.encoder_attention(qkv, b, t, m.num_heads, m.d_kv, key_mask, w["inv_freq"], adt, out=attn)
+            yield
             has_next = i + 1 < len(blocks)
             if not has_next:
                 final = torch.empty(rows, d, dtype=torch.float32, device=dev)
             if self.fused_norm:
                 # residual add + next RMS LayerNorm in the GEMM epilogue (3-CTA clusters own a 768-wide row panel)
                 ops.gemm_rownorm(attn, bw["o"], inner, rows, d, prec, None, bw["ln_g"], h2, h2, adt, xn, m.eps)
+                yield
                 ops.gemm_rownorm(xn, bw["ov"], d, rows, d, prec, None, bw["ln_f"], h2, h2, adt, xn, m.eps)
+                yield
                 ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
+                yield
                 if has_next:
                     ops.gemm_rownorm(u, bw["wo"], m.d_ff, rows, d, prec, None, blocks[i + 1]["ln_t"], h2, h2, adt, xn, m.eps)
+                    yield
                 else:
                     ops.gemm_rownorm(u, bw["wo"], m.d_ff, rows, d, prec, None, w["final_ln"], h2, h2, DT_F32, final, m.eps)
+                    yield
             else:
                 ops.gemm([(attn, bw["o"], inner)], rows, d, a, mid_dt, precision=prec)
+                yield
                 ops.norm_residual_norm(a, h2, None, bw["ln_g"], m.eps, h2, adt, xn)
+                yield
                 ops.gemm([(xn, bw["ov"], d)], rows, d, a, mid_dt, precision=prec)
+                yield
                 ops.norm_residual_norm(a, h2, None, bw["ln_f"], m.eps, h2, adt, xn)
+                yield
                 ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
+                yield
                 ops.gemm([(u, bw["wo"], m.d_ff)], rows, d, a, mid_dt, precision=prec)
+                yield
                 if has_next:
                     ops.norm_residual_norm(a, h2, None, blocks[i + 1]["ln_t"], m.eps, h2, adt, xn)
+                    yield
                 else:
                     ops.norm_residual_norm(a, h2, None, w["final_ln"], m.eps, h2, DT_F32, final)
+                    yield
         return final.view(b, t, d)[:, -nop:].contiguous()
 
     def postprocess(
