@@ -382,10 +382,13 @@ class ChronosT5Adapter(TsfmAdapter):
             return self._decode_eager(encoder_states, attention_mask, horizon, forced_ids, return_logits)
         self._weights()  # pack (if needed) outside the capture
         params = tuple((q.data_ptr(), q._version) for q in self._model.parameters())
-        key = (tuple(encoder_states.shape), horizon, self.precision, encoder_states.device.index, params)
+        # one graph (and one set of static buffers) per launching stream: two series lanes of the same shape must not
+        # share them, their replays overlap in time
+        key = (tuple(encoder_states.shape), horizon, self.precision, encoder_states.device.index,
+               torch.cuda.current_stream().cuda_stream, params)
         entry = self._graphs.get(key)
         if entry is None:
-            if len(self._graphs) >= 2:  # each graph pins its KV caches: keep two shapes at most
+            if len(self._graphs) >= 4:  # each graph pins its KV caches: keep a few shapes at most
                 self._graphs.clear()
             static_enc = encoder_states.float().contiguous().clone()
             static_mask = attention_mask.bool().contiguous().clone()

@@ -131,3 +131,27 @@ def test_decoder_parity_and_greedy_ids(layers, context, horizon, padded, tied):
         _, logits16 = dec.adapter.decode(enc_ref.to(DEV), am.to(DEV), horizon, forced_ids=ref_tokens.to(DEV),
                                          return_logits=True)
     assert rel_max(logits16.cpu(), ref_logits) < BF16_TOL
+
+
+def test_graph_replay_and_series_lanes_give_the_eager_tokens():
+    """Greedy decoding replayed from CUDA graphs, with the batch cut into two series lanes on separate streams (each
+    lane owns its graph and static buffers), must reproduce the eager single-stream tokens exactly."""
+    dec, _ = build(2, seed=5, tied=False)
+    dec.set_precision("bf16")
+    ctx, masks, text = batch(288, 64, True, seed=13)   # 288 x 65 tokens >= 2 x 8192: the decoder really uses two lanes
+    text_tok = dec.adapter.expand_text_embeddings(text, 64)
+    ctx, masks, text_tok = ctx.to(DEV), masks.to(DEV), text_tok.to(DEV)
+    try:
+        with torch.no_grad():
+            dec.lanes, dec.adapter.use_cuda_graphs = 1, False
+            eager = dec.forward_full(12, ctx, masks, text_tok)
+            dec.adapter.use_cuda_graphs = True
+            graphed = dec.forward_full(12, ctx, masks, text_tok)
+            dec.lanes = 2
+            assert dec._lane_count(ctx) == 2
+            first = dec.forward_full(12, ctx, masks, text_tok)    # captures one graph per lane stream
+            again = dec.forward_full(12, ctx, masks, text_tok)    # replays both, overlapping in time
+        torch.cuda.synchronize()
+    finally:
+        dec.lanes, dec.adapter.use_cuda_graphs = 2, True
+    assert torch.equal(eager, graphed) and torch.equal(eager, first) and torch.equal(eager, again)
