@@ -212,8 +212,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int NT>  // number of 16-row tiles: N <= 16 * NT
-__global__ void __launch_bounds__(256) timesfm_attention_mma_kernel(
+template <int NT>  // number of 16-row tiles: N <= 16 * NT; NT warps share one (series, head), one query tile each
+__global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_kernel(
     const __nv_bfloat16* __restrict__ qkv, int64_t batch, int num_patches, int num_heads,
     const uint8_t* __restrict__ patch_mask, const int32_t* __restrict__ num_masked,
     const float* __restrict__ inv_freq, const float* __restrict__ q_ln_w, const float* __restrict__ k_ln_w,
@@ -229,7 +229,16 @@ __global__ void __launch_bounds__(256) timesfm_attention_mma_kernel(
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = num_patches;
-  __nv_bfloat16* sQ = s_tiles + warp * 3 * TILE;
+  // unit = one (series, head); its NT warps stage and condition the rows together, then warp wq owns query tile wq
+  const int units_per_block = warps_per_block / NT;
+  const int unit_in_block = warp / NT, wq = warp - unit_in_block * NT;
+  const int ulane = wq * 32 + lane;          // lane index inside the unit
+  constexpr int UTHREADS = 32 * NT;
+  auto unit_sync = [&]() {
+    if constexpr (NT == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + unit_in_block), "n"(UTHREADS) : "memory");
+  };
+  __nv_bfloat16* sQ = s_tiles + unit_in_block * 3 * TILE;
   __nv_bfloat16* sK = sQ + TILE;
   __nv_bfloat16* sV = sK + TILE;
 
@@ -252,22 +261,22 @@ __global__ void __launch_bounds__(256) timesfm_attention_mma_kernel(
   const int g = lane >> 2, t = lane & 3;
   const int ntk = (N + 15) >> 4;  // 16-row tiles actually populated
 
-  for (int64_t unit = static_cast<int64_t>(blockIdx.x) * warps_per_block + warp; unit < total;
-       unit += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+  for (int64_t unit = static_cast<int64_t>(blockIdx.x) * units_per_block + unit_in_block; unit < total;
+       unit += static_cast<int64_t>(gridDim.x) * units_per_block) {
     const int64_t b = unit / num_heads;
     const int h = static_cast<int>(unit - b * num_heads);
     const int nm = num_masked != nullptr ? num_masked[b] : 0;
 
     // ---- async fetch of the raw q / k / v rows (10 x 16 B per row)
     const __nv_bfloat16* gbase = qkv + b * N * qkv_ld + h * MMA_HD;
-    for (int c = lane; c < 3 * N * 10; c += 32) {
+    for (int c = ulane; c < 3 * N * 10; c += UTHREADS) {
       const int which = c / (N * 10);
       const int rem = c - which * (N * 10);
       const int row = rem / 10, ch = rem - row * 10;
       cp_async_16(sQ + which * TILE + row * MMA_LD + ch * 8, gbase + row * qkv_ld + which * width + ch * 8);
     }
     // rows beyond N (only when N is not a multiple of 16): zero so the MMAs see finite data
-    for (int c = lane; c < 3 * (ntk * 16 - N) * 10; c += 32) {
+    for (int c = ulane; c < 3 * (ntk * 16 - N) * 10; c += UTHREADS) {
       const int which = c / ((ntk * 16 - N) * 10);
       const int rem = c - which * ((ntk * 16 - N) * 10);
       const int row = N + rem / 10, ch = rem % 10;
@@ -282,11 +291,12 @@ __global__ void __launch_bounds__(256) timesfm_attention_mma_kernel(
               (static_cast<uint64_t>(__ballot_sync(0xffffffffu, v1)) << 32);
     }
     cp_async_wait_all();
-    __syncwarp();
+    unit_sync();
 
-    // ---- condition q and k in place: lane pair (2r, 2r+1) owns row r; each lane 20 rotary pairs
-#pragma unroll
-    for (int rt = 0; rt < NT; ++rt) {
+    // ---- condition q and k in place: lane pair (2r, 2r+1) owns row r; each lane 20 rotary pairs; warp wq takes the
+    //      16 rows of its own tile
+    {
+      const int rt = wq;
       const int r = rt * 16 + (lane >> 1);
       if (rt < ntk) {
         const int hf = lane & 1;
@@ -346,12 +356,12 @@ __global__ void __launch_bounds__(256) timesfm_attention_mma_kernel(
         }
       }
     }
-    __syncwarp();
+    unit_sync();  // every warp of the unit needs all conditioned k rows
 
-    // ---- per 16-query tile: S = Q K^T (tensor cores) -> masked softmax (registers) -> O = P V
+    // ---- this warp's 16-query tile: S = Q K^T (tensor cores) -> masked softmax (registers) -> O = P V
     const uint32_t sq_addr = smem_u32(sQ), sk_addr = smem_u32(sK), sv_addr = smem_u32(sV);
-#pragma unroll
-    for (int qi = 0; qi < NT; ++qi) {
+    {
+      const int qi = wq;
       if (qi < ntk) {
         uint32_t qa[5][4];
         {
@@ -461,13 +471,15 @@ __global__ void __launch_bounds__(256) timesfm_attention_mma_kernel(
       }
     }
     __syncwarp();
+    // each warp stores the 16 rows it produced (staged in its own Q rows)
     __nv_bfloat16* obase = out + b * N * width + h * MMA_HD;
-    for (int c = lane; c < N * 10; c += 32) {
-      const int row = c / 10, ch = c - row * 10;
-      *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * width + ch * 8) =
-          *reinterpret_cast<const uint4*>(sQ + row * MMA_LD + ch * 8);
+    for (int c = lane; c < 16 * 10; c += 32) {
+      const int row = wq * 16 + c / 10, ch = c % 10;
+      if (row < N)
+        *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * width + ch * 8) =
+            *reinterpret_cast<const uint4*>(sQ + row * MMA_LD + ch * 8);
     }
-    __syncwarp();
+    unit_sync();  // the next unit's cp.async must not overwrite k / v rows another warp still reads
   }
 }
 
@@ -476,11 +488,13 @@ int launch_attention_mma(const void* qkv, int64_t batch, int N, int H, const uin
                          const float* inv_freq, const float* qw, const float* kw, const float* qs, float eps, void* out,
                          cudaStream_t stream) {
   constexpr int ROWS = 16 * NT;
-  constexpr int per_warp = 3 * ROWS * MMA_LD * 2;
+  constexpr int per_unit = 3 * ROWS * MMA_LD * 2;
   constexpr int fixed = 2 * ROWS * 40 * 8 + 2 * MMA_HD * 4;
-  int wpb = (200 * 1024 - fixed) / per_warp;
-  if (wpb > 8) wpb = 8;
-  const int smem = fixed + wpb * per_warp;
+  int upb = (200 * 1024 - fixed) / per_unit;                 // units ((series, head) pairs) per block
+  const int max_units = NT == 1 ? 8 : 512 / (32 * NT);       // NT warps per unit, <= 512 threads per block
+  if (upb > max_units) upb = max_units;
+  const int wpb = upb * NT;
+  const int smem = fixed + upb * per_unit;
   auto kern = timesfm_attention_mma_kernel<NT>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -490,7 +504,7 @@ int launch_attention_mma(const void* qkv, int64_t batch, int N, int H, const uin
     }
   }
   const int64_t total = batch * H;
-  const int64_t blocks = (total + wpb - 1) / wpb;
+  const int64_t blocks = (total + upb - 1) / upb;
   const int per_sm = (220 * 1024) / smem > 0 ? (220 * 1024) / smem : 1;
   const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
