@@ -258,6 +258,17 @@ int tsfmx_encoder_attention_mma(const void* qkv, int64_t batch, int32_t seq, int
                                 const uint8_t* key_mask, const float* rope_table, void* out, void* stream);
 
 /*
+ * Backward of tsfmx_encoder_attention: d_out [B*T, H*64] -> dqkv [B*T, 3*H*64] = [dq | dk | dv] (fusion fine-tune
+ * through the frozen Chronos-2 encoder; the reference trains the fusion module with either adapter,
+ * scripts/tune_time_mmd_sweep.py:124-126).  fp32 arithmetic; stats_workspace: B*H*T float4 scratch (row max, 1 / sum,
+ * delta, has-key flag), 16-byte aligned.  All-masked series pass gradient like the reference's additive mask.
+ */
+int tsfmx_encoder_attention_bwd(const void* qkv, int32_t qkv_dtype, const void* d_out, int32_t dout_dtype, int64_t batch,
+                                int32_t seq, int32_t num_heads, int32_t head_dim, const uint8_t* key_mask,
+                                const float* rope_table, float* stats_workspace, int32_t dqkv_dtype, void* dqkv,
+                                void* stream);
+
+/*
  * Chronos-T5 backbone stages (BASELINE.json configs[2]; upstream chronos.ChronosModel -> transformers T5ForConditionalGeneration,
  * HF twin transformers/models/t5/modeling_t5.py; not part of the reference, which only wraps Chronos-2).
  *

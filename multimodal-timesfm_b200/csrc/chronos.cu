@@ -364,6 +364,144 @@ int launch_encoder_attention_mma(const void* qkv, int64_t batch, int seq, int nu
   return check_last_launch("encoder_attention_mma");
 }
 
+// ----------------------------------------------------------------------------------------
+// Backward of the encoder attention core (fusion fine-tune through the frozen Chronos-2 encoder; the reference trains
+// the fusion module with either adapter, scripts/tune_time_mmd_sweep.py:124-126).  fp32 SIMT, any T, exact up to
+// summation order: pass A gives one warp to a query row (P, dP, delta, dS -> dq, and the row's softmax statistics
+// to a workspace), pass B one warp to a key row (dk, dv from the recomputed P and dS).  Lane l holds head dims l and
+// l + 32, i.e. one rotary pair, so RoPE and its transpose are lane-local.
+// ----------------------------------------------------------------------------------------
+template <int OUT>
+__device__ __forceinline__ void enc_store2(void* out, int64_t row, int64_t row_elems, int c, float v0, float v1) {
+  // row_elems = 3 * width (columns of one dqkv row); c and c + 32 are the two columns written
+  if constexpr (OUT == TSFMX_DT_F32) {
+    float* o = reinterpret_cast<float*>(out) + row * row_elems;
+    o[c] = v0, o[c + 32] = v1;
+  } else if constexpr (OUT == TSFMX_DT_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + row * row_elems;
+    o[c] = __float2bfloat16_rn(v0), o[c + 32] = __float2bfloat16_rn(v1);
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + row * 2 * row_elems;  // [hi(3W) | lo(3W)]
+    split_bf16(v0, o[c], o[row_elems + c]);
+    split_bf16(v1, o[c + 32], o[row_elems + c + 32]);
+  }
+}
+
+template <int OUT>
+__global__ void __launch_bounds__(128) encoder_attention_bwd_q_kernel(
+    const void* __restrict__ qkv, int qkv_dtype, const void* __restrict__ dout, int dout_dtype, int64_t batch, int seq,
+    int num_heads, const uint8_t* __restrict__ key_mask, const float2* __restrict__ rope, float4* __restrict__ stats,
+    void* dqkv) {
+  extern __shared__ float s_enc_bwd[];  // [4 warps][2][T]: probabilities, dP
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = seq;
+  float* sp = s_enc_bwd + warp * 2 * T;
+  float* sdp = sp + T;
+  const int width = num_heads * 64;
+  const int64_t ld = 3 * static_cast<int64_t>(width);
+  const int64_t units = batch * num_heads * T;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * 4 + warp; u < units; u += static_cast<int64_t>(gridDim.x) * 4) {
+    const int i = static_cast<int>(u % T);
+    const int64_t bh = u / T;
+    const int h = static_cast<int>(bh % num_heads);
+    const int64_t b = bh / num_heads;
+    const int64_t row_i = b * T + i;
+    const int64_t base = b * T * ld + h * 64;
+    const uint8_t* km = key_mask != nullptr ? key_mask + b * T : nullptr;
+    const float2 ri = __ldg(rope + i * 32 + lane);
+    const float qa = ld_any(qkv, qkv_dtype, base + i * ld + lane), qb = ld_any(qkv, qkv_dtype, base + i * ld + lane + 32);
+    const float q0 = qa * ri.x - qb * ri.y, q1 = qb * ri.x + qa * ri.y;
+    const float g0 = ld_any(dout, dout_dtype, row_i * width + h * 64 + lane);
+    const float g1 = ld_any(dout, dout_dtype, row_i * width + h * 64 + lane + 32);
+    float mx = -INFINITY;
+    bool any = false;
+    for (int j = 0; j < T; ++j) {
+      const float2 rj = __ldg(rope + j * 32 + lane);
+      const int64_t kr = base + j * ld + width;
+      const float ka = ld_any(qkv, qkv_dtype, kr + lane), kb = ld_any(qkv, qkv_dtype, kr + lane + 32);
+      const float k0 = ka * rj.x - kb * rj.y, k1 = kb * rj.x + ka * rj.y;
+      const float s = warp_sum(q0 * k0 + q1 * k1);
+      const float dp = warp_sum(g0 * ld_any(qkv, qkv_dtype, kr + width + lane) + g1 * ld_any(qkv, qkv_dtype, kr + width + lane + 32));
+      const bool ok = km == nullptr || km[j] != 0;
+      if (lane == 0) sp[j] = ok ? s : -INFINITY, sdp[j] = dp;
+      if (ok) mx = fmaxf(mx, s), any = true;
+    }
+    __syncwarp();
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float e = any ? (sp[j] == -INFINITY ? 0.f : expf(sp[j] - mx)) : 1.f;  // all keys masked: uniform
+      sp[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+    float delta = 0.f;
+    for (int j = lane; j < T; j += 32) delta += sp[j] * inv * sdp[j];
+    delta = warp_sum(delta);
+    float dq0 = 0.f, dq1 = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const float ds = sp[j] * inv * (sdp[j] - delta);
+      if (ds != 0.f) {
+        const float2 rj = __ldg(rope + j * 32 + lane);
+        const int64_t kr = base + j * ld + width;
+        const float ka = ld_any(qkv, qkv_dtype, kr + lane), kb = ld_any(qkv, qkv_dtype, kr + lane + 32);
+        dq0 = fmaf(ds, ka * rj.x - kb * rj.y, dq0);
+        dq1 = fmaf(ds, kb * rj.x + ka * rj.y, dq1);
+      }
+    }
+    // transpose of the rotation
+    enc_store2<OUT>(dqkv, row_i, ld, h * 64 + lane, dq0 * ri.x + dq1 * ri.y, dq1 * ri.x - dq0 * ri.y);
+    if (lane == 0) stats[(b * num_heads + h) * T + i] = make_float4(mx, inv, delta, any ? 1.f : 0.f);
+    __syncwarp();
+  }
+}
+
+template <int OUT>
+__global__ void __launch_bounds__(128) encoder_attention_bwd_kv_kernel(
+    const void* __restrict__ qkv, int qkv_dtype, const void* __restrict__ dout, int dout_dtype, int64_t batch, int seq,
+    int num_heads, const uint8_t* __restrict__ key_mask, const float2* __restrict__ rope,
+    const float4* __restrict__ stats, void* dqkv) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = seq;
+  const int width = num_heads * 64;
+  const int64_t ld = 3 * static_cast<int64_t>(width);
+  const int64_t units = batch * num_heads * T;
+  for (int64_t u = static_cast<int64_t>(blockIdx.x) * 4 + warp; u < units; u += static_cast<int64_t>(gridDim.x) * 4) {
+    const int j = static_cast<int>(u % T);
+    const int64_t bh = u / T;
+    const int h = static_cast<int>(bh % num_heads);
+    const int64_t b = bh / num_heads;
+    const int64_t base = b * T * ld + h * 64;
+    const bool ok = key_mask == nullptr || key_mask[b * T + j] != 0;
+    const float2 rj = __ldg(rope + j * 32 + lane);
+    const int64_t kr = base + j * ld + width;
+    const float ka = ld_any(qkv, qkv_dtype, kr + lane), kb = ld_any(qkv, qkv_dtype, kr + lane + 32);
+    const float k0 = ka * rj.x - kb * rj.y, k1 = kb * rj.x + ka * rj.y;
+    const float v0 = ld_any(qkv, qkv_dtype, kr + width + lane), v1 = ld_any(qkv, qkv_dtype, kr + width + lane + 32);
+    float dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+    const float4* st = stats + (b * num_heads + h) * T;
+    for (int i = 0; i < T; ++i) {
+      const float4 si = __ldg(st + i);  // (max, 1 / sum, delta, has_key)
+      if (si.w != 0.f && !ok) continue;  // a masked key takes part only in the all-masked (uniform) case
+      const float2 ri = __ldg(rope + i * 32 + lane);
+      const float qa = ld_any(qkv, qkv_dtype, base + i * ld + lane), qb = ld_any(qkv, qkv_dtype, base + i * ld + lane + 32);
+      const float q0 = qa * ri.x - qb * ri.y, q1 = qb * ri.x + qa * ri.y;
+      const int64_t orow = (b * T + i) * width + h * 64;
+      const float g0 = ld_any(dout, dout_dtype, orow + lane), g1 = ld_any(dout, dout_dtype, orow + lane + 32);
+      const float s = warp_sum(q0 * k0 + q1 * k1);
+      const float dp = warp_sum(g0 * v0 + g1 * v1);
+      const float p = (si.w != 0.f ? expf(s - si.x) : 1.f) * si.y;
+      const float ds = p * (dp - si.z);
+      dk0 = fmaf(ds, q0, dk0), dk1 = fmaf(ds, q1, dk1);
+      dv0 = fmaf(p, g0, dv0), dv1 = fmaf(p, g1, dv1);
+    }
+    const int64_t row_j = b * T + j;
+    enc_store2<OUT>(dqkv, row_j, ld, width + h * 64 + lane, dk0 * rj.x + dk1 * rj.y, dk1 * rj.x - dk0 * rj.y);
+    enc_store2<OUT>(dqkv, row_j, ld, 2 * width + h * 64 + lane, dv0, dv1);
+  }
+}
+
 __global__ void chronos2_finalize_kernel(const float* __restrict__ preds, int64_t batch, int num_patches_used,
                                          int num_quantiles, int patch, int horizon, int use_arcsinh,
                                          const float* __restrict__ loc, const float* __restrict__ scale,
@@ -451,6 +589,53 @@ extern "C" int tsfmx_encoder_attention_mma(const void* qkv, int64_t batch, int32
   if (seq <= 112) return launch_encoder_attention_mma<7>(qkv, batch, seq, num_heads, key_mask, rope_table, out, stream);
   if (seq <= 144) return launch_encoder_attention_mma<9>(qkv, batch, seq, num_heads, key_mask, rope_table, out, stream);
   return launch_encoder_attention_mma<13>(qkv, batch, seq, num_heads, key_mask, rope_table, out, stream);
+}
+
+extern "C" int tsfmx_encoder_attention_bwd(const void* qkv, int32_t qkv_dtype, const void* d_out, int32_t dout_dtype,
+                                           int64_t batch, int32_t seq, int32_t num_heads, int32_t head_dim,
+                                           const uint8_t* key_mask, const float* rope_table, float* stats_workspace,
+                                           int32_t dqkv_dtype, void* dqkv, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(qkv != nullptr && d_out != nullptr && dqkv != nullptr && rope_table != nullptr && stats_workspace != nullptr,
+                "encoder_attention_bwd: NULL pointer");
+  TSFMX_REQUIRE(batch >= 0 && seq > 0 && num_heads > 0, "encoder_attention_bwd: bad sizes");
+  TSFMX_REQUIRE((qkv_dtype == TSFMX_DT_F32 || qkv_dtype == TSFMX_DT_BF16) &&
+                    (dout_dtype == TSFMX_DT_F32 || dout_dtype == TSFMX_DT_BF16),
+                "encoder_attention_bwd: qkv / d_out must be f32 or bf16");
+  TSFMX_REQUIRE(dqkv_dtype >= TSFMX_DT_F32 && dqkv_dtype <= TSFMX_DT_BF16_SPLIT, "encoder_attention_bwd: bad dqkv_dtype");
+  TSFMX_REQUIRE(reinterpret_cast<uintptr_t>(stats_workspace) % 16 == 0, "encoder_attention_bwd: workspace must be 16-byte aligned");
+  if (head_dim != 64) {
+    set_error("encoder_attention_bwd: head_dim %d unsupported (Chronos-2 uses 64)", head_dim);
+    return TSFMX_ERR_UNSUPPORTED;
+  }
+  if (batch == 0) return TSFMX_OK;
+  const int smem = 4 * 2 * seq * static_cast<int>(sizeof(float));
+  TSFMX_REQUIRE(smem <= 200 * 1024, "encoder_attention_bwd: %d tokens need %d bytes of shared memory", seq, smem);
+  const int64_t units = batch * num_heads * seq;
+  const int64_t blocks = (units + 3) / 4;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  const float2* rope = reinterpret_cast<const float2*>(rope_table);
+  float4* stats = reinterpret_cast<float4*>(stats_workspace);
+  auto launch = [&](auto kq, auto kkv) -> int {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) {
+        set_error("encoder_attention_bwd: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+        return TSFMX_ERR_CUDA;
+      }
+    }
+    kq<<<grid, 128, smem, stream>>>(qkv, qkv_dtype, d_out, dout_dtype, batch, seq, num_heads, key_mask, rope, stats, dqkv);
+    int rc = check_last_launch("encoder_attention_bwd_q");
+    if (rc != TSFMX_OK) return rc;
+    kkv<<<grid, 128, 0, stream>>>(qkv, qkv_dtype, d_out, dout_dtype, batch, seq, num_heads, key_mask, rope, stats, dqkv);
+    return check_last_launch("encoder_attention_bwd_kv");
+  };
+  if (dqkv_dtype == TSFMX_DT_F32)
+    return launch(encoder_attention_bwd_q_kernel<TSFMX_DT_F32>, encoder_attention_bwd_kv_kernel<TSFMX_DT_F32>);
+  if (dqkv_dtype == TSFMX_DT_BF16)
+    return launch(encoder_attention_bwd_q_kernel<TSFMX_DT_BF16>, encoder_attention_bwd_kv_kernel<TSFMX_DT_BF16>);
+  return launch(encoder_attention_bwd_q_kernel<TSFMX_DT_BF16_SPLIT>, encoder_attention_bwd_kv_kernel<TSFMX_DT_BF16_SPLIT>);
 }
 
 extern "C" int tsfmx_chronos2_finalize(const float* preds, int64_t batch, int32_t num_patches_used,

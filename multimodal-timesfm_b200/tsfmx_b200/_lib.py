@@ -119,6 +119,11 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int32,
         [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    "tsfmx_encoder_attention_bwd": (
+        c_int32,
+        [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+         c_void_p, c_void_p],
+    ),
     "tsfmx_rope_table": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "tsfmx_encoder_attention_mma": (
         c_int32,

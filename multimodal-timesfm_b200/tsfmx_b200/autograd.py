@@ -47,10 +47,10 @@ class FusedForecastFunction(torch.autograd.Function):
         ctx.saved = None  # release the activations as early as possible
         b, n, d, horizon = ctx.shape
         precision = PRECISIONS[adapter.precision]
-        d_last = adapter.postprocess_backward(head_saved, grad_forecast.contiguous().float())  # [B, D]
-        d_out = torch.zeros(b, n, d, dtype=torch.float32, device=d_last.device)
-        d_out[:, -1, :] = d_last  # only the last patch feeds the head (reference timesfm.py:129)
-        d_emb = adapter.forward_backward(stack_saved, d_out.view(b * n, d))  # [M, D] fp32
+        # gradient w.r.t. the adapter's output embeddings (TimesFM: only the last patch feeds the head, reference
+        # timesfm.py:129; Chronos-2: the first ceil(horizon / 16) forecast positions), then back through the stack
+        d_out = adapter.postprocess_backward(head_saved, grad_forecast.contiguous().float())  # [B, N_out, D] fp32
+        d_emb = adapter.forward_backward(stack_saved, d_out.reshape(-1, d))  # [B * N, D] fp32
         grads = fusion_backward(fusion, fusion_saved, d_emb, precision)
         return (None, None, None, None, None, *grads)
 

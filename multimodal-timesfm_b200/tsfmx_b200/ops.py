@@ -435,6 +435,27 @@ def encoder_attention(
     return out
 
 
+def encoder_attention_bwd(
+    qkv: torch.Tensor, d_out: torch.Tensor, batch: int, seq: int, num_heads: int, head_dim: int,
+    key_mask: torch.Tensor | None, inv_freq: torch.Tensor, dqkv_dtype: int, dqkv: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """d_out [B*T, H*hd] -> dqkv [B*T, 3*H*hd] (split: [B*T, 6*H*hd]) of the Chronos-2 encoder attention core."""
+    lib = _lib.load()
+    _lib.require_cuda(qkv, d_out)
+    if dqkv is None:
+        dqkv = alloc(batch * seq, 3 * num_heads * head_dim, dqkv_dtype, qkv.device)
+    km = None if key_mask is None else _as_u8(key_mask)
+    table = rope_table(inv_freq, seq)
+    stats = torch.empty(batch * num_heads * seq, 4, dtype=torch.float32, device=qkv.device)
+    check(
+        lib.tsfmx_encoder_attention_bwd(
+            ptr(qkv), _dt(qkv), ptr(d_out), _dt(d_out), batch, seq, num_heads, head_dim, ptr(km), ptr(table), ptr(stats),
+            dqkv_dtype, ptr(dqkv), stream(),
+        )
+    )
+    return dqkv
+
+
 def chronos2_finalize(
     preds: torch.Tensor, batch: int, patches_used: int, num_quantiles: int, patch: int, horizon: int,
     use_arcsinh: bool, loc: torch.Tensor, scale: torch.Tensor,

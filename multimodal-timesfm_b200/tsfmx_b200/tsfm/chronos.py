@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .._lib import ACT_RELU, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
+from .._lib import ACT_RELU, ACT_RELU_GRAD, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
 from ..fusion import _pad_k
 from ..lanes import drain
 from .base import PreprocessResult, TsfmAdapter
@@ -123,6 +123,15 @@ def init_random_(model: nn.Module, seed: int = 0) -> None:
             else:
                 v = 0.03 * torch.randn(p.shape, generator=gen)
             p.copy_(v.to(p.device))
+
+
+def _round64(k: int) -> int:
+    return (k + 63) // 64 * 64
+
+
+def _hi(t: torch.Tensor, cols: int) -> torch.Tensor:
+    """relu'(h) only needs the sign: the hi half of a split activation is enough."""
+    return t[:, :cols] if t.shape[1] != cols else t
 
 
 class Chronos2Adapter(TsfmAdapter):
@@ -376,6 +385,185 @@ class Chronos2Adapter(TsfmAdapter):
                  bias=w["out_out_b"])
         return ops.chronos2_finalize(preds, b, used, nq, ps, horizon, cc.use_arcsinh, normalization_stats["loc"],
                                      normalization_stats["scale"])
+
+    # ------------------------------------------------------------------ training path (frozen backbone)
+    def _weights_t(self) -> dict[str, object]:
+        """Transposed (dgrad) packs of the frozen weights: dX = dY W as a K-major GEMM on W^T."""
+        w = self._weights()
+        if "t" not in w:
+            prec = PRECISIONS[self.precision]
+            adt = ops.act_dtype(prec)
+            m = self._model
+
+            def pack_t(wt: torch.Tensor) -> torch.Tensor:
+                return ops.cast_rows(_pad_k(wt.detach().float().t().contiguous()), adt)
+
+            ope = m.output_patch_embedding
+            blocks = []
+            for blk in m.encoder.block:
+                t_att, g_att, ff = blk.layer[0], blk.layer[1], blk.layer[2]
+                ta, ga = t_att.self_attention, g_att.self_attention
+                w_ov = (ga.o.weight.detach().double() @ ga.v.weight.detach().double()).float()
+                blocks.append({
+                    "qkv": pack_t(torch.cat([ta.q.weight, ta.k.weight, ta.v.weight], dim=0)), "o": pack_t(ta.o.weight),
+                    "ov": pack_t(w_ov), "wi": pack_t(ff.mlp.wi.weight), "wo": pack_t(ff.mlp.wo.weight),
+                })
+            w["t"] = {"blocks": blocks, "out_hidden": pack_t(ope.hidden_layer.weight),
+                      "out_out": pack_t(ope.output_layer.weight), "out_res": pack_t(ope.residual_layer.weight)}
+        return w["t"]
+
+    def forward_saving(self, input_embeddings: torch.Tensor, masks: torch.Tensor):
+        """``forward`` that keeps what the activation-gradient pass needs: the residual stream at the input of every
+        RMS LayerNorm, the raw qkv of every time attention and the ReLU outputs of every MLP."""
+        m, cc = self._model, self._model.chronos_config
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32
+        w = self._weights()
+        dev = input_embeddings.device
+        b, n, d = input_embeddings.shape
+        nop = cc.max_output_patches
+        extra = 1 if cc.use_reg_token else 0
+        t = n + extra + nop
+        h = torch.empty(b, t, d, dtype=torch.float32, device=dev)
+        h[:, :n] = input_embeddings
+        if extra:
+            h[:, n] = w["reg"]
+        h[:, n + extra:] = self._future_embeds(w, prec, dev)
+        key_mask = torch.ones(b, t, dtype=torch.bool, device=dev)
+        key_mask[:, :n] = ~masks.bool()
+        rows = b * t
+        cur = h.view(rows, d)
+        blocks = w["blocks"]
+        inner = m.num_heads * m.d_kv
+        saved = {"shape": (b, n, t, d), "key_mask": key_mask, "blocks": []}
+        xn = ops.rmsnorm(cur, blocks[0]["ln_t"], m.eps, adt) if blocks else None
+        attn = ops.alloc(rows, inner, adt, dev)
+        a = ops.alloc(rows, d, mid_dt, dev)
+        for i, bw in enumerate(blocks):
+            qkv = ops.alloc(rows, 3 * inner, mid_dt, dev)
+            u = ops.alloc(rows, m.d_ff, adt, dev)
+            h1 = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            h2 = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            h3 = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            ops.gemm([(xn, bw["qkv"], d)], rows, 3 * inner, qkv, mid_dt, precision=prec)
+            ops.encoder_attention(qkv, b, t, m.num_heads, m.d_kv, key_mask, w["inv_freq"], adt, out=attn)
+            ops.gemm([(attn, bw["o"], inner)], rows, d, a, mid_dt, precision=prec)
+            ops.norm_residual_norm(a, cur, None, bw["ln_g"], m.eps, h1, adt, xn)
+            ops.gemm([(xn, bw["ov"], d)], rows, d, a, mid_dt, precision=prec)
+            ops.norm_residual_norm(a, h1, None, bw["ln_f"], m.eps, h2, adt, xn)
+            ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
+            ops.gemm([(u, bw["wo"], m.d_ff)], rows, d, a, mid_dt, precision=prec)
+            nxt = blocks[i + 1]["ln_t"] if i + 1 < len(blocks) else w["final_ln"]
+            last = i + 1 == len(blocks)
+            final = torch.empty(rows, d, dtype=torch.float32, device=dev) if last else None
+            ops.norm_residual_norm(a, h2, None, nxt, m.eps, h3, DT_F32 if last else adt, final if last else xn)
+            saved["blocks"].append({"h0": cur, "h1": h1, "h2": h2, "qkv": qkv, "u": u})
+            cur = h3
+        if not blocks:
+            final = ops.rmsnorm(cur, w["final_ln"], m.eps, DT_F32)
+        saved["h_last"] = cur
+        return final.view(b, t, d)[:, -nop:].contiguous(), saved
+
+    def forward_backward(self, saved, d_out: torch.Tensor) -> torch.Tensor:
+        """dL/d(returned forecast-position embeddings) [B * 64, D] -> dL/d(input embeddings) [B * N, D] fp32."""
+        m = self._model
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32
+        w, wt = self._weights(), self._weights_t()
+        b, n, t, d = saved["shape"]
+        rows = b * t
+        dev = d_out.device
+        nop = m.chronos_config.max_output_patches
+        inner = m.num_heads * m.d_kv
+        g_final = torch.zeros(b, t, d, dtype=torch.float32, device=dev)
+        g_final[:, -nop:] = d_out.view(b, nop, d)
+        g = torch.empty(rows, d, dtype=torch.float32, device=dev)  # running dL/d(residual stream)
+        ops.rmsnorm_bwd_chain(None, saved["h_last"], w["final_ln"], g_final.view(rows, d), None, None, m.eps, g, adt, None,
+                              rows, d)
+        du = ops.alloc(rows, m.d_ff, adt, dev)
+        dxn = ops.alloc(rows, d, mid_dt, dev)
+        dattn = ops.alloc(rows, inner, mid_dt, dev)
+        dqkv = ops.alloc(rows, 3 * inner, adt, dev)
+        blocks, tblocks = w["blocks"], wt["blocks"]
+        for i in reversed(range(len(blocks))):
+            bw, tw, s = blocks[i], tblocks[i], saved["blocks"][i]
+            # feed-forward: h3 = h2 + relu(rms(h2) Wi) Wo
+            ga = ops.cast_rows(g, adt)
+            ops.gemm([(ga, tw["wo"], d)], rows, m.d_ff, du, adt, precision=prec, act=ACT_RELU_GRAD, aux=_hi(s["u"], m.d_ff),
+                     split_off=m.d_ff)
+            ops.gemm([(du, tw["wi"], m.d_ff)], rows, d, dxn, mid_dt, precision=prec)
+            ops.rmsnorm_bwd_chain(g, s["h2"], bw["ln_f"], dxn, None, None, m.eps, g, adt, None, rows, d)
+            # group attention (degenerate: one GEMM): h2 = h1 + rms(h1) Wov
+            ga = ops.cast_rows(g, adt)
+            ops.gemm([(ga, tw["ov"], d)], rows, d, dxn, mid_dt, precision=prec)
+            ops.rmsnorm_bwd_chain(g, s["h1"], bw["ln_g"], dxn, None, None, m.eps, g, adt, None, rows, d)
+            # time attention: h1 = h0 + attn(rms(h0) Wqkv) Wo
+            ga = ops.cast_rows(g, adt)
+            ops.gemm([(ga, tw["o"], d)], rows, inner, dattn, mid_dt, precision=prec)
+            ops.encoder_attention_bwd(s["qkv"], dattn, b, t, m.num_heads, m.d_kv, saved["key_mask"], w["inv_freq"], adt,
+                                      dqkv=dqkv)
+            ops.gemm([(dqkv, tw["qkv"], 3 * inner)], rows, d, dxn, mid_dt, precision=prec)
+            ops.rmsnorm_bwd_chain(g, s["h0"], bw["ln_t"], dxn, None, None, m.eps, g, adt, None, rows, d)
+        return g.view(b, t, d)[:, :n].reshape(b * n, d).contiguous()
+
+    def postprocess_saving(self, horizon: int, output_embeddings: torch.Tensor, normalization_stats):
+        """``postprocess`` that keeps the head's ReLU output and raw predictions for the backward pass."""
+        m, cc = self._model, self._model.chronos_config
+        nop, ps = cc.max_output_patches, cc.output_patch_size
+        if horizon > nop * ps:
+            raise ValueError(
+                f"horizon ({horizon}) exceeds the maximum prediction length ({nop * ps} = {nop} patches * {ps} steps)."
+            )
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        b, _, d = output_embeddings.shape
+        used = (horizon + ps - 1) // ps
+        x = output_embeddings[:, :used].float().reshape(b * used, d).contiguous()
+        xa = ops.cast_rows(x, adt)
+        rows = b * used
+        hid = ops.alloc(rows, m.d_ff, adt, x.device)
+        ops.gemm([(xa, w["out_hidden"], d)], rows, m.d_ff, hid, adt, precision=prec, act=ACT_RELU, bias=w["out_hidden_b"])
+        nq = m.num_quantiles
+        preds = torch.empty(rows, nq * ps, dtype=torch.float32, device=x.device)
+        ops.gemm([(hid, w["out_out"], m.d_ff), (xa, w["out_res"], d)], rows, nq * ps, preds, DT_F32, precision=prec,
+                 bias=w["out_out_b"])
+        out = ops.chronos2_finalize(preds, b, used, nq, ps, horizon, cc.use_arcsinh, normalization_stats["loc"],
+                                    normalization_stats["scale"])
+        saved = {"hid": hid, "preds": preds, "scale": normalization_stats["scale"].reshape(b), "b": b, "used": used,
+                 "horizon": horizon, "d": d}
+        return out, saved
+
+    def postprocess_backward(self, saved, grad_forecast: torch.Tensor) -> torch.Tensor:
+        """dL/d(forecast) [B, h, 21] -> dL/d(output embeddings) [B, 64, D] fp32 (non-zero in the used patches)."""
+        m, cc = self._model, self._model.chronos_config
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        wt = self._weights_t()
+        b, used, horizon, d = saved["b"], saved["used"], saved["horizon"], saved["d"]
+        nop, ps, nq = cc.max_output_patches, cc.output_patch_size, m.num_quantiles
+        rows = b * used
+        dev = grad_forecast.device
+        # undo the finalize epilogue: out[b, t, q] = sinh(preds[b, t // ps, q, t % ps]) * scale[b] + loc[b]
+        g = torch.zeros(b, used * ps, nq, dtype=torch.float32, device=dev)
+        g[:, :horizon] = grad_forecast.reshape(b, horizon, nq) * saved["scale"][:, None, None]
+        g = g.view(b, used, ps, nq).permute(0, 1, 3, 2).reshape(rows, nq * ps)
+        if cc.use_arcsinh:
+            g = g * torch.cosh(saved["preds"])
+        kp = _round64(nq * ps)
+        dpre32 = torch.zeros(rows, kp, dtype=torch.float32, device=dev)
+        dpre32[:, : nq * ps] = g
+        dpre = ops.cast_rows(dpre32, adt)
+        dhid = ops.alloc(rows, m.d_ff, adt, dev)
+        ops.gemm([(dpre, wt["out_out"], kp)], rows, m.d_ff, dhid, adt, precision=prec, act=ACT_RELU_GRAD,
+                 aux=_hi(saved["hid"], m.d_ff), split_off=m.d_ff)
+        dx = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        ops.gemm([(dhid, wt["out_hidden"], m.d_ff), (dpre, wt["out_res"], kp)], rows, d, dx, DT_F32, precision=prec)
+        d_out = torch.zeros(b, nop, d, dtype=torch.float32, device=dev)
+        d_out[:, :used] = dx.view(b, used, d)
+        return d_out
 
     # ------------------------------------------------------------------ checkpoints / freezing
     def load_checkpoint(self, path: str) -> None:

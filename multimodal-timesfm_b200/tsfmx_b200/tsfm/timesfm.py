@@ -469,10 +469,10 @@ class TimesFM2p5Adapter(TsfmAdapter):
         out = torch.empty(b, horizon * m.q, dtype=torch.float32, device=last.device)
         ops.gemm([(hid, w["head_out"], m.md), (a, w["head_res"], d)], b, m.o * m.q, out, DT_F32, precision=prec,
                  row_scale=sigma_last, row_shift=mu_last, n_store=horizon * m.q)
-        return out.view(b, horizon, m.q), {"z": z, "sigma": sigma_last, "horizon": horizon, "b": b}
+        return out.view(b, horizon, m.q), {"z": z, "sigma": sigma_last, "horizon": horizon, "b": b, "n": n}
 
     def postprocess_backward(self, saved, grad_forecast: torch.Tensor) -> torch.Tensor:
-        """dL/d(forecast) [B, h, 10] -> dL/d(last-patch embedding) [B, D] fp32."""
+        """dL/d(forecast) [B, h, 10] -> dL/d(output embeddings) [B, N, D] fp32 (non-zero in the last patch only)."""
         m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -488,7 +488,9 @@ class TimesFM2p5Adapter(TsfmAdapter):
         d_last = torch.empty(b, m.md, dtype=torch.float32, device=dev)
         ops.gemm([(dz, wt["head_hidden"], m.md), (dpre, wt["head_res"], m.o * m.q)], b, m.md, d_last, DT_F32,
                  precision=prec)
-        return d_last
+        d_out = torch.zeros(b, saved["n"], m.md, dtype=torch.float32, device=dev)
+        d_out[:, -1, :] = d_last  # only the last patch feeds the head (reference timesfm.py:129)
+        return d_out
 
     # ------------------------------------------------------------------ checkpoints / freezing
     def load_checkpoint(self, path: str) -> None:

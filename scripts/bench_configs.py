@@ -96,6 +96,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=2048)
+    ap.add_argument("--finetune-batch", type=int, default=1024, help="series per GPU of the fine-tune step")
     args = ap.parse_args()
     rank, world, local_rank = tdist.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
@@ -142,7 +143,7 @@ def main():
         torch.cuda.empty_cache()
 
     if want("finetune"):
-        fb = min(B, 1024)
+        fb = min(B, args.finetune_batch)
         dec = timesfm_decoder(50, dev)
         dec.adapter.freeze_parameters()
         dec.train()

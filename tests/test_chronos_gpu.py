@@ -157,3 +157,63 @@ def test_horizon_limit_error():
         dec.forward_full(1025, ctx.to(DEV), masks.to(DEV), None)
     with pytest.raises(ValueError, match="exceeds the maximum prediction length"):
         oracle.forward_full(1025, ctx, masks, None)
+
+
+# ----------------------------------------------------------------------------- fusion fine-tune through Chronos-2
+@pytest.mark.parametrize("t", [97, 40, 130])
+def test_encoder_attention_bwd(t):
+    """fp32 SIMT backward of the encoder attention core against fp64 torch autograd (partly / fully masked series)."""
+    b, h, hd = 4, 12, 64
+    gen = torch.Generator(device=DEV).manual_seed(t)
+    qkv = torch.randn(b * t, 3 * h * hd, generator=gen, device=DEV)
+    qkv[:, : 2 * h * hd] *= 0.35
+    dout = torch.randn(b * t, h * hd, generator=gen, device=DEV)
+    km = torch.ones(b, t, dtype=torch.bool, device=DEV)
+    km[1, : t // 3] = False
+    km[2, :] = False
+    km[3, 2::3] = False
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(DEV)
+    qd = qkv.double().requires_grad_(True)
+    q, k, v = qd.reshape(b, t, 3, h, hd).permute(2, 0, 3, 1, 4)
+    freqs = torch.arange(t, device=DEV).float()[:, None] * inv_freq[None, :]
+    emb = torch.cat([freqs, freqs], -1)
+    cos, sin = emb.cos().double(), emb.sin().double()
+    q = q * cos + C.rotate_half(q) * sin
+    k = k * cos + C.rotate_half(k) * sin
+    s = q @ k.transpose(-1, -2) + ((~km)[:, None, None, :] * torch.finfo(torch.float32).min).double()
+    out = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, h * hd)
+    (ref,) = torch.autograd.grad(out, qd, dout.double())
+    got = ops.encoder_attention_bwd(qkv, dout, b, t, h, hd, km, inv_freq, DT_F32)
+    for name, sl in (("dq", slice(0, h * hd)), ("dk", slice(h * hd, 2 * h * hd)), ("dv", slice(2 * h * hd, None))):
+        err = ((got[:, sl].double() - ref[:, sl]).norm() / ref[:, sl].norm().clamp_min(1e-30)).item()
+        assert err < 2e-5, (name, err)
+    got_s = ops.encoder_attention_bwd(qkv.to(torch.bfloat16), dout.to(torch.bfloat16), b, t, h, hd, km, inv_freq, DT_BF16_SPLIT)
+    assert rel_max(ops.split_to_float(got_s), ref.float()) < 3e-2
+
+
+@pytest.mark.parametrize("layers,context,horizon,padded", [(2, 512, 64, False), (3, 160, 40, True)])
+def test_fusion_gradient_through_chronos2_matches_oracle(layers, context, horizon, padded):
+    """MSE of the point forecast -> gradient of the fusion weight, CUDA path (hand-written backward through the frozen
+    Chronos-2 encoder) against the restated oracle under torch autograd."""
+    dec, oracle = build(layers)
+    dec.set_precision("bf16x3")
+    dec.adapter.freeze_parameters()
+    dec.train()
+    ctx, masks, text = batch(6, context, horizon, padded)
+    target = torch.randn(6, horizon, generator=torch.Generator().manual_seed(3))
+    for p in oracle.fusion.parameters():
+        p.requires_grad_(True)
+    ref_loss = torch.nn.functional.mse_loss(oracle(horizon, ctx, masks, text), target)
+    (ref_grad,) = torch.autograd.grad(ref_loss, [oracle.fusion.projection[0].weight])
+    loss = torch.nn.functional.mse_loss(dec(horizon, ctx.to(DEV), masks.to(DEV), text.to(DEV)), target.to(DEV))
+    loss.backward()
+    got = dec.fusion.linears()[0].weight.grad.cpu()
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    rel = ((got.double() - ref_grad.double()).norm() / ref_grad.double().norm()).item()
+    assert rel < 1e-3, rel
+    dec.set_precision("bf16")
+    dec.zero_grad()
+    torch.nn.functional.mse_loss(dec(horizon, ctx.to(DEV), masks.to(DEV), text.to(DEV)), target.to(DEV)).backward()
+    got16 = dec.fusion.linears()[0].weight.grad.cpu()
+    rel16 = ((got16.double() - ref_grad.double()).norm() / ref_grad.double().norm()).item()
+    assert rel16 < 1.5e-1, rel16  # bf16 operands through 2-3 blocks of forward and backward GEMMs; stated separately
