@@ -365,6 +365,357 @@ int launch_encoder_attention_mma(const void* qkv, int64_t batch, int seq, int nu
 }
 
 // ----------------------------------------------------------------------------------------
+// Tensor-core backward of the encoder attention core (bf16 qkv / dO in, bf16 dqkv out, T <= 112): one CTA of 7 warps
+// per (series, head), same staging as the forward kernel plus dO.
+//   pass A  warp w owns query tile w: S = QK^T and dP = dO V^T on mma.sync, softmax / delta / dS in registers,
+//           dQ = dS K on the tensor cores, RoPE transposed in registers (a thread's C fragment holds dims d and d + 32
+//           of its rows), row statistics to shared memory
+//   pass B  warp w owns key tile w: P and dS blocks recomputed per query tile, transposed in registers (movmatrix),
+//           dV = P^T dO and dK = dS^T Q; dK un-rotated in registers
+// Results are staged as bf16 tiles and leave with 16-byte coalesced stores.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t enc_movmatrix(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(ENC_WARPS * 32, 1) encoder_attention_bwd_mma_kernel(
+    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, int seq, int num_heads,
+    const uint8_t* __restrict__ key_mask, const float2* __restrict__ rope, __nv_bfloat16* __restrict__ dqkv) {
+  constexpr int ROWS = 16 * NT;
+  constexpr int HALF = ENC_HD / 2;
+  constexpr int TILE = ROWS * ENC_LD;
+  extern __shared__ __align__(16) uint8_t smem_encb[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_encb);
+  __nv_bfloat16* sK = sQ + TILE;
+  __nv_bfloat16* sV = sK + TILE;
+  __nv_bfloat16* sDO = sV + TILE;
+  __nv_bfloat16* sDQ = sDO + TILE;
+  __nv_bfloat16* sDK = sDQ + TILE;
+  __nv_bfloat16* sDV = sDK + TILE;
+  float* sMx = reinterpret_cast<float*>(sDV + TILE);
+  float* sInv = sMx + ROWS;
+  float* sDelta = sInv + ROWS;
+  uint8_t* s_valid = reinterpret_cast<uint8_t*>(sDelta + ROWS);
+  __shared__ int s_any;
+  const int T = seq;
+  const int b = blockIdx.x / num_heads, h = blockIdx.x - b * num_heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int width = num_heads * ENC_HD;
+  const int64_t ld = 3 * static_cast<int64_t>(width);
+  const __nv_bfloat16* gbase = qkv + static_cast<int64_t>(b) * T * ld + h * ENC_HD;
+  const __nv_bfloat16* dobase = dout + static_cast<int64_t>(b) * T * width + h * ENC_HD;
+
+  if (threadIdx.x == 0) s_any = 0;
+  for (int c = threadIdx.x; c < T * 8; c += blockDim.x) {
+    const int row = c >> 3, ch = c & 7;
+    enc_cp_async_16(sV + row * ENC_LD + ch * 8, gbase + row * ld + 2 * width + ch * 8);
+    enc_cp_async_16(sDO + row * ENC_LD + ch * 8, dobase + static_cast<int64_t>(row) * width + ch * 8);
+  }
+  for (int c = threadIdx.x; c < (ROWS - T) * 8 * 4; c += blockDim.x) {
+    const int which = c / ((ROWS - T) * 8), rem = c - which * ((ROWS - T) * 8);
+    const int row = T + (rem >> 3), ch = rem & 7;
+    *reinterpret_cast<uint4*>(sQ + which * TILE + row * ENC_LD + ch * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  {
+    int any = 0;
+    for (int j = threadIdx.x; j < ROWS; j += blockDim.x) {
+      const uint8_t v = j < T && (key_mask == nullptr || key_mask[static_cast<int64_t>(b) * T + j] != 0) ? 1 : 0;
+      s_valid[j] = v;
+      any |= v;
+    }
+    if (any) s_any = 1;
+  }
+  for (int c = threadIdx.x; c < T * 4; c += blockDim.x) {
+    const int row = c >> 2, ch = c & 3;
+    const __nv_bfloat16* g = gbase + row * ld + ch * 8;
+    const uint4 qa = *reinterpret_cast<const uint4*>(g), qb = *reinterpret_cast<const uint4*>(g + HALF);
+    const uint4 ka = *reinterpret_cast<const uint4*>(g + width), kb = *reinterpret_cast<const uint4*>(g + width + HALF);
+    const float4* rp = reinterpret_cast<const float4*>(rope + row * HALF + ch * 8);
+    const uint32_t qaw[4] = {qa.x, qa.y, qa.z, qa.w}, qbw[4] = {qb.x, qb.y, qb.z, qb.w};
+    const uint32_t kaw[4] = {ka.x, ka.y, ka.z, ka.w}, kbw[4] = {kb.x, kb.y, kb.z, kb.w};
+    uint32_t oq1[4], oq2[4], ok1[4], ok2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 cs = __ldg(rp + i);
+      const float q1a = bf16_lo(qaw[i]), q1b = bf16_hi(qaw[i]), q2a = bf16_lo(qbw[i]), q2b = bf16_hi(qbw[i]);
+      const float k1a = bf16_lo(kaw[i]), k1b = bf16_hi(kaw[i]), k2a = bf16_lo(kbw[i]), k2b = bf16_hi(kbw[i]);
+      oq1[i] = pack_bf16x2(q1a * cs.x - q2a * cs.y, q1b * cs.z - q2b * cs.w);
+      oq2[i] = pack_bf16x2(q2a * cs.x + q1a * cs.y, q2b * cs.z + q1b * cs.w);
+      ok1[i] = pack_bf16x2(k1a * cs.x - k2a * cs.y, k1b * cs.z - k2b * cs.w);
+      ok2[i] = pack_bf16x2(k2a * cs.x + k1a * cs.y, k2b * cs.z + k1b * cs.w);
+    }
+    *reinterpret_cast<uint4*>(sQ + row * ENC_LD + ch * 8) = make_uint4(oq1[0], oq1[1], oq1[2], oq1[3]);
+    *reinterpret_cast<uint4*>(sQ + row * ENC_LD + HALF + ch * 8) = make_uint4(oq2[0], oq2[1], oq2[2], oq2[3]);
+    *reinterpret_cast<uint4*>(sK + row * ENC_LD + ch * 8) = make_uint4(ok1[0], ok1[1], ok1[2], ok1[3]);
+    *reinterpret_cast<uint4*>(sK + row * ENC_LD + HALF + ch * 8) = make_uint4(ok2[0], ok2[1], ok2[2], ok2[3]);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  const bool has_key = s_any != 0;
+  const int g = lane >> 2, t = lane & 3;
+  const int ntk = (T + 15) >> 4;
+  const uint32_t sq_addr = smem_u32(sQ), sk_addr = smem_u32(sK), sv_addr = smem_u32(sV), sdo_addr = smem_u32(sDO);
+  const float inv_T = 1.0f / static_cast<float>(T);
+
+  // un-rotate a 16 x 64 fp32 C-fragment block (rows row0 = base + g and row0 + 8) and park it as bf16
+  auto unrotate_store = [&](float (&acc)[8][4], int tile_row0, __nv_bfloat16* dst) {
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int row = tile_row0 + g + 8 * hrow;
+      const int rr = row < T ? row : 0;
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(rope + rr * HALF + dt * 8 + 2 * t));  // dims d, d + 1
+        const float a0 = acc[dt][2 * hrow], a1 = acc[dt][2 * hrow + 1];          // dims d, d + 1
+        const float b0 = acc[dt + 4][2 * hrow], b1 = acc[dt + 4][2 * hrow + 1];  // dims d + 32, d + 33
+        *reinterpret_cast<uint32_t*>(dst + row * ENC_LD + dt * 8 + 2 * t) = pack_bf16x2(a0 * cs.x + b0 * cs.y, a1 * cs.z + b1 * cs.w);
+        *reinterpret_cast<uint32_t*>(dst + row * ENC_LD + HALF + dt * 8 + 2 * t) =
+            pack_bf16x2(b0 * cs.x - a0 * cs.y, b1 * cs.z - a1 * cs.w);
+      }
+    }
+  };
+
+  // ---- pass A: per query tile
+  for (int qi = warp; qi < ntk; qi += ENC_WARPS) {
+    uint32_t qf[4][4], df[4][4];
+    {
+      const int row = qi * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+      const int col = 8 * (lane >> 4);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        enc_ldmatrix_x4(sq_addr + (row * ENC_LD + col + 16 * ks) * 2, qf[ks]);
+        enc_ldmatrix_x4(sdo_addr + (row * ENC_LD + col + 16 * ks) * 2, df[ks]);
+      }
+    }
+    float s[NT][2][4], dp[NT][2][4];
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[kj][nt][e] = 0.f, dp[kj][nt][e] = 0.f;
+      if (kj < ntk) {
+        const int key = kj * 16 + (lane & 7) + 8 * (lane >> 4);
+        const int col = 8 * ((lane >> 3) & 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t kb[4], vb[4];
+          enc_ldmatrix_x4(sk_addr + (key * ENC_LD + col + 16 * ks) * 2, kb);
+          enc_mma_16816(s[kj][0], qf[ks], kb[0], kb[1]);
+          enc_mma_16816(s[kj][1], qf[ks], kb[2], kb[3]);
+          enc_ldmatrix_x4(sv_addr + (key * ENC_LD + col + 16 * ks) * 2, vb);
+          enc_mma_16816(dp[kj][0], df[ks], vb[0], vb[1]);
+          enc_mma_16816(dp[kj][1], df[ks], vb[2], vb[3]);
+        }
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int key = kj * 16 + nt * 8 + 2 * t;
+        const uint32_t vv = *reinterpret_cast<const uint16_t*>(s_valid + key);
+        const bool ok0 = has_key ? (vv & 0xffu) != 0 : key < T;
+        const bool ok1 = has_key ? (vv >> 8) != 0 : key + 1 < T;
+        s[kj][nt][0] = ok0 ? (has_key ? s[kj][nt][0] : 0.f) : -INFINITY;
+        s[kj][nt][1] = ok1 ? (has_key ? s[kj][nt][1] : 0.f) : -INFINITY;
+        s[kj][nt][2] = ok0 ? (has_key ? s[kj][nt][2] : 0.f) : -INFINITY;
+        s[kj][nt][3] = ok1 ? (has_key ? s[kj][nt][3] : 0.f) : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[kj][nt][0], s[kj][nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[kj][nt][2], s[kj][nt][3]));
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float mx = (e & 2) ? mx1 : mx0;
+          const float p = s[kj][nt][e] == -INFINITY ? 0.f : __expf(s[kj][nt][e] - mx);
+          s[kj][nt][e] = p;
+          if (e & 2) sum1 += p; else sum0 += p;
+        }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p = s[kj][nt][e] * ((e & 2) ? inv1 : inv0);
+          s[kj][nt][e] = p;
+          if (e & 2) dl1 += p * dp[kj][nt][e]; else dl0 += p * dp[kj][nt][e];
+        }
+    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
+    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
+    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+    const int row0 = qi * 16 + g, row1 = row0 + 8;
+    if (t == 0) {
+      sMx[row0] = mx0, sInv[row0] = inv0, sDelta[row0] = dl0;
+      sMx[row1] = mx1, sInv[row1] = inv1, sDelta[row1] = dl1;
+    }
+    float dq[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dq[dt][e] = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < NT; ++kj) {
+      if (kj < ntk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[kj][0][0] * (dp[kj][0][0] - dl0), s[kj][0][1] * (dp[kj][0][1] - dl0));
+        pa[1] = pack_bf16x2(s[kj][0][2] * (dp[kj][0][2] - dl1), s[kj][0][3] * (dp[kj][0][3] - dl1));
+        pa[2] = pack_bf16x2(s[kj][1][0] * (dp[kj][1][0] - dl0), s[kj][1][1] * (dp[kj][1][1] - dl0));
+        pa[3] = pack_bf16x2(s[kj][1][2] * (dp[kj][1][2] - dl1), s[kj][1][3] * (dp[kj][1][3] - dl1));
+        const int key = kj * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int col = 8 * (lane >> 4);
+#pragma unroll
+        for (int dpp = 0; dpp < 4; ++dpp) {
+          uint32_t kb[4];
+          enc_ldmatrix_x4_trans(sk_addr + (key * ENC_LD + col + 16 * dpp) * 2, kb);
+          enc_mma_16816(dq[2 * dpp], pa, kb[0], kb[1]);
+          enc_mma_16816(dq[2 * dpp + 1], pa, kb[2], kb[3]);
+        }
+      }
+    }
+    unrotate_store(dq, qi * 16, sDQ);
+  }
+  __syncthreads();
+
+  // ---- pass B: per key tile
+  for (int kj = warp; kj < ntk; kj += ENC_WARPS) {
+    float dv[8][4], dk[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dv[dt][e] = 0.f, dk[dt][e] = 0.f;
+    uint32_t kf[4][4], vf[4][4];
+    {
+      const int key = kj * 16 + (lane & 7) + 8 * (lane >> 4);
+      const int col = 8 * ((lane >> 3) & 1);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        enc_ldmatrix_x4(sk_addr + (key * ENC_LD + col + 16 * ks) * 2, kf[ks]);
+        enc_ldmatrix_x4(sv_addr + (key * ENC_LD + col + 16 * ks) * 2, vf[ks]);
+      }
+    }
+    bool okk[2][2];  // [nt][e & 1]: validity of this thread's keys in the tile
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int key = kj * 16 + nt * 8 + 2 * t;
+      const uint32_t vv = *reinterpret_cast<const uint16_t*>(s_valid + key);
+      okk[nt][0] = has_key ? (vv & 0xffu) != 0 : key < T;
+      okk[nt][1] = has_key ? (vv >> 8) != 0 : key + 1 < T;
+    }
+#pragma unroll 1
+    for (int qi = 0; qi < ntk; ++qi) {
+      float s2[2][4], dp2[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s2[nt][e] = 0.f, dp2[nt][e] = 0.f;
+      const int qrow = qi * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+      const int qcol = 8 * (lane >> 4);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qa[4], da[4];
+        enc_ldmatrix_x4(sq_addr + (qrow * ENC_LD + qcol + 16 * ks) * 2, qa);
+        enc_ldmatrix_x4(sdo_addr + (qrow * ENC_LD + qcol + 16 * ks) * 2, da);
+        enc_mma_16816(s2[0], qa, kf[ks][0], kf[ks][1]);
+        enc_mma_16816(s2[1], qa, kf[ks][2], kf[ks][3]);
+        enc_mma_16816(dp2[0], da, vf[ks][0], vf[ks][1]);
+        enc_mma_16816(dp2[1], da, vf[ks][2], vf[ks][3]);
+      }
+      const int row0 = qi * 16 + g, row1 = row0 + 8;
+      const float mx0 = sMx[row0], mx1 = sMx[row1], inv0 = sInv[row0], inv1 = sInv[row1];
+      const float dl0 = sDelta[row0], dl1 = sDelta[row1];
+      float p[2][4], ds[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = (e & 2) ? row1 : row0;
+          float pv = 0.f;
+          if (okk[nt][e & 1] && row < T)
+            pv = has_key ? __expf(s2[nt][e] - ((e & 2) ? mx1 : mx0)) * ((e & 2) ? inv1 : inv0) : inv_T;
+          p[nt][e] = pv;
+          ds[nt][e] = pv * (dp2[nt][e] - ((e & 2) ? dl1 : dl0));
+        }
+      uint32_t pT[4], dsT[4];
+      pT[0] = enc_movmatrix(pack_bf16x2(p[0][0], p[0][1]));
+      pT[1] = enc_movmatrix(pack_bf16x2(p[1][0], p[1][1]));
+      pT[2] = enc_movmatrix(pack_bf16x2(p[0][2], p[0][3]));
+      pT[3] = enc_movmatrix(pack_bf16x2(p[1][2], p[1][3]));
+      dsT[0] = enc_movmatrix(pack_bf16x2(ds[0][0], ds[0][1]));
+      dsT[1] = enc_movmatrix(pack_bf16x2(ds[1][0], ds[1][1]));
+      dsT[2] = enc_movmatrix(pack_bf16x2(ds[0][2], ds[0][3]));
+      dsT[3] = enc_movmatrix(pack_bf16x2(ds[1][2], ds[1][3]));
+#pragma unroll
+      for (int dpp = 0; dpp < 4; ++dpp) {
+        uint32_t ob[4], qb[4];
+        enc_ldmatrix_x4_trans(sdo_addr + (qrow * ENC_LD + qcol + 16 * dpp) * 2, ob);
+        enc_mma_16816(dv[2 * dpp], pT, ob[0], ob[1]);
+        enc_mma_16816(dv[2 * dpp + 1], pT, ob[2], ob[3]);
+        enc_ldmatrix_x4_trans(sq_addr + (qrow * ENC_LD + qcol + 16 * dpp) * 2, qb);
+        enc_mma_16816(dk[2 * dpp], dsT, qb[0], qb[1]);
+        enc_mma_16816(dk[2 * dpp + 1], dsT, qb[2], qb[3]);
+      }
+    }
+    unrotate_store(dk, kj * 16, sDK);
+    const int key0 = kj * 16 + g, key1 = key0 + 8;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      *reinterpret_cast<uint32_t*>(sDV + key0 * ENC_LD + dt * 8 + 2 * t) = pack_bf16x2(dv[dt][0], dv[dt][1]);
+      *reinterpret_cast<uint32_t*>(sDV + key1 * ENC_LD + dt * 8 + 2 * t) = pack_bf16x2(dv[dt][2], dv[dt][3]);
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* obase = dqkv + static_cast<int64_t>(b) * T * ld + h * ENC_HD;
+  for (int c = threadIdx.x; c < T * 8; c += blockDim.x) {
+    const int row = c >> 3, ch = c & 7;
+    __nv_bfloat16* o = obase + row * ld + ch * 8;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(sDQ + row * ENC_LD + ch * 8);
+    *reinterpret_cast<uint4*>(o + width) = *reinterpret_cast<const uint4*>(sDK + row * ENC_LD + ch * 8);
+    *reinterpret_cast<uint4*>(o + 2 * width) = *reinterpret_cast<const uint4*>(sDV + row * ENC_LD + ch * 8);
+  }
+}
+
+template <int NT>
+int launch_encoder_attention_bwd_mma(const void* qkv, const void* dout, int64_t batch, int seq, int num_heads,
+                                     const uint8_t* key_mask, const float* rope, void* dqkv, cudaStream_t stream) {
+  constexpr int smem = 7 * 16 * NT * ENC_LD * 2 + 3 * 16 * NT * 4 + 16 * NT;
+  auto kern = encoder_attention_bwd_mma_kernel<NT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("encoder_attention_bwd_mma: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+      return TSFMX_ERR_CUDA;
+    }
+  }
+  kern<<<static_cast<int>(batch * num_heads), ENC_WARPS * 32, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout), seq, num_heads, key_mask,
+      reinterpret_cast<const float2*>(rope), reinterpret_cast<__nv_bfloat16*>(dqkv));
+  return check_last_launch("encoder_attention_bwd_mma");
+}
+
+// ----------------------------------------------------------------------------------------
 // Backward of the encoder attention core (fusion fine-tune through the frozen Chronos-2 encoder; the reference trains
 // the fusion module with either adapter, scripts/tune_time_mmd_sweep.py:124-126).  fp32 SIMT, any T, exact up to
 // summation order: pass A gives one warp to a query row (P, dP, delta, dS -> dq, and the row's softmax statistics
@@ -609,6 +960,16 @@ extern "C" int tsfmx_encoder_attention_bwd(const void* qkv, int32_t qkv_dtype, c
     return TSFMX_ERR_UNSUPPORTED;
   }
   if (batch == 0) return TSFMX_OK;
+  {
+    auto al16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
+    if (qkv_dtype == TSFMX_DT_BF16 && dout_dtype == TSFMX_DT_BF16 && dqkv_dtype == TSFMX_DT_BF16 && seq <= 112 &&
+        al16(qkv) && al16(d_out) && al16(dqkv) && al16(rope_table) && !g_force_simt_attention &&
+        batch * num_heads < (int64_t(1) << 31)) {
+      if (seq <= 64)
+        return launch_encoder_attention_bwd_mma<4>(qkv, d_out, batch, seq, num_heads, key_mask, rope_table, dqkv, stream);
+      return launch_encoder_attention_bwd_mma<7>(qkv, d_out, batch, seq, num_heads, key_mask, rope_table, dqkv, stream);
+    }
+  }
   const int smem = 4 * 2 * seq * static_cast<int>(sizeof(float));
   TSFMX_REQUIRE(smem <= 200 * 1024, "encoder_attention_bwd: %d tokens need %d bytes of shared memory", seq, smem);
   const int64_t units = batch * num_heads * seq;

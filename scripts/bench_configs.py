@@ -172,6 +172,35 @@ def main():
         del dec, trainer, data
         torch.cuda.empty_cache()
 
+    if want("finetune_chronos2"):
+        fb = min(B, args.finetune_batch)
+        dec = chronos2_decoder(dev)
+        dec.adapter.freeze_parameters()
+        dec.train()
+        targs = types.SimpleNamespace(per_device_train_batch_size=fb, per_device_eval_batch_size=fb,
+                                      gradient_accumulation_steps=1, max_grad_norm=1.0, learning_rate=1e-4,
+                                      weight_decay=0.01, num_train_epochs=1, logging_steps=1, seed=0)
+        from tsfmx_b200.trainer import MultimodalTrainer
+
+        dummy = [{"context": torch.zeros(512).numpy(), "horizon": torch.zeros(128).numpy(),
+                  "text_embeddings": torch.zeros(32, 384).numpy(), "metadata": {}}]
+        trainer = MultimodalTrainer(dec, targs, dummy, dummy, "multimodal", dev)
+        trainer.rank, trainer.world_size = 0, 1  # the batches below are already this rank's shard
+        data = [batch_for(dec.adapter, fb, 512, 128, 4321 + 17 * rank + i, dev) for i in range(2)]
+
+        def step_c2(i):
+            c, m, t, h = data[i % 2]
+            loss = trainer._forward_loss({"context": c, "horizon": h, "text_embeddings": t})
+            loss.backward()
+            trainer.optimizer_step()
+
+        ms, n = timed(step_c2, args.steps, args.warmup, world, dev)
+        emit(rank, "cfg4-finetune-chronos2", f"Chronos-2 (12 x 768) + 1-layer fusion, ctx 512 / h 128, {fb} series per GPU, "
+             "fusion fine-tune step (fwd + dgrad + fusion wgrad + all-reduce + AdamW)", fb, ms, args.steps, args.warmup,
+             world, n)
+        del dec, trainer, data
+        torch.cuda.empty_cache()
+
     if want("longctx"):
         dec = timesfm_decoder(50, dev).eval()
         data = [batch_for(dec.adapter, B, 2048, 128, 99 + 17 * rank + i, dev) for i in range(2)]

@@ -189,6 +189,20 @@ def test_encoder_attention_bwd(t):
         assert err < 2e-5, (name, err)
     got_s = ops.encoder_attention_bwd(qkv.to(torch.bfloat16), dout.to(torch.bfloat16), b, t, h, hd, km, inv_freq, DT_BF16_SPLIT)
     assert rel_max(ops.split_to_float(got_s), ref.float()) < 3e-2
+    # bf16 in / bf16 out: the tensor-core kernel for T <= 112, the SIMT one above
+    qb, db = qkv.to(torch.bfloat16), dout.to(torch.bfloat16)
+    qd2 = qb.double().requires_grad_(True)
+    q2, k2, v2 = qd2.reshape(b, t, 3, h, hd).permute(2, 0, 3, 1, 4)
+    q2 = q2 * cos + C.rotate_half(q2) * sin
+    k2 = k2 * cos + C.rotate_half(k2) * sin
+    s2 = q2 @ k2.transpose(-1, -2) + ((~km)[:, None, None, :] * torch.finfo(torch.float32).min).double()
+    out2 = (torch.softmax(s2, -1) @ v2).transpose(1, 2).reshape(b * t, h * hd)
+    (ref2,) = torch.autograd.grad(out2, qd2, db.double())
+    got_b = ops.encoder_attention_bwd(qb, db, b, t, h, hd, km, inv_freq, DT_BF16)
+    assert got_b.dtype == torch.bfloat16
+    for name, sl in (("dq", slice(0, h * hd)), ("dk", slice(h * hd, 2 * h * hd)), ("dv", slice(2 * h * hd, None))):
+        err = ((got_b[:, sl].double() - ref2[:, sl]).norm() / ref2[:, sl].norm().clamp_min(1e-30)).item()
+        assert err < 2e-2, (name, err, t)
 
 
 @pytest.mark.parametrize("layers,context,horizon,padded", [(2, 512, 64, False), (3, 160, 40, True)])
