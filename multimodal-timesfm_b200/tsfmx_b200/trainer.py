@@ -5,7 +5,8 @@ Kept from the reference: the class name, constructor arguments, "multimodal" = f
 (trainer.py:76-77,119-123), loss / accumulation / clip / step order (trainer.py:200-219), ``RuntimeError`` on empty
 datasets, checkpoint dictionary keys (types.py:42-61).  Added for the B200 box: data parallelism — each rank takes its
 slice of every batch and the fusion gradients are averaged with one NCCL all-reduce per optimizer step, before the
-clip.  Not rebuilt (host-side, out of the hot path): W&B logging, checkpoint rotation, "baseline" full fine-tuning.
+clip; checkpoints are written by rank 0.  Not rebuilt: "baseline" full fine-tuning of the adapter (needs backbone
+weight gradients).
 """
 
 from __future__ import annotations
@@ -161,12 +162,33 @@ class MultimodalTrainer:
         return float(total.item()) / num_batches
 
     def train(self) -> None:
+        """Epoch loop of the reference (trainer.py:356-399): train, validate, log, checkpoint, optionally reload the best
+        fusion weights at the end.  Raises NotImplementedError for eval strategies other than "epoch"."""
+        strategy = getattr(self.args, "eval_strategy", "epoch")
+        if strategy != "epoch":
+            raise NotImplementedError(f"eval_strategy={strategy!r} is not supported; only 'epoch' is implemented.")
         for epoch in range(self.args.num_train_epochs):
             self.current_epoch = epoch
-            self.train_epoch()
-            val = self.validate_epoch()
-            self.best_val_loss = min(self.best_val_loss, val)
+            epoch_lr = self.optimizer.param_groups[0]["lr"]
+            train_loss = self.train_epoch()
+            val_loss = self.validate_epoch()
+            if self._wandb_run is not None and self.rank == 0:
+                if getattr(self.args, "logging_strategy", "epoch") == "epoch":
+                    self._wandb_run.log({"train/loss": train_loss, "train/lr": epoch_lr, "val/loss": val_loss},
+                                        step=self.global_step)
+                else:
+                    self._wandb_run.log({"val/loss": val_loss}, step=self.global_step)
+            if getattr(self.args, "save_strategy", "no") in ("epoch", "best"):
+                self.save_checkpoint(val_loss)
+            else:
+                self.best_val_loss = min(self.best_val_loss, val_loss)
+        if getattr(self.args, "load_best_model_at_end", False):
+            best = self.args.checkpoint_dir / "best_model.pt"
+            world_barrier()  # rank 0 has finished writing
+            if best.exists():
+                self._load_checkpoint_state(torch.load(best, weights_only=True, map_location=self.device))
 
+    # ------------------------------------------------------------------ checkpoints (rank 0 writes; every rank reads)
     def build_checkpoint(self) -> dict[str, Any]:
         """Same keys as the reference ``MultimodalCheckpoint`` (types.py:42-56, trainer.py:285-303)."""
         return {
@@ -177,3 +199,46 @@ class MultimodalTrainer:
             "best_val_loss": self.best_val_loss,
             "fusion_state_dict": self.model.fusion.state_dict(),
         }
+
+    _build_checkpoint = build_checkpoint  # the reference's (private) name
+
+    def _load_checkpoint_state(self, checkpoint: dict[str, Any]) -> None:
+        """Restore the trained module from a checkpoint dict (reference trainer.py:305-310)."""
+        self.model.fusion.load_state_dict(checkpoint["fusion_state_dict"])
+
+    def _rotate_checkpoints(self) -> None:
+        """Keep the ``save_total_limit`` most recent ``checkpoint_epoch_*.pt`` files (reference trainer.py:312-323)."""
+        limit = getattr(self.args, "save_total_limit", None)
+        if limit is None:
+            return
+        files = sorted(self.args.checkpoint_dir.glob("checkpoint_epoch_*.pt"), key=lambda f: int(f.stem.rsplit("_", 1)[-1]))
+        for stale in files[: max(0, len(files) - limit)]:
+            stale.unlink()
+
+    def save_checkpoint(self, val_loss: float) -> None:
+        """"epoch": write ``checkpoint_epoch_{n}.pt`` every epoch (rotated) and ``best_model.pt`` on improvement;
+        "best": write ``best_model.pt`` only on improvement (reference trainer.py:325-354).  Data-parallel runs hold
+        identical weights on every rank, so only rank 0 touches the file system."""
+        is_best = val_loss < self.best_val_loss
+        if is_best:
+            self.best_val_loss = val_loss
+        strategy = getattr(self.args, "save_strategy", "epoch")
+        if strategy == "best" and not is_best:
+            return
+        if self.rank != 0:
+            return
+        checkpoint = self.build_checkpoint()
+        self.args.checkpoint_dir.mkdir(parents=True, exist_ok=True)
+        if strategy == "epoch":
+            torch.save(checkpoint, self.args.checkpoint_dir / f"checkpoint_epoch_{self.current_epoch}.pt")
+            self._rotate_checkpoints()
+        if is_best:
+            torch.save(checkpoint, self.args.checkpoint_dir / "best_model.pt")
+
+
+def world_barrier() -> None:
+    """Barrier across ranks when a process group exists (checkpoint files are written by rank 0 only)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()

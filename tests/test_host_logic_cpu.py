@@ -84,3 +84,42 @@ def test_state_dict_keys_follow_upstream_names():
         assert k in t5, k
     dec = MultimodalDecoder(TimesFM2p5Adapter(num_layers=1, with_quantile_head=False), MultimodalDecoderConfig(384, 3, [512, 256]))
     assert [k for k in dec.fusion.state_dict()] == ["projection.0.weight", "projection.2.weight", "projection.4.weight"]
+
+
+def test_trainer_checkpoint_strategies(tmp_path):
+    """save_checkpoint / rotation / best-model reload follow the reference (trainer.py:285-354); pure host logic, driven
+    on a trainer object whose model never runs."""
+    import types
+
+    from tsfmx_b200.trainer import MultimodalTrainer
+
+    dec = MultimodalDecoder(TimesFM2p5Adapter(num_layers=1, with_quantile_head=False), MultimodalDecoderConfig())
+    args = types.SimpleNamespace(per_device_train_batch_size=2, per_device_eval_batch_size=2, gradient_accumulation_steps=1,
+                                 max_grad_norm=1.0, learning_rate=1e-3, weight_decay=0.0, num_train_epochs=1, seed=0,
+                                 save_strategy="epoch", save_total_limit=2, checkpoint_dir=tmp_path / "ckpt")
+    dummy = [{"context": torch.zeros(64).numpy(), "horizon": torch.zeros(8).numpy(),
+              "text_embeddings": torch.zeros(2, 384).numpy(), "metadata": {}}] * 2
+    tr = MultimodalTrainer(dec, args, dummy, dummy, "multimodal", torch.device("cpu"))
+    assert all(not p.requires_grad for p in dec.adapter.parameters())  # multimodal mode freezes the adapter
+    for epoch, val in enumerate([0.9, 0.5, 0.7, 0.6]):
+        tr.current_epoch = epoch
+        tr.save_checkpoint(val)
+    names = sorted(p.name for p in args.checkpoint_dir.iterdir())
+    assert names == ["best_model.pt", "checkpoint_epoch_2.pt", "checkpoint_epoch_3.pt"]
+    best = torch.load(args.checkpoint_dir / "best_model.pt", weights_only=True)
+    assert best["epoch"] == 1 and best["best_val_loss"] == 0.5
+    assert set(best) == {"epoch", "global_step", "optimizer_state_dict", "scheduler_state_dict", "best_val_loss",
+                         "fusion_state_dict"}
+    with torch.no_grad():
+        dec.fusion.linears()[0].weight.zero_()
+    tr._load_checkpoint_state(best)
+    assert float(dec.fusion.linears()[0].weight.detach().abs().sum()) > 0
+    args.save_strategy = "best"
+    tr.current_epoch = 4
+    tr.save_checkpoint(0.8)  # not an improvement: nothing written
+    assert not (args.checkpoint_dir / "checkpoint_epoch_4.pt").exists()
+    args.eval_strategy = "steps"
+    with pytest.raises(NotImplementedError):
+        tr.train()
+    with pytest.raises(NotImplementedError):
+        MultimodalTrainer(dec, args, dummy, dummy, "baseline", torch.device("cpu"))
