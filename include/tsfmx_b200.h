@@ -281,6 +281,8 @@ int tsfmx_encoder_attention_bwd(const void* qkv, int32_t qkv_dtype, const void* 
  *     a query whose admissible keys are all masked attends uniformly to them (finfo.min semantics).
  *   q [B, tq] rows of stride ldq (series stride q_batch_stride, both in elements), k / v likewise with tk rows;
  *   head h owns columns [64 h, 64 h + 64) of every row; out rows of stride ldo, width num_heads * 64.
+ *   kv_batch_div >= 1: query series b reads the keys / values / mask of series b / kv_batch_div (the sample paths of
+ *   one series share the encoder-side keys and values).
  *
  * tsfmx_t5_encoder_attention_mma: throughput mode of the encoder self-attention (bidirectional, key mask, bias table
  *   [num_heads, 2 seq - 1] indexed by (key - query) + seq - 1): qkv bf16 [B*seq, 3*H*64] = [q | k | v], out bf16
@@ -292,7 +294,8 @@ int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, int64_t q_ba
                        int32_t kv_dtype, int64_t ldk, int64_t ldv, int64_t kv_batch_stride, int64_t batch, int32_t tq,
                        int32_t tk, int32_t num_heads, int32_t head_dim, int32_t q_pos0, int32_t causal,
                        const uint8_t* key_mask, const float* bias, int32_t bias_len, int32_t bias_zero,
-                       int32_t out_dtype, void* out, int64_t ldo, int64_t o_batch_stride, void* stream);
+                       int32_t out_dtype, void* out, int64_t ldo, int64_t o_batch_stride, int32_t kv_batch_div,
+                       void* stream);
 int tsfmx_t5_encoder_attention_mma(const void* qkv, int64_t batch, int32_t seq, int32_t num_heads, int32_t head_dim,
                                    const uint8_t* key_mask, const float* bias, void* out, void* stream);
 

@@ -44,6 +44,8 @@ struct T5AttnParams {
   int q_dtype, kv_dtype;
   int64_t ldq, ldk, ldv;        // row strides in elements
   int64_t q_batch_stride, kv_batch_stride;  // elements between consecutive series
+  int kv_batch_div;             // query batch index b reads keys / values / mask of series b / kv_batch_div (sample paths
+                                // of one series share the encoder's cross-attention keys and values)
   int tq, tk, num_heads;
   int q_pos0;                   // position of query row 0 (decode step); key j has position j
   int causal;                   // key allowed iff j <= q_pos0 + i
@@ -93,10 +95,11 @@ __global__ void __launch_bounds__(128) t5_attention_kernel(const T5AttnParams p)
     const int64_t qoff = b * p.q_batch_stride + i * p.ldq + h * T5_HD;
     float q[T5_HD];
     t5_load_row64(p.q, p.q_dtype, qoff, q);
-    const uint8_t* km = p.key_mask != nullptr ? p.key_mask + static_cast<int64_t>(b) * p.tk : nullptr;
+    const int64_t bk = b / p.kv_batch_div;
+    const uint8_t* km = p.key_mask != nullptr ? p.key_mask + bk * p.tk : nullptr;
     const float* bias = p.bias != nullptr ? p.bias + static_cast<int64_t>(h) * p.bias_len : nullptr;
     const int jend = p.causal ? min(p.tk, qpos + 1) : p.tk;
-    const int64_t kbase = b * p.kv_batch_stride + h * T5_HD;
+    const int64_t kbase = bk * p.kv_batch_stride + h * T5_HD;
     float mx = -INFINITY;
     bool any = false;
     for (int j = lane; j < jend; j += 32) {
@@ -413,7 +416,7 @@ extern "C" int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, i
                                   int64_t batch, int32_t tq, int32_t tk, int32_t num_heads, int32_t head_dim,
                                   int32_t q_pos0, int32_t causal, const uint8_t* key_mask, const float* bias,
                                   int32_t bias_len, int32_t bias_zero, int32_t out_dtype, void* out, int64_t ldo,
-                                  int64_t o_batch_stride, void* stream_) {
+                                  int64_t o_batch_stride, int32_t kv_batch_div, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TSFMX_REQUIRE(q != nullptr && k != nullptr && v != nullptr && out != nullptr, "t5_attention: NULL pointer");
   TSFMX_REQUIRE(batch >= 0 && tq > 0 && tk > 0 && num_heads > 0, "t5_attention: bad sizes");
@@ -441,6 +444,7 @@ extern "C" int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, i
   p.tq = tq, p.tk = tk, p.num_heads = num_heads, p.q_pos0 = q_pos0, p.causal = causal;
   p.key_mask = key_mask, p.bias = bias, p.bias_len = bias_len, p.bias_zero = bias_zero;
   p.out = out, p.out_dtype = out_dtype, p.ldo = ldo, p.o_batch_stride = o_batch_stride;
+  p.kv_batch_div = kv_batch_div < 1 ? 1 : kv_batch_div;
   const int smem = 4 * tk * static_cast<int>(sizeof(float));
   if (smem > 200 * 1024) {
     set_error("t5_attention: %d keys need %d bytes of shared memory; unsupported", tk, smem);

@@ -113,7 +113,7 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int32,
         [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32,
          c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64,
-         c_int64, c_void_p],
+         c_int64, c_int32, c_void_p],
     ),
     "tsfmx_t5_encoder_attention_mma": (
         c_int32,

@@ -504,6 +504,7 @@ def t5_attention(
     key_mask: torch.Tensor | None = None,
     bias: torch.Tensor | None = None,
     bias_zero: int = 0,
+    kv_batch_div: int = 1,
 ) -> torch.Tensor:
     """General T5 attention core (fp32 SIMT).  ``*_rows`` = (row stride, series stride) in elements of the q / k,v /
     out buffers; ``q``, ``k``, ``v`` may be views into one buffer (e.g. a [B, L, 3W] cache)."""
@@ -514,7 +515,8 @@ def t5_attention(
         lib.tsfmx_t5_attention(
             ptr(q), _dt(q), q_rows[0], q_rows[1], ptr(k), ptr(v), _dt(k), kv_rows[0], kv_rows[0] if ldv is None else ldv,
             kv_rows[1], batch, tq, tk, num_heads, 64, q_pos0, int(causal), ptr(km), ptr(bias),
-            0 if bias is None else bias.shape[-1], bias_zero, out_dtype, ptr(out), out_rows[0], out_rows[1], stream(),
+            0 if bias is None else bias.shape[-1], bias_zero, out_dtype, ptr(out), out_rows[0], out_rows[1], kv_batch_div,
+            stream(),
         )
     )
     return out

@@ -196,6 +196,14 @@ class ChronosT5Adapter(TsfmAdapter):
         self._bias_tables: dict[tuple, torch.Tensor] = {}
         self._graphs: dict[tuple, tuple] = {}
         self.use_cuda_graphs = True  # replay the greedy decoding loop from a captured graph
+        # num_samples = 1: greedy decoding, one output channel.  num_samples > 1: upstream's probabilistic forecast -
+        # that many sampled token paths per series (temperature / top-k as in ChronosConfig: 1.0 / 50), reduced to the
+        # ``quantile_levels`` over the paths; the point forecast is the median channel.
+        self.num_samples = 1
+        self.temperature = 1.0
+        self.top_k = 50
+        self.quantile_levels = (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9)
+        self.generator: torch.Generator | None = None  # optional CUDA generator for reproducible sampling
 
     def set_precision(self, precision: str) -> None:
         if precision not in PRECISIONS:
@@ -213,11 +221,13 @@ class ChronosT5Adapter(TsfmAdapter):
     @property
     def num_outputs(self) -> int:
         """Channels of the ``postprocess`` output (not part of the reference contract; used for empty batches)."""
-        return 1
+        return 1 if self.num_samples <= 1 else len(self.quantile_levels)
 
     @property
     def point_forecast_index(self) -> int:
-        return 0
+        if self.num_samples <= 1:
+            return 0
+        return min(range(len(self.quantile_levels)), key=lambda i: abs(self.quantile_levels[i] - 0.5))
 
     def expand_text_embeddings(self, text_embeddings: torch.Tensor, context: int) -> torch.Tensor:
         """(batch, ceil(context / text_patch_len), E) per-patch text embeddings -> (batch, context + 1, E) per token;
@@ -363,9 +373,16 @@ class ChronosT5Adapter(TsfmAdapter):
         """Greedy decoding of ``horizon`` tokens + de-quantisation -> (batch, horizon, 1)."""
         ids = normalization_stats["token_ids"]
         attention_mask = ids != self._model.pad_token_id
-        tokens, _ = self.decode(output_embeddings, attention_mask, horizon)
-        values = self.tokenizer.output_transform(tokens, normalization_stats["scale"])
-        return values.unsqueeze(-1)
+        scale = normalization_stats["scale"]
+        if self.num_samples <= 1:
+            tokens, _ = self.decode(output_embeddings, attention_mask, horizon)
+            return self.tokenizer.output_transform(tokens, scale).unsqueeze(-1)
+        b, s = output_embeddings.shape[0], self.num_samples
+        tokens, _ = self._decode_eager(output_embeddings, attention_mask, horizon, None, False, num_samples=s)
+        values = self.tokenizer.output_transform(tokens, scale.repeat_interleave(s))  # [B * S, horizon]
+        paths = values.view(b, s, horizon)
+        q = torch.tensor(self.quantile_levels, dtype=torch.float32, device=paths.device)
+        return torch.quantile(paths, q, dim=1).permute(1, 2, 0).contiguous()  # (batch, horizon, quantiles)
 
     def decode(self, encoder_states: torch.Tensor, attention_mask: torch.Tensor, horizon: int,
                forced_ids: torch.Tensor | None = None, return_logits: bool = False):
@@ -410,7 +427,9 @@ class ChronosT5Adapter(TsfmAdapter):
         return tokens.clone(), None
 
     def _decode_eager(self, encoder_states: torch.Tensor, attention_mask: torch.Tensor, horizon: int,
-                      forced_ids: torch.Tensor | None, return_logits: bool):
+                      forced_ids: torch.Tensor | None, return_logits: bool, num_samples: int = 1):
+        """``num_samples`` > 1: every series decodes that many sampled paths (rows b * S + s); the encoder-side keys /
+        values are projected once per series and shared by its paths."""
         m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -430,6 +449,8 @@ class ChronosT5Adapter(TsfmAdapter):
             ops.gemm([(enc, lw["ckv"], d)], rows, 2 * inner, kv, mid_dt, precision=prec)
             cross.append(kv)
         del enc
+        samples = max(1, int(num_samples))
+        b = b * samples  # decode rows: series-major, sample-minor (encoder-side tensors keep the series batch)
         caches = [ops.alloc(b * length, 3 * inner, mid_dt, dev).view(b, length, 3 * inner) for _ in layers]
         bias, bias_zero = self._bias_table("dec", length, w)
         attn = ops.alloc(b, inner, adt, dev)
@@ -456,7 +477,8 @@ class ChronosT5Adapter(TsfmAdapter):
                 ops.gemm([(xn, lw["cq"], d)], b, inner, cq, mid_dt, precision=prec)
                 kv = cross[i]
                 ops.t5_attention(cq, kv, kv[:, inner:], b, 1, t, heads, adt, attn, q_rows=(inner, inner),
-                                 kv_rows=(2 * inner, t * 2 * inner), out_rows=(inner, inner), key_mask=key_mask)
+                                 kv_rows=(2 * inner, t * 2 * inner), out_rows=(inner, inner), key_mask=key_mask,
+                                 kv_batch_div=samples)
                 ops.gemm([(attn, lw["co"], inner)], b, d, a, mid_dt, precision=prec)
                 ops.norm_residual_norm(a, x, None, lw["ln2"], m.eps, x, adt, xn)
                 ops.gemm([(xn, lw["wi"], d)], b, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
@@ -467,7 +489,16 @@ class ChronosT5Adapter(TsfmAdapter):
             if all_logits is not None:
                 all_logits[:, step] = logits
             logits[:, m.eos_token_id] = float("-inf")  # min_new_tokens = horizon: no EOS before the horizon is full
-            cur = logits.argmax(-1)
+            if samples == 1:
+                cur = logits.argmax(-1)
+            else:  # temperature / top-k sampling, as upstream's generate(do_sample=True, top_k=50, temperature=1.0)
+                scaled = logits / self.temperature if self.temperature != 1.0 else logits
+                if self.top_k and self.top_k < m.vocab_size:
+                    top_v, top_i = torch.topk(scaled, self.top_k, dim=-1)
+                    pick = torch.multinomial(torch.softmax(top_v, -1), 1, generator=self.generator)
+                    cur = top_i.gather(-1, pick).squeeze(-1)
+                else:
+                    cur = torch.multinomial(torch.softmax(scaled, -1), 1, generator=self.generator).squeeze(-1)
             tokens[:, step] = cur
             if forced_ids is not None:
                 cur = forced_ids[:, step].to(torch.int64).contiguous()

@@ -155,3 +155,33 @@ def test_graph_replay_and_series_lanes_give_the_eager_tokens():
     finally:
         dec.lanes, dec.adapter.use_cuda_graphs = 2, True
     assert torch.equal(eager, graphed) and torch.equal(eager, first) and torch.equal(eager, again)
+
+
+def test_sampled_decoding_paths_and_quantiles():
+    """num_samples > 1: sampled token paths share the encoder-side keys / values of their series.  top_k = 1 makes
+    sampling deterministic, so every path must equal the greedy path; with top_k = 50 the quantile channels are ordered
+    and reproducible under a seeded generator."""
+    dec, _ = build(2, seed=7, tied=False)
+    dec.set_precision("bf16x3")
+    ad = dec.adapter
+    ctx, masks, text = batch(5, 64, True, seed=17)
+    text_tok = ad.expand_text_embeddings(text, 64)
+    ctx, masks, text_tok = ctx.to(DEV), masks.to(DEV), text_tok.to(DEV)
+    try:
+        with torch.no_grad():
+            greedy = dec.forward_full(10, ctx, masks, text_tok)                      # (5, 10, 1)
+            ad.num_samples, ad.top_k = 4, 1
+            same = dec.forward_full(10, ctx, masks, text_tok)                        # (5, 10, 9): all paths = greedy
+            assert same.shape == (5, 10, 9) and ad.point_forecast_index == 4
+            assert torch.equal(same, greedy.expand(-1, -1, 9))
+            ad.top_k = 50
+            ad.generator = torch.Generator(device=DEV).manual_seed(123)
+            first = dec.forward_full(10, ctx, masks, text_tok)
+            ad.generator.manual_seed(123)
+            again = dec.forward_full(10, ctx, masks, text_tok)
+            point = dec(10, ctx, masks, text_tok)
+    finally:
+        ad.num_samples, ad.top_k, ad.generator = 1, 50, None
+    assert torch.equal(first, again)
+    assert bool((first[..., 1:] >= first[..., :-1]).all())                            # quantiles are ordered
+    assert point.shape == (5, 10) and torch.isfinite(first).all()
