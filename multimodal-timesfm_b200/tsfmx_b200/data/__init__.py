@@ -1,5 +1,6 @@
-"""Batch plumbing (reference tsfmx/data/collate.py:9-29): numpy-stack collate with optional pinned staging."""
+"""Host-side data helpers: the reference's collate functions and the packed, pinned sample store."""
 
 from .collate import baseline_collate_fn, multimodal_collate_fn
+from .packed import PackedSamples
 
-__all__ = ["baseline_collate_fn", "multimodal_collate_fn"]
+__all__ = ["baseline_collate_fn", "multimodal_collate_fn", "PackedSamples"]

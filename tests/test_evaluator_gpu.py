@@ -35,3 +35,24 @@ def test_evaluator_matches_oracle_metrics():
     assert ev.evaluate(iter(batches)) == got  # generators work too, and the result is reproducible
     with pytest.raises(RuntimeError, match="empty"):
         ev.evaluate([])
+
+
+def test_packed_store_feeds_the_evaluator():
+    """Pinned zero-copy batches of the packed sample store through the staged evaluator = the per-sample collate path."""
+    from tsfmx_b200.data import PackedSamples, multimodal_collate_fn
+
+    adapter = TimesFM2p5Adapter(num_layers=1, with_quantile_head=False)
+    init_random_(adapter, seed=0)
+    torch.manual_seed(100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, [])).to("cuda").eval()
+    ctx, _m, text, hor = O.synthetic_batch(37, 512, 32, seed=8)
+    samples = [{"context": ctx[i].numpy(), "horizon": hor[i].numpy(), "text_embeddings": text[i].numpy(), "metadata": {"i": i}}
+               for i in range(37)]
+    store = PackedSamples.from_samples(samples)
+    assert store.context.is_pinned() and store.text_embeddings.is_pinned()
+    ev = MultimodalEvaluator(dec, torch.device("cuda"))
+    packed = ev.evaluate(store.batches(8))
+    collated = ev.evaluate(multimodal_collate_fn(samples[i : i + 8]) for i in range(0, 37, 8))
+    assert packed == collated
+    shuffled = ev.evaluate(store.batches(8, shuffle=True, generator=torch.Generator().manual_seed(1)))
+    assert shuffled["mse"] == pytest.approx(packed["mse"], rel=1e-5)  # same samples, other batch composition
