@@ -258,6 +258,15 @@ int tsfmx_encoder_attention_mma(const void* qkv, int64_t batch, int32_t seq, int
                                 const uint8_t* key_mask, const float* rope_table, void* out, void* stream);
 
 /*
+ * Column reductions of the full fine-tune ("baseline" mode, reference tsfmx/trainer.py:78-79,123): normalize != 0:
+ * out[c] += sum_r g[r, c] * v[r, c] * rsqrt(mean(v[r]^2) + eps) (gradient of an RMSNorm scale); normalize == 0:
+ * out[c] += sum_r g[r, c] (gradient of a bias).  v, g [rows, cols] f32 / bf16, cols in {1280, 768}; out fp32 [cols],
+ * accumulated into (zero it first).
+ */
+int tsfmx_colsum_wgrad(const void* v, int32_t v_dtype, const void* g, int32_t g_dtype, int64_t rows, int32_t cols, float eps,
+                       int32_t normalize, float* out, void* stream);
+
+/*
  * Backward of tsfmx_encoder_attention: d_out [B*T, H*64] -> dqkv [B*T, 3*H*64] = [dq | dk | dv] (fusion fine-tune
  * through the frozen Chronos-2 encoder; the reference trains the fusion module with either adapter,
  * scripts/tune_time_mmd_sweep.py:124-126).  fp32 arithmetic; stats_workspace: B*H*T float4 scratch (row max, 1 / sum,
@@ -328,12 +337,14 @@ int tsfmx_rmsnorm_bwd_chain(const float* g_res, const void* v1, int32_t v1_dtype
  * Gradient of tsfmx_timesfm_attention w.r.t. its qkv input: recomputes the conditioned q / k and the
  * probabilities, then dV = P^T dO, dS = P (dO V^T - rowsum), dq' = dS k', dk' = dS^T q' and back through
  * per-dim scale, RMSNorm and RoPE.  d_out [B*N, H*hd] f32 / bf16; dqkv [B*N, 3*H*hd] of dqkv_dtype.
+  * dparams (NULL when the adapter is frozen): fp32 [2 * head_dim], accumulated into - [0, hd) gets
+ * d/d(q_ln_w * q_scale) = sum dq' * qhat, [hd, 2 hd) gets d/d(k_ln_w) = sum dk' * khat (full fine-tuning, "baseline" mode).
  */
 int tsfmx_timesfm_attention_bwd(const void* qkv, int32_t qkv_dtype, const void* d_out, int32_t dout_dtype,
                                 int64_t batch, int32_t num_patches, int32_t num_heads, int32_t head_dim,
                                 const uint8_t* patch_mask, const int32_t* num_masked, const float* inv_freq,
                                 const float* q_ln_w, const float* k_ln_w, const float* q_scale, float eps,
-                                int32_t dqkv_dtype, void* dqkv, void* stream);
+                                int32_t dqkv_dtype, void* dqkv, float* dparams, void* stream);
 
 /*
  * out[c, r] = (mask == NULL || mask[r, c] > 0) ? in[r, c] : 0 for r < rows, zero for rows <= r < ld_out.

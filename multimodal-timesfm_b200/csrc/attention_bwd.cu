@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
     const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, int64_t batch, int num_patches,
     int num_heads, const uint8_t* __restrict__ patch_mask, const int32_t* __restrict__ num_masked,
     const float* __restrict__ inv_freq, const float* __restrict__ q_ln_w, const float* __restrict__ k_ln_w,
-    const float* __restrict__ q_scale, float eps, __nv_bfloat16* __restrict__ dqkv) {
+    const float* __restrict__ q_scale, float eps, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dparams) {
   constexpr int ROWS = 16 * NT;
   constexpr int HALF = BW_HD / 2;
   constexpr int TILE = ROWS * BW_LD;    // bf16 elements
@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
   float2* s_rope = reinterpret_cast<float2*>(smem_bw);             // [2 * ROWS][40] (cos, sin), positions -N .. N-1
   float* s_wq = reinterpret_cast<float*>(s_rope + 2 * ROWS * HALF);  // [80] q_ln_w * q_scale
   float* s_wk = s_wq + BW_HD;
-  uint8_t* warp_base = reinterpret_cast<uint8_t*>(s_wk + BW_HD);
+  float* s_dw = s_wk + BW_HD;  // [warps][2 * 80] per-warp sums of dq' * qhat and dk' * khat (full fine-tune only)
+  uint8_t* warp_base = reinterpret_cast<uint8_t*>(s_dw + 8 * 2 * BW_HD);
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = num_patches;
@@ -94,7 +95,9 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
     s_wq[i] = __ldg(q_ln_w + i) * __ldg(q_scale + i);
     s_wk[i] = __ldg(k_ln_w + i);
   }
+  for (int i = threadIdx.x; i < 8 * 2 * BW_HD; i += blockDim.x) s_dw[i] = 0.f;
   __syncthreads();
+  float* my_dw = s_dw + warp * 2 * BW_HD;
 
   const int width = num_heads * BW_HD;
   const int64_t qkv_ld = 3 * static_cast<int64_t>(width);
@@ -488,6 +491,24 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
         ck += __shfl_xor_sync(0xffffffffu, ck, 1);
         const float rq = rsqrtf(qss * (1.0f / BW_HD) + eps), rk = rsqrtf(kss * (1.0f / BW_HD) + eps);
         const float fq = rq * rq * rq * cq * (1.0f / BW_HD), fk = rk * rk * rk * ck * (1.0f / BW_HD);
+        if (dparams != nullptr) {
+          // parameter gradients: the 16 lanes with the same half (one per row of the tile) hold contributions to the
+          // same 40 dims -> fold them with shuffles, one lane per half adds into the warp's private slot
+#pragma unroll
+          for (int idx = 0; idx < 20; ++idx) {
+            float a = dqp[idx] * q1[idx] * rq, bq2 = dqp[HALF + idx] * q2[idx] * rq;
+            float c = dkp[idx] * k1[idx] * rk, d2 = dkp[HALF + idx] * k2[idx] * rk;
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o), bq2 += __shfl_xor_sync(0xffffffffu, bq2, o);
+              c += __shfl_xor_sync(0xffffffffu, c, o), d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if (lane < 2) {  // lane 0: half 0, lane 1: half 1
+              my_dw[20 * hf + idx] += a, my_dw[20 * hf + HALF + idx] += bq2;
+              my_dw[BW_HD + 20 * hf + idx] += c, my_dw[BW_HD + 20 * hf + HALF + idx] += d2;
+            }
+          }
+        }
         __nv_bfloat16* qrow = sQ + r * BW_LD + 20 * hf;
         __nv_bfloat16* krow = sK + r * BW_LD + 20 * hf;
         if (live) {
@@ -528,15 +549,23 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
     }
     __syncwarp();
   }
+  if (dparams != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * BW_HD; i += blockDim.x) {
+      float t2 = 0.f;
+      for (int w2 = 0; w2 < warps_per_block; ++w2) t2 += s_dw[w2 * 2 * BW_HD + i];
+      atomicAdd(dparams + i, t2);
+    }
+  }
 }
 
 template <int NT>
 int launch_bwd_mma(const void* qkv, const void* dout, int64_t batch, int N, int H, const uint8_t* pm, const int32_t* nm,
                    const float* inv_freq, const float* qw, const float* kw, const float* qs, float eps, void* dqkv,
-                   cudaStream_t stream) {
+                   float* dparams, cudaStream_t stream) {
   constexpr int ROWS = 16 * NT;
   constexpr int per_warp = 6 * ROWS * BW_LD * 2 + 2 * ROWS * BW_LDF * 4 + 4 * ROWS * 4;
-  constexpr int fixed = 2 * ROWS * 40 * 8 + 2 * BW_HD * 4;
+  constexpr int fixed = 2 * ROWS * 40 * 8 + 2 * BW_HD * 4 + 8 * 2 * BW_HD * 4;
   int wpb = (220 * 1024 - fixed) / per_warp;
   if (wpb > 8) wpb = 8;
   if (wpb < 1) {
@@ -559,7 +588,7 @@ int launch_bwd_mma(const void* qkv, const void* dout, int64_t batch, int N, int 
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
   kern<<<grid, wpb * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                           reinterpret_cast<const __nv_bfloat16*>(dout), batch, N, H, pm, nm, inv_freq, qw,
-                                          kw, qs, eps, reinterpret_cast<__nv_bfloat16*>(dqkv));
+                                          kw, qs, eps, reinterpret_cast<__nv_bfloat16*>(dqkv), dparams);
   return check_last_launch("timesfm_attention_bwd_mma");
 }
 
@@ -568,10 +597,10 @@ int launch_bwd_mma(const void* qkv, const void* dout, int64_t batch, int N, int 
 // Used by tsfmx_timesfm_attention_bwd (backward.cu) when qkv, dO and dqkv are all bf16 and N <= 64.
 int launch_timesfm_attention_bwd_mma(const void* qkv, const void* dout, int64_t batch, int N, int H, const uint8_t* pm,
                                      const int32_t* nm, const float* inv_freq, const float* qw, const float* kw,
-                                     const float* qs, float eps, void* dqkv, cudaStream_t stream) {
-  if (N <= 16) return launch_bwd_mma<1>(qkv, dout, batch, N, H, pm, nm, inv_freq, qw, kw, qs, eps, dqkv, stream);
-  if (N <= 32) return launch_bwd_mma<2>(qkv, dout, batch, N, H, pm, nm, inv_freq, qw, kw, qs, eps, dqkv, stream);
-  return launch_bwd_mma<4>(qkv, dout, batch, N, H, pm, nm, inv_freq, qw, kw, qs, eps, dqkv, stream);
+                                     const float* qs, float eps, void* dqkv, float* dparams, cudaStream_t stream) {
+  if (N <= 16) return launch_bwd_mma<1>(qkv, dout, batch, N, H, pm, nm, inv_freq, qw, kw, qs, eps, dqkv, dparams, stream);
+  if (N <= 32) return launch_bwd_mma<2>(qkv, dout, batch, N, H, pm, nm, inv_freq, qw, kw, qs, eps, dqkv, dparams, stream);
+  return launch_bwd_mma<4>(qkv, dout, batch, N, H, pm, nm, inv_freq, qw, kw, qs, eps, dqkv, dparams, stream);
 }
 
 }  // namespace tsfmx

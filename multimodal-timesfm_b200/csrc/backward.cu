@@ -110,6 +110,57 @@ __global__ void __launch_bounds__(WARPS * 32) rmsnorm_bwd_chain_kernel(
 }
 
 // ----------------------------------------------------------------------------------------
+// Column reductions of the full fine-tune ("baseline" mode, reference tsfmx/trainer.py:78-79): gradient of an RMSNorm
+// scale, dscale[c] = sum_r g[r, c] * v[r, c] * rsqrt(mean(v[r]^2) + eps), or (normalize = 0) a bias gradient
+// dbias[c] = sum_r g[r, c].  Rows stream once; every warp keeps its column partials in registers, the block folds
+// them in shared memory and adds one value per column to the (pre-zeroed) output.
+// ----------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32) colsum_wgrad_kernel(const void* __restrict__ v, int v_dtype,
+                                                                   const void* __restrict__ g, int g_dtype, int64_t rows,
+                                                                   float eps, int normalize, float* __restrict__ out) {
+  constexpr int COLS = NV * 128;
+  __shared__ float s_part[WARPS][COLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * WARPS + warp; r < rows; r += static_cast<int64_t>(gridDim.x) * WARPS) {
+    float4 gg[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) gg[j] = load4(g, g_dtype, r * COLS + 4 * (lane + 32 * j));
+    if (normalize) {
+      float4 vv[NV];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        vv[j] = load4(v, v_dtype, r * COLS + 4 * (lane + 32 * j));
+        ss += vv[j].x * vv[j].x + vv[j].y * vv[j].y + vv[j].z * vv[j].z + vv[j].w * vv[j].w;
+      }
+      ss = warp_sum(ss);
+      const float rs = 1.0f / sqrtf(ss / static_cast<float>(COLS) + eps);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        acc[j].x = fmaf(gg[j].x, vv[j].x * rs, acc[j].x), acc[j].y = fmaf(gg[j].y, vv[j].y * rs, acc[j].y);
+        acc[j].z = fmaf(gg[j].z, vv[j].z * rs, acc[j].z), acc[j].w = fmaf(gg[j].w, vv[j].w * rs, acc[j].w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc[j].x += gg[j].x, acc[j].y += gg[j].y, acc[j].z += gg[j].z, acc[j].w += gg[j].w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) *reinterpret_cast<float4*>(&s_part[warp][4 * (lane + 32 * j)]) = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < COLS; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) t += s_part[w][c];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // attention backward (fp32 SIMT; one warp per (series, head))
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ float load_elem(const void* base, int dtype, int64_t idx) {
@@ -124,8 +175,12 @@ __global__ void timesfm_attention_bwd_kernel(const void* __restrict__ qkv, int q
                                              const int32_t* __restrict__ num_masked,
                                              const float* __restrict__ inv_freq, const float* __restrict__ q_ln_w,
                                              const float* __restrict__ k_ln_w, const float* __restrict__ q_scale,
-                                             float eps, void* dqkv) {
+                                             float eps, void* dqkv, float* __restrict__ dparams) {
   constexpr int DPL = (HD + 31) / 32;
+  // full fine-tune only (dparams != NULL): d/d(q_ln_w * q_scale)[d] = sum dq'[d] * qhat[d], d/d(k_ln_w)[d] = sum dk'[d] * khat[d]
+  float dwq[DPL], dwk[DPL];
+#pragma unroll
+  for (int t = 0; t < DPL; ++t) dwq[t] = 0.f, dwk[t] = 0.f;
   constexpr int HALF = HD / 2;
   constexpr int LD = HD + 1;
   extern __shared__ float smem[];
@@ -306,6 +361,8 @@ __global__ void timesfm_attention_bwd_kernel(const void* __restrict__ qkv, int q
         if (d < HD) {
           tq[t] = __ldg(q_ln_w + d) * __ldg(q_scale + d) * sDQ[n * LD + d];
           tk[t] = __ldg(k_ln_w + d) * sDK[n * LD + d];
+          dwq[t] = fmaf(sDQ[n * LD + d], sQr[n * LD + d] * rq, dwq[t]);
+          dwk[t] = fmaf(sDK[n * LD + d], sKr[n * LD + d] * rk, dwk[t]);
           cq += sQr[n * LD + d] * tq[t];
           ck += sKr[n * LD + d] * tk[t];
         }
@@ -354,6 +411,16 @@ __global__ void timesfm_attention_bwd_kernel(const void* __restrict__ qkv, int q
         }
       }
       __syncwarp();
+    }
+  }
+  if (dparams != nullptr) {
+#pragma unroll
+    for (int t = 0; t < DPL; ++t) {
+      const int d = lane + 32 * t;
+      if (d < HD) {
+        atomicAdd(dparams + d, dwq[t]);
+        atomicAdd(dparams + HD + d, dwk[t]);
+      }
     }
   }
 }
@@ -477,12 +544,33 @@ extern "C" int tsfmx_rmsnorm_bwd_chain(const float* g_res, const void* v1, int32
   }
 }
 
+extern "C" int tsfmx_colsum_wgrad(const void* v, int32_t v_dtype, const void* g, int32_t g_dtype, int64_t rows, int32_t cols,
+                                  float eps, int32_t normalize, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(g != nullptr && out != nullptr && (!normalize || v != nullptr), "colsum_wgrad: NULL pointer");
+  TSFMX_REQUIRE(rows >= 0, "colsum_wgrad: bad rows");
+  auto dt_ok = [](int d) { return d == TSFMX_DT_F32 || d == TSFMX_DT_BF16; };
+  TSFMX_REQUIRE(dt_ok(g_dtype) && (!normalize || dt_ok(v_dtype)), "colsum_wgrad: inputs must be f32 or bf16");
+  if (rows == 0) return TSFMX_OK;
+  int64_t blocks = (rows + WARPS - 1) / WARPS;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 2;
+  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  switch (cols) {
+    case 1280: colsum_wgrad_kernel<10><<<grid, WARPS * 32, 0, stream>>>(v, v_dtype, g, g_dtype, rows, eps, normalize, out); break;
+    case 768: colsum_wgrad_kernel<6><<<grid, WARPS * 32, 0, stream>>>(v, v_dtype, g, g_dtype, rows, eps, normalize, out); break;
+    default:
+      set_error("colsum_wgrad: cols=%d unsupported (1280 or 768)", cols);
+      return TSFMX_ERR_UNSUPPORTED;
+  }
+  return check_last_launch("colsum_wgrad");
+}
+
 extern "C" int tsfmx_timesfm_attention_bwd(const void* qkv, int32_t qkv_dtype, const void* d_out, int32_t dout_dtype,
                                            int64_t batch, int32_t num_patches, int32_t num_heads, int32_t head_dim,
                                            const uint8_t* patch_mask, const int32_t* num_masked,
                                            const float* inv_freq, const float* q_ln_w, const float* k_ln_w,
                                            const float* q_scale, float eps, int32_t dqkv_dtype, void* dqkv,
-                                           void* stream_) {
+                                           float* dparams, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TSFMX_REQUIRE(qkv != nullptr && d_out != nullptr && dqkv != nullptr && inv_freq != nullptr && q_ln_w != nullptr &&
                     k_ln_w != nullptr && q_scale != nullptr,
@@ -503,7 +591,7 @@ extern "C" int tsfmx_timesfm_attention_bwd(const void* qkv, int32_t qkv_dtype, c
   if (qkv_dtype == TSFMX_DT_BF16 && dout_dtype == TSFMX_DT_BF16 && dqkv_dtype == TSFMX_DT_BF16 && aligned && N <= 64 &&
       !g_force_simt_attention)
     return launch_timesfm_attention_bwd_mma(qkv, d_out, batch, N, num_heads, patch_mask, num_masked, inv_freq, q_ln_w,
-                                            k_ln_w, q_scale, eps, dqkv, stream);
+                                            k_ln_w, q_scale, eps, dqkv, dparams, stream);
   const int per_warp_bytes = (9 * N * 81 + 4 * N) * 4;
   int wpb = (200 * 1024) / per_warp_bytes;
   if (wpb > 4) wpb = 4;
@@ -526,7 +614,7 @@ extern "C" int tsfmx_timesfm_attention_bwd(const void* qkv, int32_t qkv_dtype, c
       }
     }
     kern<<<grid, wpb * 32, smem, stream>>>(qkv, qkv_dtype, d_out, dout_dtype, batch, N, num_heads, patch_mask, num_masked,
-                                           inv_freq, q_ln_w, k_ln_w, q_scale, eps, dqkv);
+                                           inv_freq, q_ln_w, k_ln_w, q_scale, eps, dqkv, dparams);
     return check_last_launch("timesfm_attention_bwd");
   };
   if (dqkv_dtype == TSFMX_DT_F32) return launch(timesfm_attention_bwd_kernel<80, TSFMX_DT_F32>);

@@ -119,6 +119,9 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int32,
         [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    "tsfmx_colsum_wgrad": (
+        c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_float, c_int32, c_void_p, c_void_p]
+    ),
     "tsfmx_encoder_attention_bwd": (
         c_int32,
         [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
@@ -146,7 +149,7 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "tsfmx_timesfm_attention_bwd": (
         c_int32,
         [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-         c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p],
+         c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p, c_void_p],
     ),
     "tsfmx_transpose_mask": (
         c_int32,

@@ -317,6 +317,19 @@ def rmsnorm_bwd_chain(
     )
 
 
+def colsum_wgrad(g: torch.Tensor, v: torch.Tensor | None = None, eps: float = 0.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``out[c] += sum_r g[r, c] * v_hat[r, c]`` (RMSNorm scale gradient, ``v_hat`` = RMS-normalised ``v``) or, without
+    ``v``, ``out[c] += sum_r g[r, c]`` (bias gradient).  ``out`` fp32 [cols] is created zeroed when not given."""
+    lib = _lib.load()
+    _lib.require_cuda(g, v)
+    rows, cols = g.shape
+    if out is None:
+        out = torch.zeros(cols, dtype=torch.float32, device=g.device)
+    check(lib.tsfmx_colsum_wgrad(ptr(v), _dt(v) if v is not None else 0, ptr(g), _dt(g), rows, cols, eps,
+                                 int(v is not None), ptr(out), stream()))
+    return out
+
+
 def timesfm_attention_bwd(
     qkv: torch.Tensor,
     d_out: torch.Tensor,
@@ -333,7 +346,9 @@ def timesfm_attention_bwd(
     eps: float,
     dqkv_dtype: int,
     dqkv: torch.Tensor | None = None,
+    dparams: torch.Tensor | None = None,
 ) -> torch.Tensor:
+    """``dparams``: optional fp32 [2 * head_dim] accumulator for d/d(q_ln_w * q_scale) and d/d(k_ln_w)."""
     lib = _lib.load()
     _lib.require_cuda(qkv, d_out)
     if dqkv is None:
@@ -342,7 +357,8 @@ def timesfm_attention_bwd(
     check(
         lib.tsfmx_timesfm_attention_bwd(
             ptr(qkv), _dt(qkv), ptr(d_out), _dt(d_out), batch, num_patches, num_heads, head_dim, ptr(pm),
-            ptr(num_masked), ptr(inv_freq), ptr(q_ln_w), ptr(k_ln_w), ptr(q_scale), eps, dqkv_dtype, ptr(dqkv), stream(),
+            ptr(num_masked), ptr(inv_freq), ptr(q_ln_w), ptr(k_ln_w), ptr(q_scale), eps, dqkv_dtype, ptr(dqkv),
+            ptr(dparams), stream(),
         )
     )
     return dqkv

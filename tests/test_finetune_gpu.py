@@ -132,6 +132,59 @@ def test_attention_bwd_tensor_core_path(n):
     assert e_simt < 2e-2, (e_ref, e_simt)
 
 
+@pytest.mark.parametrize("n,use_bf16", [(16, False), (5, False), (40, False), (16, True), (64, True)])
+def test_attention_bwd_parameter_gradients(n, use_bf16):
+    """Full fine-tuning needs the gradients of q_ln / k_ln scales and the per-dim scale: both backward kernels return
+    d/d(q_ln_w * q_scale) and d/d(k_ln_w); check them (chain rule applied here) against fp64 torch autograd."""
+    b, h, hd = 5, 16, 80
+    gen = torch.Generator(device=DEV).manual_seed(200 + n)
+    qkv = torch.randn(b * n, 3 * h * hd, generator=gen, device=DEV)
+    dout = torch.randn(b * n, h * hd, generator=gen, device=DEV)
+    if use_bf16:
+        qkv, dout = qkv.to(torch.bfloat16), dout.to(torch.bfloat16)
+    pm = torch.zeros(b, n, dtype=torch.bool, device=DEV)
+    pm[1, : n // 2] = True
+    pm[2, :1] = True
+    nm = pm.sum(-1).int()
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd)).to(DEV)
+    qw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    kw = 1 + 0.1 * torch.randn(hd, generator=gen, device=DEV)
+    per_dim = 0.5 * torch.randn(hd, generator=gen, device=DEV)
+    c = 1.442695041 / math.sqrt(hd)
+    q_scale = (torch.nn.functional.softplus(per_dim) * c).contiguous()
+    qwd, kwd, pdd = (t.double().requires_grad_(True) for t in (qw, kw, per_dim))
+    out = _attn_fwd_torch(qkv.double(), b, n, h, hd, pm, inv_freq, qwd, kwd, pdd)
+    g_qw, g_kw, g_pd = torch.autograd.grad(out, [qwd, kwd, pdd], dout.double())
+    dparams = torch.zeros(2 * hd, dtype=torch.float32, device=DEV)
+    ops.timesfm_attention_bwd(qkv, dout, b, n, h, hd, pm, nm, inv_freq, qw, kw, q_scale, 1e-6,
+                              DT_BF16 if use_bf16 else DT_F32, dparams=dparams)
+    d_eff, d_kw = dparams[:hd].double(), dparams[hd:].double()
+    got_qw = d_eff * q_scale.double()
+    got_pd = d_eff * qw.double() * c * torch.sigmoid(per_dim.double())
+    tol = 3e-2 if use_bf16 else 1e-4
+    for name, got, ref in (("q_ln", got_qw, g_qw), ("k_ln", d_kw, g_kw), ("per_dim", got_pd, g_pd)):
+        err = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+        assert err < tol, (name, err)
+
+
+@pytest.mark.parametrize("cols", [1280, 768])
+def test_colsum_wgrad(cols):
+    rows = 1003
+    gen = torch.Generator(device=DEV).manual_seed(cols)
+    v = torch.randn(rows, cols, generator=gen, device=DEV) * 2
+    g = torch.randn(rows, cols, generator=gen, device=DEV)
+    vhat = v.double() * torch.rsqrt(v.double().pow(2).mean(-1, keepdim=True) + 1e-6)
+    ref_scale = (g.double() * vhat).sum(0)
+    ref_bias = g.double().sum(0)
+    got = ops.colsum_wgrad(g, v, 1e-6)
+    assert rel_l2(got, ref_scale.float()) < 1e-5
+    assert rel_l2(ops.colsum_wgrad(g), ref_bias.float()) < 1e-5
+    got16 = ops.colsum_wgrad(g.to(torch.bfloat16), v, 1e-6)
+    assert rel_l2(got16, ref_scale.float()) < 1e-2
+    acc = ops.colsum_wgrad(g, v, 1e-6, out=got.clone())   # accumulates into `out`
+    assert rel_l2(acc, 2 * ref_scale.float()) < 1e-5
+
+
 def test_gemm_grad_epilogues_and_pre_act():
     m, n, k = 200, 1280, 1280
     gen = torch.Generator(device=DEV).manual_seed(2)
