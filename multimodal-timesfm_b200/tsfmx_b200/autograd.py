@@ -55,6 +55,50 @@ class FusedForecastFunction(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
+class FullFineTuneFunction(torch.autograd.Function):
+    """forecast = decoder(horizon, inputs, masks, text or None); differentiable w.r.t. EVERY adapter parameter (and the
+    fusion weights when text is given) - the reference's "baseline" mode unfreezes the adapter (trainer.py:78-79,123).
+    Forward = the inference kernels + saved GEMM operands; backward = the activation-gradient chain of the fusion
+    fine-tune plus one K = tokens weight-gradient GEMM per Linear, column reductions for norm scales / biases and the
+    attention kernels' q_ln / k_ln / per-dim-scale gradients."""
+
+    @staticmethod
+    def forward(ctx, decoder, horizon, inputs, masks, text, names, num_fusion, *params):  # noqa: D401
+        adapter, fusion = decoder.adapter, decoder.fusion
+        precision = PRECISIONS[adapter.precision]
+        pre, tok_saved = adapter.preprocess_saving(inputs, masks)
+        emb = pre.input_embeddings
+        b, n, d = emb.shape
+        fusion_saved = None
+        if text is not None:
+            fused, fusion_saved = fusion_forward_saving(fusion, emb.reshape(b * n, d), text.reshape(b * n, -1), precision)
+            emb = fused.view(b, n, d)
+        out_emb, stack_saved = adapter.forward_saving(emb, pre.masks, for_wgrad=True)
+        forecast, head_saved = adapter.postprocess_saving(horizon, out_emb, pre.normalization_stats)
+        ctx.decoder, ctx.names, ctx.num_fusion = decoder, names, num_fusion
+        ctx.saved = (tok_saved, fusion_saved, stack_saved, head_saved)
+        ctx.shape = (b, n, d)
+        return forecast
+
+    @staticmethod
+    def backward(ctx, grad_forecast):
+        decoder = ctx.decoder
+        adapter, fusion = decoder.adapter, decoder.fusion
+        tok_saved, fusion_saved, stack_saved, head_saved = ctx.saved
+        ctx.saved = None
+        b, n, d = ctx.shape
+        precision = PRECISIONS[adapter.precision]
+        grads: dict[str, torch.Tensor] = {}
+        d_out = adapter.postprocess_backward(head_saved, grad_forecast.contiguous().float(), grads)
+        d_emb = adapter.forward_backward(stack_saved, d_out.reshape(-1, d), grads)
+        adapter.preprocess_backward(tok_saved, d_emb, grads)
+        fusion_grads = [None] * ctx.num_fusion
+        if fusion_saved is not None and ctx.num_fusion:
+            fusion_grads = fusion_backward(fusion, fusion_saved, d_emb, precision)
+        ordered = [grads.get(name) for name in ctx.names]
+        return (None, None, None, None, None, None, None, *fusion_grads, *ordered)
+
+
 def fusion_forward_saving(fusion, ts2: torch.Tensor, tx2: torch.Tensor, precision: int):
     """MultimodalFusion.forward (reference fusion.py:44-47) that also keeps what the backward pass needs."""
     adt = ops.act_dtype(precision)

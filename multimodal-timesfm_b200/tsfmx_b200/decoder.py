@@ -118,13 +118,18 @@ class MultimodalDecoder(nn.Module):
     def _forward_full_training(self, horizon, inputs, masks, text_embeddings):
         """Differentiable path of the reference's "multimodal" training mode (trainer.py:76-77,119-123): frozen
         adapter, trainable fusion.  Full fine-tuning of the adapter ("baseline" mode) is SURVEY.md section 8(f) rank 4."""
-        from .autograd import FusedForecastFunction
+        from .autograd import FullFineTuneFunction, FusedForecastFunction
 
         if any(p.requires_grad for p in self.adapter.parameters()):
-            raise NotImplementedError(
-                "baseline mode (adapter.unfreeze_parameters) needs backbone weight gradients, which the B200 path does "
-                "not produce yet; call adapter.freeze_parameters() to train the fusion module (multimodal mode)"
-            )
+            # "baseline" mode of the reference (trainer.py:78-79,123): the whole adapter is trained
+            if not hasattr(self.adapter, "preprocess_backward"):
+                raise NotImplementedError(
+                    f"{type(self.adapter).__name__} has no full fine-tuning path; freeze it to train the fusion module"
+                )
+            named = [(k, v) for k, v in self.adapter._model.named_parameters()]
+            fusion_w = [lin.weight for lin in self.fusion.linears()] if text_embeddings is not None else []
+            return FullFineTuneFunction.apply(self, horizon, inputs, masks, text_embeddings, tuple(k for k, _ in named),
+                                              len(fusion_w), *fusion_w, *[v for _, v in named])
         if text_embeddings is None:
             raise ValueError("training the fusion module needs text_embeddings")
         if not hasattr(self.adapter, "forward_saving"):

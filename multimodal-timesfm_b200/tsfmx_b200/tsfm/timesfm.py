@@ -206,6 +206,7 @@ class TimesFM2p5Adapter(TsfmAdapter):
         if "t" not in w:
             m, pack_t = self._model, w["_pack_t"]
             w["t"] = {
+                "tok_out": pack_t(m.tokenizer.output_layer),
                 "head_hidden": pack_t(m.output_projection_point.hidden_layer),
                 "head_out": pack_t(m.output_projection_point.output_layer),
                 "head_res": pack_t(m.output_projection_point.residual_layer),
@@ -362,9 +363,10 @@ class TimesFM2p5Adapter(TsfmAdapter):
         return out.view(b, horizon, m.q)
 
     # ------------------------------------------------------------------ training path (frozen backbone)
-    def forward_saving(self, input_embeddings: torch.Tensor, masks: torch.Tensor):
+    def forward_saving(self, input_embeddings: torch.Tensor, masks: torch.Tensor, for_wgrad: bool = False):
         """``forward`` that also keeps, per layer, what the activation-gradient pass needs: the layer input x,
-        the mid-layer stream y, the raw qkv, the out-proj / ff1 outputs a1 / a2 and the ff0 pre-activation u."""
+        the mid-layer stream y, the raw qkv, the out-proj / ff1 outputs a1 / a2 and the ff0 pre-activation u.
+        ``for_wgrad`` (full fine-tuning) additionally keeps the four GEMM inputs of every layer."""
         m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -385,28 +387,52 @@ class TimesFM2p5Adapter(TsfmAdapter):
         hbuf = ops.alloc(rows, m.ff, adt, dev)
         cur = x
         for i, lw in enumerate(layers):
+            last = i == len(layers) - 1
+            xn1 = xn  # normed layer input (operand of the qkv GEMM)
+            if for_wgrad:  # the weight-gradient GEMMs read these later: one set per layer instead of reused scratch
+                attn = ops.alloc(rows, d, adt, dev)
+                hbuf = ops.alloc(rows, m.ff, adt, dev)
+                xn2 = ops.alloc(rows, d, adt, dev)
+                nxt = None if last else ops.alloc(rows, d, adt, dev)
+            else:
+                xn2, nxt = xn, (None if last else xn)  # one scratch buffer, rewritten at both norm junctions
             qkv = ops.alloc(rows, 3 * d, mid_dt, dev)
             a1 = ops.alloc(rows, d, mid_dt, dev)
             a2 = ops.alloc(rows, d, mid_dt, dev)
             u = ops.alloc(rows, m.ff, mid_dt, dev)
             y = torch.empty(rows, d, dtype=torch.float32, device=dev)
             z = torch.empty(rows, d, dtype=torch.float32, device=dev)
-            ops.gemm([(xn, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
+            ops.gemm([(xn1, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
             ops.timesfm_attention(qkv, b, n, m.h, m.hd, patch_mask, num_masked, w["inv_freq"], lw["q_ln"], lw["k_ln"],
                                   lw["q_scale"], m.eps, adt, out=attn)
             ops.gemm([(attn, lw["out"], d)], rows, d, a1, mid_dt, precision=prec)
-            ops.norm_residual_norm(a1, cur, lw["post_attn"], lw["pre_ff"], m.eps, y, adt, xn)
-            ops.gemm([(xn, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU, pre_act=u)
+            ops.norm_residual_norm(a1, cur, lw["post_attn"], lw["pre_ff"], m.eps, y, adt, xn2)
+            ops.gemm([(xn2, lw["ff0"], d)], rows, m.ff, hbuf, adt, precision=prec, act=ACT_SILU, pre_act=u)
             ops.gemm([(hbuf, lw["ff1"], m.ff)], rows, d, a2, mid_dt, precision=prec)
-            last = i == len(layers) - 1
-            ops.norm_residual_norm(a2, y, lw["post_ff"], None if last else layers[i + 1]["pre_attn"], m.eps, z, adt,
-                                   None if last else xn)
-            saved["layers"].append({"x": cur, "y": y, "qkv": qkv, "a1": a1, "a2": a2, "u": u})
+            ops.norm_residual_norm(a2, y, lw["post_ff"], None if last else layers[i + 1]["pre_attn"], m.eps, z, adt, nxt)
+            entry = {"x": cur, "y": y, "qkv": qkv, "a1": a1, "a2": a2, "u": u}
+            if for_wgrad:
+                entry.update({"xn1": xn1, "attn": attn, "xn2": xn2, "h": hbuf})
+            saved["layers"].append(entry)
             cur = z
+            xn = nxt
         return cur.view(b, n, d), saved
 
-    def forward_backward(self, saved, d_out: torch.Tensor) -> torch.Tensor:
-        """Activation gradient of ``forward``: dL/d(output embeddings) [M, D] fp32 -> dL/d(input embeddings)."""
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, k_in: int) -> torch.Tensor:
+        """dW [n_out, k_in] = dY^T X as a K-major tcgen05 GEMM with K = rows (both operands transposed once)."""
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        dy_t, kpad = ops.transpose_mask(dy, rows, n_out, adt)
+        x_t, _ = ops.transpose_mask(x, rows, k_in, adt)
+        gw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy.device)
+        ops.gemm([(dy_t, x_t, kpad)], n_out, k_in, gw, DT_F32, precision=prec)
+        return gw
+
+    def forward_backward(self, saved, d_out: torch.Tensor, param_grads: dict[str, torch.Tensor] | None = None) -> torch.Tensor:
+        """Activation gradient of ``forward``: dL/d(output embeddings) [M, D] fp32 -> dL/d(input embeddings).
+
+        ``param_grads`` (full fine-tuning; needs ``forward_saving(for_wgrad=True)``): filled with the gradient of every
+        parameter of the stack under its state-dict name."""
         m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -426,26 +452,96 @@ class TimesFM2p5Adapter(TsfmAdapter):
         dqkv = ops.alloc(rows, 3 * d, adt, dev)
         # top of the stack: da2 = RMSNorm_bwd(a2, post_ff, dz)
         ops.rmsnorm_bwd_chain(g, None, None, None, sl[-1]["a2"], layers[-1]["post_ff"], m.eps, None, adt, g2, rows, d)
+        pg = param_grads
         for i in reversed(range(len(layers))):
             lw, tw, s = layers[i], tlayers[i], sl[i]
+            pre = f"stacked_xf.{i}."
+            if pg is not None:  # g = dL/dz, g2 = da2 at this point
+                pg[pre + "post_ff_ln.scale"] = ops.colsum_wgrad(g, s["a2"], m.eps)
+                pg[pre + "ff1.weight"] = self._wgrad(g2, s["h"], rows, d, m.ff)
             # dhff = da2 W1 ; du = dhff * silu'(u)
             ops.gemm([(g2, tw["ff1"], d)], rows, m.ff, du, adt, precision=prec, act=ACT_SILU_GRAD, aux=s["u"])
             # dyn = du W0
             ops.gemm([(du, tw["ff0"], m.ff)], rows, d, gmid, mid_dt, precision=prec)
+            if pg is not None:
+                pg[pre + "ff0.weight"] = self._wgrad(du, s["xn2"], rows, m.ff, d)
+                pg[pre + "pre_ff_ln.scale"] = ops.colsum_wgrad(gmid, s["y"], m.eps)
             # dy = dz + RMSNorm_bwd(y, pre_ff, dyn) ; da1 = RMSNorm_bwd(a1, post_attn, dy)
             ops.rmsnorm_bwd_chain(g, s["y"], lw["pre_ff"], gmid, s["a1"], lw["post_attn"], m.eps, g, adt, g2, rows, d)
+            if pg is not None:  # g = dL/dy, g2 = da1
+                pg[pre + "post_attn_ln.scale"] = ops.colsum_wgrad(g, s["a1"], m.eps)
+                pg[pre + "attn.out.weight"] = self._wgrad(g2, s["attn"], rows, d, d)
             # datt = da1 Wo
             ops.gemm([(g2, tw["out"], d)], rows, d, datt, mid_dt, precision=prec)
+            dparams = torch.zeros(2 * m.hd, dtype=torch.float32, device=dev) if pg is not None else None
             ops.timesfm_attention_bwd(s["qkv"], datt, b, n, m.h, m.hd, saved["patch_mask"], saved["num_masked"],
-                                      w["inv_freq"], lw["q_ln"], lw["k_ln"], lw["q_scale"], m.eps, adt, dqkv=dqkv)
+                                      w["inv_freq"], lw["q_ln"], lw["k_ln"], lw["q_scale"], m.eps, adt, dqkv=dqkv,
+                                      dparams=dparams)
             # dxn = dqkv Wqkv
             ops.gemm([(dqkv, tw["qkv"], 3 * d)], rows, d, gmid, mid_dt, precision=prec)
+            if pg is not None:
+                pg[pre + "attn.qkv_proj.weight"] = self._wgrad(dqkv, s["xn1"], rows, 3 * d, d)
+                pg[pre + "pre_attn_ln.scale"] = ops.colsum_wgrad(gmid, s["x"], m.eps)
+                # q' = (q_ln * softplus(per_dim) * c) * qhat: chain rule for the three 80-vectors
+                xf = m.stacked_xf[i].attn
+                per_dim = xf.per_dim_scale.per_dim_scale.detach().float()
+                c = 1.442695041 / math.sqrt(m.hd)
+                d_eff, d_k = dparams[: m.hd], dparams[m.hd :]
+                pg[pre + "attn.query_ln.scale"] = d_eff * lw["q_scale"]
+                pg[pre + "attn.key_ln.scale"] = d_k.clone()
+                pg[pre + "attn.per_dim_scale.per_dim_scale"] = d_eff * lw["q_ln"] * c * torch.sigmoid(per_dim)
             # dx = dy + RMSNorm_bwd(x, pre_attn, dxn) ; and, for the layer below, da2 = RMSNorm_bwd(a2, post_ff, dx)
             below = i - 1
             ops.rmsnorm_bwd_chain(g, s["x"], lw["pre_attn"], gmid, sl[below]["a2"] if below >= 0 else None,
                                   layers[below]["post_ff"] if below >= 0 else None, m.eps, g, adt,
                                   g2 if below >= 0 else None, rows, d)
         return g
+
+    def preprocess_saving(self, inputs: torch.Tensor, masks: torch.Tensor):
+        """``preprocess`` that keeps the tokenizer's operands (full fine-tuning)."""
+        m = self._model
+        batch_size, context = inputs.shape[0], inputs.shape[1]
+        if context % m.p != 0:
+            raise ValueError(f"context length ({context}) must be divisible by patch length ({m.p})")
+        if masks.shape != inputs.shape:
+            raise ValueError(f"masks shape {masks.shape} must match inputs shape {inputs.shape}")
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        mid_dt = DT_BF16 if prec == PREC_BF16 else DT_F32
+        w = self._weights()
+        n = context // m.p
+        rows = batch_size * n
+        masks = masks.bool()
+        tokens, mu, sigma, _pm, _nm = ops.timesfm_patchify_norm(inputs, masks, m.p, adt)
+        hidden = ops.alloc(rows, m.md, adt, inputs.device)
+        z = ops.alloc(rows, m.md, mid_dt, inputs.device)
+        ops.gemm([(tokens, w["tok_hidden"], 2 * m.p)], rows, m.md, hidden, adt, precision=prec, act=ACT_SILU,
+                 bias=w["tok_hidden_b"], pre_act=z)
+        emb = torch.empty(rows, m.md, dtype=torch.float32, device=inputs.device)
+        ops.gemm([(hidden, w["tok_out"], m.md), (tokens, w["tok_res"], 2 * m.p)], rows, m.md, emb, DT_F32,
+                 precision=prec, bias=w["tok_out_b"])
+        pre = PreprocessResult(emb.view(batch_size, n, m.md), masks.reshape(batch_size, n, m.p),
+                               {"context_mu": mu, "context_sigma": sigma})
+        return pre, {"tokens": tokens, "hidden": hidden, "z": z, "rows": rows}
+
+    def preprocess_backward(self, saved, d_emb: torch.Tensor, param_grads: dict[str, torch.Tensor]) -> None:
+        """Weight / bias gradients of the tokenizer ResidualBlock from dL/d(input embeddings) [M, D] fp32."""
+        m = self._model
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        wt = self._weights_t()
+        rows, tokens, hidden = saved["rows"], saved["tokens"], saved["hidden"]
+        pg = param_grads
+        pg["tokenizer.output_layer.weight"] = self._wgrad(d_emb, hidden, rows, m.md, m.md)
+        pg["tokenizer.residual_layer.weight"] = self._wgrad(d_emb, tokens, rows, m.md, 2 * m.p)
+        bias = ops.colsum_wgrad(d_emb)
+        pg["tokenizer.output_layer.bias"] = bias
+        pg["tokenizer.residual_layer.bias"] = bias.clone()
+        d_emb_a = ops.cast_rows(d_emb, adt)
+        dz32 = torch.empty(rows, m.md, dtype=torch.float32, device=d_emb.device)
+        ops.gemm([(d_emb_a, wt["tok_out"], m.md)], rows, m.md, dz32, DT_F32, precision=prec, act=ACT_SILU_GRAD, aux=saved["z"])
+        pg["tokenizer.hidden_layer.weight"] = self._wgrad(dz32, tokens, rows, m.md, 2 * m.p)
+        pg["tokenizer.hidden_layer.bias"] = ops.colsum_wgrad(dz32)
 
     def postprocess_saving(self, horizon: int, output_embeddings: torch.Tensor, normalization_stats):
         """``postprocess`` that keeps the head's pre-activation and operands for the backward pass."""
@@ -469,10 +565,13 @@ class TimesFM2p5Adapter(TsfmAdapter):
         out = torch.empty(b, horizon * m.q, dtype=torch.float32, device=last.device)
         ops.gemm([(hid, w["head_out"], m.md), (a, w["head_res"], d)], b, m.o * m.q, out, DT_F32, precision=prec,
                  row_scale=sigma_last, row_shift=mu_last, n_store=horizon * m.q)
-        return out.view(b, horizon, m.q), {"z": z, "sigma": sigma_last, "horizon": horizon, "b": b, "n": n}
+        return out.view(b, horizon, m.q), {"z": z, "sigma": sigma_last, "horizon": horizon, "b": b, "n": n, "a": a,
+                                           "hid": hid}
 
-    def postprocess_backward(self, saved, grad_forecast: torch.Tensor) -> torch.Tensor:
-        """dL/d(forecast) [B, h, 10] -> dL/d(output embeddings) [B, N, D] fp32 (non-zero in the last patch only)."""
+    def postprocess_backward(self, saved, grad_forecast: torch.Tensor,
+                             param_grads: dict[str, torch.Tensor] | None = None) -> torch.Tensor:
+        """dL/d(forecast) [B, h, 10] -> dL/d(output embeddings) [B, N, D] fp32 (non-zero in the last patch only);
+        ``param_grads`` additionally receives the head's weight gradients (full fine-tuning)."""
         m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -488,6 +587,11 @@ class TimesFM2p5Adapter(TsfmAdapter):
         d_last = torch.empty(b, m.md, dtype=torch.float32, device=dev)
         ops.gemm([(dz, wt["head_hidden"], m.md), (dpre, wt["head_res"], m.o * m.q)], b, m.md, d_last, DT_F32,
                  precision=prec)
+        if param_grads is not None:
+            head = "output_projection_point."
+            param_grads[head + "output_layer.weight"] = self._wgrad(dpre, saved["hid"], b, m.o * m.q, m.md)
+            param_grads[head + "residual_layer.weight"] = self._wgrad(dpre, saved["a"], b, m.o * m.q, m.md)
+            param_grads[head + "hidden_layer.weight"] = self._wgrad(dz, saved["a"], b, m.md, m.md)
         d_out = torch.zeros(b, saved["n"], m.md, dtype=torch.float32, device=dev)
         d_out[:, -1, :] = d_last  # only the last patch feeds the head (reference timesfm.py:129)
         return d_out

@@ -298,3 +298,63 @@ def test_baseline_mode_is_refused_loudly():
     ctx, masks, text, _ = O.synthetic_batch(2, 512, 16)
     with pytest.raises(NotImplementedError, match="baseline mode"):
         dec(16, ctx.to(DEV), masks.to(DEV), text.to(DEV))
+
+
+# ----------------------------------------------------------------------------- full fine-tuning ("baseline" mode)
+def _oracle_grads_upstream_names(o_adapter, num_layers):
+    """Gradients of the oracle adapter's parameters under the upstream (product) state-dict names."""
+    g = {}
+    for src, dst in (("hidden_layer", "input_layer"), ("output_layer", "output_layer"), ("residual_layer", "residual_layer")):
+        g[f"tokenizer.{src}.weight"] = getattr(o_adapter.tokenizer, dst).weight.grad
+        g[f"tokenizer.{src}.bias"] = getattr(o_adapter.tokenizer, dst).bias.grad
+        g[f"output_projection_point.{src}.weight"] = getattr(o_adapter.output_projection_point, dst).weight.grad
+    for i, layer in enumerate(o_adapter.stacked_xf):
+        pre = f"stacked_xf.{i}."
+        g[pre + "pre_attn_ln.scale"] = layer.input_layernorm.weight.grad
+        g[pre + "post_attn_ln.scale"] = layer.post_attention_layernorm.weight.grad
+        g[pre + "pre_ff_ln.scale"] = layer.pre_feedforward_layernorm.weight.grad
+        g[pre + "post_ff_ln.scale"] = layer.post_feedforward_layernorm.weight.grad
+        a = layer.self_attn
+        g[pre + "attn.qkv_proj.weight"] = torch.cat([a.q_proj.weight.grad, a.k_proj.weight.grad, a.v_proj.weight.grad], 0)
+        g[pre + "attn.out.weight"] = a.o_proj.weight.grad
+        g[pre + "attn.query_ln.scale"] = a.q_norm.weight.grad
+        g[pre + "attn.key_ln.scale"] = a.k_norm.weight.grad
+        g[pre + "attn.per_dim_scale.per_dim_scale"] = a.scaling.grad
+        g[pre + "ff0.weight"] = layer.mlp.fc1.weight.grad
+        g[pre + "ff1.weight"] = layer.mlp.fc2.weight.grad
+    return g
+
+
+@pytest.mark.parametrize("with_text,padded", [(False, False), (True, True)])
+def test_full_finetune_gradients_match_oracle(with_text, padded):
+    """Reference "baseline" mode (trainer.py:78-79,123): the adapter is unfrozen.  Every parameter gradient of the CUDA
+    path (weight-gradient GEMMs with K = tokens, column reductions, attention parameter gradients) against the
+    oracle's torch autograd, fp32-accumulate parity mode."""
+    dec, oracle = build(2)
+    dec.set_precision("bf16x3")
+    dec.adapter.unfreeze_parameters()
+    dec.train()
+    ctx, masks, text, target = O.synthetic_batch(6, 512, 128, padded=padded, seed=31)
+    text_arg = text if with_text else None
+    for p in oracle.parameters():
+        p.requires_grad_(True)
+    ref_loss = torch.nn.functional.mse_loss(oracle(128, ctx, masks, text_arg), target)
+    ref_loss.backward()
+    ref = _oracle_grads_upstream_names(oracle.adapter, 2)
+    loss = torch.nn.functional.mse_loss(
+        dec(128, ctx.to(DEV), masks.to(DEV), None if text_arg is None else text_arg.to(DEV)), target.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    got = {k: v.grad for k, v in dec.adapter._model.named_parameters()}
+    worst = {}
+    for name, r in ref.items():
+        assert got[name] is not None, name
+        worst[name] = ((got[name].cpu().double() - r.double()).norm() / r.double().norm().clamp_min(1e-30)).item()
+    bad = {k: v for k, v in worst.items() if v > 2e-3}
+    assert not bad, bad
+    if with_text:
+        rf = oracle.fusion.projection[0].weight.grad
+        gf = dec.fusion.linears()[0].weight.grad.cpu()
+        assert ((gf.double() - rf.double()).norm() / rf.double().norm()).item() < 2e-3
+    else:
+        assert dec.fusion.linears()[0].weight.grad is None
