@@ -55,19 +55,40 @@ def shard_batch(batch: dict, rank: int, world: int) -> dict:
     return {k: v[lo:hi] for k, v in batch.items()}
 
 
+BUCKET_ELEMS = 64 * 1024 * 1024  # floats per flattened all-reduce bucket (256 MB)
+
+
 def allreduce_mean_(tensors: Iterable[torch.Tensor], group=None) -> None:
-    """In-place mean over ranks of a list of (gradient) tensors through ONE flattened all-reduce."""
+    """In-place mean over ranks of a list of (gradient) tensors through flattened all-reduces (one per bucket)."""
     tensors = [t for t in tensors if t is not None]
     if not tensors or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.div_(dist.get_world_size(group))
-    offset = 0
+    world = dist.get_world_size(group)
+    # flattened buckets of at most BUCKET_ELEMS floats: one collective for the fusion gradients (2 MB), a handful of
+    # 256 MB ones for a full fine-tune (231 M parameters) without a second copy of all gradients at once
+    bucket: list[torch.Tensor] = []
+    count = 0
+
+    def flush() -> None:
+        nonlocal bucket, count
+        if not bucket:
+            return
+        flat = torch.cat([t.reshape(-1).to(torch.float32) for t in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        offset = 0
+        for t in bucket:
+            n = t.numel()
+            t.copy_(flat[offset : offset + n].view_as(t))
+            offset += n
+        bucket, count = [], 0
+
     for t in tensors:
-        n = t.numel()
-        t.copy_(flat[offset : offset + n].view_as(t))
-        offset += n
+        if count and count + t.numel() > BUCKET_ELEMS:
+            flush()
+        bucket.append(t)
+        count += t.numel()
+    flush()
 
 
 def allreduce_max(value: float, device: torch.device, group=None) -> float:

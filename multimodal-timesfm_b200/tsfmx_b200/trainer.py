@@ -5,8 +5,8 @@ Kept from the reference: the class name, constructor arguments, "multimodal" = f
 (trainer.py:76-77,119-123), loss / accumulation / clip / step order (trainer.py:200-219), ``RuntimeError`` on empty
 datasets, checkpoint dictionary keys (types.py:42-61).  Added for the B200 box: data parallelism — each rank takes its
 slice of every batch and the fusion gradients are averaged with one NCCL all-reduce per optimizer step, before the
-clip; checkpoints are written by rank 0.  Not rebuilt: "baseline" full fine-tuning of the adapter (needs backbone
-weight gradients).
+clip; checkpoints are written by rank 0.  "baseline" = full fine-tuning of the adapter without text (trainer.py:78-79):
+available for the TimesFM adapter (weight-gradient GEMMs for every Linear, all-reduce of all 231 M gradients).
 """
 
 from __future__ import annotations
@@ -74,11 +74,16 @@ class MultimodalTrainer:
         self.model.to(self.device)
         if mode == "multimodal":
             self.model.adapter.freeze_parameters()
+        elif mode == "baseline":
+            # full fine-tuning of the adapter, no text (reference trainer.py:78-79, baseline_collate_fn)
+            if not hasattr(self.model.adapter, "preprocess_backward"):
+                raise NotImplementedError(
+                    f"mode='baseline' needs backbone weight gradients, which {type(self.model.adapter).__name__} does "
+                    "not produce on the B200 path yet (TimesFM2p5Adapter does)"
+                )
+            self.model.adapter.unfreeze_parameters()
         else:
-            raise NotImplementedError(
-                "mode='baseline' (full fine-tuning of the adapter) needs backbone weight gradients; the B200 path "
-                "implements the reference's multimodal mode (frozen adapter, trainable fusion)"
-            )
+            raise ValueError(f"mode must be 'multimodal' or 'baseline', got {mode!r}")
         collate = multimodal_collate_fn if mode == "multimodal" else baseline_collate_fn
         pin = self.device.type == "cuda"
         self.train_loader = DataLoader(train_dataset, batch_size=args.per_device_train_batch_size * self.world_size,
@@ -98,7 +103,11 @@ class MultimodalTrainer:
         self.best_val_loss = float("inf")
 
     def _get_trainable_params(self) -> Iterator[nn.Parameter]:
-        return self.model.fusion.parameters()
+        """Fusion weights in "multimodal" mode, the adapter's trainable parameters in "baseline" mode
+        (reference trainer.py:119-123)."""
+        if self.mode == "multimodal":
+            return self.model.fusion.parameters()
+        return (p for p in self.model.adapter.parameters() if p.requires_grad)
 
     def _create_scheduler(self, total_steps: int) -> LRScheduler:
         kind = getattr(self.args, "lr_scheduler_type", "linear")
@@ -121,7 +130,7 @@ class MultimodalTrainer:
 
     def optimizer_step(self) -> None:
         """All-reduce (mean) of the fusion gradients, clip, AdamW, LR schedule (reference trainer.py:213-219)."""
-        params = list(self._get_trainable_params())
+        params = [p for p in self._get_trainable_params() if p.grad is not None]
         tdist.allreduce_mean_([p.grad for p in params])
         if self.args.max_grad_norm > 0:
             nn.utils.clip_grad_norm_(params, self.args.max_grad_norm)
@@ -190,21 +199,28 @@ class MultimodalTrainer:
 
     # ------------------------------------------------------------------ checkpoints (rank 0 writes; every rank reads)
     def build_checkpoint(self) -> dict[str, Any]:
-        """Same keys as the reference ``MultimodalCheckpoint`` (types.py:42-56, trainer.py:285-303)."""
-        return {
+        """Same keys as the reference ``MultimodalCheckpoint`` / ``BaselineCheckpoint`` (types.py:42-61, trainer.py:285-303)."""
+        ckpt = {
             "epoch": self.current_epoch,
             "global_step": self.global_step,
             "optimizer_state_dict": self.optimizer.state_dict(),
             "scheduler_state_dict": self.lr_scheduler.state_dict(),
             "best_val_loss": self.best_val_loss,
-            "fusion_state_dict": self.model.fusion.state_dict(),
         }
+        if self.mode == "multimodal":
+            ckpt["fusion_state_dict"] = self.model.fusion.state_dict()
+        else:
+            ckpt["adapter_state_dict"] = self.model.adapter.state_dict()
+        return ckpt
 
     _build_checkpoint = build_checkpoint  # the reference's (private) name
 
     def _load_checkpoint_state(self, checkpoint: dict[str, Any]) -> None:
         """Restore the trained module from a checkpoint dict (reference trainer.py:305-310)."""
-        self.model.fusion.load_state_dict(checkpoint["fusion_state_dict"])
+        if self.mode == "multimodal":
+            self.model.fusion.load_state_dict(checkpoint["fusion_state_dict"])
+        else:
+            self.model.adapter.load_state_dict(checkpoint["adapter_state_dict"])
 
     def _rotate_checkpoints(self) -> None:
         """Keep the ``save_total_limit`` most recent ``checkpoint_epoch_*.pt`` files (reference trainer.py:312-323)."""

@@ -172,6 +172,34 @@ def main():
         del dec, trainer, data
         torch.cuda.empty_cache()
 
+    if want("finetune_baseline"):
+        fb = min(B, args.finetune_batch)
+        dec = timesfm_decoder(50, dev)
+        dec.train()
+        targs = types.SimpleNamespace(per_device_train_batch_size=fb, per_device_eval_batch_size=fb,
+                                      gradient_accumulation_steps=1, max_grad_norm=1.0, learning_rate=1e-5,
+                                      weight_decay=0.01, num_train_epochs=1, logging_steps=1, seed=0)
+        from tsfmx_b200.trainer import MultimodalTrainer
+
+        dummy = [{"context": torch.zeros(512).numpy(), "horizon": torch.zeros(128).numpy(), "metadata": {}}]
+        trainer = MultimodalTrainer(dec, targs, dummy, dummy, "baseline", dev)
+        trainer.rank, trainer.world_size = 0, 1  # the batches below are already this rank's shard
+        data = [batch_for(dec.adapter, fb, 512, 128, 8321 + 17 * rank + i, dev) for i in range(2)]
+
+        def step_base(i):
+            c, m, _t, h = data[i % 2]
+            loss = trainer._forward_loss({"context": c, "horizon": h})
+            loss.backward()
+            trainer.optimizer_step()  # all-reduce of every adapter gradient (NCCL) + clip + AdamW + schedule
+
+        ms, n = timed(step_base, args.steps, args.warmup, world, dev)
+        grads = sum(p.numel() for p in dec.adapter.parameters())
+        emit(rank, "baseline-full-finetune", f"TimesFM-2.5 layout 50 layers, ctx 512 / h 128, {fb} series per GPU, full "
+             "fine-tune step (fwd + dgrad + wgrad of every Linear + all-reduce of all gradients + clip + AdamW)", fb, ms,
+             args.steps, args.warmup, world, n, {"allreduce_bytes_per_step": grads * 4 if world > 1 else 0})
+        del dec, trainer, data
+        torch.cuda.empty_cache()
+
     if want("finetune_chronos2"):
         fb = min(B, args.finetune_batch)
         dec = chronos2_decoder(dev)

@@ -36,6 +36,7 @@ def build(device):
 
 
 def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "multimodal"   # or "baseline": full fine-tuning of the adapter
     rank, world, local_rank = tdist.init_process_group("nccl")
     device = torch.device("cuda", local_rank)
     per_rank, steps = 4, 3
@@ -49,13 +50,15 @@ def main():
                                  num_train_epochs=1, logging_steps=1, seed=0)
     # distributed run: each rank sees its slice of every global batch
     dec = build(device)
-    trainer = MultimodalTrainer(dec, args, samples, samples[: per_rank * world], "multimodal", device)
+    trainer = MultimodalTrainer(dec, args, samples, samples[: per_rank * world], mode, device)
     loss = trainer.train_epoch()
-    w_dist = dec.fusion.linears()[0].weight.detach().clone()
+    pick = (lambda d: d.fusion.linears()[0].weight) if mode == "multimodal" else (
+        lambda d: d.adapter._model.stacked_xf[0].ff0.weight)
+    w_dist = pick(dec).detach().clone()
 
     # single-process reference on the same global batches (world size forced to 1 for this trainer)
     ref = build(device)
-    ref_trainer = MultimodalTrainer(ref, args, samples, samples[: per_rank * world], "multimodal", device)
+    ref_trainer = MultimodalTrainer(ref, args, samples, samples[: per_rank * world], mode, device)
     ref_trainer.rank, ref_trainer.world_size = 0, 1
     saved = tdist.allreduce_mean_
     tdist.allreduce_mean_ = lambda tensors, group=None: None
@@ -63,16 +66,16 @@ def main():
         ref_loss = ref_trainer.train_epoch()
     finally:
         tdist.allreduce_mean_ = saved
-    w_ref = ref.fusion.linears()[0].weight.detach()
+    w_ref = pick(ref).detach()
 
-    rel = ((w_dist - w_ref).norm() / (w_ref - build(device).fusion.linears()[0].weight).norm()).item()
+    rel = ((w_dist - w_ref).norm() / (w_ref - pick(build(device))).norm()).item()
     same = True
     if world > 1:
         gathered = [torch.empty_like(w_dist) for _ in range(world)]
         dist.all_gather(gathered, w_dist)
         same = all(torch.equal(gathered[0], g) for g in gathered)
     if rank == 0:
-        print(f"world={world} steps={trainer.global_step} loss dist={loss:.6f} ref={ref_loss:.6f} "
+        print(f"mode={mode} world={world} steps={trainer.global_step} loss dist={loss:.6f} ref={ref_loss:.6f} "
               f"update rel diff={rel:.3e} identical_across_ranks={same}")
     assert same, "ranks diverged"
     assert abs(loss - ref_loss) < 1e-4 * max(1.0, abs(ref_loss)), (loss, ref_loss)

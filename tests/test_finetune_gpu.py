@@ -292,11 +292,18 @@ def test_gradient_accumulation_and_bf16_mode():
     assert err < 6e-2
 
 
-def test_baseline_mode_is_refused_loudly():
-    dec, _ = build(1)
+def test_full_finetune_of_an_adapter_without_that_path_is_refused_loudly():
+    """Only the TimesFM adapter has the wgrad path; an unfrozen Chronos-2 adapter must not silently train nothing."""
+    from tsfmx_b200.tsfm.chronos import Chronos2Adapter, Chronos2Module
+    from tsfmx_b200.tsfm.chronos import init_random_ as init_chronos_
+
+    module = Chronos2Module(1)
+    init_chronos_(module, 0)
+    dec = MultimodalDecoder(Chronos2Adapter(module), MultimodalDecoderConfig(384, 1, [])).to(DEV).train()
     dec.adapter.unfreeze_parameters()
-    ctx, masks, text, _ = O.synthetic_batch(2, 512, 16)
-    with pytest.raises(NotImplementedError, match="baseline mode"):
+    ctx, masks, _t, _ = O.synthetic_batch(2, 512, 16, patch_len=16)
+    text = torch.randn(2, 32, 384)
+    with pytest.raises(NotImplementedError, match="no full fine-tuning path"):
         dec(16, ctx.to(DEV), masks.to(DEV), text.to(DEV))
 
 

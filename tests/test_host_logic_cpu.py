@@ -121,5 +121,13 @@ def test_trainer_checkpoint_strategies(tmp_path):
     args.eval_strategy = "steps"
     with pytest.raises(NotImplementedError):
         tr.train()
+    args.eval_strategy = "epoch"
+    base = MultimodalTrainer(dec, args, dummy, dummy, "baseline", torch.device("cpu"))   # TimesFM: full fine-tuning
+    assert all(p.requires_grad for p in dec.adapter.parameters())
+    assert "adapter_state_dict" in base.build_checkpoint() and "fusion_state_dict" not in base.build_checkpoint()
+    assert len(list(base._get_trainable_params())) == len(list(dec.adapter.parameters()))
+    c2 = MultimodalDecoder(Chronos2Adapter(Chronos2Module(1)), MultimodalDecoderConfig())
     with pytest.raises(NotImplementedError):
-        MultimodalTrainer(dec, args, dummy, dummy, "baseline", torch.device("cpu"))
+        MultimodalTrainer(c2, args, dummy, dummy, "baseline", torch.device("cpu"))
+    with pytest.raises(ValueError):
+        MultimodalTrainer(dec, args, dummy, dummy, "something", torch.device("cpu"))
