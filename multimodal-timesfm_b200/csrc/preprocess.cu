@@ -1036,6 +1036,192 @@ __global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_vec_kernel(
   }
 }
 
+// Staged variant (the default for context % 4 == 0, context <= 2048).  Same arithmetic as the vectorised kernel
+// above, but the tokens and mask bytes of a series go through a per-warp shared-memory row first, so that what
+// leaves the SM is re-tiled to the ROW's alignment in global memory: every 16-byte id store is one aligned pair
+// (an int64 row of context + 1 entries starts on an 8-byte boundary for every other series) and every mask store
+// is one aligned 32-bit word (a mask row of context + 1 bytes starts at any byte).  A warp store instruction then
+// covers 512 / 128 contiguous bytes instead of half-filled sectors at a 32-byte stride.  The per-element
+// magnitude test of the hoisted-reciprocal division is gone: the quotient is only trusted when it lands strictly
+// inside a cell of the uniform grid (frac in [1/256, 255/256]), and every other element takes the IEEE division
+// and the exact table search, so a quotient whose refinement under/overflowed can never pick the token.
+constexpr int T5_CHUNK = 512;  // elements staged per warp at a time (4 float4 per lane)
+
+template <bool MULTI>  // MULTI: context > T5_CHUNK, the row is read twice (the second time from L2)
+__global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_staged_kernel(
+    const float* __restrict__ x, int64_t batch, int context, const float* __restrict__ boundaries, int nb,
+    int n_special, int n_tokens, int pad_id, int eos_id, int64_t* __restrict__ ids,
+    uint8_t* __restrict__ attn_mask, float* __restrict__ scale_out) {
+  extern __shared__ __align__(16) float sp[];  // [nb + 2] table between sentinels, then the per-warp staging rows
+  __shared__ int s_nonuniform;
+  if (threadIdx.x == 0) s_nonuniform = 0;
+  for (int i = threadIdx.x; i < nb + 2; i += blockDim.x)
+    sp[i] = i == 0 ? -INFINITY : (i == nb + 1 ? NAN : boundaries[i - 1]);
+  __syncthreads();
+  const float step = (sp[nb - 1] - sp[2]) / static_cast<float>(nb - 3);
+  const float inv_step = static_cast<float>(nb - 3) / (sp[nb - 1] - sp[2]);
+  const float g_mul = inv_step, g_add = fmaf(-sp[2], inv_step, 2.0f);
+  {
+    int bad = !(step > 0.f) || nb > 8190;
+    for (int i = 1 + threadIdx.x; i <= nb - 2; i += blockDim.x) {
+      const float ideal = fmaf(static_cast<float>(i - 1), step, sp[2]);
+      bad |= !(fabsf(sp[1 + i] - ideal) <= step * (1.0f / 2048.0f));
+    }
+    if (bad) s_nonuniform = 1;
+  }
+  __syncthreads();
+  const bool uniform = s_nonuniform == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = context >> 2;
+  const int row = context + 1;
+  const int t_max = n_tokens - 1;
+  const int nchunks = MULTI ? (context + T5_CHUNK - 1) / T5_CHUNK : 1;
+  // staging row of this warp, reused chunk after chunk: token of chunk-relative element e at st_tok[4 + e]
+  // (e = -1: last token of the previous chunk), mask byte of chunk-relative position p at byte 4 + p of st_msk32
+  // (word 0: last four bytes of the previous chunk)
+  constexpr int TOK_WORDS = T5_CHUNK + 8, MSK_WORDS = (T5_CHUNK + 12) >> 2, WARP_WORDS = (TOK_WORDS + MSK_WORDS + 3) & ~3;
+  uint32_t* st_tok = reinterpret_cast<uint32_t*>(sp + ((nb + 2 + 3) & ~3)) + warp * WARP_WORDS;
+  uint32_t* st_msk32 = st_tok + TOK_WORDS;
+
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * WARPS + warp; b < batch;
+       b += static_cast<int64_t>(gridDim.x) * WARPS) {
+    const float* xr = x + b * context;
+    int64_t* idr = ids + b * row;
+    uint8_t* amr = attn_mask + b * row;
+    float4 v[4];
+    // sum(|x|) accumulated in fp64 and rounded to fp32 once: the scale (hence every id) is order independent
+    double sum = 0.0;
+    float cnt = 0.f;
+    auto load_chunk = [&](float4 (&dst)[4], int c) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = c * (T5_CHUNK / 4) + lane + 32 * j;
+        dst[j] = f < nvec ? ld_stream_f4(xr + 4 * f) : make_float4(NAN, NAN, NAN, NAN);
+      }
+    };
+    auto accumulate = [&](const float4 (&src)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xv[4] = {src[j].x, src[j].y, src[j].z, src[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool nan = isnan(xv[k]);
+          sum += nan ? 0.0 : static_cast<double>(fabsf(xv[k]));
+          cnt += nan ? 0.f : 1.f;
+        }
+      }
+    };
+    if (MULTI) {  // two chunks (eight 16-byte loads per lane) in flight
+      float4 w[4];
+      for (int c = 0; c < nchunks; c += 2) {
+        load_chunk(v, c);
+        load_chunk(w, c + 1);  // all-NaN beyond the row
+        accumulate(v);
+        accumulate(w);
+      }
+      load_chunk(v, 0);  // second read, first chunk: in flight during the reduction below
+    } else {
+      load_chunk(v, 0);
+      accumulate(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt = warp_sum(cnt);
+    float scale = __fdiv_rn(static_cast<float>(sum), cnt);  // 0/0 -> NaN -> 1 below
+    if (!(scale > 0.f)) scale = 1.f;
+    const float rscale = __frcp_rn(scale);
+    // the refined quotient is only meaningful for a scale whose reciprocal is a normal number
+    const float g_hi = (uniform && scale > 0x1p-60f && scale < 0x1p60f) ? static_cast<float>(nb - 1) : -1.f;
+    if (lane == 0 && scale_out != nullptr) scale_out[b] = scale;
+    const int s = static_cast<int>((reinterpret_cast<uintptr_t>(idr) >> 3) & 1);  // row starts in the upper half of a pair
+    const int a = static_cast<int>(reinterpret_cast<uintptr_t>(amr) & 3);
+    const int sh = 8 * (4 - a);
+
+    for (int c = 0; c < nchunks; ++c) {
+      const int len = min(T5_CHUNK, context - c * T5_CHUNK);  // elements of this chunk (a multiple of 4)
+      const bool last = c == nchunks - 1;
+      if (last && lane == 0) {
+        st_tok[4 + len] = static_cast<uint32_t>(eos_id);
+        st_msk32[1 + (len >> 2)] = 1u;  // eos byte
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = lane + 32 * j;  // float4 index inside the chunk
+        if (4 * f < len) {
+          const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          uint32_t t[4];
+          uint32_t mbytes = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool nan = isnan(xv[k]);
+            const float av = nan ? 0.f : xv[k];
+            // av / scale through the hoisted correctly rounded reciprocal and two FMA refinement steps (Markstein)
+            const float q0 = av * rscale;
+            const float q1 = fmaf(fmaf(-scale, q0, av), rscale, q0);
+            const float q = fmaf(fmaf(-scale, q1, av), rscale, q1);
+            const float g = fmaf(q, g_mul, g_add);
+            const float fl = floorf(g);
+            const float frac = g - fl;
+            int tk;
+            if (g >= 2.0f && g < g_hi && frac >= (1.0f / 256.0f) && frac <= (255.0f / 256.0f))
+              tk = static_cast<int>(fl);
+            else
+              tk = bucketize_right_sentinel(sp, nb, __fdiv_rn(av, scale), g_mul, g_add);
+            tk = max(0, min(t_max, tk + n_special));
+            t[k] = nan ? static_cast<uint32_t>(pad_id) : static_cast<uint32_t>(tk);
+            mbytes |= (nan ? 0u : 1u) << (8 * k);
+          }
+          *reinterpret_cast<uint4*>(st_tok + 4 + 4 * f) = make_uint4(t[0], t[1], t[2], t[3]);
+          st_msk32[1 + f] = mbytes;
+        }
+      }
+      if (MULTI && !last) load_chunk(v, c + 1);  // second read of the row (an L2 hit), in flight during the stores
+      __syncwarp();
+      const int top = last ? len : len - 1;  // highest chunk-relative index that holds a value (eos included)
+      // ---- ids: aligned 16-byte pairs (token e0 = 2k - s and its successor)
+      {
+        uint32_t* base = reinterpret_cast<uint32_t*>(idr + c * T5_CHUNK - s);  // 16-byte aligned
+        const int pairs = ((top + s) >> 1) + 1;
+        for (int k = lane; k < pairs; k += 32) {
+          const int e0 = 2 * k - s;
+          const uint32_t t0 = st_tok[4 + e0], t1 = st_tok[5 + e0];
+          uint32_t* o = base + 4 * k;
+          const bool lo_ok = e0 >= 0 || c > 0, hi_ok = e0 + 1 <= top;
+          if (lo_ok && hi_ok) {
+            *reinterpret_cast<uint4*>(o) = make_uint4(t0, 0u, t1, 0u);
+          } else if (!lo_ok) {
+            if (hi_ok) *reinterpret_cast<uint2*>(o + 2) = make_uint2(t1, 0u);
+          } else if (last) {  // the row ends in the lower half of its pair
+            *reinterpret_cast<uint2*>(o) = make_uint2(t0, 0u);
+          }  // else: the pair straddles the chunk boundary and leaves with the next chunk
+        }
+      }
+      // ---- mask: aligned 32-bit words; the first and last word of a row belong partly to its neighbours
+      {
+        uint8_t* base = amr + c * T5_CHUNK - a;
+        const int words = ((top + a) >> 2) + 1;
+        for (int k = lane; k < words; k += 32) {
+          const int p0 = 4 * k - a;  // chunk-relative positions p0 .. p0 + 3
+          const uint32_t w = __funnelshift_rc(st_msk32[k], st_msk32[k + 1], sh);
+          const bool lo_ok = p0 >= 0 || c > 0, hi_ok = p0 + 3 <= top;
+          if (lo_ok && hi_ok) {
+            *reinterpret_cast<uint32_t*>(base + 4 * k) = w;
+          } else if (hi_ok || last) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if ((p0 + i >= 0 || c > 0) && p0 + i <= top) base[4 * k + i] = static_cast<uint8_t>(w >> (8 * i));
+          }  // else: the word straddles the chunk boundary and leaves with the next chunk
+        }
+      }
+      __syncwarp();
+      if (!last && lane == 0) {  // carry the chunk's tail into the slots in front of the next chunk
+        st_tok[3] = st_tok[4 + T5_CHUNK - 1];
+        st_msk32[0] = st_msk32[T5_CHUNK >> 2];
+      }
+    }
+  }
+}
+
 __global__ void chronos_t5_dequantize_kernel(const int64_t* __restrict__ ids, int64_t total, int length,
                                              const float* __restrict__ centers, int n_centers, int n_special,
                                              const float* __restrict__ scale, float* __restrict__ values) {
@@ -1272,9 +1458,36 @@ extern "C" int tsfmx_chronos_t5_tokenize(const float* x, int64_t batch, int32_t 
   const dim3 block(WARPS * 32);
   const size_t smem = static_cast<size_t>(n_boundaries) * sizeof(float);
   const int variant = g_t5_variant > 0 ? g_t5_variant : (context <= 512 ? 1 : (context <= 2048 ? 2 : 3));
-  const bool vec_ok = g_t5_variant == 0 && context % 4 == 0 && context <= 2048 && n_boundaries >= 4 && pad_id >= 0 &&
+  const bool vec_ok = (g_t5_variant == 0 || g_t5_variant == 4) && context % 4 == 0 && context <= 2048 && n_boundaries >= 4 && pad_id >= 0 &&
                       reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(ids) % 16 == 0;
   const size_t smem_vec = static_cast<size_t>(n_boundaries + 2) * sizeof(float);
+  // default: the staged kernel, any context that is a multiple of 4 (g_t5_variant == 4 keeps the direct-store
+  // vectorised kernel for A/B runs)
+  const bool staged_ok = g_t5_variant == 0 && context % 4 == 0 && n_boundaries >= 4 && pad_id >= 0 &&
+                         reinterpret_cast<uintptr_t>(x) % 16 == 0;
+  if (staged_ok) {
+    const size_t warp_words = ((T5_CHUNK + 8) + ((T5_CHUNK + 12) >> 2) + 3) & ~3;
+    const size_t smem_staged = (static_cast<size_t>((n_boundaries + 2 + 3) & ~3) + WARPS * warp_words) * sizeof(float);
+    static bool attr_done[64] = {};  // per device: an 8192-entry table plus the staging rows exceed 48 KB
+    const int dev = current_device();
+    if (smem_staged > 48 * 1024 && !attr_done[dev]) {
+      if (cudaFuncSetAttribute(chronos_t5_tokenize_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               64 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(chronos_t5_tokenize_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               64 * 1024) != cudaSuccess) {
+        set_error("chronos_t5_tokenize: cannot raise the dynamic shared memory limit");
+        return TSFMX_ERR_CUDA;
+      }
+      attr_done[dev] = true;
+    }
+    if (context <= T5_CHUNK)
+      chronos_t5_tokenize_staged_kernel<false><<<grid, block, smem_staged, stream>>>(
+          x, batch, context, boundaries, n_boundaries, n_special, n_tokens, pad_id, eos_id, ids, attn_mask, scale);
+    else
+      chronos_t5_tokenize_staged_kernel<true><<<grid, block, smem_staged, stream>>>(
+          x, batch, context, boundaries, n_boundaries, n_special, n_tokens, pad_id, eos_id, ids, attn_mask, scale);
+    return check_last_launch("chronos_t5_tokenize");
+  }
   if (vec_ok && context <= 512) {
     chronos_t5_tokenize_vec_kernel<4><<<grid, block, smem_vec, stream>>>(x, batch, context, boundaries, n_boundaries,
                                                                     n_special, n_tokens, pad_id, eos_id, ids, attn_mask,

@@ -220,7 +220,7 @@ def _t5_tables():
     return centers, boundaries
 
 
-@pytest.mark.parametrize("context", [512, 2048, 100, 4099])
+@pytest.mark.parametrize("context", [512, 2048, 1024, 516, 1540, 8192, 100, 36, 4099])
 def test_chronos_t5_tokenize_bit_exact(context):
     b = 129
     gen = torch.Generator().manual_seed(context)
