@@ -563,6 +563,248 @@ __global__ void __launch_bounds__(TF_THREADS) timesfm_patchify_norm_tma_kernel(
 }
 
 // ----------------------------------------------------------------------------------------
+// Warp-private TMA variant (the default for context <= 2048).  The block-wide kernel above leaves 240 of its 256
+// threads at a barrier while one thread per series runs the dependent merge chain (ncu: 5.9 barrier-stall cycles per
+// issued instruction, 24 % of the warp slots occupied).  Here every WARP owns its tiles — about 32 patches: 2 series
+// at context 512, one series from context 1024 — with its own two-deep ring of bulk copies and its own mbarriers, and
+// no block-wide barrier after start-up: while a few lanes of one warp walk their merge chain, the scheduler runs the
+// statistics and the token stores of the other warps.  Slots are series-major (slot of patch p of the tile at p).
+// ----------------------------------------------------------------------------------------
+constexpr int TFW_WARPS = 8;
+
+// a / n, correctly rounded, for a divisor whose correctly rounded reciprocal r is known (n is a patch count, a small
+// positive integer): two FMA refinement steps of q = a * r (Markstein); operands outside the range where the exact
+// remainder argument holds take the IEEE division.
+__device__ __forceinline__ float div_known_recip(float a, float n, float r) {
+  const float aa = fabsf(a);
+  if (aa < 0x1p100f && (aa > 0x1p-100f || a == 0.f)) {
+    const float q0 = a * r;
+    const float q1 = fmaf(fmaf(-n, q0, a), r, q0);
+    return fmaf(fmaf(-n, q1, a), r, q1);
+  }
+  return __fdiv_rn(a, n);
+}
+
+// merge_stats with the new count and its reciprocal supplied (the counts do not depend on the values, so they are
+// scanned and inverted by all lanes in parallel before the dependent chain starts)
+__device__ __forceinline__ RunStats merge_stats_r(RunStats run, float inc_n, float inc_mu, float inc_sigma, float new_n,
+                                                  float r) {
+  const float new_n_safe = new_n == 0.f ? 1.f : new_n;
+  float new_mu = div_known_recip(__fadd_rn(__fmul_rn(run.n, run.mu), __fmul_rn(inc_mu, inc_n)), new_n_safe, r);
+  if (new_n == 0.f) new_mu = 0.f;
+  const float d1 = __fsub_rn(run.mu, new_mu), d2 = __fsub_rn(inc_mu, new_mu);
+  const float t1 = __fmul_rn(run.n, __fmul_rn(run.sigma, run.sigma));
+  const float t2 = __fmul_rn(inc_n, __fmul_rn(inc_sigma, inc_sigma));
+  const float t3 = __fmul_rn(run.n, __fmul_rn(d1, d1));
+  const float t4 = __fmul_rn(inc_n, __fmul_rn(d2, d2));
+  float new_var = div_known_recip(__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4), new_n_safe, r);
+  if (new_n == 0.f) new_var = 0.f;
+  return RunStats{new_n, new_mu, sqrtf(fmaxf(new_var, 0.f))};
+}
+
+template <int OUT>
+__global__ void __launch_bounds__(TFW_WARPS * 32) timesfm_patchify_norm_warp_kernel(
+    const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, int warps,
+    int warp_bytes, int g, int stages, void* tokens, float* __restrict__ mu_out, float* __restrict__ sigma_out,
+    uint8_t* __restrict__ patch_mask_out, int32_t* __restrict__ num_masked_out) {
+  // g = series per tile (<= 32; 1 when the context has more than 16 patches), stages = 1 or 2 tiles in flight
+  extern __shared__ __align__(128) uint8_t smem_tfw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pg = lane >> 3, q = lane & 7;
+  const int N = context >> 5;
+  const int stage_bytes = (g * context * 5 + 127) & ~127;
+  const int NB = (N + 7) >> 3;
+  const float inv_n = 1.0f / static_cast<float>(N);
+  uint8_t* wbase = smem_tfw + warp * warp_bytes;
+  float4* slots = reinterpret_cast<float4*>(wbase + stages * stage_bytes);  // {count, mean, sigma, padded flag} per patch
+  float4* aux = slots + g * N;  // {count so far, its reciprocal, count so far inside the block of 8, its reciprocal}
+  float4* blk = aux + g * N;    // blocked fold: [g][NB] block summaries, then the state before each block
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(blk + g * NB);
+  const int64_t num_tiles = (batch + g - 1) / g;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * warps + warp;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * warps;
+
+  auto issue = [&](int64_t tile, int stage) {
+    const int64_t b0 = tile * g;
+    const uint32_t cnt = static_cast<uint32_t>(batch - b0 < g ? batch - b0 : g);
+    uint8_t* dst = wbase + stage * stage_bytes;
+    mbar_arrive_expect_tx(&full_bar[stage], cnt * context * 5u);
+    bulk_load_1d(dst, x + b0 * context, cnt * context * 4u, &full_bar[stage]);
+    bulk_load_1d(dst + g * context * 4, mask + b0 * context, cnt * context, &full_bar[stage]);
+  };
+  if (lane == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+    if (first < num_tiles) issue(first, 0);
+    if (stages > 1 && first + stride < num_tiles) issue(first + stride, 1);
+  }
+  __syncwarp();
+
+  const int rot = lane + (lane >> 3);  // chunk rotation of phase A (bank groups), as in the block-wide kernel
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t tile = first; tile < num_tiles; tile += stride) {
+    const int64_t b0 = tile * g;
+    const int cnt = static_cast<int>(batch - b0 < g ? batch - b0 : g);
+    const int P = cnt * N;
+    const float* sx = reinterpret_cast<const float*>(wbase + stage * stage_bytes);
+    const uint8_t* sm = wbase + stage * stage_bytes + g * context * 4;
+    mbar_wait(&full_bar[stage], parity);
+
+    // ---- phase A: statistics of every patch, one lane per patch
+    for (int p = lane; p < P; p += 32) {
+      const float4* xp = reinterpret_cast<const float4*>(sx + p * 32);
+      const uint32_t* mp = reinterpret_cast<const uint32_t*>(sm + p * 32);
+      float xv[32];
+      uint32_t mbits = 0;  // bit e = element e of the patch is padded
+      float c = 0.f, sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = (j + rot) & 7;
+        const float4 v = xp[ch];
+        const uint32_t mk = mp[ch];
+        xv[4 * j + 0] = v.x, xv[4 * j + 1] = v.y, xv[4 * j + 2] = v.z, xv[4 * j + 3] = v.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool padded = ((mk >> (8 * k)) & 0xffu) != 0;
+          mbits |= (padded ? 1u : 0u) << (4 * j + k);
+          c += padded ? 0.f : 1.f;
+          sum += padded ? 0.f : xv[4 * j + k];
+        }
+      }
+      const float c_safe = c == 0.f ? 1.f : c;
+      const float inc_mu = c == 0.f ? 0.f : __fdiv_rn(sum, c_safe);
+      float sq = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float d = ((mbits >> e) & 1u) ? 0.f : xv[e] - inc_mu;
+        sq = fmaf(d, d, sq);
+      }
+      // the patch counts as padded iff its LAST element is padded (timesfm.py:97)
+      const float flag = sm[p * 32 + 31] ? 1.f : 0.f;
+      slots[p] = make_float4(c, inc_mu, c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f)), flag);
+    }
+    __syncwarp();
+    // ---- running counts and their reciprocals, one lane per patch: the counts are exact small integers (any order
+    //      of the additions gives the same value) and do not depend on the data values, so they leave the dependent
+    //      chain of phase B and all lanes take part in the IEEE reciprocals
+    for (int p = lane; p < P; p += 32) {
+      const int sr = g == 1 ? 0 : static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
+      const int k = p - sr * N;
+      const float4* row = slots + sr * N;
+      float n_before_block = 0.f, n_loc = 0.f;
+      for (int i = 0; i < (k & ~7); ++i) n_before_block += row[i].x;
+      for (int i = k & ~7; i <= k; ++i) n_loc += row[i].x;
+      const float n_cum = n_before_block + n_loc;
+      aux[p] = make_float4(n_cum, __frcp_rn(n_cum == 0.f ? 1.f : n_cum), n_loc,
+                           N > TF_BLOCKED_MIN_PATCHES ? __frcp_rn(n_loc == 0.f ? 1.f : n_loc) : 1.f);
+    }
+    __syncwarp();
+    // ---- phase B: merge of the running statistics; the slot becomes {cumulative mu, cumulative sigma,
+    //      1 / safe sigma, padded flag}
+    if (N <= TF_BLOCKED_MIN_PATCHES) {
+      // reference order exactly: lane s folds the N patches of series s one after the other
+      if (lane < cnt) {
+        RunStats st = {0.f, 0.f, 0.f};
+        int masked = 0;
+        float4* row = slots + lane * N;
+        const float4* arow = aux + lane * N;
+        for (int i = 0; i < N; ++i) {
+          const float4 inc = row[i];
+          const float4 cn = arow[i];
+          st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.x, cn.y);
+          row[i] = make_float4(st.mu, st.sigma, 0.f, inc.w);
+          masked += inc.w != 0.f ? 1 : 0;
+        }
+        if (num_masked_out != nullptr) num_masked_out[b0 + lane] = masked;
+      }
+    } else {
+      // blocked fold exactly as in the block-wide kernel (blocks of 8 patches), one lane per (series, block)
+      for (int u = lane; u < cnt * NB; u += 32) {
+        const int sr = u / NB, b = u - sr * NB;
+        const int k1 = min(N, 8 * b + 8);
+        RunStats st = {0.f, 0.f, 0.f};
+        for (int i = 8 * b; i < k1; ++i) {
+          const float4 inc = slots[sr * N + i];
+          const float4 cn = aux[sr * N + i];
+          st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.z, cn.w);
+        }
+        blk[u] = make_float4(st.n, st.mu, st.sigma, 0.f);
+      }
+      __syncwarp();
+      if (lane < cnt) {
+        RunStats st = {0.f, 0.f, 0.f};
+        for (int b = 0; b < NB; ++b) {
+          const float4 inc = blk[lane * NB + b];
+          const float4 cn = aux[lane * N + min(N, 8 * b + 8) - 1];  // count at the end of block b
+          blk[lane * NB + b] = make_float4(st.n, st.mu, st.sigma, 0.f);  // exclusive prefix
+          st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.x, cn.y);
+        }
+      }
+      __syncwarp();
+      for (int u = lane; u < ((cnt * NB + 31) & ~31); u += 32) {
+        int masked = 0;
+        const int sr = u / NB, b = u - sr * NB;
+        if (u < cnt * NB) {
+          const int k1 = min(N, 8 * b + 8);
+          const float4 pre = blk[u];
+          RunStats st = {pre.x, pre.y, pre.z};
+          for (int i = 8 * b; i < k1; ++i) {
+            const float4 inc = slots[sr * N + i];
+            const float4 cn = aux[sr * N + i];
+            st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.x, cn.y);
+            slots[sr * N + i] = make_float4(st.mu, st.sigma, 0.f, inc.w);
+            masked += inc.w != 0.f ? 1 : 0;
+          }
+        }
+        // padded-patch count of every series: sum over its NB lanes (NB <= 8 here, a series never straddles rounds
+        // when NB divides 32; otherwise fall back to one atomic per lane)
+        if (num_masked_out != nullptr && u < cnt * NB) {
+          if (b == 0) num_masked_out[b0 + sr] = 0;
+        }
+        __syncwarp();
+        if (num_masked_out != nullptr && u < cnt * NB && masked) atomicAdd(&num_masked_out[b0 + sr], masked);
+      }
+    }
+    __syncwarp();
+    // ---- mu / sigma / patch mask out, coalesced (the tile's [cnt, N] block is contiguous in [B, N]); the
+    //      reciprocal of the safe sigma is taken here, one lane per patch
+    for (int i = lane; i < P; i += 32) {
+      float4 st = slots[i];
+      st.z = __fdiv_rn(1.0f, st.y < 1e-6f ? 1.f : st.y);
+      slots[i] = st;
+      if (mu_out != nullptr) mu_out[b0 * N + i] = st.x;
+      if (sigma_out != nullptr) sigma_out[b0 * N + i] = st.y;
+      if (patch_mask_out != nullptr) patch_mask_out[b0 * N + i] = st.w != 0.f ? 1 : 0;
+    }
+    __syncwarp();
+    // ---- phase C: RevIN with the cumulative stats of the own patch, zero the padded points, emit tokens
+    //      (8 lanes per patch: every store instruction writes whole 128-byte lines)
+    for (int p = pg; p < P; p += 4) {
+      const float4 st = slots[p];
+      const float4 v = *reinterpret_cast<const float4*>(sx + p * 32 + 4 * q);
+      const uint32_t mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+      float val[4], msk[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const bool padded = ((mk >> (8 * kk)) & 0xffu) != 0;
+        msk[kk] = padded ? 1.f : 0.f;
+        val[kk] = padded ? 0.f : (xv[kk] - st.x) * st.z;
+      }
+      store_token_quad<OUT>(tokens, b0 * N + p, q, val, msk);
+    }
+    __syncwarp();  // every lane is done with this stage and with the slots
+    if (lane == 0) {
+      const int64_t next = tile + static_cast<int64_t>(stages) * stride;
+      if (next < num_tiles) issue(next, stage);
+    }
+    if (++stage == stages) { stage = 0; parity ^= 1; }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // Chronos-2 context preparation.
 // ----------------------------------------------------------------------------------------
 template <int OUT>
@@ -1291,6 +1533,42 @@ int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, in
     const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm * 2;
     const int grid = static_cast<int>(blocks < cap ? blocks : cap);
     kern<<<grid, warps * 32, smem, stream>>>(x, mask, batch, context, G, tokens, mu, sigma, patch_mask, num_masked);
+    return check_last_launch("timesfm_patchify_norm");
+  }
+  if ((g_tf_variant == 0 || g_tf_variant == 2) && context <= 2048) {  // warp-private tiles, no block-wide barriers
+    // series per tile: phase B keeps one lane per series busy, so more series per tile means fewer (mostly idle)
+    // warp instructions per series; the tile still has to leave room for >= 12 warps per SM
+    int g = g_tf_group > 0 ? g_tf_group : 2048 / context;
+    if (g > 32) g = 32;
+    if (g < 1) g = 1;
+    int stages = (g_tf_warps >> 8) > 0 ? (g_tf_warps >> 8) : (g * context * 5 <= 6 * 1024 ? 2 : 1);
+    if (stages > 2) stages = 2;
+    const int stage_bytes = (g * context * 5 + 127) & ~127;
+    const int warp_bytes = (stages * stage_bytes + (2 * g * N + g * ((N + 7) >> 3)) * 16 + 16 + 127) & ~127;
+    int warps = (g_tf_warps & 0xff) > 0 ? (g_tf_warps & 0xff) : TFW_WARPS;
+    if (warps > TFW_WARPS) warps = TFW_WARPS;
+    while (warps > 1 && warps * warp_bytes > 110 * 1024) --warps;  // at least two blocks per SM
+    const int smem = warps * warp_bytes;
+    auto kern = timesfm_patchify_norm_warp_kernel<OUT>;
+    static int smem_set_dev[64] = {0};  // cudaFuncSetAttribute is per device
+    int& smem_set = smem_set_dev[current_device()];
+    if (smem > 48 * 1024 && smem > smem_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) {
+        set_error("timesfm_patchify_norm: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+        return TSFMX_ERR_CUDA;
+      }
+      smem_set = smem;
+    }
+    const int64_t tiles = (batch + g - 1) / g;
+    const int64_t blocks = (tiles + warps - 1) / warps;
+    int per_sm = (224 * 1024) / (smem + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * warps > 48) per_sm = 48 / warps > 0 ? 48 / warps : 1;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+    const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+    kern<<<grid, warps * 32, smem, stream>>>(x, mask, batch, context, warps, warp_bytes, g, stages, tokens, mu, sigma,
+                                             patch_mask, num_masked);
     return check_last_launch("timesfm_patchify_norm");
   }
   // TMA-pipelined kernel: tiles of G series (<= 32: one merge thread per series), `stages` tiles in flight per block
