@@ -415,7 +415,8 @@ def run_b200_arm(args) -> None:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps,
                 "api": "MultimodalEvaluator.evaluate(loader of pinned host batches): H2D of context, horizon target and text "
-                       "embeddings staged one batch ahead on a copy stream, per-batch (mse, mae) read back (16 B)"},
+                       "embeddings staged one batch ahead on a copy stream into two persistent device slots, the forecast of "
+                       "a slot replayed from a CUDA graph of the same kernels, per-batch (mse, mae) read back (16 B)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks.summary(),

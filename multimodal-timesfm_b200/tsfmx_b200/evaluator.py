@@ -6,7 +6,10 @@ Same class, constructor and ``evaluate`` contract as the reference.  Differences
   host-to-device transfer of batch i + 1 - the text embeddings are ten times the series bytes - overlaps the
   kernels of batch i;
 * the per-batch ``.item()`` host syncs of the reference (evaluator.py:61-62) become asynchronous 16-byte read-backs
-  into pinned memory that are summed once at the end.
+  into pinned memory that are summed once at the end;
+* the staging buffers live as long as the evaluator, and the forecast of a staged batch is replayed from a CUDA graph
+  (one per staging slot, ``MultimodalDecoder._graphed_forecast``), so the host's per-launch Python cost is off the
+  step (``graphs=False`` keeps the eager launches).
 """
 
 from __future__ import annotations
@@ -29,21 +32,31 @@ class MultimodalEvaluator:
 
     _KEYS = ("context", "horizon", "text_embeddings")
 
-    def __init__(self, model: MultimodalDecoder, device: torch.device) -> None:
+    def __init__(self, model: MultimodalDecoder, device: torch.device, *, graphs: bool | None = None) -> None:
         self.model = model
         self.device = torch.device(device)
+        self.graphs = self.device.type == "cuda" if graphs is None else bool(graphs)
+        # device staging slots (and their padding masks), reused across evaluate() calls: stable addresses are what
+        # lets the forecast graphs be replayed
+        self._slots: list[dict[str, torch.Tensor]] = [{}, {}]
+        self._copy_stream: torch.cuda.Stream | None = None
 
     def _staged(self, dataloader: Iterable[dict]) -> Iterator[dict]:
         """Yield device-resident batches; with a CUDA device the next batch is already in flight on a copy stream."""
         if self.device.type != "cuda":
             for batch in dataloader:
-                yield {k: batch[k].to(self.device) for k in self._KEYS if k in batch}
+                out = {k: batch[k].to(self.device) for k in self._KEYS if k in batch}
+                out["input_padding"] = torch.zeros_like(out["context"], dtype=torch.bool)  # reference evaluator.py:52
+                yield out
             return
         main = torch.cuda.current_stream(self.device)
-        copy = torch.cuda.Stream(device=self.device)
-        # two sets of device staging buffers, reused for the whole pass (no allocator traffic per batch): slot s is
-        # refilled on the copy stream only after the kernels that consumed its previous contents have finished
-        slots: list[dict[str, torch.Tensor]] = [{}, {}]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy = self._copy_stream
+        copy.wait_stream(main)  # kernels of an earlier pass may still be reading the slots
+        # two sets of device staging buffers, reused for the evaluator's lifetime (no allocator traffic per batch): slot
+        # s is refilled on the copy stream only after the kernels that consumed its previous contents have finished
+        slots = self._slots
         consumed: list[torch.cuda.Event | None] = [None, None]
 
         def stage(batch: dict, slot: int):
@@ -55,13 +68,24 @@ class MultimodalEvaluator:
                     if k not in batch:
                         continue
                     src = batch[k]
-                    buf = slots[slot].get(k)
-                    if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
-                        buf = torch.empty(src.shape, dtype=src.dtype, device=self.device)
-                        buf.record_stream(main)
-                        slots[slot][k] = buf
+                    # the slot keeps its largest batch: a ragged last batch is a leading view of the same storage, so
+                    # the addresses (and the graphs bound to them) survive from pass to pass
+                    full = slots[slot].get(k)
+                    if (full is None or full.shape[1:] != src.shape[1:] or full.dtype != src.dtype
+                            or full.shape[0] < src.shape[0]):
+                        full = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                        full.record_stream(main)
+                        slots[slot][k] = full
+                    buf = full[: src.shape[0]]
                     buf.copy_(src, non_blocking=True)
                     out[k] = buf
+                pad = slots[slot].get("input_padding")
+                want = out["context"].shape
+                if pad is None or pad.shape[1:] != want[1:] or pad.shape[0] < want[0]:
+                    pad = torch.zeros(want, dtype=torch.bool, device=self.device)
+                    pad.record_stream(main)
+                    slots[slot]["input_padding"] = pad
+                out["input_padding"] = pad[: want[0]]
                 done = torch.cuda.Event()
                 done.record(copy)
             return out, done
@@ -89,6 +113,16 @@ class MultimodalEvaluator:
         """Raises RuntimeError if the loader yields no samples (reference evaluator.py:65-66)."""
         self.model.eval()
         cuda = self.device.type == "cuda"
+        graphs_before = getattr(self.model, "graphs", False)
+        if cuda and hasattr(self.model, "graphs"):
+            self.model.graphs = self.graphs
+        try:
+            return self._evaluate(dataloader, cuda)
+        finally:
+            if hasattr(self.model, "graphs"):
+                self.model.graphs = graphs_before
+
+    def _evaluate(self, dataloader: Iterable[dict], cuda: bool) -> EvaluationMetrics:
         sums: list[torch.Tensor] = []   # per batch [mean squared error, mean absolute error] * n
         ring = torch.empty(256, 2, dtype=torch.float64, pin_memory=True) if cuda else None  # one pinned allocation
         used = 0
@@ -96,8 +130,8 @@ class MultimodalEvaluator:
         with torch.no_grad():
             for batch in self._staged(dataloader):
                 context, horizon = batch["context"], batch["horizon"]
-                input_padding = torch.zeros_like(context, dtype=torch.bool)  # reference evaluator.py:52
-                point = self.model(horizon.shape[-1], context, input_padding, batch.get("text_embeddings"))
+                # all-False padding mask (reference evaluator.py:52), one per staging slot
+                point = self.model(horizon.shape[-1], context, batch["input_padding"], batch.get("text_embeddings"))
                 err = point - horizon
                 n = context.size(0)
                 stat = torch.stack([err.square().mean(), err.abs().mean()]).double() * n

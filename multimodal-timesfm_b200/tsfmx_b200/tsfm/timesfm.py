@@ -617,6 +617,12 @@ class TimesFM2p5Adapter(TsfmAdapter):
         for param in self.parameters():
             param.requires_grad = False
 
+    @property
+    def graph_safe(self) -> bool:
+        """The forecast path makes no host synchronisation and no allocation outside torch's allocator, so
+        ``MultimodalDecoder`` may capture it into a CUDA graph."""
+        return True
+
     def unfreeze_parameters(self) -> None:
         for param in self.parameters():
             param.requires_grad = True

@@ -56,3 +56,62 @@ def test_packed_store_feeds_the_evaluator():
     assert packed == collated
     shuffled = ev.evaluate(store.batches(8, shuffle=True, generator=torch.Generator().manual_seed(1)))
     assert shuffled["mse"] == pytest.approx(packed["mse"], rel=1e-5)  # same samples, other batch composition
+
+
+def _small_decoder(layers=2):
+    adapter = TimesFM2p5Adapter(num_layers=layers, with_quantile_head=False)
+    init_random_(adapter, seed=0)
+    torch.manual_seed(100)
+    return MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, [])).to("cuda").eval()
+
+
+def test_graph_replay_gives_the_eager_forecast():
+    """decoder.graphs: the forecast replayed from a CUDA graph is bit-identical to the eager launches, follows the
+    contents of the caller's buffers, and is captured afresh when a parameter changes in place."""
+    dec = _small_decoder()
+    ctx, masks, text, _ = O.synthetic_batch(24, 512, 128, seed=3, padded=True)
+    ctx, masks, text = ctx.cuda(), masks.cuda(), text.cuda()
+    with torch.no_grad():
+        eager = dec.forward_full(128, ctx, masks, text).clone()
+        dec.graphs = True
+        first = dec.forward_full(128, ctx, masks, text).clone()
+        assert torch.equal(first, eager)
+        assert len(dec._graph_cache) == 1
+        # new contents in the same buffers: same graph, new forecast
+        ctx2, masks2, text2, _ = O.synthetic_batch(24, 512, 128, seed=4, padded=True)
+        ctx.copy_(ctx2.cuda()); masks.copy_(masks2.cuda()); text.copy_(text2.cuda())
+        replayed = dec.forward_full(128, ctx, masks, text).clone()
+        assert len(dec._graph_cache) == 1
+        dec.graphs = False
+        assert torch.equal(replayed, dec.forward_full(128, ctx, masks, text))
+        assert not torch.equal(replayed, eager)
+        # an in-place parameter update invalidates the graph (the packed bf16 copies are rebuilt)
+        dec.graphs = True
+        dec.fusion.linears()[0].weight.mul_(1.5)
+        updated = dec.forward_full(128, ctx, masks, text).clone()
+        dec.graphs = False
+        assert torch.equal(updated, dec.forward_full(128, ctx, masks, text))
+        assert not torch.equal(updated, replayed)
+        # no text embeddings, other horizon: separate graphs
+        dec.graphs = True
+        assert torch.equal(dec.forward_full(64, ctx, masks), dec._forecast(64, ctx, masks, None))
+    assert len(dec._graph_cache) <= MultimodalDecoder.GRAPH_CACHE_ENTRIES
+
+
+def test_evaluator_graphs_match_eager_and_are_reused():
+    dec = _small_decoder()
+    batches = []
+    for i, b in enumerate((16, 16, 16, 5)):  # ragged last batch
+        ctx, _m, text, hor = O.synthetic_batch(b, 512, 64, seed=70 + i)
+        batches.append({"context": ctx.pin_memory(), "horizon": hor.pin_memory(), "text_embeddings": text.pin_memory()})
+    eager = MultimodalEvaluator(dec, torch.device("cuda"), graphs=False).evaluate(batches)
+    ev = MultimodalEvaluator(dec, torch.device("cuda"))
+    assert ev.graphs and not dec.graphs
+    got = ev.evaluate(batches)
+    assert got == eager
+    assert not dec.graphs  # restored
+    captured = len(dec._graph_cache)
+    assert 1 <= captured <= 3  # two staging slots, plus the ragged tail of one of them
+    keys = set(dec._graph_cache)
+    assert ev.evaluate(batches) == eager  # second pass: stable staging addresses, nothing captured again
+    assert set(dec._graph_cache) == keys
