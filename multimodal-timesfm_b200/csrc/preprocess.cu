@@ -1694,6 +1694,10 @@ extern "C" int tsfmx_chronos2_patchify_norm(const float* x, const uint8_t* mask,
       if (out_dtype == TSFMX_DT_F32) TSFMX_C2_LAUNCH(4, TSFMX_DT_F32);
       else if (out_dtype == TSFMX_DT_BF16) TSFMX_C2_LAUNCH(4, TSFMX_DT_BF16);
       else TSFMX_C2_LAUNCH(4, TSFMX_DT_BF16_SPLIT);
+    } else if (context <= 1024) {
+      if (out_dtype == TSFMX_DT_F32) TSFMX_C2_LAUNCH(8, TSFMX_DT_F32);
+      else if (out_dtype == TSFMX_DT_BF16) TSFMX_C2_LAUNCH(8, TSFMX_DT_BF16);
+      else TSFMX_C2_LAUNCH(8, TSFMX_DT_BF16_SPLIT);
     } else {
       if (out_dtype == TSFMX_DT_F32) TSFMX_C2_LAUNCH(16, TSFMX_DT_F32);
       else if (out_dtype == TSFMX_DT_BF16) TSFMX_C2_LAUNCH(16, TSFMX_DT_BF16);
