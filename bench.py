@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-norm", action="store_true", help="A/B: norm/residual junctions in the GEMM epilogue")
     ap.add_argument("--lanes", type=int, default=2, help="series lanes per GPU (1 = everything on one stream)")
+    ap.add_argument("--no-graphs", action="store_true", help="time the eager launches instead of the CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -352,14 +353,19 @@ def run_b200_arm(args) -> None:
         return ms
 
     with torch.no_grad():
-        for i in range(args.warmup):
+        # value pass: the forecast of each resident batch is replayed from a CUDA graph of the same kernel launches
+        # (MultimodalDecoder.graphs; captured during the warm-up, one graph per resident batch), so the number does not
+        # depend on how fast this box's host can issue ~720 launches per step next to the clock sampler's thread
+        dec.graphs = not args.no_graphs
+        for i in range(max(args.warmup, 2 * n_host_batches)):
             step_resident(i)
         run_e2e(max(2, args.warmup // 2))
         torch.cuda.synchronize()
-        launches0 = _lib.launch_count()
+        launches0 = _lib.launch_count() + dec.graph_launches_replayed
         with ClockSampler(local_rank, enabled=rank == 0) as clocks:
             ms_resident = timed(step_resident, args.steps)
-            launches = _lib.launch_count() - launches0
+            launches = _lib.launch_count() + dec.graph_launches_replayed - launches0
+            dec.graphs = False
             ms_e2e = timed(lambda i: run_e2e(args.steps) if i == 0 else None, 1)
             # roofline pass: the same steps with one lane, so that every kernel runs alone on one stream and the CUDA
             # events around a GEMM launch measure that launch (with lanes the events would also count the time a
@@ -406,8 +412,8 @@ def run_b200_arm(args) -> None:
         "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": workload_name(args), "parallelism": f"series-sharded x{world}, no collectives",
-            "lanes": f"{args.lanes} series lanes per GPU on separate streams (GEMMs of one lane overlap the HBM-bound "
-                     f"kernels of the other)",
+            "launch": "eager launches, " + f"{args.lanes} series lanes per GPU on separate streams" if args.no_graphs else
+                      "CUDA-graph replay of the forward's kernel launches (one graph per resident batch, single stream)",
             "weights": "random-init (seed 0)", "precision": "bf16 operands, fp32 accumulate (tcgen05 kind::f16)",
             "l2": "per-step working set (activations ~2.5 GB at batch 4096) >> 126 MB L2; inputs alternate "
                   "between two resident batches",

@@ -268,15 +268,24 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
     const int nm = num_masked != nullptr ? num_masked[b] : 0;
 
     // ---- async fetch of the raw q / k / v rows (10 x 16 B per row)
+    //      a row is 10 chunks: lane (fr, fch) walks rows fr, fr + RPI, ... with pointer increments only (the
+    //      index arithmetic of a flat chunk loop - divisions by N * 10 and 10 - was 38 % of this kernel's instructions)
     const __nv_bfloat16* gbase = qkv + b * N * qkv_ld + h * MMA_HD;
-    for (int c = ulane; c < 3 * N * 10; c += UTHREADS) {
-      const int which = c / (N * 10);
-      const int rem = c - which * (N * 10);
-      const int row = rem / 10, ch = rem - row * 10;
-      cp_async_16(sQ + which * TILE + row * MMA_LD + ch * 8, gbase + row * qkv_ld + which * width + ch * 8);
+    {
+      constexpr int RPI = UTHREADS / 10;  // rows per iteration
+      const int fr = ulane / 10, fch = ulane - fr * 10;
+      if (fr < RPI) {
+        const __nv_bfloat16* gp = gbase + fr * qkv_ld + fch * 8;
+        __nv_bfloat16* sp = sQ + fr * MMA_LD + fch * 8;
+        for (int row = fr; row < N; row += RPI, gp += RPI * qkv_ld, sp += RPI * MMA_LD) {
+          cp_async_16(sp, gp);
+          cp_async_16(sp + TILE, gp + width);
+          cp_async_16(sp + 2 * TILE, gp + 2 * width);
+        }
+      }
     }
     // rows beyond N (only when N is not a multiple of 16): zero so the MMAs see finite data
-    for (int c = ulane; c < 3 * (ntk * 16 - N) * 10; c += UTHREADS) {
+    if (N & 15) for (int c = ulane; c < 3 * (ntk * 16 - N) * 10; c += UTHREADS) {
       const int which = c / ((ntk * 16 - N) * 10);
       const int rem = c - which * ((ntk * 16 - N) * 10);
       const int row = N + rem / 10, ch = rem % 10;
@@ -473,11 +482,16 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
     __syncwarp();
     // each warp stores the 16 rows it produced (staged in its own Q rows)
     __nv_bfloat16* obase = out + b * N * width + h * MMA_HD;
-    for (int c = lane; c < 16 * 10; c += 32) {
-      const int row = wq * 16 + c / 10, ch = c % 10;
-      if (row < N)
-        *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * width + ch * 8) =
-            *reinterpret_cast<const uint4*>(sQ + row * MMA_LD + ch * 8);
+    {
+      const int sr = lane / 10, sch = lane - sr * 10;  // three rows of 10 chunks per pass, two lanes idle
+      if (sr < 3) {
+        const int row_first = wq * 16 + sr;
+        const int row_end = min(N, wq * 16 + 16);
+        __nv_bfloat16* gp = obase + static_cast<int64_t>(row_first) * width + sch * 8;
+        const __nv_bfloat16* sp = sQ + row_first * MMA_LD + sch * 8;
+        for (int row = row_first; row < row_end; row += 3, gp += 3 * width, sp += 3 * MMA_LD)
+          *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+      }
     }
     unit_sync();  // the next unit's cp.async must not overwrite k / v rows another warp still reads
   }

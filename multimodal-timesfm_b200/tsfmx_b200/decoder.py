@@ -46,6 +46,7 @@ class MultimodalDecoder(nn.Module):
         # forward cost ~13 ms of Python per call, which a slow host cannot hide behind an 80 ms step
         self.graphs = False
         self._graph_cache: dict[tuple, tuple] = {}
+        self.graph_launches_replayed = 0  # kernels launched through graph replays (each replay = its captured launches)
 
     def set_precision(self, precision: str) -> None:
         """"bf16" (throughput) or "bf16x3" (parity: <= 1e-3 relative against the fp32 reference)."""
@@ -99,19 +100,24 @@ class MultimodalDecoder(nn.Module):
         if entry is None:
             # eager pass first: argument checks (the reference's ValueErrors), lazily built tables and packed weights
             lanes_before, self.lanes = self.lanes, 1  # single-stream capture; without launch gaps lanes buy nothing
+            from . import _lib
+
             try:
                 self._forecast(horizon, inputs, masks, text_embeddings)
                 graph = torch.cuda.CUDAGraph()
+                launches = _lib.launch_count()
                 with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=inputs.device)):
                     out = self._forecast(horizon, inputs, masks, text_embeddings)
+                launches = _lib.launch_count() - launches  # C-ABI kernel launches recorded into the graph
             finally:
                 self.lanes = lanes_before
             while len(self._graph_cache) >= self.GRAPH_CACHE_ENTRIES:
                 self._graph_cache.pop(next(iter(self._graph_cache)))
             # the inputs are kept alive with the graph: their addresses are baked into it
-            entry = (graph, out, (inputs, masks, text_embeddings))
+            entry = (graph, out, (inputs, masks, text_embeddings), launches)
             self._graph_cache[key] = entry
         entry[0].replay()
+        self.graph_launches_replayed += entry[3]
         return entry[1]
 
     def _forecast(self, horizon, inputs, masks, text_embeddings):
