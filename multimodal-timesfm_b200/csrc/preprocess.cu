@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(TF_THREADS) timesfm_patchify_norm_tma_kernel(
 }
 
 // ----------------------------------------------------------------------------------------
-// Warp-private TMA variant (the default for context <= 2048).  The block-wide kernel above leaves 240 of its 256
+// Warp-private TMA variant (the default for context <= 4096).  The block-wide kernel above leaves 240 of its 256
 // threads at a barrier while one thread per series runs the dependent merge chain (ncu: 5.9 barrier-stall cycles per
 // issued instruction, 24 % of the warp slots occupied).  Here every WARP owns its tiles — about 32 patches: 2 series
 // at context 512, one series from context 1024 — with its own two-deep ring of bulk copies and its own mbarriers, and
@@ -1535,7 +1535,7 @@ int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, in
     kern<<<grid, warps * 32, smem, stream>>>(x, mask, batch, context, G, tokens, mu, sigma, patch_mask, num_masked);
     return check_last_launch("timesfm_patchify_norm");
   }
-  if ((g_tf_variant == 0 || g_tf_variant == 2) && context <= 2048) {  // warp-private tiles, no block-wide barriers
+  if ((g_tf_variant == 0 || g_tf_variant == 2) && context <= 4096) {  // warp-private tiles, no block-wide barriers
     // series per tile: phase B keeps one lane per series busy, so more series per tile means fewer (mostly idle)
     // warp instructions per series; the tile still has to leave room for >= 12 warps per SM
     int g = g_tf_group > 0 ? g_tf_group : 2048 / context;

@@ -180,7 +180,7 @@ def _random_left_padding(b, c, gen):
     return torch.arange(c, device=DEV)[None, :] < pad[:, None]
 
 
-@pytest.mark.parametrize("context", [32, 512, 2048, 96, 1056])
+@pytest.mark.parametrize("context", [32, 512, 2048, 96, 1056, 4096])
 @pytest.mark.parametrize("tokens_dtype", [DT_F32, DT_BF16, DT_BF16_SPLIT])
 def test_timesfm_patchify_norm(context, tokens_dtype):
     b = 67
