@@ -59,6 +59,7 @@ struct alignas(64) GemmParams {
   int64_t ldd;
   int32_t n_store, split_off;
   int32_t vec_ok;  // all pointers / leading dims allow 16-byte vector access
+  int32_t aux_vec_ok, pre_vec_ok;  // same for the saved-activation input / pre-activation output of the training path
   const void* aux;  // *_GRAD activations: the saved pre-activation (SiLU) / activation output (ReLU)
   int64_t ld_aux;
   int32_t aux_dtype;
@@ -83,6 +84,37 @@ struct Cfg {
 __device__ __forceinline__ float load_aux(const void* base, int dtype, int64_t idx) {
   return dtype == TSFMX_DT_F32 ? reinterpret_cast<const float*>(base)[idx]
                                : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+
+// 32 consecutive saved activations of one row (the *_GRAD epilogues): 16-byte loads when the layout allows.  The
+// element-wise version cost a warp 32 load instructions of 32 scattered sectors each and made the SiLU' dgrad GEMM
+// four times slower than its mainloop.
+__device__ __forceinline__ void load_aux32(const void* base, int dtype, int64_t idx, bool vec, int valid, float (&u)[32]) {
+  if (vec && valid == 32) {
+    if (dtype == TSFMX_DT_F32) {
+      const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = p4[i];
+        u[4 * i + 0] = t.x, u[4 * i + 1] = t.y, u[4 * i + 2] = t.z, u[4 * i + 3] = t.w;
+      }
+    } else {
+      const uint4* p4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 t = p4[i];
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          u[8 * i + 2 * k + 0] = __uint_as_float(w[k] << 16);
+          u[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) u[i] = i < valid ? load_aux(base, dtype, idx + i) : 0.0f;
+  }
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -117,32 +149,46 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
   if (p.pre_act != nullptr) {
     // training forward: keep the pre-activation for the backward pass
+    if (col0 + 32 <= n_store && p.pre_vec_ok) {
+      if (p.pre_dtype == TSFMX_DT_F32) {
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.pre_act) + row * p.ld_pre + col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (col0 + i < n_store) {
-        const int64_t o = row * p.ld_pre + col0 + i;
-        if (p.pre_dtype == TSFMX_DT_F32) reinterpret_cast<float*>(p.pre_act)[o] = v[i];
-        else reinterpret_cast<__nv_bfloat16*>(p.pre_act)[o] = __float2bfloat16_rn(v[i]);
+        for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pre_act) + row * p.ld_pre + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          o4[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i < n_store) {
+          const int64_t o = row * p.ld_pre + col0 + i;
+          if (p.pre_dtype == TSFMX_DT_F32) reinterpret_cast<float*>(p.pre_act)[o] = v[i];
+          else reinterpret_cast<__nv_bfloat16*>(p.pre_act)[o] = __float2bfloat16_rn(v[i]);
+        }
       }
     }
   }
   if (p.act == TSFMX_ACT_SILU || p.act == TSFMX_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-  } else if (p.act == TSFMX_ACT_SILU_GRAD) {
-    // v = dL/d silu(u)  ->  dL/du = v * sigmoid(u) * (1 + u * (1 - sigmoid(u)))
+  } else if (p.act == TSFMX_ACT_SILU_GRAD || p.act == TSFMX_ACT_RELU_GRAD) {
+    float u[32];
+    const int valid = n_store - col0 < 32 ? n_store - col0 : 32;
+    load_aux32(p.aux, p.aux_dtype, row * p.ld_aux + col0, p.aux_vec_ok != 0, valid, u);
+    if (p.act == TSFMX_ACT_SILU_GRAD) {
+      // v = dL/d silu(u)  ->  dL/du = v * sigmoid(u) * (1 + u * (1 - sigmoid(u)))
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (col0 + i < n_store) {
-        const float u = load_aux(p.aux, p.aux_dtype, row * p.ld_aux + col0 + i);
-        const float sg = 1.0f / (1.0f + __expf(-u));
-        v[i] *= sg * (1.0f + u * (1.0f - sg));
+      for (int i = 0; i < 32; ++i) {
+        const float sg = __fdividef(1.0f, 1.0f + __expf(-u[i]));
+        v[i] *= sg * (1.0f + u[i] * (1.0f - sg));
       }
-    }
-  } else if (p.act == TSFMX_ACT_RELU_GRAD) {
+    } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (col0 + i < n_store) v[i] = load_aux(p.aux, p.aux_dtype, row * p.ld_aux + col0 + i) > 0.0f ? v[i] : 0.0f;
+      for (int i = 0; i < 32; ++i) v[i] = u[i] > 0.0f ? v[i] : 0.0f;
     }
   }
   if (p.row_scale != nullptr) {
@@ -944,6 +990,11 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
   if (a->residual != nullptr) vec = vec && (reinterpret_cast<uintptr_t>(a->residual) % 16 == 0) && (a->ldr % 4 == 0);
   if (a->bias != nullptr) vec = vec && (reinterpret_cast<uintptr_t>(a->bias) % 16 == 0);
   p.vec_ok = vec ? 1 : 0;
+  {
+    const int ae = a->aux_dtype == TSFMX_DT_F32 ? 4 : 2, pe = a->pre_act_dtype == TSFMX_DT_F32 ? 4 : 2;
+    p.aux_vec_ok = a->aux != nullptr && reinterpret_cast<uintptr_t>(a->aux) % 16 == 0 && (a->ld_aux * ae) % 16 == 0;
+    p.pre_vec_ok = a->pre_act != nullptr && reinterpret_cast<uintptr_t>(a->pre_act) % 16 == 0 && (a->ld_pre * pe) % 16 == 0;
+  }
 
   int nx = 0;
   for (int s = 0; s < a->num_segments; ++s) {
