@@ -182,6 +182,10 @@ typedef struct {
 int tsfmx_gemm(const tsfmx_gemm_args* args, void* stream);
 /* test / tuning hook: 0 = automatic, 1 = one CTA per tile (UMMA 128xN), 2 = CTA pairs (cta_group::2, UMMA 256xN) */
 int tsfmx_gemm_set_cta_group(int cta_group);
+/* test / tuning hook for split-K (used automatically for plain fp32 outputs with fewer tiles than SMs, i.e. the weight
+ * gradients dW = dY^T X of the full fine-tuning path, reference trainer.py:78-79, where K = tokens): 0 = automatic,
+ * 1 = never, 2..16 = that many splits wherever splitting is legal */
+int tsfmx_gemm_set_split_k(int mode);
 
 /*
  * GEMM with the norm / residual junction of a transformer layer fused into its epilogue (one launch instead

@@ -60,6 +60,8 @@ struct alignas(64) GemmParams {
   int32_t n_store, split_off;
   int32_t vec_ok;  // all pointers / leading dims allow 16-byte vector access
   int32_t aux_vec_ok, pre_vec_ok;  // same for the saved-activation input / pre-activation output of the training path
+  int32_t split_k;  // > 1: every (m, n) tile is computed by split_k tiles over disjoint k-block ranges that add their
+                    // fp32 partial sums into a zero-filled D with vector reductions (weight gradients: K = tokens)
   const void* aux;  // *_GRAD activations: the saved pre-activation (SiLU) / activation output (ReLU)
   int64_t ld_aux;
   int32_t aux_dtype;
@@ -212,6 +214,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
   }
 
+  if (p.split_k > 1) {  // fp32 D, 16-byte aligned rows (checked by the launcher): add this k-range's partial sums
+    float* dp = reinterpret_cast<float*>(p.d) + row * p.ldd + col0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (col0 + 4 * i + 4 <= n_store) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                     "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                     : "memory");
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (col0 + 4 * i + k < n_store) atomicAdd(dp + 4 * i + k, v[4 * i + k]);
+      }
+    }
+    return;
+  }
   if (p.d_dtype == TSFMX_DT_F32) {
     float* dp = reinterpret_cast<float*>(p.d) + row * p.ldd + col0;
     if (full) {
@@ -309,7 +327,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.split_k;
   const int first_tile = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
   const int tile_step = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
 
@@ -318,14 +336,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        const int mn = tile / p.split_k, ks = tile - mn * p.split_k;
+        const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
         const int32_t a_row = (m_blk * CG + static_cast<int>(cta_rank)) * BM;
         const int32_t b_row = n_blk * BN + static_cast<int>(cta_rank) * C::B_ROWS;
         for (int s = 0; s < p.num_xseg; ++s) {
           const XSeg sg = p.xseg[s];
           const CUtensorMap* ta = &p.tma_a[sg.a_idx];
           const CUtensorMap* tb = &p.tma_b[sg.b_idx];
-          for (int kb = 0; kb < sg.nkb; ++kb) {
+          const int kb_end = (ks + 1) * sg.nkb / p.split_k;
+          for (int kb = ks * sg.nkb / p.split_k; kb < kb_end; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             void* sa = smem_a + stage * C::A_BYTES;
             void* sb = smem_b + stage * C::B_BYTES;
@@ -355,8 +375,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         uint32_t accumulate = 0;
+        const int ks = tile % p.split_k;
         for (int s = 0; s < p.num_xseg; ++s) {
-          const int nkb = p.xseg[s].nkb;
+          const int nkb = (ks + 1) * p.xseg[s].nkb / p.split_k - ks * p.xseg[s].nkb / p.split_k;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
@@ -383,7 +404,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
     const int chalf = (warp - EPI_WARP0) >> 2;   // which half of the tile's columns this warp drains
     uint32_t iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int mn = tile / p.split_k;
+      const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
@@ -766,7 +788,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
           } else if (row_ok) {
             GemmParams gp = {};
             gp.d = p.yn, gp.ldd = (p.yn_dtype == TSFMX_DT_BF16_SPLIT ? 2 : 1) * static_cast<int64_t>(p.n);
-            gp.d_dtype = p.yn_dtype, gp.n_store = p.n, gp.split_off = p.n, gp.vec_ok = 1;
+            gp.d_dtype = p.yn_dtype, gp.n_store = p.n, gp.split_off = p.n, gp.vec_ok = 1, gp.split_k = 1;
             epilogue_chunk(gp, r, row, col0);
           }
         }
@@ -777,7 +799,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rownorm_tcgen05_kernel(co
         const float rs_y = 1.0f / sqrtf(tot * inv_n + p.eps);
         GemmParams gp = {};
         gp.d = p.yn, gp.ldd = (p.yn_dtype == TSFMX_DT_BF16_SPLIT ? 2 : 1) * static_cast<int64_t>(p.n);
-        gp.d_dtype = p.yn_dtype, gp.n_store = p.n, gp.split_off = p.n, gp.vec_ok = 1;
+        gp.d_dtype = p.yn_dtype, gp.n_store = p.n, gp.split_off = p.n, gp.vec_ok = 1, gp.split_k = 1;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -890,7 +912,7 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const int total = p.tiles_m * p.tiles_n;
+  const int total = p.tiles_m * p.tiles_n * p.split_k;
   int units = num_sms() / CG;  // CTAs (or CTA pairs) resident at once: persistent grid
   if (units > total) units = total;
   cudaLaunchConfig_t cfg = {};
@@ -918,6 +940,7 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 }
 
 int g_force_cta_group = 0;  // test hook: 0 = auto, 1 / 2 = force
+int g_split_k_mode = 0;     // tune key 4: 0 = auto, 1 = never split K, n > 1 = force n splits where splitting is legal
 
 }  // namespace
 }  // namespace tsfmx
@@ -930,6 +953,15 @@ extern "C" int tsfmx_gemm_set_cta_group(int cg) {
     return TSFMX_ERR_INVALID_ARGUMENT;
   }
   g_force_cta_group = cg;
+  return TSFMX_OK;
+}
+
+extern "C" int tsfmx_gemm_set_split_k(int mode) {
+  if (mode < 0 || mode > 16) {
+    set_error("split_k mode must be 0 (auto), 1 (never) or 2..16 (forced where legal)");
+    return TSFMX_ERR_INVALID_ARGUMENT;
+  }
+  g_split_k_mode = mode;
   return TSFMX_OK;
 }
 
@@ -1020,6 +1052,41 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
     }
   }
   p.num_xseg = nx;
+
+  // split-K for short-and-wide problems (weight gradients: M, N = features, K = tokens): a 1280 x 1280 output is 25
+  // tiles for 74 CTA pairs.  Only for a plain fp32 store (or an in-place accumulation into D), where the partial sums
+  // can be added with vector reductions into a zero-filled D.
+  p.split_k = 1;
+  {
+    const int units = cg == 2 ? num_sms() / 2 : num_sms();
+    const int base = p.tiles_m * p.tiles_n;
+    const bool in_place = a->residual != nullptr && a->residual == a->d && a->ldr == a->ldd;
+    int min_nkb = 1 << 30;
+    for (int s = 0; s < nx; ++s) min_nkb = p.xseg[s].nkb < min_nkb ? p.xseg[s].nkb : min_nkb;
+    if (g_split_k_mode != 1 && base * 10 < units * 9 && a->d_dtype == TSFMX_DT_F32 && a->act == TSFMX_ACT_NONE &&
+        a->bias == nullptr && a->row_scale == nullptr && a->pre_act == nullptr && (a->residual == nullptr || in_place) &&
+        reinterpret_cast<uintptr_t>(a->d) % 16 == 0 && a->ldd % 4 == 0 && min_nkb >= 32) {
+      double best = static_cast<double>(base) / units;  // no split: one partial wave
+      for (int sk = 2; sk <= 16 && min_nkb / sk >= 16; ++sk) {
+        const int tiles = base * sk, waves = (tiles + units - 1) / units;
+        const double kbs = static_cast<double>(min_nkb) / sk;
+        const double score = static_cast<double>(tiles) / (waves * units) * kbs / (kbs + 4.0);
+        if (score > best * 1.03) best = score, p.split_k = sk;
+      }
+      if (g_split_k_mode > 1) p.split_k = g_split_k_mode;
+    }
+    if (p.split_k > 1) {
+      p.residual = nullptr;  // in-place accumulation: the reductions add to what D already holds
+      if (!in_place) {
+        const cudaError_t e = cudaMemset2DAsync(a->d, static_cast<size_t>(a->ldd) * 4, 0, static_cast<size_t>(p.n_store) * 4,
+                                                static_cast<size_t>(a->m), stream);
+        if (e != cudaSuccess) {
+          set_error("gemm: cudaMemset2DAsync: %s", cudaGetErrorString(e));
+          return TSFMX_ERR_CUDA;
+        }
+      }
+    }
+  }
 
   if (cg == 2) return launch_gemm<256, 2>(p, stream);
   return launch_gemm<256, 1>(p, stream);

@@ -95,6 +95,7 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "tsfmx_cast_rows": (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
     "tsfmx_gemm": (c_int32, [POINTER(GemmArgs), c_void_p]),
     "tsfmx_gemm_set_cta_group": (c_int32, [c_int32]),
+    "tsfmx_gemm_set_split_k": (c_int32, [c_int32]),
     "tsfmx_gemm_rownorm": (
         c_int32,
         [POINTER(GemmSegment), c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,

@@ -66,6 +66,38 @@ def test_gemm_bf16_plain(cta_group, m, n, k):
 
 
 @pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("split", [0, 3, 16])
+@pytest.mark.parametrize("m,n,k", [(1280, 1280, 16384), (3840, 1280, 4096), (300, 336, 8192)])
+def test_gemm_split_k(cta_group, split, m, n, k):
+    """Weight-gradient shapes (few output tiles, K = tokens): split-K tiles add their partial sums with reductions."""
+    lib = _lib.load()
+    _lib.check(lib.tsfmx_gemm_set_cta_group(cta_group))
+    _lib.check(lib.tsfmx_gemm_set_split_k(split))
+    try:
+        gen = torch.Generator(device=DEV).manual_seed(m + n + k + split)
+        a, af = _make_operand(m, k, PREC_BF16, gen)
+        b, bf = _make_operand(n, k, PREC_BF16, gen)
+        ref = (af.double() @ bf.double().t()).float()
+        out = torch.full((m, n), float("nan"), device=DEV, dtype=torch.float32)
+        ops.gemm([(a, b, k)], m, n, out, DT_F32)
+        assert _rel(out, ref) < 2e-5
+        # in-place accumulation (residual = D): D <- D + A B^T
+        acc = torch.randn(m, n, generator=gen, device=DEV)
+        want = acc + ref
+        ops.gemm([(a, b, k)], m, n, acc, DT_F32, residual=acc)
+        assert _rel(acc, want) < 2e-5
+        # fp32-accurate mode splits its three segments the same way
+        a3, af3 = _make_operand(m, k, PREC_BF16X3, gen)
+        b3, bf3 = _make_operand(n, k, PREC_BF16X3, gen)
+        out3 = torch.empty(m, n, device=DEV, dtype=torch.float32)
+        ops.gemm([(a3, b3, k)], m, n, out3, DT_F32, precision=PREC_BF16X3)
+        assert _rel(out3, (af3.double() @ bf3.double().t()).float()) < 3e-5
+    finally:
+        _lib.check(lib.tsfmx_gemm_set_cta_group(0))
+        _lib.check(lib.tsfmx_gemm_set_split_k(0))
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
 def test_gemm_bf16x3_close_to_fp32(cta_group):
     lib = _lib.load()
     _lib.check(lib.tsfmx_gemm_set_cta_group(cta_group))
