@@ -1055,7 +1055,9 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
 
   // split-K for short-and-wide problems (weight gradients: M, N = features, K = tokens): a 1280 x 1280 output is 25
   // tiles for 74 CTA pairs.  Only for a plain fp32 store (or an in-place accumulation into D), where the partial sums
-  // can be added with vector reductions into a zero-filled D.
+  // can be added with vector reductions into a zero-filled D, and only from K = 4096 up: the order of those
+  // reductions varies from run to run, which is fine for a gradient summed over tokens but would take away the
+  // run-to-run bit-reproducibility of the model GEMMs (K <= 3840 in every adapter here).
   p.split_k = 1;
   {
     const int units = cg == 2 ? num_sms() / 2 : num_sms();
@@ -1065,15 +1067,15 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
     for (int s = 0; s < nx; ++s) min_nkb = p.xseg[s].nkb < min_nkb ? p.xseg[s].nkb : min_nkb;
     if (g_split_k_mode != 1 && base * 10 < units * 9 && a->d_dtype == TSFMX_DT_F32 && a->act == TSFMX_ACT_NONE &&
         a->bias == nullptr && a->row_scale == nullptr && a->pre_act == nullptr && (a->residual == nullptr || in_place) &&
-        reinterpret_cast<uintptr_t>(a->d) % 16 == 0 && a->ldd % 4 == 0 && min_nkb >= 32) {
+        reinterpret_cast<uintptr_t>(a->d) % 16 == 0 && a->ldd % 4 == 0 && (min_nkb >= 64 || g_split_k_mode > 1)) {
       double best = static_cast<double>(base) / units;  // no split: one partial wave
-      for (int sk = 2; sk <= 16 && min_nkb / sk >= 16; ++sk) {
+      for (int sk = 2; sk <= 16 && min_nkb / sk >= 16; ++sk) {  // at least 16 k-blocks (1024 of K) per split
         const int tiles = base * sk, waves = (tiles + units - 1) / units;
         const double kbs = static_cast<double>(min_nkb) / sk;
         const double score = static_cast<double>(tiles) / (waves * units) * kbs / (kbs + 4.0);
         if (score > best * 1.03) best = score, p.split_k = sk;
       }
-      if (g_split_k_mode > 1) p.split_k = g_split_k_mode;
+      if (g_split_k_mode > 1) p.split_k = g_split_k_mode < min_nkb ? g_split_k_mode : min_nkb;
     }
     if (p.split_k > 1) {
       p.residual = nullptr;  // in-place accumulation: the reductions add to what D already holds
