@@ -47,6 +47,7 @@ class MultimodalDecoder(nn.Module):
         self.graphs = False
         self._graph_cache: dict[tuple, tuple] = {}
         self.graph_launches_replayed = 0  # kernels launched through graph replays (each replay = its captured launches)
+        self.graph_captures = 0  # graphs captured so far (a caller whose shapes keep changing should stop asking)
 
     def set_precision(self, precision: str) -> None:
         """"bf16" (throughput) or "bf16x3" (parity: <= 1e-3 relative against the fp32 reference)."""
@@ -116,6 +117,7 @@ class MultimodalDecoder(nn.Module):
             # the inputs are kept alive with the graph: their addresses are baked into it
             entry = (graph, out, (inputs, masks, text_embeddings), launches)
             self._graph_cache[key] = entry
+            self.graph_captures += 1
         entry[0].replay()
         self.graph_launches_replayed += entry[3]
         return entry[1]

@@ -31,6 +31,7 @@ class MultimodalEvaluator:
     """Computes evaluation metrics for a multimodal decoder (text embeddings are fused when the batch has them)."""
 
     _KEYS = ("context", "horizon", "text_embeddings")
+    MAX_CAPTURES_PER_PASS = 6  # two staging slots x (full batch, ragged tail) and some slack
 
     def __init__(self, model: MultimodalDecoder, device: torch.device, *, graphs: bool | None = None) -> None:
         self.model = model
@@ -127,9 +128,14 @@ class MultimodalEvaluator:
         ring = torch.empty(256, 2, dtype=torch.float64, pin_memory=True) if cuda else None  # one pinned allocation
         used = 0
         num_samples = 0
+        captures_at_start = getattr(self.model, "graph_captures", 0)
         with torch.no_grad():
             for batch in self._staged(dataloader):
                 context, horizon = batch["context"], batch["horizon"]
+                # a loader whose batch shapes keep changing would capture a graph (two forwards) per batch: after
+                # MAX_CAPTURES_PER_PASS of them the rest of the pass runs the eager launches
+                if getattr(self.model, "graph_captures", 0) - captures_at_start >= self.MAX_CAPTURES_PER_PASS:
+                    self.model.graphs = False
                 # all-False padding mask (reference evaluator.py:52), one per staging slot
                 point = self.model(horizon.shape[-1], context, batch["input_padding"], batch.get("text_embeddings"))
                 err = point - horizon

@@ -1,5 +1,9 @@
 """Probe: does running the 4096-series batch as sequential chunks (each chunk through all layers before the next)
-keep the residual stream L2-resident and pay?  Prints series/s per chunk size.  Not a bench line."""
+keep the residual stream L2-resident and pay?  Prints series/s per chunk size.  Not a bench line.
+
+Result on one B200 (round 1): no.  With the host cost removed by CUDA graphs: 4096 series per chunk 48.3 k series/s,
+1024: 45.9 k, 512: 41.6 k, 256: 35.2 k - the GEMMs lose more at small M (wave quantisation, prologue/epilogue not
+amortised) than the norm junctions gain from L2."""
 import os
 import sys
 
@@ -72,8 +76,8 @@ for chunk in (4096, 1024, 896, 512, 448, 256, 224):
     torch.cuda.synchronize()
     print(f"graph chunk={chunk:5d}: {ms:8.2f} ms/step {n / ms * 1e3:9.0f} series/s   (eager enqueue of one chunk: {host_ms:.1f} ms host)", flush=True)
     del go
-sys.exit(0)
 
+# the same chunking with eager launches (host-bound below ~512 series per chunk: ~13 ms of Python per forward)
 for chunk, lanes in ((4096, 2), (4096, 1), (2048, 1), (1024, 1), (896, 1), (448, 1), (512, 1), (224, 1), (256, 1), (448, 2), (896, 2)):
     for _ in range(3):
         run(chunk, lanes)

@@ -115,3 +115,16 @@ def test_evaluator_graphs_match_eager_and_are_reused():
     keys = set(dec._graph_cache)
     assert ev.evaluate(batches) == eager  # second pass: stable staging addresses, nothing captured again
     assert set(dec._graph_cache) == keys
+
+
+def test_evaluator_stops_capturing_when_shapes_keep_changing():
+    dec = _small_decoder(1)
+    batches = []
+    for i, b in enumerate((9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20)):  # a new batch size every time
+        ctx, _m, text, hor = O.synthetic_batch(b, 512, 32, seed=90 + i)
+        batches.append({"context": ctx.pin_memory(), "horizon": hor.pin_memory(), "text_embeddings": text.pin_memory()})
+    eager = MultimodalEvaluator(dec, torch.device("cuda"), graphs=False).evaluate(batches)
+    ev = MultimodalEvaluator(dec, torch.device("cuda"))
+    assert ev.evaluate(batches) == eager
+    assert dec.graph_captures == MultimodalEvaluator.MAX_CAPTURES_PER_PASS
+    assert not dec.graphs
