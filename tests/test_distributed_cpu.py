@@ -48,6 +48,20 @@ def _worker(rank: int, world: int, port: int, result_dir: str):
     assert torch.allclose(fusion.weight.grad, g_full, atol=1e-6)
     assert torch.allclose(extra, torch.full((3,), (world - 1) / 2))
     assert tdist.allreduce_max(10.0 + rank, torch.device("cpu")) == 10.0 + world - 1
+    # bucketed path of the full fine-tune (all adapter gradients): several flattened collectives, a tensor larger than
+    # a bucket on its own, mixed shapes; every element must come back as the mean over ranks
+    saved, tdist.BUCKET_ELEMS = tdist.BUCKET_ELEMS, 64
+    try:
+        gen = torch.Generator().manual_seed(5)
+        shapes = [(7, 5), (64,), (3, 3, 3), (200,), (1,), (63,), (2, 40)]
+        base = [torch.randn(sh, generator=gen) for sh in shapes]
+        mine = [b * (rank + 1) for b in base]
+        tdist.allreduce_mean_(mine)
+        scale = sum(r + 1 for r in range(world)) / world
+        for got, b in zip(mine, base):
+            assert torch.allclose(got, b * scale, atol=1e-6)
+    finally:
+        tdist.BUCKET_ELEMS = saved
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(result_dir, f"ok{rank}"), "w").close()
