@@ -88,7 +88,10 @@ class MultimodalDecoder(nn.Module):
         evaluator's staging slots) replays one graph per slot.  The returned tensor is the graph's output buffer: it is
         overwritten by the next call with the same key, so consume it (on the same stream) before calling again.
         Parameters are tracked by (data_ptr, version): an optimizer step, ``load_state_dict`` or ``set_precision``
-        makes the next call capture afresh."""
+        makes the next call capture afresh.  The capture (first call per key) runs in torch's default global capture
+        mode: another thread that allocates pinned or device memory at that moment (a ``DataLoader`` pin thread)
+        makes it fail with torch's capture error — stage the first batch before starting such threads, or leave
+        ``graphs`` off."""
         stream = torch.cuda.current_stream(inputs.device)
         key = (
             horizon, inputs.data_ptr(), tuple(inputs.shape), inputs.dtype, masks.data_ptr(),
