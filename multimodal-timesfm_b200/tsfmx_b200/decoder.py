@@ -88,10 +88,7 @@ class MultimodalDecoder(nn.Module):
         evaluator's staging slots) replays one graph per slot.  The returned tensor is the graph's output buffer: it is
         overwritten by the next call with the same key, so consume it (on the same stream) before calling again.
         Parameters are tracked by (data_ptr, version): an optimizer step, ``load_state_dict`` or ``set_precision``
-        makes the next call capture afresh.  The capture (first call per key) runs in torch's default global capture
-        mode: another thread that allocates pinned or device memory at that moment (a ``DataLoader`` pin thread)
-        makes it fail with torch's capture error — stage the first batch before starting such threads, or leave
-        ``graphs`` off."""
+        makes the next call capture afresh."""
         stream = torch.cuda.current_stream(inputs.device)
         key = (
             horizon, inputs.data_ptr(), tuple(inputs.shape), inputs.dtype, masks.data_ptr(),
@@ -110,7 +107,11 @@ class MultimodalDecoder(nn.Module):
                 self._forecast(horizon, inputs, masks, text_embeddings)
                 graph = torch.cuda.CUDAGraph()
                 launches = _lib.launch_count()
-                with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=inputs.device)):
+                # thread-local capture mode: CUDA calls of OTHER threads (a DataLoader's pin-memory thread allocating
+                # host memory, the bench's clock sampler) must not invalidate the capture; this thread's own calls are
+                # checked exactly as in the default mode
+                with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=inputs.device),
+                                      capture_error_mode="thread_local"):
                     out = self._forecast(horizon, inputs, masks, text_embeddings)
                 launches = _lib.launch_count() - launches  # C-ABI kernel launches recorded into the graph
             finally:
