@@ -173,8 +173,9 @@ class MultimodalDecoder(nn.Module):
         return max(1, min(want, tokens // 8192))
 
     def _forward_full_training(self, horizon, inputs, masks, text_embeddings):
-        """Differentiable path of the reference's "multimodal" training mode (trainer.py:76-77,119-123): frozen
-        adapter, trainable fusion.  Full fine-tuning of the adapter ("baseline" mode) is SURVEY.md section 8(f) rank 4."""
+        """Differentiable paths of the reference's two training modes: "multimodal" (trainer.py:76-77,119-123: frozen
+        adapter, trainable fusion -> ``FusedForecastFunction``) and "baseline" (trainer.py:78-79: the whole adapter is
+        trained -> ``FullFineTuneFunction``, for adapters that provide ``preprocess_backward``)."""
         from .autograd import FullFineTuneFunction, FusedForecastFunction
 
         if any(p.requires_grad for p in self.adapter.parameters()):
