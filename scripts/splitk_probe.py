@@ -1,3 +1,7 @@
+"""Probe: split-K GEMM numerics on the Chronos-2 FFN shapes (K = 3072) with poisoned output buffers, against fp64
+matmul, for split modes never / auto / forced 3.  Printed worst relative errors were 1e-6..7e-6 in every mode (the
+split sums are slightly MORE accurate); the run-to-run variation of a gradient test came from the reduction order,
+which is why automatic splitting starts at K = 4096 (see csrc/gemm.cu).  Not a bench line."""
 import sys, torch
 sys.path.insert(0, "/root/repo/multimodal-timesfm_b200"); sys.path.insert(0, "/root/repo")
 from tsfmx_b200 import _lib, ops
