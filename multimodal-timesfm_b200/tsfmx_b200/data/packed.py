@@ -5,7 +5,9 @@ The reference keeps a ``list[PreprocessedSample]`` (one dict of small numpy arra
 ``collate_fn`` (reference tsfmx/data/collate.py:9-29).  At 50 k series/s per GPU that is 2.8 GB/s of host traffic in
 24.6 KB pieces, so here the list is packed ONCE into three contiguous page-locked tensors - context ``[S, C]``, horizon
 ``[S, h]``, text embeddings ``[S, N, E]`` - and a batch is a set of zero-copy slices of them: the evaluator's copy
-stream can DMA straight out of pinned memory, and shuffled epochs use one index_select into a reusable pinned buffer.
+stream can DMA straight out of pinned memory, and shuffled epochs use one index_select per batch into a page-locked
+buffer taken from torch's caching host allocator (which recycles a block only after every asynchronous copy that
+read it has completed, so a consumer may run any number of batches ahead of the device).
 Batches carry the same keys as the reference ``Batch`` TypedDict (types.py:33-39).
 """
 
@@ -32,7 +34,6 @@ class PackedSamples:
         if horizon.shape[0] != context.shape[0] or (text_embeddings is not None and text_embeddings.shape[0] != context.shape[0]):
             raise ValueError("context, horizon and text_embeddings must hold the same number of samples")
         self.context, self.horizon, self.text_embeddings, self.metadata = context, horizon, text_embeddings, metadata
-        self._scratch: dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -92,11 +93,12 @@ class PackedSamples:
             src = getattr(self, key)
             if src is None:
                 continue
-            buf = self._scratch.get(key)
-            if buf is None or buf.shape[0] < idx.numel():
-                buf = _pinned((idx.numel(), *src.shape[1:]), src.dtype, src.is_pinned())
-                self._scratch[key] = buf
-            dst = buf[: idx.numel()]
+            # a FRESH page-locked tensor per batch, never a reused scratch: a consumer that stages batches with
+            # ``copy_(non_blocking=True)`` (MultimodalEvaluator, MultimodalTrainer) only ENQUEUES the copy before it
+            # asks for the next batch, so a shared buffer would be overwritten by this gather while the DMA of the
+            # previous batch is still pending.  torch's caching host allocator records the copying stream on the
+            # block and hands it out again only once that copy has finished, so steady state allocates nothing.
+            dst = _pinned((idx.numel(), *src.shape[1:]), src.dtype, src.is_pinned())
             torch.index_select(src, 0, idx, out=dst)
             out[key] = dst
         return out
@@ -104,8 +106,8 @@ class PackedSamples:
     def batches(self, batch_size: int, shuffle: bool = False, generator: torch.Generator | None = None,
                 drop_last: bool = False) -> Iterator[dict[str, Any]]:
         """Batches with the reference's ``Batch`` keys.  In order: zero-copy slices of the pinned store.  Shuffled: one
-        gather per batch into a reusable pinned buffer - the consumer must have finished with (or enqueued the copy of)
-        a shuffled batch before asking for the next one, which ``MultimodalEvaluator`` / ``MultimodalTrainer`` do."""
+        gather per batch into its own page-locked tensor (recycled by torch's caching host allocator once the copies
+        that read it are done), so the consumer may hold or be copying any number of earlier batches."""
         if batch_size < 1:
             raise ValueError(f"batch_size must be >= 1, got {batch_size}")
         n = len(self)

@@ -48,6 +48,7 @@ class MultimodalDecoder(nn.Module):
         self._graph_cache: dict[tuple, tuple] = {}
         self.graph_launches_replayed = 0  # kernels launched through graph replays (each replay = its captured launches)
         self.graph_captures = 0  # graphs captured so far (a caller whose shapes keep changing should stop asking)
+        self._lanes_warm_key: tuple | None = None  # (weights, precision, context) the lazily built caches were made for
 
     def set_precision(self, precision: str) -> None:
         """"bf16" (throughput) or "bf16x3" (parity: <= 1e-3 relative against the fp32 reference)."""
@@ -73,6 +74,15 @@ class MultimodalDecoder(nn.Module):
             if outputs is None:
                 raise ValueError("empty batch and the adapter does not declare num_outputs")
             return torch.empty(0, horizon, outputs, dtype=torch.float32, device=inputs.device)
+        if inputs.is_cuda and inputs.device.index != torch.cuda.current_device():
+            # streams, lane streams, graph capture and the library's per-device state all follow the CURRENT device:
+            # run the whole call on the device that holds the inputs (a model built with device=cuda:1 in a process
+            # that never called torch.cuda.set_device)
+            with torch.cuda.device(inputs.device):
+                return self._dispatch(horizon, inputs, masks, text_embeddings)
+        return self._dispatch(horizon, inputs, masks, text_embeddings)
+
+    def _dispatch(self, horizon, inputs, masks, text_embeddings):
         # train() mode with autograd on = the reference's fine-tune step; eval() / no_grad = plain forecasting
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_full_training(horizon, inputs, masks, text_embeddings)
@@ -126,8 +136,26 @@ class MultimodalDecoder(nn.Module):
         self.graph_launches_replayed += entry[3]
         return entry[1]
 
+    def _caches_key(self, inputs: torch.Tensor, text_embeddings: torch.Tensor | None) -> tuple:
+        """What the lazily built device caches depend on: packed bf16 weight copies (adapter and fusion), the Chronos-2
+        future-patch embeddings and the RoPE tables are rebuilt when a parameter, the precision, the device or the
+        context length changes."""
+        return (
+            tuple((p.data_ptr(), p._version) for p in self.parameters()),
+            getattr(self.adapter, "precision", None), self.fusion.precision, inputs.device, inputs.shape[1],
+            text_embeddings is not None,
+        )
+
     def _forecast(self, horizon, inputs, masks, text_embeddings):
         count = self._lane_count(inputs)
+        if count > 1:
+            # The stages build their caches lazily, i.e. with kernels on whichever stream first asks for them.  In a
+            # lane run that is lane 0's stream, and the other lanes would read the half-built tensors from theirs with
+            # nothing ordering the two.  So the first forecast after anything the caches depend on has changed runs on
+            # the caller's stream alone; the lane streams of every later call wait for that stream on entry.
+            key = self._caches_key(inputs, text_embeddings)
+            if key != self._lanes_warm_key:
+                count = 1
         if count > 1:
             if text_embeddings is not None and text_embeddings.shape[0] != inputs.shape[0]:
                 raise ValueError(
@@ -145,7 +173,10 @@ class MultimodalDecoder(nn.Module):
                 inputs.device,
             )
             return torch.cat(parts, dim=0)
-        return lanes.drain(self._forecast_steps(horizon, inputs, masks, text_embeddings))
+        out = lanes.drain(self._forecast_steps(horizon, inputs, masks, text_embeddings))
+        if inputs.is_cuda:
+            self._lanes_warm_key = self._caches_key(inputs, text_embeddings)
+        return out
 
     def _forecast_steps(self, horizon, inputs, masks, text_embeddings):
         """preprocess -> fusion -> forward -> postprocess (reference decoder.py:65-72) as one step generator."""

@@ -56,40 +56,63 @@ def shard_batch(batch: dict, rank: int, world: int) -> dict:
     return {k: v[lo:hi] for k, v in batch.items()}
 
 
-BUCKET_ELEMS = 64 * 1024 * 1024  # floats per flattened all-reduce bucket (256 MB)
+BUCKET_ELEMS = 4 * 1024 * 1024  # floats per flattened bucket of SMALL tensors (16 MB)
+DIRECT_ELEMS = 256 * 1024  # tensors of at least this many floats are all-reduced in place, without flattening
 
 
-def allreduce_mean_(tensors: Iterable[torch.Tensor], group=None) -> None:
-    """In-place mean over ranks of a list of (gradient) tensors through flattened all-reduces (one per bucket)."""
+def allreduce_(tensors: Iterable[torch.Tensor], op: str = "mean", group=None) -> None:
+    """In-place all-reduce ("sum" or "mean" over ranks) of a list of fp32 (gradient) tensors.
+
+    Large contiguous tensors are reduced where they are; the small ones (norm scales, biases, the 80-float attention
+    vectors: hundreds of them in a full fine-tune) travel in flattened buckets so that the step does not pay one
+    collective launch per tensor.  No tensor is copied more than once each way and nothing the size of the whole model
+    is ever allocated (the first version ``torch.cat``-ed 256 MB buckets: three extra passes over 1.99 GB)."""
+    if op not in ("sum", "mean"):
+        raise ValueError(f"op must be 'sum' or 'mean', got {op!r}")
     tensors = [t for t in tensors if t is not None]
     if not tensors or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     world = dist.get_world_size(group)
-    # flattened buckets of at most BUCKET_ELEMS floats: one collective for the fusion gradients (2 MB), a handful of
-    # 256 MB ones for a full fine-tune (498 M parameters at 50 layers) without a second copy of all gradients at once
+    works = []
+    small: list[torch.Tensor] = []
+    for t in tensors:
+        if t.numel() >= DIRECT_ELEMS and t.is_contiguous() and t.dtype == torch.float32:
+            works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        else:
+            small.append(t)
+    flats: list[tuple[torch.Tensor, list[torch.Tensor]]] = []
     bucket: list[torch.Tensor] = []
     count = 0
 
     def flush() -> None:
         nonlocal bucket, count
-        if not bucket:
-            return
-        flat = torch.cat([t.reshape(-1).to(torch.float32) for t in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world)
-        offset = 0
-        for t in bucket:
-            n = t.numel()
-            t.copy_(flat[offset : offset + n].view_as(t))
-            offset += n
-        bucket, count = [], 0
+        if bucket:
+            flat = torch.cat([t.reshape(-1).to(torch.float32) for t in bucket])
+            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
+            flats.append((flat, bucket))
+            bucket, count = [], 0
 
-    for t in tensors:
+    for t in small:
         if count and count + t.numel() > BUCKET_ELEMS:
             flush()
         bucket.append(t)
         count += t.numel()
     flush()
+    for w in works:
+        w.wait()
+    for flat, members in flats:
+        offset = 0
+        for t in members:
+            n = t.numel()
+            t.copy_(flat[offset : offset + n].view_as(t))
+            offset += n
+    if op == "mean":
+        torch._foreach_div_(tensors, float(world))
+
+
+def allreduce_mean_(tensors: Iterable[torch.Tensor], group=None) -> None:
+    """In-place mean over ranks (see ``allreduce_``)."""
+    allreduce_(tensors, "mean", group)
 
 
 def allreduce_max(value: float, device: torch.device, group=None) -> float:

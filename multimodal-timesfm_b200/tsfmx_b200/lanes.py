@@ -60,6 +60,9 @@ def run_lanes(make_gen: Callable[[int], Generator[None, None, Any]], count: int,
     Tensors a lane returns were allocated on the lane's stream; they are handed to the caller's stream with
     ``record_stream`` so that the caching allocator does not recycle them early.
     """
+    if device.index is not None and device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):  # set_stream() below selects a stream, not a device
+            return run_lanes(make_gen, count, device)
     main = torch.cuda.current_stream(device)
     streams = lane_streams(device, count)
     for s in streams:

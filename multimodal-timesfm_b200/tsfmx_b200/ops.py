@@ -8,12 +8,55 @@ Storage conventions: ``DT_BF16`` -> ``torch.bfloat16 [R, K]``; ``DT_BF16_SPLIT``
 from __future__ import annotations
 
 import ctypes
+import functools
 from collections.abc import Sequence
 
 import torch
 
 from . import _lib
 from ._lib import ACT_NONE, DT_BF16, DT_BF16_SPLIT, DT_F32, PREC_BF16, PREC_BF16X3, GemmArgs, check, ptr, stream
+
+
+def _arg_tensors(args, kwargs):
+    for a in (*args, *kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            yield a
+        elif isinstance(a, (list, tuple)):  # gemm segments: [(A, B, k), ...]
+            for item in a:
+                if isinstance(item, torch.Tensor):
+                    yield item
+                elif isinstance(item, (list, tuple)):
+                    for t in item:
+                        if isinstance(t, torch.Tensor):
+                            yield t
+
+
+def _on_operand_device(fn):
+    """Run an entry point on the device that holds its operands.
+
+    The C ABI takes raw pointers and a stream; kernels, TMA descriptors and the SM count all belong to the CURRENT
+    device.  A caller that built its model on ``cuda:1`` without ``torch.cuda.set_device(1)`` would otherwise launch on
+    GPU 0's stream with GPU 1's pointers (illegal address, or silent execution on the wrong GPU with peer access on).
+    Operands on different devices raise ``TsfmxError``."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        index = None
+        for t in _arg_tensors(args, kwargs):
+            if not t.is_cuda:
+                continue
+            if index is None:
+                index = t.device.index
+            elif t.device.index != index:
+                raise _lib.TsfmxError(
+                    f"{fn.__name__}: operands live on different devices (cuda:{index} and cuda:{t.device.index})"
+                )
+        if index is None or index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(index):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 def act_dtype(precision: int) -> int:
@@ -37,6 +80,7 @@ def _as_u8(mask: torch.Tensor) -> torch.Tensor:
     return (mask != 0).contiguous().view(torch.uint8)
 
 
+@_on_operand_device
 def timesfm_patchify_norm(
     x: torch.Tensor, mask: torch.Tensor, patch_len: int = 32, tokens_dtype: int = DT_F32
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -60,6 +104,7 @@ def timesfm_patchify_norm(
     return tokens, mu, sigma, pm.view(torch.bool), nm
 
 
+@_on_operand_device
 def chronos2_patchify_norm(
     x: torch.Tensor,
     mask: torch.Tensor,
@@ -90,6 +135,7 @@ def chronos2_patchify_norm(
     return patched, am.view(torch.bool), loc, scale
 
 
+@_on_operand_device
 def chronos_t5_tokenize(
     x: torch.Tensor,
     boundaries: torch.Tensor,
@@ -116,6 +162,7 @@ def chronos_t5_tokenize(
     return ids, am.view(torch.bool), scale
 
 
+@_on_operand_device
 def chronos_t5_dequantize(ids: torch.Tensor, centers: torch.Tensor, scale: torch.Tensor, n_special: int = 2) -> torch.Tensor:
     _lib.require_cuda(ids, centers, scale)
     lib = _lib.load()
@@ -132,6 +179,7 @@ def chronos_t5_dequantize(ids: torch.Tensor, centers: torch.Tensor, scale: torch
     return out
 
 
+@_on_operand_device
 def cast_rows(x: torch.Tensor, out_dtype: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """fp32 [R, K] (row stride allowed) -> bf16 [R, K] or split bf16 [R, 2K]."""
     _lib.require_cuda(x)
@@ -144,6 +192,7 @@ def cast_rows(x: torch.Tensor, out_dtype: int, out: torch.Tensor | None = None) 
     return out
 
 
+@_on_operand_device
 def gemm(
     segments: Sequence[tuple[torch.Tensor, torch.Tensor, int]],
     m: int,
@@ -193,6 +242,7 @@ def gemm(
     return out
 
 
+@_on_operand_device
 def gemm_rownorm(
     a: torch.Tensor,
     b: torch.Tensor,
@@ -220,6 +270,7 @@ def gemm_rownorm(
     )
 
 
+@_on_operand_device
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out_dtype: int, out: torch.Tensor | None = None) -> torch.Tensor:
     _lib.require_cuda(x, w)
     lib = _lib.load()
@@ -230,6 +281,7 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out_dtype: int, out: t
     return out
 
 
+@_on_operand_device
 def norm_residual_norm(
     a: torch.Tensor,
     x: torch.Tensor,
@@ -251,6 +303,7 @@ def norm_residual_norm(
     )
 
 
+@_on_operand_device
 def timesfm_attention(
     qkv: torch.Tensor,
     batch: int,
@@ -293,6 +346,7 @@ def _dt(t: torch.Tensor) -> int:
     return DT_BF16 if t.dtype == torch.bfloat16 else DT_F32
 
 
+@_on_operand_device
 def rmsnorm_bwd_chain(
     g_res: torch.Tensor | None,
     v1: torch.Tensor | None,
@@ -317,6 +371,7 @@ def rmsnorm_bwd_chain(
     )
 
 
+@_on_operand_device
 def colsum_wgrad(g: torch.Tensor, v: torch.Tensor | None = None, eps: float = 0.0, out: torch.Tensor | None = None) -> torch.Tensor:
     """``out[c] += sum_r g[r, c] * v_hat[r, c]`` (RMSNorm scale gradient, ``v_hat`` = RMS-normalised ``v``) or, without
     ``v``, ``out[c] += sum_r g[r, c]`` (bias gradient).  ``out`` fp32 [cols] is created zeroed when not given."""
@@ -330,6 +385,7 @@ def colsum_wgrad(g: torch.Tensor, v: torch.Tensor | None = None, eps: float = 0.
     return out
 
 
+@_on_operand_device
 def timesfm_attention_bwd(
     qkv: torch.Tensor,
     d_out: torch.Tensor,
@@ -370,6 +426,7 @@ def _storage_dtype(t: torch.Tensor, logical_cols: int) -> int:
     return DT_BF16_SPLIT if t.shape[1] == 2 * logical_cols else DT_BF16
 
 
+@_on_operand_device
 def transpose_mask(
     x: torch.Tensor, rows: int, cols: int, out_dtype: int, mask: torch.Tensor | None = None
 ) -> tuple[torch.Tensor, int]:
@@ -389,6 +446,7 @@ def transpose_mask(
     return out, kpad
 
 
+@_on_operand_device
 def mask_cast_rows(x: torch.Tensor, mask: torch.Tensor, out_dtype: int) -> torch.Tensor:
     """fp32 [R, C] gated by mask[r, c] > 0 -> f32 / bf16 / split [R, C]."""
     lib = _lib.load()
@@ -408,6 +466,7 @@ _force_simt_encoder_attention = False  # test hook: run the fp32 SIMT kernel whe
 _rope_tables: dict[tuple, torch.Tensor] = {}
 
 
+@_on_operand_device
 def rope_table(inv_freq: torch.Tensor, seq: int) -> torch.Tensor:
     """(cos, sin) of position * inv_freq for positions [0, seq): fp32 [seq, half, 2], cached per inv_freq tensor."""
     key = (inv_freq.data_ptr(), inv_freq._version, inv_freq.device, seq)
@@ -421,6 +480,7 @@ def rope_table(inv_freq: torch.Tensor, seq: int) -> torch.Tensor:
     return table
 
 
+@_on_operand_device
 def encoder_attention(
     qkv: torch.Tensor,
     batch: int,
@@ -451,6 +511,7 @@ def encoder_attention(
     return out
 
 
+@_on_operand_device
 def encoder_attention_bwd(
     qkv: torch.Tensor, d_out: torch.Tensor, batch: int, seq: int, num_heads: int, head_dim: int,
     key_mask: torch.Tensor | None, inv_freq: torch.Tensor, dqkv_dtype: int, dqkv: torch.Tensor | None = None,
@@ -472,6 +533,7 @@ def encoder_attention_bwd(
     return dqkv
 
 
+@_on_operand_device
 def chronos2_finalize(
     preds: torch.Tensor, batch: int, patches_used: int, num_quantiles: int, patch: int, horizon: int,
     use_arcsinh: bool, loc: torch.Tensor, scale: torch.Tensor,
@@ -489,6 +551,7 @@ def chronos2_finalize(
 
 
 # ----------------------------------------------------------------------------- Chronos-T5
+@_on_operand_device
 def embed_rows(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     """ids (any shape, int64) -> fp32 [ids.numel(), dims] rows of the fp32 ``table`` [vocab, dims]."""
     lib = _lib.load()
@@ -500,6 +563,7 @@ def embed_rows(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_operand_device
 def t5_attention(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -538,6 +602,7 @@ def t5_attention(
     return out
 
 
+@_on_operand_device
 def t5_encoder_attention(
     qkv: torch.Tensor, batch: int, seq: int, num_heads: int, key_mask: torch.Tensor | None, bias: torch.Tensor | None,
     out_dtype: int, out: torch.Tensor | None = None,

@@ -3,9 +3,12 @@ gradient clipping, AdamW, per-step LR schedule.
 
 Kept from the reference: the class name, constructor arguments, "multimodal" = frozen adapter + trainable fusion
 (trainer.py:76-77,119-123), loss / accumulation / clip / step order (trainer.py:200-219), ``RuntimeError`` on empty
-datasets, checkpoint dictionary keys (types.py:42-61).  Added for the B200 box: data parallelism — each rank takes its
-slice of every batch and the fusion gradients are averaged with one NCCL all-reduce per optimizer step, before the
-clip; checkpoints are written by rank 0.  "baseline" = full fine-tuning of the adapter without text (trainer.py:78-79):
+datasets, checkpoint dictionary keys (types.py:42-61), the warm-up semantics of ``TrainingArguments.warmup_steps``
+(training_args.py:111-121).  Added for the B200 box: data parallelism — each rank takes its slice of every batch,
+weights its loss by slice size / batch size and the gradients are summed with NCCL all-reduces per optimizer step,
+before the clip (equal to the single-process global-batch step for any slice sizes, empty ones included); the slice of
+the next batch is copied host -> device on a copy stream while the current one computes; checkpoints are written by
+rank 0.  "baseline" = full fine-tuning of the adapter without text (trainer.py:78-79):
 available for the TimesFM adapter (weight-gradient GEMMs for every Linear, all-reduce of all 231 M gradients).
 """
 
@@ -101,6 +104,7 @@ class MultimodalTrainer:
         self.current_epoch = 0
         self.global_step = 0
         self.best_val_loss = float("inf")
+        self._copy_stream: torch.cuda.Stream | None = None
 
     def _get_trainable_params(self) -> Iterator[nn.Parameter]:
         """Fusion weights in "multimodal" mode, the adapter's trainable parameters in "baseline" mode
@@ -109,29 +113,102 @@ class MultimodalTrainer:
             return self.model.fusion.parameters()
         return (p for p in self.model.adapter.parameters() if p.requires_grad)
 
+    def _warmup_steps(self, total_steps: int) -> int:
+        """The reference's ``TrainingArguments.warmup_steps`` is a float: values >= 1 are absolute optimizer steps,
+        values in [0, 1) a ratio of the total (``ceil(total * ratio)``, reference training_args.py:111-121)."""
+        getter = getattr(self.args, "get_warmup_steps", None)
+        if callable(getter):
+            return int(getter(total_steps))
+        ws = float(getattr(self.args, "warmup_steps", 0.0) or 0.0)
+        return int(ws) if ws >= 1 else math.ceil(total_steps * ws)
+
     def _create_scheduler(self, total_steps: int) -> LRScheduler:
         kind = getattr(self.args, "lr_scheduler_type", "linear")
-        warmup = int(getattr(self.args, "warmup_steps", 0) or round(getattr(self.args, "warmup_ratio", 0.0) * total_steps))
+        warmup = self._warmup_steps(total_steps)
         if kind == "linear":
             return linear_schedule_with_warmup(self.optimizer, warmup, total_steps)
         if kind == "cosine":
             return cosine_schedule_with_warmup(self.optimizer, warmup, total_steps)
         raise NotImplementedError(f"Unknown lr_scheduler_type: {kind}")
 
+    # ------------------------------------------------------------------ data path: shard, stage one batch ahead
+    _KEYS = ("context", "horizon", "text_embeddings")
+
+    def _staged(self, loader) -> Iterator[dict]:
+        """Yield this rank's shard of every global batch, already on the device.
+
+        On a CUDA device the shard of batch i + 1 is copied (pinned host memory -> HBM, ``non_blocking``) on a copy
+        stream while the kernels of batch i run: the reference's loop (trainer.py:200-206) does three synchronous
+        ``.to(device)`` per micro-batch in front of the forward.  Each yielded dict also carries ``global_size``, the
+        number of samples of the global batch the shard was cut from."""
+        cuda = self.device.type == "cuda"
+        if not cuda:
+            for batch in loader:
+                n = len(batch["context"])
+                shard = tdist.shard_batch(batch, self.rank, self.world_size)
+                out = {k: shard[k].to(self.device) for k in self._KEYS if k in shard}
+                out["global_size"] = n
+                yield out
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy = self._copy_stream
+
+        def stage(batch: dict):
+            n = len(batch["context"])
+            shard = tdist.shard_batch(batch, self.rank, self.world_size)
+            out: dict[str, Any] = {"global_size": n}
+            with torch.cuda.stream(copy):
+                for k in self._KEYS:
+                    if k in shard:
+                        dst = shard[k].to(self.device, non_blocking=True)  # allocated on the copy stream ...
+                        dst.record_stream(main)  # ... consumed on the caller's: keep the block until main is done
+                        out[k] = dst
+                done = torch.cuda.Event()
+                done.record(copy)
+            return out, done
+
+        it = iter(loader)
+        try:
+            pending = stage(next(it))
+        except StopIteration:
+            return
+        while pending is not None:
+            cur, done = pending
+            try:
+                pending = stage(next(it))
+            except StopIteration:
+                pending = None
+            main.wait_event(done)
+            yield cur
+
     # ------------------------------------------------------------------ one micro-batch / one optimizer step
     def _forward_loss(self, batch: dict) -> torch.Tensor:
-        batch = tdist.shard_batch(batch, self.rank, self.world_size)
-        context = batch["context"].to(self.device, non_blocking=True)
-        horizon = batch["horizon"].to(self.device, non_blocking=True)
+        """This rank's share of the global-batch MSE: ``mse(shard) * shard_size / global_size``.  Summed over ranks
+        that is exactly the reference's ``MSELoss`` over the whole batch (trainer.py:105,208), whatever the shard sizes
+        are - a ragged last batch may leave ranks with fewer samples than the others, or with none (their share is a
+        constant zero)."""
+        context = batch["context"]
+        n_local, n_global = context.shape[0], batch["global_size"]
+        if n_local == 0:
+            return torch.zeros((), dtype=torch.float32, device=self.device)
+        horizon = batch["horizon"]
         input_padding = torch.zeros_like(context, dtype=torch.bool)  # reference trainer.py:204
-        text = batch["text_embeddings"].to(self.device, non_blocking=True) if "text_embeddings" in batch else None
-        point = self.model(horizon.shape[-1], context, input_padding, text)
-        return self.loss_fn(point, horizon)
+        point = self.model(horizon.shape[-1], context, input_padding, batch.get("text_embeddings"))
+        loss = self.loss_fn(point, horizon)
+        return loss if n_local == n_global else loss * (n_local / n_global)
 
     def optimizer_step(self) -> None:
-        """All-reduce (mean) of the fusion gradients, clip, AdamW, LR schedule (reference trainer.py:213-219)."""
-        params = [p for p in self._get_trainable_params() if p.grad is not None]
-        tdist.allreduce_mean_([p.grad for p in params])
+        """All-reduce (sum of the ranks' shares) of the gradients, clip, AdamW, LR schedule (reference
+        trainer.py:213-219).  The all-reduce comes before the clip so that the clip sees the global-batch norm."""
+        params = list(self._get_trainable_params())
+        if self.world_size > 1:
+            for p in params:  # a rank whose shards were all empty still takes part in the collective
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            tdist.allreduce_([p.grad for p in params], "sum")
+        params = [p for p in params if p.grad is not None]
         if self.args.max_grad_norm > 0:
             nn.utils.clip_grad_norm_(params, self.args.max_grad_norm)
         self.optimizer.step()
@@ -140,7 +217,7 @@ class MultimodalTrainer:
         self.global_step += 1
 
     def train_epoch(self) -> float:
-        """Average training loss of the epoch (mean over ranks of the per-shard losses).
+        """Average training loss of the epoch (global-batch MSE per micro-batch, averaged over micro-batches).
 
         Raises RuntimeError if the training dataset is empty (reference trainer.py:196-197)."""
         self.model.train()
@@ -149,14 +226,15 @@ class MultimodalTrainer:
             raise RuntimeError("Training dataset is empty.")
         accum = self.args.gradient_accumulation_steps
         losses = []
-        for i, batch in enumerate(self.train_loader):
+        for i, batch in enumerate(self._staged(self.train_loader)):
             loss = self._forward_loss(batch) / accum
-            loss.backward()
+            if loss.requires_grad:
+                loss.backward()
             losses.append(loss.detach() * accum)  # no per-micro-batch .item() sync (reference trainer.py:211)
             if (i + 1) % accum == 0 or (i + 1) == num_batches:
                 self.optimizer_step()
         total = torch.stack(losses).sum()
-        tdist.allreduce_mean_([total])
+        tdist.allreduce_([total], "sum")
         return float(total.item()) / num_batches
 
     def validate_epoch(self) -> float:
@@ -166,8 +244,8 @@ class MultimodalTrainer:
         if num_batches == 0:
             raise RuntimeError("Validation dataset is empty.")
         with torch.no_grad():
-            total = torch.stack([self._forward_loss(batch) for batch in self.val_loader]).sum()
-        tdist.allreduce_mean_([total])
+            total = torch.stack([self._forward_loss(batch) for batch in self._staged(self.val_loader)]).sum()
+        tdist.allreduce_([total], "sum")
         return float(total.item()) / num_batches
 
     def train(self) -> None:

@@ -68,3 +68,17 @@ def test_rejects_empty_and_ragged():
         PackedSamples.from_samples(bad, pin=False)
     with pytest.raises(ValueError, match="batch_size"):
         list(PackedSamples.from_samples(_samples(2), pin=False).batches(0))
+
+
+def test_shuffled_batches_do_not_alias_each_other():
+    """A consumer may hold (or still be copying) earlier shuffled batches when it asks for the next one: every batch
+    owns its storage.  (A shared scratch buffer here silently corrupted evaluations whose H2D copies ran behind.)"""
+    samples = _samples(12)
+    store = PackedSamples.from_samples(samples, pin=False)
+    held = list(store.batches(4, shuffle=True, generator=torch.Generator().manual_seed(9)))
+    assert len({b["context"].data_ptr() for b in held}) == len(held)
+    for b in held:
+        for row, meta in enumerate(b["metadata"]):
+            assert np.array_equal(b["context"][row].numpy(), samples[meta["i"]]["context"])
+            assert np.array_equal(b["horizon"][row].numpy(), samples[meta["i"]]["horizon"])
+            assert np.array_equal(b["text_embeddings"][row].numpy(), samples[meta["i"]]["text_embeddings"])

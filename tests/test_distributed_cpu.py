@@ -4,6 +4,7 @@ all-reduce of the fine-tune step, and the bench-style max-over-ranks reduction."
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -78,3 +79,78 @@ def test_single_process_is_a_no_op():
     tdist.allreduce_mean_([t])
     assert torch.equal(t, torch.ones(4))
     assert tdist.world_info()[1] >= 1
+
+
+# ------------------------------------------------------------------------------------------------ trainer, ragged tail
+class _StubAdapter(torch.nn.Module):
+    """Stands in for a frozen backbone so that the trainer's HOST logic (sharding, loss weighting, the gradient
+    all-reduce, the optimizer step order) can run on CPU ranks; the product adapters are CUDA-only."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.ones(1))
+
+    def freeze_parameters(self):
+        self.w.requires_grad = False
+
+
+class _StubDecoder(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.adapter = _StubAdapter()
+        self.fusion = torch.nn.Linear(6, 4, bias=False)
+
+    def forward(self, horizon, context, padding, text):
+        return context[:, -horizon:] * self.adapter.w + torch.relu(self.fusion(text.mean(1)))[:, :horizon]
+
+
+def _trainer_dataset(n=5):
+    g = torch.Generator().manual_seed(3)
+    return [{"context": torch.randn(8, generator=g).numpy(), "horizon": torch.randn(4, generator=g).numpy(),
+             "text_embeddings": torch.randn(2, 6, generator=g).numpy(), "metadata": {"i": i}} for i in range(n)]
+
+
+def _run_trainer(per_device: int, epochs: int = 2):
+    import types
+
+    from tsfmx_b200.trainer import MultimodalTrainer
+
+    torch.manual_seed(11)
+    model = _StubDecoder()
+    args = types.SimpleNamespace(per_device_train_batch_size=per_device, per_device_eval_batch_size=per_device,
+                                 gradient_accumulation_steps=1, max_grad_norm=0.5, learning_rate=1e-2, weight_decay=0.0,
+                                 num_train_epochs=epochs, seed=4, warmup_steps=0.0, save_strategy="no")
+    data = _trainer_dataset()
+    tr = MultimodalTrainer(model, args, data, data, "multimodal", torch.device("cpu"))
+    losses = [tr.train_epoch() for _ in range(epochs)]
+    return model.fusion.weight.detach().clone(), losses, tr.validate_epoch()
+
+
+def _trainer_worker(rank: int, world: int, port: int, result_dir: str):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    tdist.init_process_group("gloo")
+    w, losses, val = _run_trainer(per_device=2)  # global batch 4 over 5 samples: the tail batch has ONE sample
+    torch.save({"w": w, "losses": losses, "val": val}, os.path.join(result_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trainer_ragged_tail_equals_the_single_process_step(tmp_path):
+    """5 samples, 2 ranks x 2 per device: the last global batch holds one sample, so rank 1's shard is EMPTY.  Every
+    rank must still join the gradient all-reduce (no hang, no NaN), and weights and losses must equal the
+    single-process run over the same global batches (4 + 1)."""
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        os.environ.pop(k, None)
+    ref_w, ref_losses, ref_val = _run_trainer(per_device=4)
+    world, port = 2, _free_port()
+    mp.spawn(_trainer_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        os.environ.pop(k, None)
+    outs = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    assert torch.equal(outs[0]["w"], outs[1]["w"])
+    assert torch.allclose(outs[0]["w"], ref_w, atol=1e-6)
+    for got in outs:
+        assert got["losses"] == pytest.approx(ref_losses, rel=1e-5)
+        assert got["val"] == pytest.approx(ref_val, rel=1e-5)
+        assert all(v == v for v in got["losses"])  # no NaN from the empty shard

@@ -80,3 +80,31 @@ def test_uneven_lanes_match_single_stream(pair):
         dec.lanes = 2
         dec.set_precision("bf16x3")
     assert torch.equal(one, two)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_a_non_current_device():
+    """A decoder built on cuda:1 in a process whose current device is cuda:0: every entry point must run on the device
+    that holds its operands (stream, TMA descriptors, SM count), and mixing devices must raise instead of launching."""
+    from tsfmx_b200 import ops
+    from tsfmx_b200._lib import DT_BF16, TsfmxError
+
+    assert torch.cuda.current_device() == 0
+    adapter = TimesFM2p5Adapter(num_layers=2, with_quantile_head=False)
+    init_random_(adapter, seed=0)
+    torch.manual_seed(100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig())
+    ctx, masks, text, _ = O.synthetic_batch(520, 512, 128, padded=True)  # enough tokens for two series lanes
+    with torch.no_grad():
+        dec0 = dec.to("cuda:0").eval()
+        want = dec0.forward_full(128, ctx.to("cuda:0"), masks.to("cuda:0"), text.to("cuda:0")).cpu()
+        dec1 = dec.to("cuda:1").eval()
+        a = dec1.forward_full(128, ctx.to("cuda:1"), masks.to("cuda:1"), text.to("cuda:1"))
+        b = dec1.forward_full(128, ctx.to("cuda:1"), masks.to("cuda:1"), text.to("cuda:1"))  # second call: lanes
+        dec1.graphs = True
+        c = dec1.forward_full(128, ctx.to("cuda:1"), masks.to("cuda:1"), text.to("cuda:1"))
+    assert a.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(a.cpu(), want) and torch.equal(b.cpu(), want) and torch.equal(c.cpu(), want)
+    x0 = torch.randn(64, 128, device="cuda:0")
+    with pytest.raises(TsfmxError, match="different devices"):
+        ops.cast_rows(x0, DT_BF16, out=torch.empty(64, 128, dtype=torch.bfloat16, device="cuda:1"))

@@ -128,3 +128,25 @@ def test_evaluator_stops_capturing_when_shapes_keep_changing():
     assert ev.evaluate(batches) == eager
     assert dec.graph_captures == MultimodalEvaluator.MAX_CAPTURES_PER_PASS
     assert not dec.graphs
+
+
+def test_shuffled_store_with_a_lagging_copy_stream():
+    """Large shuffled batches while the copy stream runs far behind the host (a spin kernel parked on it): every sample
+    must still be evaluated exactly once.  With one reusable pinned gather buffer the host overwrote batch i while its
+    DMA was still queued, and the metrics came out silently wrong."""
+    from tsfmx_b200.data import PackedSamples
+
+    dec = _small_decoder(1)
+    n, b = 1536, 256  # 6 batches of 256 series: 6.3 MB of text embeddings per batch
+    ctx, _m, text, hor = O.synthetic_batch(n, 512, 32, seed=21)
+    hor = hor + torch.arange(n, dtype=torch.float32)[:, None] * 0.01  # per-sample targets: duplicates shift the metrics
+    store = PackedSamples(ctx.pin_memory(), hor.pin_memory(), text.pin_memory(), [{"i": i} for i in range(n)])
+    ev = MultimodalEvaluator(dec, torch.device("cuda"))
+    in_order = ev.evaluate(store.batches(b))
+    for seed in (1, 2):
+        ev._copy_stream = ev._copy_stream or torch.cuda.Stream()
+        with torch.cuda.stream(ev._copy_stream):
+            torch.cuda._sleep(400_000_000)  # ~0.2 s: the host gathers all six batches before the first DMA starts
+        got = ev.evaluate(store.batches(b, shuffle=True, generator=torch.Generator().manual_seed(seed)))
+        assert got["mse"] == pytest.approx(in_order["mse"], rel=1e-5)
+        assert got["mae"] == pytest.approx(in_order["mae"], rel=1e-5)

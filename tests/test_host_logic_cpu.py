@@ -131,3 +131,46 @@ def test_trainer_checkpoint_strategies(tmp_path):
         MultimodalTrainer(c2, args, dummy, dummy, "baseline", torch.device("cpu"))
     with pytest.raises(ValueError):
         MultimodalTrainer(dec, args, dummy, dummy, "something", torch.device("cpu"))
+
+
+def test_warmup_steps_follow_the_reference_semantics():
+    """``TrainingArguments.warmup_steps`` (reference training_args.py:28-35,111-121): a float; >= 1 means absolute steps,
+    [0, 1) a ratio of the total, rounded UP.  ``warmup_steps=0.1`` must not truncate to zero warm-up steps."""
+    import math
+    import types
+
+    from tsfmx_b200.trainer import MultimodalTrainer
+
+    dec = MultimodalDecoder(TimesFM2p5Adapter(num_layers=1, with_quantile_head=False), MultimodalDecoderConfig())
+    dummy = [{"context": torch.zeros(64).numpy(), "horizon": torch.zeros(8).numpy(),
+              "text_embeddings": torch.zeros(2, 384).numpy(), "metadata": {}}] * 6
+
+    def trainer(**kw):
+        args = types.SimpleNamespace(per_device_train_batch_size=2, per_device_eval_batch_size=2, gradient_accumulation_steps=1,
+                                     max_grad_norm=1.0, learning_rate=1.0, weight_decay=0.0, num_train_epochs=7, seed=0, **kw)
+        return MultimodalTrainer(dec, args, dummy, dummy, "multimodal", torch.device("cpu"))
+
+    total = 7 * 3
+    for ws, want in [(0.0, 0), (0.1, math.ceil(total * 0.1)), (0.5, 11), (1.0, 1), (5, 5), (5.9, 5)]:
+        tr = trainer(warmup_steps=ws)
+        assert tr._warmup_steps(total) == want, (ws, want)
+    tr = trainer(warmup_steps=0.1)  # 3 warm-up steps: the LR ramps 0, 1/3, 2/3, 1 instead of starting at 1
+    assert tr.optimizer.param_groups[0]["lr"] == 0.0
+    # an args object that carries the reference's own method is asked directly
+    tr = trainer(warmup_steps=0.25, get_warmup_steps=lambda n: 4)
+    assert tr._warmup_steps(total) == 4
+    try:
+        import sys
+        sys.path.insert(0, "/root/reference/src")
+        from tsfmx.training_args import TrainingArguments  # only in the build container
+    except Exception:
+        return
+    finally:
+        if sys.path[0] == "/root/reference/src":
+            sys.path.pop(0)
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        for ws in (0.0, 0.1, 0.5, 1.0, 5.0):
+            ref = TrainingArguments(output_dir=d, warmup_steps=ws)
+            assert trainer(warmup_steps=ws)._warmup_steps(total) == ref.get_warmup_steps(total)
