@@ -30,7 +30,6 @@ SOURCES = [
     "attention_bwd.cu",
     "chronos.cu",
     "t5.cu",
-    "model.cu",
 ]
 
 NVCC_FLAGS = [
@@ -74,7 +73,10 @@ def _compile_one(nvcc: str, src: Path, obj: Path, verbose: bool) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    srcs = [CSRC / s for s in SOURCES]
+    missing = [str(p) for p in srcs if not p.exists()]
+    if missing:
+        raise RuntimeError(f"missing CUDA sources: {missing}")
     deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h"))
     stamp = OBJ_DIR / "stamp.txt"
     digest = _digest(deps)

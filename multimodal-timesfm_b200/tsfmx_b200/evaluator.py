@@ -41,6 +41,7 @@ class MultimodalEvaluator:
         # lets the forecast graphs be replayed
         self._slots: list[dict[str, torch.Tensor]] = [{}, {}]
         self._copy_stream: torch.cuda.Stream | None = None
+        self._d2h_stream: torch.cuda.Stream | None = None
 
     def _staged(self, dataloader: Iterable[dict]) -> Iterator[dict]:
         """Yield device-resident batches; with a CUDA device the next batch is already in flight on a copy stream."""
@@ -109,6 +110,71 @@ class MultimodalEvaluator:
             consumed[index % 2] = torch.cuda.Event()
             consumed[index % 2].record(main)
             index += 1
+
+    def predict(self, dataloader: Iterable[dict], horizon: int | None = None, *, full: bool = True,
+                copy: bool = True) -> Iterator[torch.Tensor]:
+        """Forecasts of every batch of ``dataloader`` as HOST tensors: ``(B, horizon, Q)`` quantile forecasts
+        (``full``) or the ``(B, horizon)`` point forecast.  Not in the reference (its only consumer of forecasts is
+        ``evaluate``); this is the same staged loop for callers that want the numbers themselves.
+
+        The inputs are staged one batch ahead like in ``evaluate``; every forecast is copied device -> host on its own
+        stream into one of three page-locked buffers while the next batch computes.  ``copy=False`` yields views of
+        those buffers: each stays valid until two more batches have been requested.  ``horizon`` defaults to the
+        length of the batch's ``"horizon"`` target."""
+        self.model.eval()
+        cuda = self.device.type == "cuda"
+        graphs_before = getattr(self.model, "graphs", False)
+        if cuda and hasattr(self.model, "graphs"):
+            self.model.graphs = self.graphs
+        try:
+            yield from self._predict(dataloader, horizon, full, copy, cuda)
+        finally:
+            if hasattr(self.model, "graphs"):
+                self.model.graphs = graphs_before
+
+    def _predict(self, dataloader, horizon, full, copy, cuda) -> Iterator[torch.Tensor]:
+        fn = self.model.forward_full if full else self.model
+        ring: list[torch.Tensor | None] = [None, None, None]
+        copied: list[torch.cuda.Event | None] = [None, None, None]
+        pending: list[tuple[int, tuple[int, ...]]] = []  # (ring slot, shape) of forecasts whose read-back is in flight
+        main = torch.cuda.current_stream(self.device) if cuda else None
+        if cuda and self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream(device=self.device)
+        d2h = self._d2h_stream
+
+        def land(slot: int, shape: tuple[int, ...]) -> torch.Tensor:
+            copied[slot].synchronize()
+            view = ring[slot][: shape[0]]
+            return view.clone() if copy else view
+
+        with torch.no_grad():
+            for index, batch in enumerate(self._staged(dataloader)):
+                context = batch["context"]
+                h = int(horizon if horizon is not None else batch["horizon"].shape[-1])
+                if not cuda:
+                    yield fn(h, context, batch["input_padding"], batch.get("text_embeddings"))
+                    continue
+                slot = index % 3
+                if index >= 2:
+                    # the staging slot this batch sits in (index % 2) fed the forecast of batch index - 2, whose
+                    # output buffer a graph replay is about to overwrite: its read-back must have finished
+                    main.wait_event(copied[(index - 2) % 3])
+                out = fn(h, context, batch["input_padding"], batch.get("text_embeddings"))
+                if ring[slot] is None or ring[slot].shape[1:] != out.shape[1:] or ring[slot].shape[0] < out.shape[0]:
+                    ring[slot] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                computed = torch.cuda.Event()
+                computed.record(main)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(computed)
+                    ring[slot][: out.shape[0]].copy_(out, non_blocking=True)
+                    out.record_stream(d2h)
+                    copied[slot] = torch.cuda.Event()
+                    copied[slot].record(d2h)
+                pending.append((slot, tuple(out.shape)))
+                if len(pending) == 2:  # hand out batch i - 1 while batch i computes
+                    yield land(*pending.pop(0))
+        for slot, shape in pending:
+            yield land(slot, shape)
 
     def evaluate(self, dataloader: Iterable[dict]) -> EvaluationMetrics:
         """Raises RuntimeError if the loader yields no samples (reference evaluator.py:65-66)."""

@@ -309,3 +309,57 @@ def synthetic_batch(batch: int, context: int, horizon: int, text_dims: int = 384
     text = torch.randn(batch, context // patch_len, text_dims, generator=gt)
     text = text / text.norm(dim=-1, keepdim=True)
     return ctx.contiguous(), masks, text.contiguous(), hor.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# the oracle itself in bf16 (calibrates the tolerance of the product's "bf16" throughput mode)
+# ------------------------------------------------------------------------------------------------
+_BF16_OUTPUT_LINEARS = ("q_proj", "k_proj", "v_proj", "o_proj", "fc2")
+
+
+def bf16_oracle(oracle: OracleDecoder) -> OracleDecoder:
+    """A copy of ``oracle`` that computes the way a bf16 deployment of the reference would: every ``nn.Linear`` sees
+    bf16-rounded weights and bf16-rounded inputs and accumulates in fp32; the outputs of the attention projections and
+    of the second MLP matrix are rounded to bf16 as well (they are stored as bf16 activations).  Everything else -
+    statistics, norms, softmax, residual stream - stays fp32, exactly as in the fp32 oracle.
+
+    Its distance to the fp32 oracle is what bf16 operands cost on THIS model and THESE inputs, independent of any
+    kernel: SURVEY.md section 8(d) asks for the bf16 tolerance to be "calibrated against the oracle itself run with
+    bf16 weights/activations".  tests/test_parity_gpu.py and bench.py bound the product's bf16 error by a stated
+    multiple of it instead of a hand-set constant."""
+    import copy
+
+    twin = copy.deepcopy(oracle).eval()
+
+    def to_bf16(t: torch.Tensor) -> torch.Tensor:
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    def round_inputs(_module, args):
+        return tuple(to_bf16(a) if isinstance(a, torch.Tensor) and a.is_floating_point() else a for a in args)
+
+    def round_output(_module, _args, out):
+        return to_bf16(out)
+
+    with torch.no_grad():
+        for name, module in twin.named_modules():
+            if isinstance(module, nn.Linear):
+                module.weight.copy_(to_bf16(module.weight))
+                module.register_forward_pre_hook(round_inputs)
+                if name.rsplit(".", 1)[-1] in _BF16_OUTPUT_LINEARS:
+                    module.register_forward_hook(round_output)
+    return twin
+
+
+def rel_max(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max|a - b| / max|b|: the relative error the north star's 1e-3 bar is stated in."""
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+# the product's bf16 mode may deviate from the fp32 oracle by at most this multiple of the bf16 oracle's own deviation
+# (two independent bf16 realisations of the same computation differ from each other by about sqrt(2) of it; the product
+# additionally keeps P, q' and k' of the attention core in bf16 for the tensor cores)
+BF16_TOL_FACTOR = 3.0

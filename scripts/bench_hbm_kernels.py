@@ -36,29 +36,10 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--only", default="")
-    ap.add_argument("--contexts", default="", help="comma-separated context lengths (default 512,2048)")
-    ap.add_argument("--tf-group", type=int, default=0, help="series per warp of timesfm_patchify_norm (0 = default)")
-    ap.add_argument("--tf-warps", type=int, default=0, help="warps per block of timesfm_patchify_norm (0 = default)")
-    ap.add_argument("--tf-variant", type=int, default=0, help="0 = TMA-pipelined kernel (tf-group = series per tile, "
-                    "tf-warps = stages), 1 = warp-staged cp.async kernel")
-    ap.add_argument("--t5-variant", type=int, default=0, help="1/2 = register-cached row (<=512 / <=2048), 3 = re-read")
-    args = ap.parse_args()
-    from tsfmx_b200 import _lib
-
-    _lib.check(_lib.load().tsfmx_tune(0, args.tf_group))
-    _lib.check(_lib.load().tsfmx_tune(1, args.tf_warps))
-    _lib.check(_lib.load().tsfmx_tune(2, args.t5_variant))
-    _lib.check(_lib.load().tsfmx_tune(3, args.tf_variant))
-    dev = torch.device("cuda")
-    peak = peak_gbs()
+def stage_cases(dev, contexts):
+    """(name, algorithmic bytes per series, series, launch) for the three HBM-bound stages at every (context, batch)."""
     cases = []
-    ap_ctx = [(512, 262144), (2048, 65536)] if not args.contexts else [
-        (int(c), max(8192, 262144 * 512 // int(c))) for c in args.contexts.split(",")]
-    for ctx_len, batch in ap_ctx:
+    for ctx_len, batch in contexts:
         g = torch.Generator(device=dev).manual_seed(ctx_len)
         x = torch.randn(batch, ctx_len, generator=g, device=dev)
         mask = torch.zeros(batch, ctx_len, dtype=torch.bool, device=dev)
@@ -70,22 +51,51 @@ def main():
              lambda x=x, mask=mask: ops.timesfm_patchify_norm(x, mask, 32, DT_BF16)),
             (f"chronos2_patchify_norm f32-out ctx{ctx_len}", 5 * ctx_len + 3 * ctx_len * 4 + n16 + 8, batch,
              lambda x=x, mask=mask: ops.chronos2_patchify_norm(x, mask, 16, True, 8192.0, DT_F32)),
+            (f"chronos2_patchify_norm bf16-out ctx{ctx_len}", 5 * ctx_len + 3 * ctx_len * 2 + n16 + 8, batch,
+             lambda x=x, mask=mask: ops.chronos2_patchify_norm(x, mask, 16, True, 8192.0, DT_BF16)),
         ]
         centers = torch.linspace(-15.0, 15.0, 4093)
         bounds = torch.cat([torch.tensor([-1e20]), (centers[1:] + centers[:-1]) / 2, torch.tensor([1e20])]).to(dev)
         cases.append((f"chronos_t5_tokenize int64-ids ctx{ctx_len}", 4 * ctx_len + 9 * (ctx_len + 1) + 4, batch,
                       lambda x=x, bounds=bounds: ops.chronos_t5_tokenize(x, bounds)))
+    return cases
+
+
+def measure(cases, iters, peak, only=""):
+    """One record per case: achieved GB/s = algorithmic bytes x series / CUDA-event time per launch."""
+    out = []
     for name, bytes_per_series, batch, fn in cases:
-        if args.only and args.only not in name:
+        if only and only not in name:
             continue
-        ms = timeit(fn, args.iters)
+        ms = timeit(fn, iters)
         gbs = bytes_per_series * batch / (ms * 1e-3) / 1e9
-        print(json.dumps({
-            "kernel": name, "series": batch, "algorithmic_bytes_per_series": bytes_per_series, "ms": round(ms, 4),
-            "series_per_s": batch / (ms * 1e-3), "achieved_GBps": round(gbs, 1), "peak_GBps": peak,
-            "frac_of_measured_hbm_peak": round(gbs / peak, 3), "tf_group": args.tf_group, "tf_warps": args.tf_warps, "tf_variant": args.tf_variant,
+        out.append({
+            "kernel": name, "bound": "hbm", "series": batch, "algorithmic_bytes_per_series": bytes_per_series,
+            "ms": round(ms, 4), "series_per_s": batch / (ms * 1e-3), "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(gbs / peak, 3),
             "note": "time includes torch.empty of the outputs; working set >> 126 MB L2",
-        }), flush=True)
+        })
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--contexts", default="", help="comma-separated context lengths (default 512,2048)")
+    ap.add_argument("--tune", default="", help="comma-separated knob=value pairs passed to tsfmx_tune (kernel A/B)")
+    args = ap.parse_args()
+    from tsfmx_b200 import _lib
+
+    for pair in filter(None, args.tune.split(",")):
+        knob, value = pair.split("=")
+        _lib.check(_lib.load().tsfmx_tune(int(knob), int(value)))
+    dev = torch.device("cuda")
+    contexts = [(512, 262144), (2048, 65536)] if not args.contexts else [
+        (int(c), max(8192, 262144 * 512 // int(c))) for c in args.contexts.split(",")]
+    for rec in measure(stage_cases(dev, contexts), args.iters, peak_gbs(), args.only):
+        rec["tune"] = args.tune
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":

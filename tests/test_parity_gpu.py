@@ -4,7 +4,12 @@ Bars (BASELINE.json north_star):
   * patch masks: bit-exact;
   * forecasts (all quantile channels, and the point forecast): <= 1e-3 relative in the fp32-accumulate
     parity mode ("bf16x3"), where relative = max|y - y_ref| / max|y_ref| per batch, and relative L2;
-  * "bf16" throughput mode: tolerance stated separately below (BF16_TOL), calibrated on the oracle.
+  * "bf16" throughput mode: tolerance stated separately and DERIVED, not hand-set: the oracle itself is run with bf16
+    weights / activations (``oracle.timesfm_oracle.bf16_oracle``) on the same inputs, and the product's deviation from
+    the fp32 oracle must stay within ``BF16_TOL_FACTOR`` (3) times the bf16 oracle's own deviation from it
+    (SURVEY.md section 8(d)).  Measured ratio product / bf16-oracle: see DESIGN.md section 3.
+  * the benchmarked configuration itself (50 layers, 4096 series, M = 65 536 token rows) is checked on a slice of
+    series that sit on tile, lane and batch boundaries.
 """
 
 import pytest
@@ -18,7 +23,7 @@ from tsfmx_b200.tsfm.timesfm import TimesFM2p5Adapter, init_random_  # noqa: E40
 
 DEV = "cuda"
 FP32_TOL = 1e-3  # north_star: within 1e-3 relative (fp32 accumulate)
-BF16_TOL = 4e-2  # bf16 operands, fp32 accumulate: stated separately (measured: see DESIGN.md)
+BF16_TOL_FACTOR = O.BF16_TOL_FACTOR  # product bf16 error <= 3 x (bf16 oracle vs fp32 oracle), same inputs
 
 
 def rel_max(a, b):
@@ -46,6 +51,12 @@ def model2():
 @pytest.fixture(scope="module")
 def model20():
     return build(20)
+
+
+@pytest.fixture(scope="module")
+def model50():
+    """The benchmarked model: 50 layers x 1280 ("500 M shape", BASELINE.json configs[1])."""
+    return build(50)
 
 
 @pytest.mark.parametrize("padded", [False, True])
@@ -107,16 +118,81 @@ def test_forward_full_no_text_and_long_context(model2):
     assert rel_max(got, ref) < FP32_TOL
 
 
-def test_forward_full_bf16_mode(model20):
-    dec, oracle = model20
+def _bf16_calibrated(dec, oracle, ctx, masks, text, horizon=128):
+    """-> (product bf16 error, bf16-oracle error), both rel-max against the fp32 oracle on the same inputs."""
     dec.set_precision("bf16")
-    ctx, masks, text, _ = O.synthetic_batch(8, 512, 128, padded=False)
+    with torch.no_grad():
+        ref = oracle.forward_full(horizon, ctx, masks, text)
+        ref_bf16 = O.bf16_oracle(oracle).forward_full(horizon, ctx, masks, text)
+        got = dec.forward_full(horizon, ctx.to(DEV), masks.to(DEV), text.to(DEV)).cpu()
+    return rel_max(got, ref), rel_max(ref_bf16, ref), rel_l2(got, ref), rel_l2(ref_bf16, ref)
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_forward_full_bf16_mode(model20, padded):
+    dec, oracle = model20
+    ctx, masks, text, _ = O.synthetic_batch(8, 512, 128, padded=padded)
+    err, cal, err_l2, cal_l2 = _bf16_calibrated(dec, oracle, ctx, masks, text)
+    print(f"bf16 mode, 20 layers: product rel_max={err:.3e} (l2 {err_l2:.3e}); bf16 oracle rel_max={cal:.3e} "
+          f"(l2 {cal_l2:.3e}); ratio {err / cal:.2f}")
+    assert err < BF16_TOL_FACTOR * cal, (err, cal)
+    assert err_l2 < BF16_TOL_FACTOR * cal_l2, (err_l2, cal_l2)
+
+
+# ------------------------------------------------------------------ the benchmarked configuration (50 layers)
+@pytest.mark.parametrize("padded", [False, True])
+def test_forward_full_parity_50_layers(model50, padded):
+    dec, oracle = model50
+    dec.set_precision("bf16x3")
+    ctx, masks, text, _ = O.synthetic_batch(8, 512, 128, padded=padded)
     with torch.no_grad():
         ref = oracle.forward_full(128, ctx, masks, text)
         got = dec.forward_full(128, ctx.to(DEV), masks.to(DEV), text.to(DEV)).cpu()
-    err = rel_max(got, ref)
-    print(f"bf16 mode: rel_max={err:.3e} rel_l2={rel_l2(got, ref):.3e}")
-    assert err < BF16_TOL, err
+    print(f"bf16x3, 50 layers: rel_max={rel_max(got, ref):.3e} rel_l2={rel_l2(got, ref):.3e}")
+    assert rel_max(got, ref) < FP32_TOL, rel_max(got, ref)
+    assert rel_l2(got, ref) < FP32_TOL
+    err, cal, err_l2, cal_l2 = _bf16_calibrated(dec, oracle, ctx, masks, text)
+    print(f"bf16, 50 layers: product rel_max={err:.3e}; bf16 oracle rel_max={cal:.3e}; ratio {err / cal:.2f}")
+    assert err < BF16_TOL_FACTOR * cal and err_l2 < BF16_TOL_FACTOR * cal_l2, (err, cal, err_l2, cal_l2)
+
+
+# series of the 4096-series benchmark batch that sit on boundaries: first / last of the batch, the 8-series groups a
+# 128-row GEMM tile holds (16 patches per series), the 256-row CTA-pair tile (16 series), the cut between the two series
+# lanes (2048) and a few interior ones
+BENCH_SLICE = [0, 1, 7, 8, 15, 16, 17, 1023, 2047, 2048, 2049, 3071, 4079, 4080, 4094, 4095]
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_benchmark_batch_matches_oracle_on_boundary_series(model50, graphs):
+    """The timed configuration of bench.py: 50 layers, 4096 series (M = 65 536 token rows), ctx 512 / horizon 128, two
+    series lanes or graph replay.  Every series is independent, so the oracle's forecast of a subset of series IS its
+    forecast of those rows of the full batch; 16 boundary series are checked in both precision modes."""
+    dec, oracle = model50
+    ctx, masks, text, _ = O.synthetic_batch(4096, 512, 128, seed=1234)
+    idx = torch.tensor(BENCH_SLICE)
+    with torch.no_grad():
+        ref = oracle.forward_full(128, ctx[idx], masks[idx], text[idx])
+        ref_bf16 = O.bf16_oracle(oracle).forward_full(128, ctx[idx], masks[idx], text[idx])
+    cal = rel_max(ref_bf16, ref)
+    c, m, t = ctx.to(DEV), masks.to(DEV), text.to(DEV)
+    dec.graphs = graphs
+    try:
+        with torch.no_grad():
+            dec.set_precision("bf16x3")
+            dec.forward_full(128, c, m, t)  # first call warms the caches single-stream; the second one runs the lanes
+            got = dec.forward_full(128, c, m, t)[idx.to(DEV)].cpu()
+            err3 = rel_max(got, ref)
+            dec.set_precision("bf16")
+            dec.forward_full(128, c, m, t)
+            got16 = dec.forward_full(128, c, m, t)[idx.to(DEV)].cpu()
+            err16 = rel_max(got16, ref)
+    finally:
+        dec.graphs = False
+        dec._graph_cache.clear()
+    print(f"B=4096, 50 layers, graphs={graphs}: bf16x3 rel_max={err3:.3e}; bf16 rel_max={err16:.3e} "
+          f"(bf16 oracle {cal:.3e}, ratio {err16 / cal:.2f})")
+    assert err3 < FP32_TOL, err3
+    assert err16 < BF16_TOL_FACTOR * cal, (err16, cal)
 
 
 @pytest.mark.parametrize("layers,hidden", [(2, [512]), (3, [1024, 512])])
