@@ -364,6 +364,56 @@ int tsfmx_transpose_mask(const void* in, int32_t in_dtype, int64_t rows, int32_t
 int tsfmx_mask_cast_rows(const float* in, int64_t rows, int32_t cols, const void* mask, int32_t mask_dtype,
                          int64_t ld_mask, int32_t out_dtype, void* out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * TimesFM 2.5 autoregressive decode (horizon > 128) and forecast extras.
+ * Beyond the reference adapter, which raises for horizon > output_patch_len
+ * (reference tsfmx/tsfm/timesfm.py:116-119); follows upstream timesfm's decode loop
+ * (timesfm @ 8a755c9, TimesFM_2p5_200M_torch_module.decode) and the HF port's
+ * forecast extras (transformers modeling_timesfm2_5.py:797-837).
+ * ---------------------------------------------------------------------- */
+#define TSFMX_MAX_KV_REGIONS 16
+
+/*
+ * The `patches` new input patches of a decode step (the previous 128-step point forecast), with the running
+ * RevIN statistics CONTINUED from the context: state_n / state_mu / state_sigma [B] fp32 are read and updated
+ * in place (update_running_stats with an all-valid patch).  Element (b, t) of the new values is read from
+ * x[b * x_series_stride + t * x_elem_stride] (a channel of a [B, steps, Q] forecast needs no gather).
+ *   tokens [B * patches, 2 * patch_len] of tokens_dtype ([normalised values | mask = 0]); mu, sigma [B, patches].
+ */
+int tsfmx_timesfm_patchify_continue(const float* x, int64_t x_series_stride, int64_t x_elem_stride, int64_t batch,
+                                    int32_t patches, int32_t patch_len, float* state_n, float* state_mu,
+                                    float* state_sigma, int32_t tokens_dtype, void* tokens, float* mu, float* sigma,
+                                    void* stream);
+
+/*
+ * Attention of a decode step: the tokens of the LAST region are the queries, every token of every region a key
+ * (causal).  Region r is a raw qkv matrix [B * region_tokens[r], 3 * H * hd] (f32 or bf16) exactly as
+ * tsfmx_gemm left it - region 0 the prefill's, then one per earlier decode step - so the "KV cache" needs no
+ * copy.  region_ptrs / region_tokens are HOST arrays (num_regions <= TSFMX_MAX_KV_REGIONS).  patch_mask
+ * [B, n_ctx] / num_masked [B] describe the left padding of region 0 as in tsfmx_timesfm_attention.
+ *   out [B * q_tokens, H * hd] of out_dtype.
+ */
+int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, const int32_t* region_tokens, int32_t num_regions,
+                                   int32_t qkv_dtype, int64_t batch, int32_t num_heads, int32_t head_dim, int32_t n_ctx,
+                                   const uint8_t* patch_mask, const int32_t* num_masked, const float* inv_freq,
+                                   const float* q_ln_w, const float* k_ln_w, const float* q_scale, float eps,
+                                   int32_t out_dtype, void* out, void* stream);
+
+/*
+ * Forecast extras in one pass (HF modeling_timesfm2_5.py:797-837): flip-invariance combination
+ * (x - flip_quantiles(x_neg)) / 2 of the point / quantile forecasts and of the quantile spread, continuous
+ * quantile head (channel c != 0, decode_index takes spread[c] - spread[decode_index] + pf[decode_index]),
+ * horizon slice, clamp at zero for series whose context is non-negative.
+ *   pf     [(1 + flip) * B, pf_steps, Q] fp32      rows B.. are the forecasts of the negated inputs
+ *   spread [(1 + flip) * B, spread_steps, Q] fp32  or NULL;   inputs [B, context] fp32 (or NULL)
+ *   out    [B, horizon, Q] fp32
+ */
+int tsfmx_timesfm_forecast_finalize(const float* pf, const float* spread, const float* inputs, int64_t batch,
+                                    int32_t context, int32_t pf_steps, int32_t spread_steps, int32_t num_outputs,
+                                    int32_t horizon, int32_t decode_index, int32_t flip,
+                                    int32_t use_continuous_quantile_head, int32_t infer_is_positive, float* out,
+                                    void* stream);
+
 /* tuning hook: key 0 = series per warp of timesfm_patchify_norm, key 1 = its warps per block (0 = default) */
 int tsfmx_tune(int32_t key, int32_t value);
 

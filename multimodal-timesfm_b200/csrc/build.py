@@ -30,6 +30,7 @@ SOURCES = [
     "attention_bwd.cu",
     "chronos.cu",
     "t5.cu",
+    "decode.cu",
 ]
 
 NVCC_FLAGS = [

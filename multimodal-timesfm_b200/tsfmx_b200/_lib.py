@@ -21,6 +21,8 @@ PREC_BF16, PREC_BF16X3 = 0, 1
 DT_F32, DT_BF16, DT_BF16_SPLIT = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SILU_GRAD, ACT_RELU_GRAD = 0, 1, 2, 3, 4
 
+MAX_KV_REGIONS = 16  # TSFMX_MAX_KV_REGIONS
+
 PRECISIONS = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 
 
@@ -160,6 +162,21 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "tsfmx_mask_cast_rows": (
         c_int32,
         [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p],
+    ),
+    "tsfmx_timesfm_patchify_continue": (
+        c_int32,
+        [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+         c_void_p, c_void_p, c_void_p],
+    ),
+    "tsfmx_timesfm_attention_decode": (
+        c_int32,
+        [POINTER(c_void_p), POINTER(c_int32), c_int32, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p],
+    ),
+    "tsfmx_timesfm_forecast_finalize": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+         c_int32, c_void_p, c_void_p],
     ),
     "tsfmx_timesfm_attention": (
         c_int32,

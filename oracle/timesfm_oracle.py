@@ -96,16 +96,18 @@ def make_hf_config(num_layers: int) -> TimesFm2_5Config:
 class OracleTimesFM2p5Adapter(nn.Module):
     """Reference ``TimesFM2p5Adapter`` with the third-party module replaced by its HF twin."""
 
-    def __init__(self, num_layers: int = 20) -> None:
+    def __init__(self, num_layers: int = 20, with_quantile_head: bool = False) -> None:
         super().__init__()
         self.cfg = make_hf_config(num_layers)
-        self.p, self.o, self.q, self.md = 32, 128, 10, 1280
+        self.p, self.o, self.os, self.q, self.md = 32, 128, 1024, 10, 1280
         self.decode_index = 5
         c = self.cfg
         self.tokenizer = hf.TimesFm2_5ResidualBlock(c, 2 * self.p, self.md, self.md, use_bias=True)
         self.stacked_xf = nn.ModuleList(hf.TimesFm2_5DecoderLayer(c, i) for i in range(num_layers))
         self.rotary_emb = hf.TimesFm2_5RotaryEmbedding(c)
         self.output_projection_point = hf.TimesFm2_5ResidualBlock(c, self.md, self.md, self.o * self.q)
+        if with_quantile_head:  # continuous quantile head (HF :676-681); unused by the reference adapter
+            self.output_projection_quantiles = hf.TimesFm2_5ResidualBlock(c, self.md, self.md, self.os * self.q)
         self.eval()
 
     @property
@@ -193,6 +195,70 @@ class OracleTimesFM2p5Adapter(nn.Module):
         for p in self.parameters():
             p.requires_grad = True
 
+    # ------------------------------------------------------------------------------------------------
+    # beyond the reference adapter: upstream's decode loop for horizons > 128 and its
+    # forecast extras.  PARITY STATUS: the extras (continuous quantile head, flip invariance, positivity clamp) are
+    # pinned to HF ``TimesFm2_5ModelForPrediction.forward`` (modeling_timesfm2_5.py:797-837, tests/test_oracle_cpu.py);
+    # the autoregressive loop is RESTATED from upstream ``TimesFM_2p5_200M_torch_module.decode`` (timesfm @ 8a755c9,
+    # not in this container; neither the reference nor the HF port implements it) -> "parity unpinned" for h > 128.
+    # ------------------------------------------------------------------------------------------------
+    def _running_stats(self, patched_inputs, patched_masks, state=None):
+        """Per-patch running (mu, sigma) continuing from ``state`` = (n, mu, sigma); -> (mu [B,N], sigma [B,N], state)."""
+        b = patched_inputs.shape[0]
+        n, mu, sigma = state if state is not None else (torch.zeros(b), torch.zeros(b), torch.zeros(b))
+        mus, sigmas = [], []
+        for i in range(patched_inputs.shape[1]):
+            (n, mu, sigma), _ = update_running_stats(n, mu, sigma, patched_inputs[:, i], patched_masks[:, i])
+            mus.append(mu)
+            sigmas.append(sigma)
+        return torch.stack(mus, dim=1), torch.stack(sigmas, dim=1), (n, mu, sigma)
+
+    def _tokenize(self, patched_inputs, patched_masks, mu, sigma):
+        normed = revin(patched_inputs, mu, sigma, reverse=False)
+        normed = torch.where(patched_masks, 0.0, normed)
+        return self.tokenizer(torch.cat([normed, patched_masks.to(normed.dtype)], dim=-1))
+
+    def _stack(self, embeddings: torch.Tensor, patch_padding: torch.Tensor) -> torch.Tensor:
+        return self.forward(embeddings, patch_padding[..., None])  # forward() reads masks[..., -1]
+
+    def decode(self, horizon: int, inputs: torch.Tensor, masks: torch.Tensor, fuse=None):
+        """Upstream ``decode``: prefill on the context, then ``(horizon - 1) // 128`` autoregressive steps, each feeding
+        the previous 128-step point forecast (channel ``decode_index``) back as 4 new patches whose running statistics
+        continue the context's.  A causal stack gives an appended token the same output whether the prefix is cached
+        or recomputed, so the oracle simply re-runs the whole sequence every step (the product keeps a KV cache).
+
+        ``fuse(embeddings) -> embeddings`` is applied to the CONTEXT patches only (text exists for them alone).
+        Returns (point/quantile forecast [B, 128 * (steps + 1), 10], quantile spread [B, 1024, 10] or None)."""
+        b, context = inputs.shape
+        if context % self.p != 0:
+            raise ValueError(f"context length ({context}) must be divisible by patch length ({self.p})")
+        if masks.shape != inputs.shape:
+            raise ValueError(f"masks shape {masks.shape} must match inputs shape {inputs.shape}")
+        patched_inputs, patched_masks = inputs.reshape(b, -1, self.p), masks.reshape(b, -1, self.p)
+        mu, sigma, state = self._running_stats(patched_inputs, patched_masks)
+        emb = self._tokenize(patched_inputs, patched_masks, mu, sigma)
+        if fuse is not None:
+            emb = fuse(emb)
+        padding = patched_masks[..., -1]
+        out = self._stack(emb, padding)
+        pf = revin(self.output_projection_point(out[:, -1]), mu[:, -1:], sigma[:, -1:], reverse=True).reshape(b, self.o, self.q)
+        spread = None
+        if hasattr(self, "output_projection_quantiles"):
+            spread = revin(self.output_projection_quantiles(out[:, -1]), mu[:, -1:], sigma[:, -1:], reverse=True)
+            spread = spread.reshape(b, self.os, self.q)
+        outputs = [pf]
+        m = self.o // self.p
+        for _ in range((horizon - 1) // self.o):
+            new_inputs = outputs[-1][:, :, self.decode_index].reshape(b, m, self.p)
+            new_masks = torch.zeros_like(new_inputs, dtype=torch.bool)
+            new_mu, new_sigma, state = self._running_stats(new_inputs, new_masks, state)
+            emb = torch.cat([emb, self._tokenize(new_inputs, new_masks, new_mu, new_sigma)], dim=1)
+            padding = torch.cat([padding, torch.zeros(b, m, dtype=torch.bool)], dim=1)
+            out = self._stack(emb, padding)
+            step = revin(self.output_projection_point(out[:, -1]), new_mu[:, -1:], new_sigma[:, -1:], reverse=True)
+            outputs.append(step.reshape(b, self.o, self.q))
+        return torch.cat(outputs, dim=1), spread
+
     # ---- weights: from the product's (upstream-named) state dict
     @torch.no_grad()
     def load_upstream_state_dict(self, sd: dict[str, torch.Tensor], prefix: str = "") -> None:
@@ -203,6 +269,8 @@ class OracleTimesFM2p5Adapter(nn.Module):
             getattr(self.tokenizer, dst).weight.copy_(g(f"tokenizer.{src}.weight"))
             getattr(self.tokenizer, dst).bias.copy_(g(f"tokenizer.{src}.bias"))
             getattr(self.output_projection_point, dst).weight.copy_(g(f"output_projection_point.{src}.weight"))
+            if hasattr(self, "output_projection_quantiles"):
+                getattr(self.output_projection_quantiles, dst).weight.copy_(g(f"output_projection_quantiles.{src}.weight"))
         d = self.md
         for i, layer in enumerate(self.stacked_xf):
             pre = f"stacked_xf.{i}."
@@ -246,6 +314,41 @@ class OracleFusion(nn.Module):
         return ts_embeddings + self.projection(text_embeddings)
 
 
+@dataclass
+class ForecastOptions:
+    """Upstream ``ForecastConfig`` switches (HF config names :87-89).  All off = the reference adapter's behaviour."""
+
+    use_continuous_quantile_head: bool = False
+    force_flip_invariance: bool = False
+    infer_is_positive: bool = False
+
+
+def flip_quantiles(x: torch.Tensor) -> torch.Tensor:
+    """Channel 0 (mean) stays, the nine quantile channels are reversed (HF :800-801)."""
+    return torch.cat([x[..., :1], torch.flip(x[..., 1:], dims=(-1,))], dim=-1)
+
+
+def apply_forecast_extras(pf, spread, pf_neg, spread_neg, inputs, horizon, options: ForecastOptions, decode_index=5):
+    """HF ``TimesFm2_5ModelForPrediction.forward`` :797-837 on already decoded outputs: flip-invariance combination,
+    continuous quantile head, horizon slice, positivity clamp (per series, as upstream; HF clamps on the batch minimum,
+    which coincides whenever all series of the batch agree)."""
+    if options.force_flip_invariance:
+        pf = (pf - flip_quantiles(pf_neg)) / 2
+        if spread is not None:
+            spread = (spread - flip_quantiles(spread_neg)) / 2
+    full = pf[:, :horizon, :].clone()
+    if options.use_continuous_quantile_head:
+        hq = min(horizon, spread.shape[1])
+        for idx in range(1, full.shape[-1]):
+            if idx == decode_index:
+                continue
+            full[:, :hq, idx] = spread[:, :hq, idx] - spread[:, :hq, decode_index] + full[:, :hq, decode_index]
+    if options.infer_is_positive:
+        positive = (inputs.min(dim=-1).values >= 0)[:, None, None]
+        full = torch.where(positive, full.clamp_min(0.0), full)
+    return full
+
+
 class OracleDecoder(nn.Module):
     def __init__(self, adapter: nn.Module, text_dims: int = 384, num_layers: int = 1, hidden_dims=None):
         super().__init__()
@@ -264,12 +367,24 @@ class OracleDecoder(nn.Module):
     def forward(self, horizon, inputs, masks, text_embeddings=None):
         return self.forward_full(horizon, inputs, masks, text_embeddings)[..., self.adapter.point_forecast_index]
 
+    def forecast(self, horizon, inputs, masks, text_embeddings=None, options: ForecastOptions | None = None):
+        """``forward_full`` through upstream's decode loop: any horizon (AR steps of 128) + the forecast extras.  With
+        horizon <= 128 and default options it returns exactly ``forward_full``."""
+        options = options or ForecastOptions()
+        masks = masks.bool()
+        fuse = (lambda e: self.fusion(e, text_embeddings)) if text_embeddings is not None else None
+        pf, spread = self.adapter.decode(horizon, inputs, masks, fuse)
+        pf_neg = spread_neg = None
+        if options.force_flip_invariance:
+            pf_neg, spread_neg = self.adapter.decode(horizon, -inputs, masks, fuse)
+        return apply_forecast_extras(pf, spread, pf_neg, spread_neg, inputs, horizon, options, self.adapter.decode_index)
+
 
 def oracle_from_product(decoder) -> OracleDecoder:
     """Build an oracle decoder carrying the exact weights of a product ``MultimodalDecoder`` (TimesFM adapter)."""
     adapter = decoder.adapter
     num_layers = len(adapter._model.stacked_xf)
-    o_adapter = OracleTimesFM2p5Adapter(num_layers)
+    o_adapter = OracleTimesFM2p5Adapter(num_layers, with_quantile_head=hasattr(adapter._model, "output_projection_quantiles"))
     o_adapter.load_upstream_state_dict(adapter._model.state_dict())
     fus = decoder.fusion
     dims = [l.weight.shape[1] for l in fus.linears()] + [fus.linears()[-1].weight.shape[0]]

@@ -1,6 +1,6 @@
 """Summarise an ncu report (.ncu-rep) as a markdown table of the metrics the roofline discussion uses.
 
-    python scripts/ncu_summary.py gpurun_out/X.ncu-rep "title" > profiles/X.md
+    python scripts/ncu_summary.py [--all] gpurun_out/X.ncu-rep "title" > profiles/X.md
 """
 import csv
 import subprocess
@@ -25,14 +25,16 @@ METRICS = [
 
 
 def main():
-    rep, title = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else sys.argv[1])
+    argv = [a for a in sys.argv[1:] if a != "--all"]
+    every = "--all" in sys.argv  # every captured launch instead of the first of each (kernel, grid)
+    rep, title = argv[0], (argv[1] if len(argv) > 1 else argv[0])
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     keep, seen = [], {}
     for i, r in enumerate(data):  # first launch of every distinct (kernel, grid)
         key = (r[hdr.index("Kernel Name")], r[hdr.index("Grid Size")])
-        if key not in seen:
+        if every or key not in seen:
             seen[key] = i
             keep.append(i)
     print(f"# {title}\n")
