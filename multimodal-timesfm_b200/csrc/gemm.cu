@@ -119,10 +119,29 @@ __device__ __forceinline__ void load_aux32(const void* base, int dtype, int64_t 
   }
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == TSFMX_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));  // MUFU.EX2 + MUFU.RCP: keeps the epilogue off the critical path
-  if (act == TSFMX_ACT_RELU) return fmaxf(v, 0.0f);
-  return v;
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// sigmoid of four values with FIVE special-function ops instead of eight: one shared reciprocal of the product of the
+// four denominators (1 + e^-x), the individual reciprocals recovered with multiplies.  The SFU pipe (16 ops / clock /
+// SM) was the limit of the SiLU epilogue: 2 x 32768 elements per 128 x 256 tile = 4096 cycles next to ~5100 cycles of
+// MMA, which made ff0 23 % slower than the same-size plain GEMM (ncu: 187 us against 152 us, tensor pipe 59 % active).
+// Inputs are clamped at -20 (sigmoid 2e-9) so that the product of four denominators stays below 6e34.
+__device__ __forceinline__ void sigmoid4(const float (&x)[4], float (&s)[4]) {
+  float d[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] = 1.0f + ex2_approx(fmaxf(x[i], -20.0f) * -1.4426950408889634f);
+  const float d01 = d[0] * d[1], d23 = d[2] * d[3];
+  const float r = rcp_approx(d01 * d23);
+  const float r01 = r * d23, r23 = r * d01;
+  s[0] = r01 * d[1], s[1] = r01 * d[0], s[2] = r23 * d[3], s[3] = r23 * d[2];
 }
 
 // Epilogue for 32 consecutive columns [col0, col0+32) of one output row.
@@ -174,9 +193,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       }
     }
   }
-  if (p.act == TSFMX_ACT_SILU || p.act == TSFMX_ACT_RELU) {
+  if (p.act == TSFMX_ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+    for (int i = 0; i < 32; i += 4) {
+      const float x[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+      float sg[4];
+      sigmoid4(x, sg);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[i + k] *= sg[k];
+    }
+  } else if (p.act == TSFMX_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
   } else if (p.act == TSFMX_ACT_SILU_GRAD || p.act == TSFMX_ACT_RELU_GRAD) {
     float u[32];
     const int valid = n_store - col0 < 32 ? n_store - col0 : 32;
@@ -184,9 +212,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     if (p.act == TSFMX_ACT_SILU_GRAD) {
       // v = dL/d silu(u)  ->  dL/du = v * sigmoid(u) * (1 + u * (1 - sigmoid(u)))
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float sg = __fdividef(1.0f, 1.0f + __expf(-u[i]));
-        v[i] *= sg * (1.0f + u[i] * (1.0f - sg));
+      for (int i = 0; i < 32; i += 4) {
+        const float x[4] = {u[i], u[i + 1], u[i + 2], u[i + 3]};
+        float sg[4];
+        sigmoid4(x, sg);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[i + k] *= sg[k] * (1.0f + u[i + k] * (1.0f - sg[k]));
       }
     } else {
 #pragma unroll

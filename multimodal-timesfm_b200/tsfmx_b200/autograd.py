@@ -89,12 +89,22 @@ class FullFineTuneFunction(torch.autograd.Function):
         b, n, d = ctx.shape
         precision = PRECISIONS[adapter.precision]
         grads: dict[str, torch.Tensor] = {}
+        # decoder.grad_ready_hook (set by a data-parallel trainer): called with every group of finished parameter
+        # gradients, top of the network first, so that their all-reduce runs while the layers below are still in
+        # their backward pass; hook.finish() joins the collectives before autograd sees the tensors
+        hook = getattr(decoder, "grad_ready_hook", None)
         d_out = adapter.postprocess_backward(head_saved, grad_forecast.contiguous().float(), grads)
-        d_emb = adapter.forward_backward(stack_saved, d_out.reshape(-1, d), grads)
+        if hook is not None:
+            hook(list(grads.values()))
+        d_emb = adapter.forward_backward(stack_saved, d_out.reshape(-1, d), grads, on_grads=hook)
+        seen = set(grads)
         adapter.preprocess_backward(tok_saved, d_emb, grads)
         fusion_grads = [None] * ctx.num_fusion
         if fusion_saved is not None and ctx.num_fusion:
             fusion_grads = fusion_backward(fusion, fusion_saved, d_emb, precision)
+        if hook is not None:
+            hook([v for k, v in grads.items() if k not in seen] + [g for g in fusion_grads if g is not None])
+            hook.finish()
         ordered = [grads.get(name) for name in ctx.names]
         return (None, None, None, None, None, None, None, *fusion_grads, *ordered)
 

@@ -180,6 +180,18 @@ class MultimodalDecoder(nn.Module):
 
     def _forecast_steps(self, horizon, inputs, masks, text_embeddings):
         """preprocess -> fusion -> forward -> postprocess (reference decoder.py:65-72) as one step generator."""
+        options = getattr(self.adapter, "forecast_options", None)
+        if options is not None and options.active(horizon, getattr(self.adapter._model, "o", horizon)):
+            # beyond the reference: upstream's decode loop (horizon > 128) and forecast extras; the text fusion is
+            # applied to the context patches (under flip invariance also to those of the negated series)
+            fuse = None
+            if text_embeddings is not None:
+                def fuse(emb):
+                    text = text_embeddings
+                    if emb.shape[0] == 2 * text.shape[0]:
+                        text = torch.cat([text, text], dim=0)
+                    return (yield from self.fusion.forward_device_steps(emb, text))
+            return (yield from self.adapter.decode_steps(horizon, inputs, masks, fuse))
         preprocessed = yield from lanes.steps(self.adapter, "preprocess", inputs, masks)
         if text_embeddings is not None:
             if hasattr(self.fusion, "forward_device_steps") and not self.fusion.training:

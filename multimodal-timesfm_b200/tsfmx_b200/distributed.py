@@ -110,6 +110,48 @@ def allreduce_(tensors: Iterable[torch.Tensor], op: str = "mean", group=None) ->
         torch._foreach_div_(tensors, float(world))
 
 
+class OverlappedGradReducer:
+    """Sum-all-reduces groups of gradient tensors as the backward pass hands them over (``MultimodalDecoder.
+    grad_ready_hook``), so that the collective of layer i runs on NCCL's stream while the kernels of the layers below
+    are still computing; ``finish()`` joins everything before the gradients are used.
+
+    Large tensors are reduced in place, one asynchronous collective each, as soon as they arrive; the small ones (norm
+    scales, biases, 80-float attention vectors) are collected and travel in one flattened bucket at ``finish()``.
+    ``reduced`` tells the trainer that the gradients it finds in ``.grad`` are already global sums."""
+
+    def __init__(self, group=None) -> None:
+        self.group = group
+        self._works: list = []
+        self._small: list[torch.Tensor] = []
+        self.reduced = False
+        self.bytes = 0
+
+    def __call__(self, tensors: Iterable[torch.Tensor]) -> None:
+        for t in tensors:
+            if t is None:
+                continue
+            self.bytes += t.numel() * t.element_size()
+            if t.numel() >= DIRECT_ELEMS and t.is_contiguous() and t.dtype == torch.float32:
+                self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                self._small.append(t)
+
+    def finish(self) -> None:
+        small, self._small = self._small, []
+        if small:
+            flat = torch.cat([t.reshape(-1).to(torch.float32) for t in small])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            offset = 0
+            for t in small:
+                n = t.numel()
+                t.copy_(flat[offset : offset + n].view_as(t))
+                offset += n
+        for w in self._works:
+            w.wait()
+        self._works = []
+        self.reduced = True
+
+
 def allreduce_mean_(tensors: Iterable[torch.Tensor], group=None) -> None:
     """In-place mean over ranks (see ``allreduce_``)."""
     allreduce_(tensors, "mean", group)

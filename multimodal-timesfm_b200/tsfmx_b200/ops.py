@@ -461,6 +461,107 @@ def mask_cast_rows(x: torch.Tensor, mask: torch.Tensor, out_dtype: int) -> torch
     return out
 
 
+# ----------------------------------------------------------------------------- TimesFM AR decode / forecast extras
+@_on_operand_device
+def timesfm_patchify_continue(
+    values: torch.Tensor, state: tuple[torch.Tensor, torch.Tensor, torch.Tensor], patches: int, patch_len: int = 32,
+    tokens_dtype: int = DT_F32,
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The ``patches`` new input patches of a decode step.  ``values`` is a [B, patches * patch_len] fp32 VIEW (any
+    strides: a channel of the [B, steps, Q] forecast buffer); ``state`` = running (n, mu, sigma), each [B] fp32,
+    UPDATED IN PLACE.  -> tokens [B * patches, 2 * patch_len], mu [B, patches], sigma [B, patches]."""
+    _lib.require_cuda(values, *state)
+    lib = _lib.load()
+    assert values.dtype == torch.float32 and values.dim() == 2 and values.shape[1] == patches * patch_len
+    b = values.shape[0]
+    n, mu_s, sigma_s = state
+    for t in state:
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == b
+    tokens = alloc(b * patches, 2 * patch_len, tokens_dtype, values.device)
+    mu = torch.empty(b, patches, dtype=torch.float32, device=values.device)
+    sigma = torch.empty(b, patches, dtype=torch.float32, device=values.device)
+    check(
+        lib.tsfmx_timesfm_patchify_continue(
+            ptr(values), values.stride(0), values.stride(1), b, patches, patch_len, ptr(n), ptr(mu_s), ptr(sigma_s),
+            tokens_dtype, ptr(tokens), ptr(mu), ptr(sigma), stream(),
+        )
+    )
+    return tokens, mu, sigma
+
+
+@_on_operand_device
+def timesfm_attention_decode(
+    regions: Sequence[torch.Tensor],
+    batch: int,
+    num_heads: int,
+    head_dim: int,
+    patch_mask: torch.Tensor | None,
+    num_masked: torch.Tensor | None,
+    inv_freq: torch.Tensor,
+    q_ln_w: torch.Tensor,
+    k_ln_w: torch.Tensor,
+    q_scale: torch.Tensor,
+    eps: float,
+    out_dtype: int,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """Attention of the LAST region's tokens (the new patches of a decode step) against every token of every region.
+    ``regions``: raw qkv matrices [B * tokens_r, 3 * H * hd] (the prefill's first, then one per decode step) - the KV
+    cache is whatever the qkv GEMMs left in HBM."""
+    lib = _lib.load()
+    _lib.require_cuda(*regions)
+    width = 3 * num_heads * head_dim
+    n = len(regions)
+    if n < 1 or n > _lib.MAX_KV_REGIONS:
+        raise _lib.TsfmxError(f"timesfm_attention_decode: 1..{_lib.MAX_KV_REGIONS} regions, got {n}")
+    dtypes = {r.dtype for r in regions}
+    if len(dtypes) != 1:
+        raise _lib.TsfmxError("timesfm_attention_decode: all regions must share one dtype")
+    tokens = []
+    for r in regions:
+        assert r.dim() == 2 and r.shape[1] == width and r.is_contiguous() and r.shape[0] % batch == 0
+        tokens.append(r.shape[0] // batch)
+    ptrs = (ctypes.c_void_p * n)(*[r.data_ptr() for r in regions])
+    toks = (ctypes.c_int32 * n)(*tokens)
+    if out is None:
+        out = alloc(batch * tokens[-1], num_heads * head_dim, out_dtype, regions[0].device)
+    pm = None if patch_mask is None else _as_u8(patch_mask)
+    n_ctx = 0 if pm is None else pm.shape[1]
+    check(
+        lib.tsfmx_timesfm_attention_decode(
+            ptrs, toks, n, _dt(regions[0]), batch, num_heads, head_dim, n_ctx, ptr(pm), ptr(num_masked), ptr(inv_freq),
+            ptr(q_ln_w), ptr(k_ln_w), ptr(q_scale), eps, out_dtype, ptr(out), stream(),
+        )
+    )
+    return out
+
+
+@_on_operand_device
+def timesfm_forecast_finalize(
+    pf: torch.Tensor, spread: torch.Tensor | None, inputs: torch.Tensor | None, batch: int, horizon: int,
+    decode_index: int, flip: bool, use_continuous_quantile_head: bool, infer_is_positive: bool,
+) -> torch.Tensor:
+    """pf [(1 + flip) * B, steps, Q] (+ spread [(1 + flip) * B, spread_steps, Q]) -> forecast [B, horizon, Q]: flip
+    combination, continuous quantile head, positivity clamp, horizon slice in one launch."""
+    lib = _lib.load()
+    _lib.require_cuda(pf, spread, inputs)
+    assert pf.dtype == torch.float32 and pf.is_contiguous() and pf.shape[0] == (2 if flip else 1) * batch
+    nq = pf.shape[2]
+    out = torch.empty(batch, horizon, nq, dtype=torch.float32, device=pf.device)
+    if spread is not None:
+        assert spread.dtype == torch.float32 and spread.is_contiguous() and spread.shape[0] == pf.shape[0]
+    if inputs is not None:
+        inputs = inputs.contiguous().float()
+    check(
+        lib.tsfmx_timesfm_forecast_finalize(
+            ptr(pf), ptr(spread), ptr(inputs), batch, 0 if inputs is None else inputs.shape[1], pf.shape[1],
+            0 if spread is None else spread.shape[1], nq, horizon, decode_index, int(flip),
+            int(use_continuous_quantile_head), int(infer_is_positive), ptr(out), stream(),
+        )
+    )
+    return out
+
+
 # ----------------------------------------------------------------------------- Chronos-2
 _force_simt_encoder_attention = False  # test hook: run the fp32 SIMT kernel where the tensor-core one applies
 _rope_tables: dict[tuple, torch.Tensor] = {}

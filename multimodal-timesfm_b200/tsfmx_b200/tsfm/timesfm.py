@@ -17,13 +17,14 @@ from __future__ import annotations
 
 import os
 import math
+from dataclasses import dataclass
 from types import SimpleNamespace
 
 import torch
 from torch import nn
 
 from .. import ops
-from .._lib import ACT_SILU, ACT_SILU_GRAD, DT_BF16, DT_F32, PREC_BF16, PRECISIONS, TsfmxError
+from .._lib import ACT_SILU, ACT_SILU_GRAD, DT_BF16, DT_F32, MAX_KV_REGIONS, PREC_BF16, PRECISIONS, TsfmxError
 from ..lanes import drain
 from .base import PreprocessResult, TsfmAdapter
 
@@ -107,6 +108,25 @@ def init_random_(model: nn.Module, seed: int = 0) -> None:
             p.copy_(v.to(p.device))
 
 
+@dataclass
+class ForecastOptions:
+    """What upstream timesfm does around the stack and the reference adapter leaves out.
+    Everything off (the default) is exactly the reference: point head only, ``ValueError`` for horizon > 128.
+
+    ``ar_decode``: horizons above ``output_patch_len`` are decoded autoregressively, 128 steps at a time, against a KV
+    cache (upstream ``decode``).  The other three are upstream's ``ForecastConfig`` switches as the HF port spells them
+    (transformers configuration_timesfm2_5.py:87-89)."""
+
+    ar_decode: bool = False
+    use_continuous_quantile_head: bool = False
+    force_flip_invariance: bool = False
+    infer_is_positive: bool = False
+
+    def active(self, horizon: int, output_patch_len: int) -> bool:
+        return (self.ar_decode and horizon > output_patch_len) or self.use_continuous_quantile_head \
+            or self.force_flip_invariance or self.infer_is_positive
+
+
 # --------------------------------------------------------------------------- adapter
 class TimesFM2p5Adapter(TsfmAdapter):
     """Adapter for TimesFM 2.5 (200 M layout; ``num_layers=50`` gives the "500 M" shape of BASELINE.json)."""
@@ -117,6 +137,7 @@ class TimesFM2p5Adapter(TsfmAdapter):
         self.fused_norm = os.environ.get("TSFMX_FUSED_NORM", "0") == "1"  # True: norm/residual junctions in the GEMM epilogue (5-CTA clusters; measured slower, kept for A/B)
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
+        self.forecast_options = ForecastOptions()
 
     def set_precision(self, precision: str) -> None:
         if precision not in PRECISIONS:
@@ -177,6 +198,10 @@ class TimesFM2p5Adapter(TsfmAdapter):
             "inv_freq": (1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev),
             "layers": [],
         }
+        if hasattr(m, "output_projection_quantiles"):  # continuous quantile head (ForecastOptions)
+            w["qhead_hidden"] = pack(m.output_projection_quantiles.hidden_layer)
+            w["qhead_out"] = pack(m.output_projection_quantiles.output_layer)
+            w["qhead_res"] = pack(m.output_projection_quantiles.residual_layer)
         for xf in m.stacked_xf:
             w["layers"].append(
                 {
@@ -262,39 +287,58 @@ class TimesFM2p5Adapter(TsfmAdapter):
         """Run the stacked transformer layers (reference timesfm.py:85-98) -> (batch, patches, model_dims)."""
         return drain(self.forward_steps(input_embeddings, masks))
 
-    def forward_steps(self, input_embeddings: torch.Tensor, masks: torch.Tensor):
-        """``forward`` as a step generator (one ``yield`` per kernel launch, see ``tsfmx_b200.lanes``)."""
-        m = self._model
+    def forward_steps(self, input_embeddings: torch.Tensor, masks: torch.Tensor, kv_cache: list | None = None):
+        """``forward`` as a step generator (one ``yield`` per kernel launch, see ``tsfmx_b200.lanes``).
+
+        ``kv_cache``: an empty list to be filled with one ``[qkv]`` region list per layer - the raw qkv matrices are
+        then kept (one buffer per layer instead of one reused scratch) for the decode steps that follow."""
         if not input_embeddings.is_cuda:
             raise TsfmxError("TimesFM2p5Adapter runs on B200 only; there is no CPU fallback")
+        b, n, d = input_embeddings.shape
+        x = input_embeddings.reshape(b * n, d).float().contiguous()
+        patch_mask = masks[..., -1].contiguous()  # a patch is padded iff its last step is (timesfm.py:97)
+        num_masked = patch_mask.sum(-1, dtype=torch.int32)
+        y = yield from self._stack_steps(x, b, n, patch_mask, num_masked, kv_cache, decode=False)
+        return y.view(b, n, d)
+
+    def _stack_steps(self, x: torch.Tensor, b: int, n: int, patch_mask, num_masked, kv_cache: list | None, decode: bool):
+        """The decoder layers over ``n`` tokens per series, x [b * n, D] fp32 -> [b * n, D] fp32.  Prefill
+        (``decode=False``): causal attention among the n tokens.  Decode step: the n (= 4) new tokens attend to every
+        token already in ``kv_cache`` and to each other."""
+        m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
         fast = prec == PREC_BF16
         mid_dt = DT_BF16 if fast else DT_F32  # GEMM outputs consumed by the norm / attention kernels
         w = self._weights()
-        b, n, d = input_embeddings.shape
-        rows = b * n
-        dev = input_embeddings.device
-        x = input_embeddings.reshape(rows, d).float().contiguous()
-        patch_mask = masks[..., -1].contiguous()  # a patch is padded iff its last step is (timesfm.py:97)
-        num_masked = patch_mask.sum(-1, dtype=torch.int32)
+        rows, d = x.shape
+        dev = x.device
         y = torch.empty(rows, d, dtype=torch.float32, device=dev)
         layers = w["layers"]
         if not layers:
-            return x.view(b, n, d).clone()
+            return x.clone()
+        if kv_cache is not None and not kv_cache:
+            kv_cache.extend([] for _ in layers)
         xn = ops.rmsnorm(x, layers[0]["pre_attn"], m.eps, adt)
         yield
-        qkv = ops.alloc(rows, 3 * d, mid_dt, dev)
+        qkv = ops.alloc(rows, 3 * d, mid_dt, dev) if kv_cache is None else None
         attn = ops.alloc(rows, d, adt, dev)
         a = ops.alloc(rows, d, mid_dt, dev)
         hbuf = ops.alloc(rows, m.ff, adt, dev)
         for i, lw in enumerate(layers):
             last = i == len(layers) - 1
             nxt = None if last else layers[i + 1]["pre_attn"]
+            if kv_cache is not None:
+                qkv = ops.alloc(rows, 3 * d, mid_dt, dev)
+                kv_cache[i].append(qkv)
             ops.gemm([(xn, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
             yield
-            ops.timesfm_attention(qkv, b, n, m.h, m.hd, patch_mask, num_masked, w["inv_freq"], lw["q_ln"], lw["k_ln"],
-                                  lw["q_scale"], m.eps, adt, out=attn)
+            if decode:
+                ops.timesfm_attention_decode(kv_cache[i], b, m.h, m.hd, patch_mask, num_masked, w["inv_freq"],
+                                             lw["q_ln"], lw["k_ln"], lw["q_scale"], m.eps, adt, out=attn)
+            else:
+                ops.timesfm_attention(qkv, b, n, m.h, m.hd, patch_mask, num_masked, w["inv_freq"], lw["q_ln"],
+                                      lw["k_ln"], lw["q_scale"], m.eps, adt, out=attn)
             yield
             if self.fused_norm:
                 # out-proj / ff1 with post-norm + residual + next pre-norm in the GEMM epilogue (5-CTA clusters)
@@ -317,7 +361,107 @@ class TimesFM2p5Adapter(TsfmAdapter):
                 yield
                 ops.norm_residual_norm(a, y, lw["post_ff"], nxt, m.eps, y, adt, None if last else xn)
                 yield
-        return y.view(b, n, d)
+        return y
+
+    # ------------------------------------------------------------------ beyond the reference: AR decode + extras
+    def _head_steps(self, last: torch.Tensor, mu_last, sigma_last, out: torch.Tensor, head: str = "head"):
+        """ResidualBlock head on [B, D] rows with the inverse RevIN (``acc * sigma + mu``) in the epilogue; ``out`` is a
+        [B, width] fp32 view (row stride free) that receives all ``width`` columns."""
+        m = self._model
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        b, d = last.shape
+        width = out.shape[1]
+        a = ops.cast_rows(last, adt)
+        yield
+        hid = ops.alloc(b, m.md, adt, last.device)
+        ops.gemm([(a, w[head + "_hidden"], d)], b, m.md, hid, adt, precision=prec, act=ACT_SILU)
+        yield
+        ops.gemm([(hid, w[head + "_out"], m.md), (a, w[head + "_res"], d)], b, width, out, DT_F32, precision=prec,
+                 row_scale=sigma_last, row_shift=mu_last, ldd=out.stride(0))
+        yield
+
+    def decode_steps(self, horizon: int, inputs: torch.Tensor, masks: torch.Tensor, fuse=None):
+        """Forecast (batch, horizon, 10) through upstream's decode loop, as a step generator: prefill on the context,
+        ``(horizon - 1) // 128`` autoregressive steps that feed the previous 128-step point forecast back as 4 new
+        patches (running RevIN statistics continued, attention against the KV cache the qkv GEMMs left in HBM), then
+        the forecast extras of ``self.forecast_options`` in one finalize kernel.
+
+        ``fuse``: generator function ``emb [B', N, D] -> emb`` applied to the context patches (text fusion; B' = 2 B
+        under flip invariance, rows B.. being the negated series).  Raises the reference's ``ValueError`` for
+        horizon > 128 unless ``forecast_options.ar_decode`` is set."""
+        m, opts = self._model, self.forecast_options
+        if horizon > m.o and not opts.ar_decode:
+            raise ValueError(
+                f"horizon must be <= output_patch_len ({m.o}), got {horizon}. AR decode is not supported."
+            )
+        steps = (horizon - 1) // m.o
+        if steps + 1 > MAX_KV_REGIONS:
+            raise ValueError(f"horizon {horizon} needs {steps} decode steps; at most {MAX_KV_REGIONS - 1} are supported")
+        if opts.use_continuous_quantile_head and not hasattr(m, "output_projection_quantiles"):
+            raise ValueError("use_continuous_quantile_head needs an adapter built with_quantile_head=True")
+        if masks.shape != inputs.shape:
+            raise ValueError(f"masks shape {masks.shape} must match inputs shape {inputs.shape}")
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        b = inputs.shape[0]
+        flip = opts.force_flip_invariance
+        masks = masks.bool()
+        x_in = torch.cat([inputs, -inputs], dim=0) if flip else inputs
+        m_in = torch.cat([masks, masks], dim=0) if flip else masks
+        b2 = x_in.shape[0]
+        pre = yield from self.preprocess_steps(x_in, m_in)
+        emb = pre.input_embeddings
+        if fuse is not None:
+            emb = yield from fuse(emb)
+        cache: list | None = [] if steps > 0 else None
+        out_emb = yield from self.forward_steps(emb, pre.masks, kv_cache=cache)
+        mu, sigma = pre.normalization_stats["context_mu"], pre.normalization_stats["context_sigma"]
+        ht = m.o * (steps + 1)
+        width = m.o * m.q
+        pf = torch.empty(b2, ht * m.q, dtype=torch.float32, device=inputs.device)
+        last = out_emb[:, -1, :]
+        mu_last, sigma_last = mu[:, -1].contiguous(), sigma[:, -1].contiguous()
+        yield from self._head_steps(last, mu_last, sigma_last, pf[:, :width])
+        spread = None
+        if opts.use_continuous_quantile_head:
+            spread = torch.empty(b2, m.os * m.q, dtype=torch.float32, device=inputs.device)
+            yield from self._head_steps(last, mu_last, sigma_last, spread, head="qhead")
+            spread = spread.view(b2, m.os, m.q)
+        if steps:
+            per_step = m.o // m.p  # 4 new input patches per 128 forecast steps
+            state = ((~m_in).sum(-1).float(), mu_last.clone(), sigma_last.clone())  # running (n, mu, sigma)
+            patch_mask = pre.masks[..., -1].contiguous()
+            num_masked = patch_mask.sum(-1, dtype=torch.int32)
+            pf3 = pf.view(b2, ht, m.q)
+            for s in range(steps):
+                values = pf3[:, s * m.o : (s + 1) * m.o, m.config.decode_index]  # strided view, read in place
+                tokens, mu_new, sigma_new = ops.timesfm_patchify_continue(values, state, per_step, m.p, adt)
+                yield
+                rows = b2 * per_step
+                hidden = ops.alloc(rows, m.md, adt, inputs.device)
+                ops.gemm([(tokens, w["tok_hidden"], 2 * m.p)], rows, m.md, hidden, adt, precision=prec, act=ACT_SILU,
+                         bias=w["tok_hidden_b"])
+                yield
+                emb_new = torch.empty(rows, m.md, dtype=torch.float32, device=inputs.device)
+                ops.gemm([(hidden, w["tok_out"], m.md), (tokens, w["tok_res"], 2 * m.p)], rows, m.md, emb_new, DT_F32,
+                         precision=prec, bias=w["tok_out_b"])
+                yield
+                out_new = yield from self._stack_steps(emb_new, b2, per_step, patch_mask, num_masked, cache, decode=True)
+                last_new = out_new.view(b2, per_step, m.md)[:, -1, :]
+                yield from self._head_steps(last_new, mu_new[:, -1].contiguous(), sigma_new[:, -1].contiguous(),
+                                            pf[:, (s + 1) * width : (s + 2) * width])
+        out = ops.timesfm_forecast_finalize(
+            pf.view(b2, ht, m.q), spread, inputs if opts.infer_is_positive else None, b, horizon,
+            int(m.config.decode_index), flip, opts.use_continuous_quantile_head, opts.infer_is_positive,
+        )
+        yield
+        return out
+
+    def decode(self, horizon: int, inputs: torch.Tensor, masks: torch.Tensor, fuse=None) -> torch.Tensor:
+        return drain(self.decode_steps(horizon, inputs, masks, fuse))
 
     def postprocess(
         self,
@@ -428,11 +572,13 @@ class TimesFM2p5Adapter(TsfmAdapter):
         ops.gemm([(dy_t, x_t, kpad)], n_out, k_in, gw, DT_F32, precision=prec)
         return gw
 
-    def forward_backward(self, saved, d_out: torch.Tensor, param_grads: dict[str, torch.Tensor] | None = None) -> torch.Tensor:
+    def forward_backward(self, saved, d_out: torch.Tensor, param_grads: dict[str, torch.Tensor] | None = None,
+                         on_grads=None) -> torch.Tensor:
         """Activation gradient of ``forward``: dL/d(output embeddings) [M, D] fp32 -> dL/d(input embeddings).
 
         ``param_grads`` (full fine-tuning; needs ``forward_saving(for_wgrad=True)``): filled with the gradient of every
-        parameter of the stack under its state-dict name."""
+        parameter of the stack under its state-dict name.  ``on_grads(tensors)`` is called once per layer with that
+        layer's finished parameter gradients (the trainer all-reduces them while the layers below are still running)."""
         m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -456,6 +602,9 @@ class TimesFM2p5Adapter(TsfmAdapter):
         for i in reversed(range(len(layers))):
             lw, tw, s = layers[i], tlayers[i], sl[i]
             pre = f"stacked_xf.{i}."
+            if pg is not None and on_grads is not None and i + 1 < len(layers):
+                done = f"stacked_xf.{i + 1}."  # the layer above is complete: hand its gradients over
+                on_grads([v for k, v in pg.items() if k.startswith(done)])
             if pg is not None:  # g = dL/dz, g2 = da2 at this point
                 pg[pre + "post_ff_ln.scale"] = ops.colsum_wgrad(g, s["a2"], m.eps)
                 pg[pre + "ff1.weight"] = self._wgrad(g2, s["h"], rows, d, m.ff)
@@ -495,6 +644,8 @@ class TimesFM2p5Adapter(TsfmAdapter):
             ops.rmsnorm_bwd_chain(g, s["x"], lw["pre_attn"], gmid, sl[below]["a2"] if below >= 0 else None,
                                   layers[below]["post_ff"] if below >= 0 else None, m.eps, g, adt,
                                   g2 if below >= 0 else None, rows, d)
+        if pg is not None and on_grads is not None:
+            on_grads([v for k, v in pg.items() if k.startswith("stacked_xf.0.")])
         return g
 
     def preprocess_saving(self, inputs: torch.Tensor, masks: torch.Tensor):

@@ -63,6 +63,27 @@ def _worker(rank: int, world: int, port: int, result_dir: str):
             assert torch.allclose(got, b * scale, atol=1e-6)
     finally:
         tdist.BUCKET_ELEMS = saved
+    # overlapped reducer of the full fine-tune: groups of gradients handed over layer by layer, large ones reduced in
+    # place as they arrive, small ones in one flattened bucket at finish()
+    saved_direct, tdist.DIRECT_ELEMS = tdist.DIRECT_ELEMS, 32
+    try:
+        reducer = tdist.OverlappedGradReducer()
+        gen = torch.Generator().manual_seed(9)
+        groups = [[torch.randn(8, 8, generator=gen), torch.randn(5, generator=gen)], [torch.randn(3, 40, generator=gen)],
+                  [torch.randn(7, generator=gen), None, torch.randn(6, 6, generator=gen)]]
+        mine = [[None if t is None else t * (rank + 1) for t in g] for g in groups]
+        for g in mine:
+            reducer(g)
+        assert not reducer.reduced
+        reducer.finish()
+        assert reducer.reduced and reducer.bytes == 4 * sum(t.numel() for g in groups for t in g if t is not None)
+        total = sum(r + 1 for r in range(world))
+        for g_mine, g_base in zip(mine, groups):
+            for got, b in zip(g_mine, g_base):
+                if b is not None:
+                    assert torch.allclose(got, b * total, atol=1e-5)
+    finally:
+        tdist.DIRECT_ELEMS = saved_direct
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(result_dir, f"ok{rank}"), "w").close()

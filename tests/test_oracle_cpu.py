@@ -209,3 +209,77 @@ def test_chronos_t5_model_oracle_golden_and_bucket_table():
     assert np.array_equal(full.numpy(), z["forecast"])
     with pytest.raises(ValueError):
         adapter.expand_text_embeddings(torch.zeros(2, 2, 384), 96)
+
+
+# ------------------------------------------------------------------------------------------------ decode loop + extras
+def _hf_prediction_model(adapter):
+    """HF TimesFm2_5ModelForPrediction carrying the oracle adapter's weights."""
+    from transformers.models.timesfm2_5 import modeling_timesfm2_5 as hf
+
+    model = hf.TimesFm2_5ModelForPrediction(O.make_hf_config(len(adapter.stacked_xf))).eval()
+    model.model.input_ff_layer.load_state_dict(adapter.tokenizer.state_dict())
+    for dst, src in zip(model.model.layers, adapter.stacked_xf):
+        dst.load_state_dict(src.state_dict())
+    model.output_projection_point.load_state_dict(adapter.output_projection_point.state_dict())
+    model.output_projection_quantiles.load_state_dict(adapter.output_projection_quantiles.state_dict())
+    return model
+
+
+@pytest.mark.parametrize("flip", [False, True])
+@pytest.mark.parametrize("positive_inputs", [False, True])
+def test_forecast_extras_match_hf(flip, positive_inputs):
+    """The oracle's continuous quantile head / flip invariance / positivity clamp against the only importable
+    implementation, HF ``TimesFm2_5ModelForPrediction.forward`` (modeling_timesfm2_5.py:770-837).  HF normalises the
+    context globally first, so the oracle is fed the normalised series and its output is de-normalised the same way;
+    HF clamps on the BATCH minimum, the oracle per series (upstream): every series of a batch here has the same sign."""
+    torch.manual_seed(0)
+    adapter = O.OracleTimesFM2p5Adapter(2, with_quantile_head=True)
+    for prm in adapter.parameters():
+        torch.nn.init.normal_(prm, std=0.05)
+    decoder = O.OracleDecoder(adapter, 384, 1, [])
+    model = _hf_prediction_model(adapter)
+    ctx, masks, _text, _ = O.synthetic_batch(4, 512, 128, seed=3)
+    x = ctx * 3 + (20.0 if positive_inputs else 1.0)
+    assert bool((x.min(-1).values >= 0).all()) == positive_inputs
+    with torch.no_grad():
+        hf_out = model(past_values=list(x), forecast_context_len=512, truncate_negative=True, force_flip_invariance=flip)
+        mu_g, sigma_g = x.mean(1, keepdim=True), x.std(1, keepdim=True)
+        mine = decoder.forecast(128, (x - mu_g) / sigma_g, masks, None, O.ForecastOptions(True, flip, False))
+        mine = mine * sigma_g[:, :, None] + mu_g[:, :, None]
+        if positive_inputs:
+            mine = mine.clamp_min(0.0)
+    assert mine.shape == hf_out.full_predictions.shape
+    scale = hf_out.full_predictions.abs().max().item()
+    assert (mine - hf_out.full_predictions).abs().max().item() < 2e-6 * scale
+    # and the clamp itself (oracle, per series) on un-normalised inputs
+    pf = torch.randn(4, 128, 10)
+    both = torch.cat([x[:2], -x[2:]])
+    out = O.apply_forecast_extras(pf, None, None, None, both, 100, O.ForecastOptions(False, False, True))
+    if positive_inputs:
+        assert torch.equal(out[:2], pf[:2, :100].clamp_min(0.0)) and torch.equal(out[2:], pf[2:, :100])
+
+
+def test_decode_loop_reduces_to_forward_full_and_extends_it():
+    """horizon <= 128 with the options off is the reference path; longer horizons keep the first 128 steps and append
+    steps that depend on them (restated upstream decode loop: unpinned, so only its internal consistency is checked:
+    recomputing the extended sequence from scratch reproduces the AR step)."""
+    torch.manual_seed(1)
+    adapter = O.OracleTimesFM2p5Adapter(2, with_quantile_head=True)
+    for prm in adapter.parameters():
+        torch.nn.init.normal_(prm, std=0.05)
+    decoder = O.OracleDecoder(adapter, 384, 1, [])
+    ctx, masks, text, _ = O.synthetic_batch(3, 256, 128, seed=9, padded=True)
+    with torch.no_grad():
+        full = decoder.forward_full(128, ctx, masks, text)
+        short = decoder.forecast(128, ctx, masks, text)
+        long = decoder.forecast(300, ctx, masks, text)
+        assert (short - full).abs().max() < 1e-5 * full.abs().max()
+        assert long.shape == (3, 300, 10) and torch.equal(long[:, :128], short)
+        # step 2 by hand: context extended with the first 128 point forecasts, no text on the new patches
+        ext = torch.cat([ctx, short[..., 5]], dim=1)
+        ext_masks = torch.cat([masks, torch.zeros(3, 128, dtype=torch.bool)], dim=1)
+        pre = adapter.preprocess(ext, ext_masks)
+        emb = pre.input_embeddings.clone()
+        emb[:, :8] = decoder.fusion(emb[:, :8], text)
+        by_hand = adapter.postprocess(128, adapter(emb, pre.masks), pre.normalization_stats)
+        assert (long[:, 128:256] - by_hand).abs().max() < 1e-4 * by_hand.abs().max()
