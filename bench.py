@@ -57,6 +57,12 @@ def parse_args():
     ap.add_argument("--no-graphs", action="store_true", help="time the eager launches instead of the CUDA-graph replay")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
     ap.add_argument("--no-stages", action="store_true", help="skip the HBM-bound stage rooflines")
+    ap.add_argument("--workload", default="forecast", choices=["forecast", "finetune", "full-finetune"],
+                    help="forecast = BASELINE configs[1] (the driver's line); finetune = configs[3], the fusion fine-tune "
+                         "step with the NCCL gradient all-reduce; full-finetune = the reference's mode='baseline'")
+    ap.add_argument("--finetune-batch", type=int, default=1024, help="series per GPU of a fine-tune step")
+    ap.add_argument("--graph-collectives", action="store_true",
+                    help="full fine-tune on several GPUs: capture the overlapped NCCL all-reduces into the step's CUDA graph")
     return ap.parse_args()
 
 
@@ -551,6 +557,202 @@ def run_b200_arm(args) -> None:
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ fine-tune workloads
+FT_METRIC = "fine-tune series/sec (ctx512,h128)"
+
+
+def finetune_flops_per_series(layers: int, n: int, full: bool) -> float:
+    """Algorithmic FLOPs of one training step per series: forward + activation gradients of
+    the stack (2 x 12 D^2 per token and layer each, causal attention twice over) + tokenizer / fusion / head, plus, for
+    the full fine-tune, one more 12 D^2 per token and layer for the weight gradients."""
+    d, p, e = 1280, 32, TEXT_DIMS
+    tok = n * 2 * (2 * p * d + d * d + 2 * p * d)
+    fus = n * 2 * e * d
+    lin = n * 2 * 6 * d * d
+    att = 2 * d * n * (n + 1)
+    head = 2 * 3 * d * d
+    fwd = tok + fus + layers * (lin + att) + head
+    bwd = layers * (lin + 2 * att) + head + fus  # dgrad of the stack + head, fusion wgrad
+    if full:
+        bwd += layers * lin + tok + head  # wgrad of every Linear
+    return float(fwd + bwd)
+
+
+def run_finetune_arm(args, full: bool) -> None:
+    import types
+
+    import torch.distributed as dist
+
+    from oracle import timesfm_oracle as O  # synthetic input generator + cpu_baseline only
+    from tsfmx_b200 import _lib
+    from tsfmx_b200 import distributed as tdist
+    from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig
+    from tsfmx_b200.trainer import MultimodalTrainer
+    from tsfmx_b200.tsfm.timesfm import TimesFM2p5Adapter, init_random_
+
+    rank, world, local_rank = tdist.init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.check(_lib.load().tsfmx_device_check(local_rank))
+    fb = args.finetune_batch
+    adapter = TimesFM2p5Adapter(num_layers=args.layers, precision="bf16", with_quantile_head=False)
+    init_random_(adapter, seed=0)
+    torch.manual_seed(100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(TEXT_DIMS, 1, [])).to(dev)
+    targs = types.SimpleNamespace(per_device_train_batch_size=fb, per_device_eval_batch_size=fb, gradient_accumulation_steps=1,
+                                  max_grad_norm=1.0, learning_rate=1e-5 if full else 1e-4, weight_decay=0.01,
+                                  num_train_epochs=1, seed=0, warmup_steps=0.0, cuda_graphs=not args.no_graphs,
+                                  graph_collectives=args.graph_collectives)
+    n_patches = args.context // PATCH
+    dummy = [{"context": torch.zeros(args.context).numpy(), "horizon": torch.zeros(HORIZON).numpy(), "metadata": {}}]
+    if not full:
+        dummy[0]["text_embeddings"] = torch.zeros(n_patches, TEXT_DIMS).numpy()
+    trainer = MultimodalTrainer(dec, targs, dummy, dummy, "baseline" if full else "multimodal", dev)
+    # GLOBAL host batches (every rank builds the same ones and takes its shard, as MultimodalTrainer does with a
+    # DataLoader): fb * world series each, page-locked
+    host = []
+    for i in range(2):
+        ctx, _m, text, hor = O.synthetic_batch(fb * world, args.context, HORIZON, seed=4321 + i)
+        batch = {"context": ctx.pin_memory(), "horizon": hor.pin_memory()}
+        if not full:
+            batch["text_embeddings"] = text.pin_memory()
+        host.append(batch)
+    resident = []
+    for b in host:
+        shard = tdist.shard_batch(b, rank, world)
+        d = {k: v.to(dev) for k, v in shard.items()}
+        d["global_size"] = fb * world
+        resident.append(d)
+    h2d_bytes = sum(v[: fb].numel() * v.element_size() for v in host[0].values())
+
+    def step_resident(i):
+        loss = trainer._micro_batch(resident[i % 2], 1)
+        trainer.optimizer_step()
+        return loss
+
+    ring = torch.empty(64, dtype=torch.float32, pin_memory=True)
+
+    def run_e2e(steps):
+        # the trainer's own loop body (train_epoch): shard + H2D staged one batch ahead, forward + backward, optimizer
+        # step, the loss read back to the host (4 bytes per step, the reference's .item(), trainer.py:211)
+        for i, batch in enumerate(trainer._staged(host[j % 2] for j in range(steps))):
+            loss = trainer._micro_batch(batch, 1)
+            trainer.optimizer_step()
+            ring[i % 64].copy_(loss, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return tdist.allreduce_max(e0.elapsed_time(e1), dev)
+
+    dec.train()
+    for i in range(max(args.warmup, 3)):  # eager step, graph capture, first replay
+        step_resident(i)
+    run_e2e(2)
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    replays0 = trainer.graph_replays
+    with ClockSampler(local_rank, enabled=rank == 0) as clocks:
+        ms = timed(step_resident, args.steps)
+        ms_e2e = timed(lambda i: run_e2e(args.steps) if i == 0 else None, 1)
+    replays = trainer.graph_replays - replays0
+    launches_per_step = None
+    if trainer._train_graphs:
+        # kernels recorded into the graph: count them with one eager step
+        trainer.graphs = False
+        l0 = _lib.launch_count()
+        step_resident(0)
+        launches_per_step = _lib.launch_count() - l0
+        trainer.graphs = True
+    launches = (_lib.launch_count() - launches0) + (launches_per_step or 0) * replays
+    total = fb * world * args.steps
+    value, e2e_value = total / (ms * 1e-3), total / (ms_e2e * 1e-3)
+    peaks = measured_peaks()
+    flops = finetune_flops_per_series(args.layers, n_patches, full)
+    achieved = flops * value / world / 1e12
+    n_grad = sum(p.numel() for p in trainer._get_trainable_params())
+    reducer = dec.grad_ready_hook
+    line = {
+        "metric": FT_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {
+            "workload": (f"TimesFM-2.5 layout, {args.layers} layers x 1280 + 1-layer fusion, ctx {args.context} / horizon {HORIZON}, "
+                         f"{fb} series per GPU, " + ("full fine-tune step (reference mode='baseline': forward + activation and "
+                         "weight gradients of every Linear / norm / bias + all-reduce of every gradient + clip + AdamW)" if full else
+                         "fusion fine-tune step (reference mode='multimodal': frozen adapter, forward + activation gradients "
+                         "+ fusion weight gradient + all-reduce + clip + AdamW)")),
+            "parallelism": f"data parallel x{world}, gradients summed with NCCL all-reduce",
+            "collective": {"bytes_per_step": n_grad * 4 if world > 1 else 0,
+                           "kind": "none (1 GPU)" if world == 1 else
+                           ("per-layer asynchronous ncclAllReduce overlapped with the backward pass (bandwidth-bound)"
+                            if reducer is not None else "one flattened ncclAllReduce after the backward pass (latency-bound)")},
+            "launch": ("forward + backward replayed from a CUDA graph, optimizer step eager" if trainer._train_graphs
+                       else "eager launches"),
+            "weights": "random-init (seed 0)", "precision": "bf16 operands, fp32 accumulate; fp32 master weights / AdamW",
+            "l2": "per-step working set (saved activations) >> 126 MB L2; two alternating batches",
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps,
+                "api": "MultimodalTrainer loop body over page-locked host batches: shard, H2D staged one batch ahead on a copy "
+                       "stream, forward + backward, all-reduce + clip + AdamW, loss read back (4 B)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops"], "traffic": None,
+                     "kernel": "whole training step (tcgen05 GEMMs: forward, dgrad" + (", wgrad)" if full else ")"),
+                     "algorithmic_flops_per_series": flops, "peak_source": f"{peaks['source']} bf16_tflops_sustained"},
+        "clocks": clocks.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_finetune_baseline(args, full)
+    if rank == 0:
+        emit_json(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_finetune_baseline(args, full: bool, sample: int = 16, repeats: int = 2) -> dict:
+    """The oracle's training step (autograd + AdamW) on the host cores, on a bounded sample."""
+    from oracle import timesfm_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    oracle, _ = cpu_reference_model(args.layers)
+    if full:
+        oracle.adapter.unfreeze_parameters()
+        params = list(oracle.adapter.parameters())
+    else:
+        oracle.adapter.freeze_parameters()
+        params = list(oracle.fusion.parameters())
+        for p in params:
+            p.requires_grad_(True)
+    opt = torch.optim.AdamW(params, lr=1e-5)
+    ctx, masks, text, hor = O.synthetic_batch(sample, args.context, HORIZON)
+    times = []
+    for i in range(1 + repeats):
+        t0 = time.perf_counter()
+        loss = torch.nn.functional.mse_loss(oracle(HORIZON, ctx, masks, None if full else text), hor)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad()
+        if i:
+            times.append(time.perf_counter() - t0)
+    cores = torch.get_num_threads()
+    return {"value": sample / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} series, same model / ctx / horizon, fp32 oracle autograd + AdamW, best of {repeats} after 1 warm-up, "
+                      f"{cores} threads"}
+
+
 def main():
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL prints its version banner there
     # whenever NCCL_DEBUG is set) is sent to stderr, and the JSON line goes to the saved descriptor
@@ -559,8 +761,18 @@ def main():
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
     args = parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" and args.workload != "forecast":
+        if int(os.environ.get("RANK", "0")) == 0:
+            base = cpu_finetune_baseline(args, args.workload == "full-finetune", repeats=max(1, args.steps))
+            emit_json({"impl": "reference", "metric": FT_METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+                       "steps": args.steps, "warmup": 1, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                       "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "cpu_sample": base["sample"]},
+                       "cpu_baseline": base, "gpu_launches": 0,
+                       "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    elif args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload != "forecast":
+        run_finetune_arm(args, args.workload == "full-finetune")
     else:
         run_b200_arm(args)
 

@@ -186,165 +186,6 @@ __global__ void __launch_bounds__(WARPS * 32) timesfm_patchify_norm_generic_kern
 }
 
 // ----------------------------------------------------------------------------------------
-// Staged variant (the one that runs for context <= 4096): a warp stages G consecutive series in shared
-// memory with 16-byte cp.async (one bulk of loads in flight, nothing is read twice from HBM), computes the
-// per-patch statistics cooperatively (8 lanes per patch, 4 patches in flight per lane group), then lane s
-// runs the sequential merge of series s — so the dependent chain of divisions / square roots is paid once
-// per G series instead of once per series — and finally the warp normalises from shared memory and streams
-// the tokens out.  Slot layout per series: (3 N + 1) floats (odd stride: conflict-free lane-per-series scan).
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all_groups() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int OUT>
-__global__ void __launch_bounds__(256) timesfm_patchify_norm_kernel(
-    const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, int group_size,
-    void* tokens, float* __restrict__ mu_out, float* __restrict__ sigma_out, uint8_t* __restrict__ patch_mask_out,
-    int32_t* __restrict__ num_masked_out) {
-  extern __shared__ __align__(16) uint8_t smem_tf[];
-  const int warps = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = lane >> 3, q = lane & 7;
-  const int N = context >> 5;
-  const int G = group_size;
-  const int slot_stride = 3 * N + 1;
-  const int per_warp = ((G * context * 5 + G * slot_stride * 4) + 15) & ~15;
-  uint8_t* base = smem_tf + warp * per_warp;
-  float* sx = reinterpret_cast<float*>(base);
-  uint8_t* sm = base + G * context * 4;
-  float* slots = reinterpret_cast<float*>(sm + G * context);
-  const float inv_n = 1.0f / static_cast<float>(N);
-  const int64_t num_groups = (batch + G - 1) / G;
-
-  for (int64_t gi = static_cast<int64_t>(blockIdx.x) * warps + warp; gi < num_groups;
-       gi += static_cast<int64_t>(gridDim.x) * warps) {
-    const int64_t b0 = gi * G;
-    const int cnt = static_cast<int>(batch - b0 < G ? batch - b0 : G);
-    const int P = cnt * N;  // patches staged by this warp
-    // ---- stage x (fp32) and mask (u8) of `cnt` consecutive series
-    {
-      const float* gx = x + b0 * context;
-      const uint8_t* gm = mask + b0 * context;
-      const int nx = cnt * context / 4, nmk = cnt * context / 16;
-      for (int i = lane; i < nx; i += 32) cp_async16(sx + 4 * i, gx + 4 * i);
-      for (int i = lane; i < nmk; i += 32) cp_async16(sm + 16 * i, gm + 16 * i);
-      cp_async_wait_all_groups();
-      __syncwarp();
-    }
-    // ---- per-patch statistics: 8 lanes per patch, 4 independent patches per lane group and iteration
-    for (int p0 = 0; p0 < P; p0 += 16) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = p0 + grp + 4 * j;
-        const bool live = p < P;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t mk = 0x01010101u;
-        if (live) {
-          v = *reinterpret_cast<const float4*>(sx + p * 32 + 4 * q);
-          mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
-        }
-        const float xv[4] = {v.x, v.y, v.z, v.w};
-        float valid[4];
-        float c = 0.f, sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          valid[k] = ((mk >> (8 * k)) & 0xffu) ? 0.f : 1.f;
-          c += valid[k];
-          sum += xv[k] * valid[k];
-        }
-        c = group8_sum(c);
-        sum = group8_sum(sum);
-        const float c_safe = c == 0.f ? 1.f : c;
-        const float inc_mu = c == 0.f ? 0.f : __fdiv_rn(sum, c_safe);
-        float sq = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float d = (xv[k] - inc_mu) * valid[k];
-          sq += d * d;
-        }
-        sq = group8_sum(sq);
-        if (live && q == 0) {
-          const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
-          const int k = p - s * N;
-          float* slot = slots + s * slot_stride + 3 * k;
-          slot[0] = c;
-          slot[1] = inc_mu;
-          slot[2] = c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f));
-        }
-        // the patch counts as padded iff its LAST element is padded (timesfm.py:97)
-        if (live && q == 7 && patch_mask_out != nullptr) patch_mask_out[b0 * N + p] = (mk >> 24) ? 1 : 0;
-      }
-    }
-    __syncwarp();
-    // ---- sequential merge (reference order and formula; HF twin modeling_timesfm2_5.py:528-568): lane s = series s
-    if (lane < cnt) {
-      float* slot = slots + lane * slot_stride;
-      const uint8_t* mrow = sm + lane * context;
-      float run_n = 0.f, run_mu = 0.f, run_sigma = 0.f;
-      int masked = 0;
-      for (int i = 0; i < N; ++i) {
-        const float inc_n = slot[3 * i], inc_mu = slot[3 * i + 1], inc_sigma = slot[3 * i + 2];
-        const float new_n = __fadd_rn(run_n, inc_n);
-        const float new_n_safe = new_n == 0.f ? 1.f : new_n;
-        float new_mu = __fdiv_rn(__fadd_rn(__fmul_rn(run_n, run_mu), __fmul_rn(inc_mu, inc_n)), new_n_safe);
-        if (new_n == 0.f) new_mu = 0.f;
-        const float d1 = __fsub_rn(run_mu, new_mu), d2 = __fsub_rn(inc_mu, new_mu);
-        const float t1 = __fmul_rn(run_n, __fmul_rn(run_sigma, run_sigma));
-        const float t2 = __fmul_rn(inc_n, __fmul_rn(inc_sigma, inc_sigma));
-        const float t3 = __fmul_rn(run_n, __fmul_rn(d1, d1));
-        const float t4 = __fmul_rn(inc_n, __fmul_rn(d2, d2));
-        float new_var = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4), new_n_safe);
-        if (new_n == 0.f) new_var = 0.f;
-        run_n = new_n;
-        run_mu = new_mu;
-        run_sigma = sqrtf(fmaxf(new_var, 0.f));
-        slot[3 * i] = run_mu;  // the slot now holds the cumulative stats of this patch
-        slot[3 * i + 1] = run_sigma;
-        masked += mrow[32 * i + 31] ? 1 : 0;
-      }
-      if (num_masked_out != nullptr) num_masked_out[b0 + lane] = masked;
-    }
-    __syncwarp();
-    // ---- mu / sigma out, coalesced (the group's [cnt, N] block is contiguous in [B, N])
-    for (int i = lane; i < P; i += 32) {
-      const int s = static_cast<int>((static_cast<float>(i) + 0.5f) * inv_n);
-      const int k = i - s * N;
-      const float* slot = slots + s * slot_stride + 3 * k;
-      if (mu_out != nullptr) mu_out[b0 * N + i] = slot[0];
-      if (sigma_out != nullptr) sigma_out[b0 * N + i] = slot[1];
-    }
-    // ---- RevIN with the cumulative stats of the own patch, zero the padded points, emit tokens
-    for (int p0 = 0; p0 < P; p0 += 16) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = p0 + grp + 4 * j;
-        if (p < P) {
-          const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
-          const int k = p - s * N;
-          const float* slot = slots + s * slot_stride + 3 * k;
-          const float mu_p = slot[0], sigma_p = slot[1];
-          const float inv_sig = __fdiv_rn(1.0f, sigma_p < 1e-6f ? 1.f : sigma_p);
-          const float4 v = *reinterpret_cast<const float4*>(sx + p * 32 + 4 * q);
-          const uint32_t mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
-          const float xv[4] = {v.x, v.y, v.z, v.w};
-          float val[4], msk[4];
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const bool padded = ((mk >> (8 * kk)) & 0xffu) != 0;
-            msk[kk] = padded ? 1.f : 0.f;
-            val[kk] = padded ? 0.f : (xv[kk] - mu_p) * inv_sig;
-          }
-          store_token_quad<OUT>(tokens, b0 * N + p, q, val, msk);
-        }
-      }
-    }
-    __syncwarp();  // the next group's cp.async must not overwrite tiles still being read
-  }
-}
-
-// ----------------------------------------------------------------------------------------
 // TMA-pipelined variant (the default for context <= 4096): a persistent block walks over tiles of G consecutive
 // series.  One thread keeps a ring of STAGES tiles in flight with 1-D bulk copies (cp.async.bulk, completion on an
 // mbarrier), so the HBM reads of the next tiles overlap the arithmetic of the current one and cost no load
@@ -1117,162 +958,6 @@ __global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_kernel(
         const float v = __ldg(xr + e);
         idr[e] = tok(v);
         amr[e] = isnan(v) ? 0 : 1;
-      }
-    }
-  }
-}
-
-// Vectorised variant (context % 4 == 0, 16-byte aligned rows): lane l owns float4 #(l + 32 j).  The boundary table
-// sits in shared memory between two sentinels (-inf below, NaN above) so the search needs no bounds checks; the
-// uniform-grid guess is verified against its two neighbouring entries and only a miss walks the table (exact for
-// any ascending table).  ids leave as 16-byte pairs and the attention-mask bytes as one 32-bit word whenever the
-// row's alignment allows (it is the same for the whole row, so the branch is warp-uniform).
-__device__ __forceinline__ int bucketize_right_sentinel(const float* __restrict__ sp, int nb, float v, float g_mul,
-                                                        float g_add) {
-  // sp[0] = -inf, sp[1 + i] = boundaries[i], sp[nb + 1] = NaN; returns #boundaries <= v (v is not NaN)
-  float g = fmaf(v, g_mul, g_add);
-  g = fminf(fmaxf(g, 0.f), static_cast<float>(nb));
-  int i = static_cast<int>(g);  // candidate count in [0, nb]
-  const float lo = sp[i], hi = sp[i + 1];
-  if (!(lo <= v) || hi <= v) {
-    while (!(sp[i] <= v)) --i;
-    while (sp[i + 1] <= v) ++i;
-  }
-  return i;
-}
-
-template <int NV>
-__global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_vec_kernel(
-    const float* __restrict__ x, int64_t batch, int context, const float* __restrict__ boundaries, int nb,
-    int n_special, int n_tokens, int pad_id, int eos_id, int64_t* __restrict__ ids,
-    uint8_t* __restrict__ attn_mask, float* __restrict__ scale_out) {
-  extern __shared__ float sp[];
-  __shared__ int s_nonuniform;
-  if (threadIdx.x == 0) s_nonuniform = 0;
-  for (int i = threadIdx.x; i < nb + 2; i += blockDim.x)
-    sp[i] = i == 0 ? -INFINITY : (i == nb + 1 ? NAN : boundaries[i - 1]);
-  __syncthreads();
-  // guess: interior boundaries b[1 .. nb-2] are evenly spaced -> count ~ g = (v - b[1]) / step + 2
-  const float step = (sp[nb - 1] - sp[2]) / static_cast<float>(nb - 3);
-  const float inv_step = static_cast<float>(nb - 3) / (sp[nb - 1] - sp[2]);
-  const float g_mul = inv_step, g_add = fmaf(-sp[2], inv_step, 2.0f);
-  // Table-free fast path: if every interior boundary lies within step/2048 of the uniform grid (checked here, per
-  // block; torch's linspace table is within step/7000), then g is within 1/400 of the exact grid coordinate for
-  // every in-range v (table deviation 1/2048 + fp32 evaluation error of g <= 8190 * 2^-22), so a g whose
-  // fractional part is in [1/256, 255/256] pins the count to floor(g) without touching the table.  Everything else
-  // takes the exact table search.
-  {
-    int bad = !(step > 0.f) || nb > 8190;
-    for (int i = 1 + threadIdx.x; i <= nb - 2; i += blockDim.x) {
-      const float ideal = fmaf(static_cast<float>(i - 1), step, sp[2]);
-      bad |= !(fabsf(sp[1 + i] - ideal) <= step * (1.0f / 2048.0f));
-    }
-    if (bad) s_nonuniform = 1;
-  }
-  __syncthreads();
-  const bool uniform = s_nonuniform == 0;
-  const float g_hi = static_cast<float>(nb - 1);  // g in [2, nb - 1): v inside the interior grid
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nvec = context >> 2;
-  const int row = context + 1;
-  const int t_max = n_tokens - 1;
-  for (int64_t b = static_cast<int64_t>(blockIdx.x) * WARPS + warp; b < batch;
-       b += static_cast<int64_t>(gridDim.x) * WARPS) {
-    const float* xr = x + b * context;
-    int64_t* idr = ids + b * row;
-    uint8_t* amr = attn_mask + b * row;
-    float4 v[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int f = lane + 32 * j;
-      v[j] = f < nvec ? ld_stream_f4(xr + 4 * f) : make_float4(NAN, NAN, NAN, NAN);
-    }
-    // sum(|x|) accumulated in fp64 and rounded to fp32 once: the scale (hence every id) is order independent
-    double sum = 0.0;
-    float cnt = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool nan = isnan(xv[k]);
-        sum += nan ? 0.0 : static_cast<double>(fabsf(xv[k]));
-        cnt += nan ? 0.f : 1.f;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    cnt = warp_sum(cnt);
-    float scale = __fdiv_rn(static_cast<float>(sum), cnt);  // 0/0 -> NaN -> 1 below
-    if (!(scale > 0.f)) scale = 1.f;
-    if (lane == 0) {
-      if (scale_out != nullptr) scale_out[b] = scale;
-      idr[context] = eos_id;
-      amr[context] = 1;
-    }
-    const bool ids16 = (reinterpret_cast<uintptr_t>(idr) & 15) == 0;  // row starts on a 16-byte boundary
-    const int am_align = static_cast<int>(reinterpret_cast<uintptr_t>(amr) & 3);
-    const float rscale = __frcp_rn(scale);
-    const bool scale_mid = scale > 0x1p-60f && scale < 0x1p60f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int f = lane + 32 * j;
-      if (f < nvec) {
-        const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-        uint32_t t[4];
-        uint32_t mbytes = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool nan = isnan(xv[k]);
-          const float a = nan ? 0.f : xv[k];
-          // a / scale, correctly rounded (= torch's fp32 division).  The divisor is the same for the whole series,
-          // so its correctly rounded reciprocal is hoisted and the quotient comes from two FMA refinement steps
-          // (Markstein: a faithful q1 corrected with r = RN(1/scale) rounds to RN(a/scale)); operands far from the
-          // normal range, where the exact-remainder argument breaks, take the IEEE division instruction sequence.
-          float q;
-          const float aa = fabsf(a);
-          if (scale_mid && (a == 0.f || (aa > 0x1p-60f && aa < 0x1p60f))) {
-            const float q0 = a * rscale;
-            const float q1 = fmaf(fmaf(-scale, q0, a), rscale, q0);
-            q = fmaf(fmaf(-scale, q1, a), rscale, q1);
-          } else {
-            q = __fdiv_rn(a, scale);
-          }
-          int tk;
-          {
-            const float g = fmaf(q, g_mul, g_add);
-            const float fl = floorf(g);
-            const float frac = g - fl;
-            if (uniform && g >= 2.0f && g < g_hi && frac >= (1.0f / 256.0f) && frac <= (255.0f / 256.0f))
-              tk = static_cast<int>(fl);
-            else
-              tk = bucketize_right_sentinel(sp, nb, q, g_mul, g_add);
-          }
-          tk = max(0, min(t_max, tk + n_special));
-          t[k] = static_cast<uint32_t>(nan ? pad_id : tk);
-          mbytes |= (nan ? 0u : 1u) << (8 * k);
-        }
-        // ids are non-negative: the int64 is (low word, 0)
-        uint32_t* ip = reinterpret_cast<uint32_t*>(idr + 4 * f);
-        if (ids16) {
-          *reinterpret_cast<uint4*>(ip) = make_uint4(t[0], 0u, t[1], 0u);
-          *reinterpret_cast<uint4*>(ip + 4) = make_uint4(t[2], 0u, t[3], 0u);
-        } else {
-          *reinterpret_cast<uint2*>(ip) = make_uint2(t[0], 0u);
-          *reinterpret_cast<uint4*>(ip + 2) = make_uint4(t[1], 0u, t[2], 0u);
-          *reinterpret_cast<uint2*>(ip + 6) = make_uint2(t[3], 0u);
-        }
-        uint8_t* mp = amr + 4 * f;
-        if (am_align == 0) {
-          *reinterpret_cast<uint32_t*>(mp) = mbytes;
-        } else if (am_align == 2) {
-          *reinterpret_cast<uint16_t*>(mp) = static_cast<uint16_t>(mbytes);
-          *reinterpret_cast<uint16_t*>(mp + 2) = static_cast<uint16_t>(mbytes >> 16);
-        } else {
-          mp[0] = mbytes & 0xffu;
-          *reinterpret_cast<uint16_t*>(mp + 1) = static_cast<uint16_t>(mbytes >> 8);
-          mp[3] = mbytes >> 24;
-        }
       }
     }
   }

@@ -461,6 +461,17 @@ def mask_cast_rows(x: torch.Tensor, mask: torch.Tensor, out_dtype: int) -> torch
     return out
 
 
+def wgrad(dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, k_in: int, precision: int) -> torch.Tensor:
+    """Weight gradient of ``y = x W^T``: dW [n_out, k_in] = dY^T X as a K-major tcgen05 GEMM with K = rows (both operands
+    transposed once; split-K inside the GEMM when the tile count is small)."""
+    adt = act_dtype(precision)
+    dy_t, kpad = transpose_mask(dy, rows, n_out, adt)
+    x_t, _ = transpose_mask(x, rows, k_in, adt)
+    gw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy.device)
+    gemm([(dy_t, x_t, kpad)], n_out, k_in, gw, DT_F32, precision=precision)
+    return gw
+
+
 # ----------------------------------------------------------------------------- TimesFM AR decode / forecast extras
 @_on_operand_device
 def timesfm_patchify_continue(

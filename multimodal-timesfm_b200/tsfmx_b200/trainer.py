@@ -106,6 +106,14 @@ class MultimodalTrainer:
         self.best_val_loss = float("inf")
         self._copy_stream: torch.cuda.Stream | None = None
         self._micro_batches_since_step = 0
+        # CUDA-graph replay of forward + loss + backward for micro-batch shapes that repeat (every full batch of an
+        # epoch): a full fine-tune step is ~5 800 kernel launches and was bound by the host's launch rate.  The optimizer
+        # step (all-reduce, clip, AdamW) stays outside the graph.  Not with gradient accumulation (a replay overwrites
+        # the gradients of the previous micro-batch) and not around the overlapped NCCL reducer.
+        self.graphs = bool(getattr(args, "cuda_graphs", self.device.type == "cuda")) and self.device.type == "cuda"
+        self._train_graphs: dict[tuple, "_GraphedMicroBatch"] = {}
+        self._graph_seen: dict[tuple, int] = {}
+        self.graph_replays = 0
         # full fine-tuning on several GPUs: all-reduce each layer's gradients while the backward pass continues below
         # it (1.99 GB per step at 50 layers).  Only without gradient accumulation - with it the collective runs once
         # per optimizer step on the accumulated gradients instead of once per micro-batch.
@@ -207,6 +215,35 @@ class MultimodalTrainer:
         loss = self.loss_fn(point, horizon)
         return loss if n_local == n_global else loss * (n_local / n_global)
 
+    MAX_TRAIN_GRAPHS = 2  # full batches (and at most one other repeating shape); each graph owns a step's activations
+
+    def _graph_key(self, batch: dict) -> tuple | None:
+        if not self.graphs or self.args.gradient_accumulation_steps != 1:
+            return None
+        if self.model.grad_ready_hook is not None and not getattr(self.args, "graph_collectives", False):
+            return None  # the overlapped NCCL all-reduces would be captured too: opt-in (args.graph_collectives)
+        if batch["context"].shape[0] == 0 or not getattr(self.model.adapter, "graph_safe", False):
+            return None
+        return tuple((k, tuple(batch[k].shape)) for k in self._KEYS if k in batch) + (batch["global_size"],)
+
+    def _micro_batch(self, batch: dict, accum: int) -> torch.Tensor:
+        """Forward, loss and backward of one micro-batch -> the (detached) loss.  The second time a micro-batch shape
+        shows up its forward + backward are captured into a CUDA graph and replayed from then on."""
+        key = self._graph_key(batch)
+        if key is not None:
+            entry = self._train_graphs.get(key)
+            if entry is None and len(self._train_graphs) < self.MAX_TRAIN_GRAPHS:
+                self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+                if self._graph_seen[key] >= 2:  # the first occurrence ran eagerly and built every lazy cache
+                    entry = self._train_graphs[key] = _GraphedMicroBatch(self, batch)
+            if entry is not None:
+                self._micro_batches_since_step += 1
+                self.graph_replays += 1
+                return entry.run(batch)
+        loss = self._forward_loss(batch) / accum
+        self._backward(loss, batch["global_size"])
+        return loss.detach() * accum
+
     def _backward(self, loss: torch.Tensor, global_size: int | None = None) -> None:
         """``loss.backward()``.  A global batch with fewer samples than ranks leaves some rank with an empty shard, a
         constant loss and no backward pass; every rank can tell from ``global_size`` alone, so for such a batch ALL
@@ -256,9 +293,7 @@ class MultimodalTrainer:
         accum = self.args.gradient_accumulation_steps
         losses = []
         for i, batch in enumerate(self._staged(self.train_loader)):
-            loss = self._forward_loss(batch) / accum
-            self._backward(loss, batch["global_size"])
-            losses.append(loss.detach() * accum)  # no per-micro-batch .item() sync (reference trainer.py:211)
+            losses.append(self._micro_batch(batch, accum))  # no per-micro-batch .item() sync (reference trainer.py:211)
             if (i + 1) % accum == 0 or (i + 1) == num_batches:
                 self.optimizer_step()
         total = torch.stack(losses).sum()
@@ -356,6 +391,46 @@ class MultimodalTrainer:
             self._rotate_checkpoints()
         if is_best:
             torch.save(checkpoint, self.args.checkpoint_dir / "best_model.pt")
+
+
+class _GraphedMicroBatch:
+    """Forward + loss + backward of one micro-batch shape as a CUDA graph over static input buffers.
+
+    Captured with the gradients unset, so the backward pass allocates every ``.grad`` from the graph's private pool;
+    a replay overwrites them in place, and ``run`` re-attaches them to the parameters (``zero_grad`` drops them after
+    every optimizer step).  Packed bf16 copies of weights that changed since the last step are rebuilt by kernels
+    inside the graph - they read the parameters at their (fixed) addresses."""
+
+    def __init__(self, trainer: "MultimodalTrainer", batch: dict) -> None:
+        self.static = {k: batch[k].clone() for k in trainer._KEYS if k in batch}
+        self.static["global_size"] = batch["global_size"]
+        params = list(trainer._get_trainable_params())
+        trainer.optimizer.zero_grad(set_to_none=True)
+        torch.cuda.synchronize(trainer.device)
+        self.graph = torch.cuda.CUDAGraph()
+        # thread-local error mode: the DataLoader's pin-memory thread may allocate page-locked memory meanwhile; the
+        # backward pass runs on autograd's worker thread but on the capturing stream, so it is recorded all the same
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            loss = trainer._forward_loss(self.static)
+            loss.backward()
+        self.loss = loss.detach()
+        # with the overlapped reducer active the per-layer all-reduces were captured as well: a replay leaves globally
+        # summed gradients behind, which optimizer_step has to be told
+        self.reducer = trainer.model.grad_ready_hook
+        self.grads = [(p, p.grad) for p in params if p.grad is not None]
+        for p, _ in self.grads:  # nothing has run yet: the first replay produces the values
+            p.grad = None
+
+    def run(self, batch: dict) -> torch.Tensor:
+        for k, buf in self.static.items():
+            if k != "global_size":
+                buf.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        for p, g in self.grads:
+            p.grad = g
+        if self.reducer is not None:
+            self.reducer.reduced = True
+        return self.loss.clone()
 
 
 def world_barrier() -> None:

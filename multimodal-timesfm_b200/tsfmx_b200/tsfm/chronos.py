@@ -143,6 +143,10 @@ class Chronos2Adapter(TsfmAdapter):
         self.fused_norm = os.environ.get("TSFMX_FUSED_NORM", "0") == "1"  # True: residual + RMS LayerNorm junctions in the GEMM epilogue (measured slower, kept for A/B)
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
+        mm = self._model  # RoPE frequencies as a (non-persistent) buffer: no host-to-device copy inside _weights()
+        self.register_buffer(
+            "_inv_freq", 1.0 / (mm.rope_theta ** (torch.arange(0, mm.d_kv, 2, dtype=torch.int64).float() / mm.d_kv)),
+            persistent=False)
 
     def set_precision(self, precision: str) -> None:
         if precision not in PRECISIONS:
@@ -194,7 +198,7 @@ class Chronos2Adapter(TsfmAdapter):
             "out_out_b": f32(ope.output_layer.bias + ope.residual_layer.bias),
             "final_ln": f32(m.encoder.final_layer_norm.weight),
             "reg": f32(m.shared.weight[m.config.reg_token_id]),
-            "inv_freq": (1.0 / (m.rope_theta ** (torch.arange(0, m.d_kv, 2, dtype=torch.int64).float() / m.d_kv))).to(dev),
+            "inv_freq": self._inv_freq.to(dev),
             "blocks": [],
         }
         for blk in m.encoder.block:
@@ -217,8 +221,9 @@ class Chronos2Adapter(TsfmAdapter):
         self._packed[key] = w
         return w
 
-    def _embed_patches(self, patched: torch.Tensor, rows: int, w: dict, prec: int) -> torch.Tensor:
-        """input_patch_embedding: ResidualBlock 48(->64 padded) -> 3072 -> 768, bias, ReLU -> fp32 [rows, 768]."""
+    def _embed_patches(self, patched: torch.Tensor, rows: int, w: dict, prec: int, keep: dict | None = None) -> torch.Tensor:
+        """input_patch_embedding: ResidualBlock 48(->64 padded) -> 3072 -> 768, bias, ReLU -> fp32 [rows, 768].
+        ``keep`` (full fine-tuning) receives the block's operands for ``_embed_backward``."""
         m = self._model
         adt = ops.act_dtype(prec)
         hidden = ops.alloc(rows, m.d_ff, adt, patched.device)
@@ -227,7 +232,42 @@ class Chronos2Adapter(TsfmAdapter):
         emb = torch.empty(rows, m.model_dim, dtype=torch.float32, device=patched.device)
         ops.gemm([(hidden, w["in_out"], m.d_ff), (patched, w["in_res"], 64)], rows, m.model_dim, emb, DT_F32,
                  precision=prec, bias=w["in_out_b"])
+        if keep is not None:
+            keep.update({"patched": patched, "hidden": hidden, "rows": rows})
         return emb
+
+    def _future_patches(self, prec: int, dev: torch.device) -> torch.Tensor:
+        """Tokenizer input rows of the 64 future patches: fixed time encoding, zero values, zero mask."""
+        cc = self._model.chronos_config
+        nop, ps = cc.max_output_patches, cc.output_patch_size
+        x = torch.zeros(nop, 64, dtype=torch.float32, device=dev)
+        x[:, :ps] = (torch.arange(0, nop * ps, dtype=torch.float32, device=dev) / cc.time_encoding_scale).view(nop, ps)
+        return ops.cast_rows(x, ops.act_dtype(prec))
+
+    def _embed_backward(self, kept: dict, d_emb: torch.Tensor, pg: dict[str, torch.Tensor]) -> None:
+        """Weight / bias gradients of input_patch_embedding from dL/d(embeddings) [rows, 768] fp32, ACCUMULATED into
+        ``pg`` (the block embeds the context patches and, once per step, the 64 future patches)."""
+        m = self._model
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        wt = self._weights_t()
+        rows, patched, hidden = kept["rows"], kept["patched"], kept["hidden"]
+        ps3 = 3 * m.chronos_config.input_patch_size
+        d_a = ops.cast_rows(d_emb, adt)
+        dh32 = torch.empty(rows, m.d_ff, dtype=torch.float32, device=d_emb.device)
+        ops.gemm([(d_a, wt["in_out"], m.model_dim)], rows, m.d_ff, dh32, DT_F32, precision=prec, act=ACT_RELU_GRAD,
+                 aux=_hi(hidden, m.d_ff))
+        bias = ops.colsum_wgrad(d_emb)
+        new = {
+            "input_patch_embedding.output_layer.weight": ops.wgrad(d_a, hidden, rows, m.model_dim, m.d_ff, prec),
+            "input_patch_embedding.residual_layer.weight": ops.wgrad(d_a, patched, rows, m.model_dim, 64, prec)[:, :ps3],
+            "input_patch_embedding.output_layer.bias": bias,
+            "input_patch_embedding.residual_layer.bias": bias,
+            "input_patch_embedding.hidden_layer.weight": ops.wgrad(dh32, patched, rows, m.d_ff, 64, prec)[:, :ps3],
+            "input_patch_embedding.hidden_layer.bias": ops.colsum_wgrad(dh32),
+        }
+        for k, v in new.items():
+            pg[k] = pg[k] + v if k in pg else v.contiguous().clone()
 
     # ------------------------------------------------------------------ stages
     def preprocess(self, inputs: torch.Tensor, masks: torch.Tensor) -> PreprocessResult:
@@ -260,11 +300,8 @@ class Chronos2Adapter(TsfmAdapter):
         same for every series (reference chronos.py:82-100 recomputes them B times)."""
         key = ("future", prec)
         if key not in w:
-            cc = self._model.chronos_config
-            nop, ps = cc.max_output_patches, cc.output_patch_size
-            x = torch.zeros(nop, 64, dtype=torch.float32, device=dev)
-            x[:, :ps] = (torch.arange(0, nop * ps, dtype=torch.float32, device=dev) / cc.time_encoding_scale).view(nop, ps)
-            w[key] = self._embed_patches(ops.cast_rows(x, ops.act_dtype(prec)), nop, w, prec)
+            w[key] = self._embed_patches(self._future_patches(prec, dev), self._model.chronos_config.max_output_patches,
+                                         w, prec)
         return w[key]
 
     def forward(self, input_embeddings: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
@@ -409,12 +446,14 @@ class Chronos2Adapter(TsfmAdapter):
                     "ov": pack_t(w_ov), "wi": pack_t(ff.mlp.wi.weight), "wo": pack_t(ff.mlp.wo.weight),
                 })
             w["t"] = {"blocks": blocks, "out_hidden": pack_t(ope.hidden_layer.weight),
-                      "out_out": pack_t(ope.output_layer.weight), "out_res": pack_t(ope.residual_layer.weight)}
+                      "out_out": pack_t(ope.output_layer.weight), "out_res": pack_t(ope.residual_layer.weight),
+                      "in_out": pack_t(m.input_patch_embedding.output_layer.weight)}
         return w["t"]
 
-    def forward_saving(self, input_embeddings: torch.Tensor, masks: torch.Tensor):
+    def forward_saving(self, input_embeddings: torch.Tensor, masks: torch.Tensor, for_wgrad: bool = False):
         """``forward`` that keeps what the activation-gradient pass needs: the residual stream at the input of every
-        RMS LayerNorm, the raw qkv of every time attention and the ReLU outputs of every MLP."""
+        RMS LayerNorm, the raw qkv of every time attention and the ReLU outputs of every MLP.  ``for_wgrad`` (full
+        fine-tuning) also keeps the input of every GEMM and the operands of the future-patch embedding."""
         m, cc = self._model, self._model.chronos_config
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -429,14 +468,18 @@ class Chronos2Adapter(TsfmAdapter):
         h[:, :n] = input_embeddings
         if extra:
             h[:, n] = w["reg"]
-        h[:, n + extra:] = self._future_embeds(w, prec, dev)
+        future_kept: dict | None = {} if for_wgrad else None
+        if for_wgrad:  # the future-patch embeddings depend on the weights being trained: fresh, with operands kept
+            h[:, n + extra:] = self._embed_patches(self._future_patches(prec, dev), nop, w, prec, keep=future_kept)
+        else:
+            h[:, n + extra:] = self._future_embeds(w, prec, dev)
         key_mask = torch.ones(b, t, dtype=torch.bool, device=dev)
         key_mask[:, :n] = ~masks.bool()
         rows = b * t
         cur = h.view(rows, d)
         blocks = w["blocks"]
         inner = m.num_heads * m.d_kv
-        saved = {"shape": (b, n, t, d), "key_mask": key_mask, "blocks": []}
+        saved = {"shape": (b, n, t, d), "key_mask": key_mask, "blocks": [], "future": future_kept}
         xn = ops.rmsnorm(cur, blocks[0]["ln_t"], m.eps, adt) if blocks else None
         attn = ops.alloc(rows, inner, adt, dev)
         a = ops.alloc(rows, d, mid_dt, dev)
@@ -446,27 +489,42 @@ class Chronos2Adapter(TsfmAdapter):
             h1 = torch.empty(rows, d, dtype=torch.float32, device=dev)
             h2 = torch.empty(rows, d, dtype=torch.float32, device=dev)
             h3 = torch.empty(rows, d, dtype=torch.float32, device=dev)
-            ops.gemm([(xn, bw["qkv"], d)], rows, 3 * inner, qkv, mid_dt, precision=prec)
+            xn_t = xn  # normed block input (operand of the qkv GEMM)
+            if for_wgrad:  # the weight-gradient GEMMs read these later: one set per block instead of reused scratch
+                attn = ops.alloc(rows, inner, adt, dev)
+                xn_g, xn_f = ops.alloc(rows, d, adt, dev), ops.alloc(rows, d, adt, dev)
+            else:
+                xn_g = xn_f = xn
+            ops.gemm([(xn_t, bw["qkv"], d)], rows, 3 * inner, qkv, mid_dt, precision=prec)
             ops.encoder_attention(qkv, b, t, m.num_heads, m.d_kv, key_mask, w["inv_freq"], adt, out=attn)
             ops.gemm([(attn, bw["o"], inner)], rows, d, a, mid_dt, precision=prec)
-            ops.norm_residual_norm(a, cur, None, bw["ln_g"], m.eps, h1, adt, xn)
-            ops.gemm([(xn, bw["ov"], d)], rows, d, a, mid_dt, precision=prec)
-            ops.norm_residual_norm(a, h1, None, bw["ln_f"], m.eps, h2, adt, xn)
-            ops.gemm([(xn, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
+            ops.norm_residual_norm(a, cur, None, bw["ln_g"], m.eps, h1, adt, xn_g)
+            ops.gemm([(xn_g, bw["ov"], d)], rows, d, a, mid_dt, precision=prec)
+            ops.norm_residual_norm(a, h1, None, bw["ln_f"], m.eps, h2, adt, xn_f)
+            ops.gemm([(xn_f, bw["wi"], d)], rows, m.d_ff, u, adt, precision=prec, act=ACT_RELU)
             ops.gemm([(u, bw["wo"], m.d_ff)], rows, d, a, mid_dt, precision=prec)
             nxt = blocks[i + 1]["ln_t"] if i + 1 < len(blocks) else w["final_ln"]
             last = i + 1 == len(blocks)
             final = torch.empty(rows, d, dtype=torch.float32, device=dev) if last else None
+            xn = None if last else (ops.alloc(rows, d, adt, dev) if for_wgrad else xn)
             ops.norm_residual_norm(a, h2, None, nxt, m.eps, h3, DT_F32 if last else adt, final if last else xn)
-            saved["blocks"].append({"h0": cur, "h1": h1, "h2": h2, "qkv": qkv, "u": u})
+            entry = {"h0": cur, "h1": h1, "h2": h2, "qkv": qkv, "u": u}
+            if for_wgrad:
+                entry.update({"xn_t": xn_t, "attn": attn, "xn_g": xn_g, "xn_f": xn_f})
+            saved["blocks"].append(entry)
             cur = h3
         if not blocks:
             final = ops.rmsnorm(cur, w["final_ln"], m.eps, DT_F32)
         saved["h_last"] = cur
         return final.view(b, t, d)[:, -nop:].contiguous(), saved
 
-    def forward_backward(self, saved, d_out: torch.Tensor) -> torch.Tensor:
-        """dL/d(returned forecast-position embeddings) [B * 64, D] -> dL/d(input embeddings) [B * N, D] fp32."""
+    def forward_backward(self, saved, d_out: torch.Tensor, param_grads: dict[str, torch.Tensor] | None = None,
+                         on_grads=None) -> torch.Tensor:
+        """dL/d(returned forecast-position embeddings) [B * 64, D] -> dL/d(input embeddings) [B * N, D] fp32.
+
+        ``param_grads`` (full fine-tuning, needs ``forward_saving(for_wgrad=True)``): receives the gradient of every
+        encoder parameter under its state-dict name, of the [REG] embedding, and the future patches' share of the
+        input_patch_embedding gradients.  ``on_grads(tensors)``: called with each finished block's gradients."""
         m = self._model
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -482,6 +540,9 @@ class Chronos2Adapter(TsfmAdapter):
         g = torch.empty(rows, d, dtype=torch.float32, device=dev)  # running dL/d(residual stream)
         ops.rmsnorm_bwd_chain(None, saved["h_last"], w["final_ln"], g_final.view(rows, d), None, None, m.eps, g, adt, None,
                               rows, d)
+        pg = param_grads
+        if pg is not None:
+            pg["encoder.final_layer_norm.weight"] = ops.colsum_wgrad(g_final.view(rows, d), saved["h_last"], m.eps)
         du = ops.alloc(rows, m.d_ff, adt, dev)
         dxn = ops.alloc(rows, d, mid_dt, dev)
         dattn = ops.alloc(rows, inner, mid_dt, dev)
@@ -489,24 +550,87 @@ class Chronos2Adapter(TsfmAdapter):
         blocks, tblocks = w["blocks"], wt["blocks"]
         for i in reversed(range(len(blocks))):
             bw, tw, s = blocks[i], tblocks[i], saved["blocks"][i]
+            pre = f"encoder.block.{i}.layer."
+            if pg is not None and on_grads is not None and i + 1 < len(blocks):
+                done = f"encoder.block.{i + 1}."  # the block above is complete: hand its gradients over
+                on_grads([v for k, v in pg.items() if k.startswith(done)])
             # feed-forward: h3 = h2 + relu(rms(h2) Wi) Wo
             ga = ops.cast_rows(g, adt)
+            if pg is not None:
+                pg[pre + "2.mlp.wo.weight"] = ops.wgrad(ga, s["u"], rows, d, m.d_ff, prec)
             ops.gemm([(ga, tw["wo"], d)], rows, m.d_ff, du, adt, precision=prec, act=ACT_RELU_GRAD, aux=_hi(s["u"], m.d_ff),
                      split_off=m.d_ff)
             ops.gemm([(du, tw["wi"], m.d_ff)], rows, d, dxn, mid_dt, precision=prec)
+            if pg is not None:
+                pg[pre + "2.mlp.wi.weight"] = ops.wgrad(du, s["xn_f"], rows, m.d_ff, d, prec)
+                pg[pre + "2.layer_norm.weight"] = ops.colsum_wgrad(dxn, s["h2"], m.eps)
             ops.rmsnorm_bwd_chain(g, s["h2"], bw["ln_f"], dxn, None, None, m.eps, g, adt, None, rows, d)
             # group attention (degenerate: one GEMM): h2 = h1 + rms(h1) Wov
             ga = ops.cast_rows(g, adt)
             ops.gemm([(ga, tw["ov"], d)], rows, d, dxn, mid_dt, precision=prec)
+            if pg is not None:
+                # W_ov = W_o W_v: dW_o = dW_ov W_v^T, dW_v = W_o^T dW_ov (two 768^3 products in parameter space); with
+                # group_ids = arange(B) every softmax of the group attention has ONE key, so q and k get no gradient
+                att = m.encoder.block[i].layer[1].self_attention
+                d_ov = ops.wgrad(ga, s["xn_g"], rows, d, d, prec)
+                pg[pre + "1.self_attention.o.weight"] = d_ov @ att.v.weight.detach().float().t()
+                pg[pre + "1.self_attention.v.weight"] = att.o.weight.detach().float().t() @ d_ov
+                pg[pre + "1.self_attention.q.weight"] = torch.zeros_like(att.q.weight, dtype=torch.float32)
+                pg[pre + "1.self_attention.k.weight"] = torch.zeros_like(att.k.weight, dtype=torch.float32)
+                pg[pre + "1.layer_norm.weight"] = ops.colsum_wgrad(dxn, s["h1"], m.eps)
             ops.rmsnorm_bwd_chain(g, s["h1"], bw["ln_g"], dxn, None, None, m.eps, g, adt, None, rows, d)
             # time attention: h1 = h0 + attn(rms(h0) Wqkv) Wo
             ga = ops.cast_rows(g, adt)
+            if pg is not None:
+                pg[pre + "0.self_attention.o.weight"] = ops.wgrad(ga, s["attn"], rows, d, inner, prec)
             ops.gemm([(ga, tw["o"], d)], rows, inner, dattn, mid_dt, precision=prec)
             ops.encoder_attention_bwd(s["qkv"], dattn, b, t, m.num_heads, m.d_kv, saved["key_mask"], w["inv_freq"], adt,
                                       dqkv=dqkv)
             ops.gemm([(dqkv, tw["qkv"], 3 * inner)], rows, d, dxn, mid_dt, precision=prec)
+            if pg is not None:
+                d_qkv_w = ops.wgrad(dqkv, s["xn_t"], rows, 3 * inner, d, prec)
+                for j, name in enumerate("qkv"):
+                    pg[pre + f"0.self_attention.{name}.weight"] = d_qkv_w[j * inner : (j + 1) * inner]
+                pg[pre + "0.layer_norm.weight"] = ops.colsum_wgrad(dxn, s["h0"], m.eps)
             ops.rmsnorm_bwd_chain(g, s["h0"], bw["ln_t"], dxn, None, None, m.eps, g, adt, None, rows, d)
-        return g.view(b, t, d)[:, :n].reshape(b * n, d).contiguous()
+        g3 = g.view(b, t, d)
+        if pg is not None:
+            if on_grads is not None and blocks:
+                on_grads([v for k, v in pg.items() if k.startswith("encoder.block.0.")])
+            cc = m.chronos_config
+            extra = 1 if cc.use_reg_token else 0
+            reg = torch.zeros_like(m.shared.weight, dtype=torch.float32)
+            if extra:
+                reg[m.config.reg_token_id] = g3[:, n].sum(0)  # the [REG] embedding row feeds position n of every series
+            pg["shared.weight"] = reg
+            # the 64 future-patch embeddings are shared by every series: their gradient is the batch sum
+            self._embed_backward(saved["future"], g3[:, n + extra:].sum(0).contiguous(), pg)
+        return g3[:, :n].reshape(b * n, d).contiguous()
+
+    def preprocess_saving(self, inputs: torch.Tensor, masks: torch.Tensor):
+        """``preprocess`` that keeps the input ResidualBlock's operands (full fine-tuning)."""
+        if not inputs.is_cuda:
+            raise TsfmxError("Chronos2Adapter runs on B200 only; there is no CPU fallback")
+        m, cc = self._model, self._model.chronos_config
+        prec = PRECISIONS[self.precision]
+        adt = ops.act_dtype(prec)
+        w = self._weights()
+        if inputs.shape[-1] > cc.context_length:
+            inputs, masks = inputs[..., -cc.context_length:], masks[..., -cc.context_length:]
+        b = inputs.shape[0]
+        patched, attn_mask, loc, scale = ops.chronos2_patchify_norm(
+            inputs, masks.bool(), cc.input_patch_size, cc.use_arcsinh, float(cc.time_encoding_scale), adt, out_cols=64
+        )
+        n = attn_mask.shape[1]
+        kept: dict = {}
+        emb = self._embed_patches(patched, b * n, w, prec, keep=kept)
+        pre = PreprocessResult(emb.view(b, n, m.model_dim), ~attn_mask, {"loc": loc.view(b, 1), "scale": scale.view(b, 1)})
+        return pre, kept
+
+    def preprocess_backward(self, saved, d_emb: torch.Tensor, param_grads: dict[str, torch.Tensor]) -> None:
+        """Context patches' share of the input_patch_embedding gradients (added to the future patches' share that
+        ``forward_backward`` left in ``param_grads``)."""
+        self._embed_backward(saved, d_emb, param_grads)
 
     def postprocess_saving(self, horizon: int, output_embeddings: torch.Tensor, normalization_stats):
         """``postprocess`` that keeps the head's ReLU output and raw predictions for the backward pass."""
@@ -533,11 +657,13 @@ class Chronos2Adapter(TsfmAdapter):
         out = ops.chronos2_finalize(preds, b, used, nq, ps, horizon, cc.use_arcsinh, normalization_stats["loc"],
                                     normalization_stats["scale"])
         saved = {"hid": hid, "preds": preds, "scale": normalization_stats["scale"].reshape(b), "b": b, "used": used,
-                 "horizon": horizon, "d": d}
+                 "horizon": horizon, "d": d, "xa": xa}
         return out, saved
 
-    def postprocess_backward(self, saved, grad_forecast: torch.Tensor) -> torch.Tensor:
-        """dL/d(forecast) [B, h, 21] -> dL/d(output embeddings) [B, 64, D] fp32 (non-zero in the used patches)."""
+    def postprocess_backward(self, saved, grad_forecast: torch.Tensor,
+                             param_grads: dict[str, torch.Tensor] | None = None) -> torch.Tensor:
+        """dL/d(forecast) [B, h, 21] -> dL/d(output embeddings) [B, 64, D] fp32 (non-zero in the used patches);
+        ``param_grads`` additionally receives the output ResidualBlock's gradients (full fine-tuning)."""
         m, cc = self._model, self._model.chronos_config
         prec = PRECISIONS[self.precision]
         adt = ops.act_dtype(prec)
@@ -556,9 +682,23 @@ class Chronos2Adapter(TsfmAdapter):
         dpre32 = torch.zeros(rows, kp, dtype=torch.float32, device=dev)
         dpre32[:, : nq * ps] = g
         dpre = ops.cast_rows(dpre32, adt)
-        dhid = ops.alloc(rows, m.d_ff, adt, dev)
-        ops.gemm([(dpre, wt["out_out"], kp)], rows, m.d_ff, dhid, adt, precision=prec, act=ACT_RELU_GRAD,
-                 aux=_hi(saved["hid"], m.d_ff), split_off=m.d_ff)
+        if param_grads is None:
+            dhid = ops.alloc(rows, m.d_ff, adt, dev)
+            ops.gemm([(dpre, wt["out_out"], kp)], rows, m.d_ff, dhid, adt, precision=prec, act=ACT_RELU_GRAD,
+                     aux=_hi(saved["hid"], m.d_ff), split_off=m.d_ff)
+        else:
+            dhid32 = torch.empty(rows, m.d_ff, dtype=torch.float32, device=dev)
+            ops.gemm([(dpre, wt["out_out"], kp)], rows, m.d_ff, dhid32, DT_F32, precision=prec, act=ACT_RELU_GRAD,
+                     aux=_hi(saved["hid"], m.d_ff))
+            dhid = ops.cast_rows(dhid32, adt)
+            head, width = "output_patch_embedding.", nq * ps
+            bias = ops.colsum_wgrad(dpre32)[:width].contiguous()
+            param_grads[head + "output_layer.weight"] = ops.wgrad(dpre, saved["hid"], rows, kp, m.d_ff, prec)[:width]
+            param_grads[head + "residual_layer.weight"] = ops.wgrad(dpre, saved["xa"], rows, kp, d, prec)[:width]
+            param_grads[head + "output_layer.bias"] = bias
+            param_grads[head + "residual_layer.bias"] = bias.clone()
+            param_grads[head + "hidden_layer.weight"] = ops.wgrad(dhid32, saved["xa"], rows, m.d_ff, d, prec)
+            param_grads[head + "hidden_layer.bias"] = ops.colsum_wgrad(dhid32)
         dx = torch.empty(rows, d, dtype=torch.float32, device=dev)
         ops.gemm([(dhid, wt["out_hidden"], m.d_ff), (dpre, wt["out_res"], kp)], rows, d, dx, DT_F32, precision=prec)
         d_out = torch.zeros(b, nop, d, dtype=torch.float32, device=dev)

@@ -138,6 +138,11 @@ class TimesFM2p5Adapter(TsfmAdapter):
         self.set_precision(precision)
         self._packed: dict[object, dict[str, object]] = {}
         self.forecast_options = ForecastOptions()
+        # RoPE frequencies: computed once on the CPU (bit-identical to the reference's), moved with the module - a
+        # host-to-device copy inside _weights() would be illegal while a training step is being captured into a graph
+        hd = self._model.hd
+        self.register_buffer("_inv_freq", 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd)),
+                             persistent=False)
 
     def set_precision(self, precision: str) -> None:
         if precision not in PRECISIONS:
@@ -195,7 +200,7 @@ class TimesFM2p5Adapter(TsfmAdapter):
             "head_hidden": pack(m.output_projection_point.hidden_layer),
             "head_out": pack(m.output_projection_point.output_layer),
             "head_res": pack(m.output_projection_point.residual_layer),
-            "inv_freq": (1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev),
+            "inv_freq": self._inv_freq.to(dev),
             "layers": [],
         }
         if hasattr(m, "output_projection_quantiles"):  # continuous quantile head (ForecastOptions)
@@ -563,14 +568,8 @@ class TimesFM2p5Adapter(TsfmAdapter):
         return cur.view(b, n, d), saved
 
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, k_in: int) -> torch.Tensor:
-        """dW [n_out, k_in] = dY^T X as a K-major tcgen05 GEMM with K = rows (both operands transposed once)."""
-        prec = PRECISIONS[self.precision]
-        adt = ops.act_dtype(prec)
-        dy_t, kpad = ops.transpose_mask(dy, rows, n_out, adt)
-        x_t, _ = ops.transpose_mask(x, rows, k_in, adt)
-        gw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy.device)
-        ops.gemm([(dy_t, x_t, kpad)], n_out, k_in, gw, DT_F32, precision=prec)
-        return gw
+        """dW [n_out, k_in] = dY^T X as a K-major tcgen05 GEMM with K = rows (``ops.wgrad``)."""
+        return ops.wgrad(dy, x, rows, n_out, k_in, PRECISIONS[self.precision])
 
     def forward_backward(self, saved, d_out: torch.Tensor, param_grads: dict[str, torch.Tensor] | None = None,
                          on_grads=None) -> torch.Tensor:

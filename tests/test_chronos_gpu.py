@@ -234,3 +234,63 @@ def test_fusion_gradient_through_chronos2_matches_oracle(layers, context, horizo
     got16 = dec.fusion.linears()[0].weight.grad.cpu()
     rel16 = ((got16.double() - ref_grad.double()).norm() / ref_grad.double().norm()).item()
     assert rel16 < 1.5e-1, rel16  # bf16 operands through 2-3 blocks of forward and backward GEMMs; stated separately
+
+
+def _oracle_grads_by_product_name(model):
+    """Gradients of the oracle Chronos-2 model under the upstream (product) state-dict names."""
+    g = {"shared.weight": model.shared.weight.grad, "encoder.final_layer_norm.weight": model.final_layer_norm.weight.grad}
+    for blk_name, blk in (("input_patch_embedding", model.input_patch_embedding),
+                          ("output_patch_embedding", model.output_patch_embedding)):
+        for lin in ("hidden_layer", "output_layer", "residual_layer"):
+            g[f"{blk_name}.{lin}.weight"] = getattr(blk, lin).weight.grad
+            g[f"{blk_name}.{lin}.bias"] = getattr(blk, lin).bias.grad
+    for i, blk in enumerate(model.blocks):
+        pre = f"encoder.block.{i}.layer."
+        for j, (attn, ln) in enumerate(((blk.time_attn, blk.time_ln), (blk.group_attn, blk.group_ln))):
+            for proj in "qkvo":
+                g[f"{pre}{j}.self_attention.{proj}.weight"] = getattr(attn, proj).weight.grad
+            g[f"{pre}{j}.layer_norm.weight"] = ln.weight.grad
+        g[pre + "2.mlp.wi.weight"] = blk.wi.weight.grad
+        g[pre + "2.mlp.wo.weight"] = blk.wo.weight.grad
+        g[pre + "2.layer_norm.weight"] = blk.ff_ln.weight.grad
+    return g
+
+
+@pytest.mark.parametrize("with_text,context,horizon,padded", [(False, 512, 64, False), (True, 160, 40, True)])
+def test_full_finetune_gradients_through_chronos2_match_oracle(with_text, context, horizon, padded):
+    """The reference's baseline sweep trains either adapter (scripts/tune_baseline_sweep.py:82-87, trainer.py:78-79,123).
+    Every Chronos-2 parameter gradient of the CUDA path - weight-gradient GEMMs, norm-scale reductions, the [REG]
+    embedding row, the batch-shared future-patch embeddings' share of the input block, the folded W_o W_v of the group
+    attention unfolded into dW_o / dW_v (its q / k get exactly zero) - against the restated oracle's torch autograd."""
+    dec, oracle = build(2)
+    dec.set_precision("bf16x3")
+    dec.adapter.unfreeze_parameters()
+    dec.train()
+    ctx, masks, text = batch(6, context, horizon, padded)
+    text_arg = text if with_text else None
+    target = torch.randn(6, horizon, generator=torch.Generator().manual_seed(3))
+    for p in oracle.parameters():
+        p.requires_grad_(True)
+    ref_loss = torch.nn.functional.mse_loss(oracle(horizon, ctx, masks, text_arg), target)
+    ref_loss.backward()
+    ref = _oracle_grads_by_product_name(oracle.adapter._model)
+    loss = torch.nn.functional.mse_loss(
+        dec(horizon, ctx.to(DEV), masks.to(DEV), None if text_arg is None else text_arg.to(DEV)), target.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    got = {k: v.grad for k, v in dec.adapter._model.named_parameters()}
+    assert set(got) == set(ref)
+    worst = {}
+    for name, r in ref.items():
+        assert got[name] is not None, name
+        if r is None or float(r.abs().max()) == 0.0:  # group-attention q / k, the PAD embedding row
+            assert float(got[name].abs().max()) == 0.0, name
+            continue
+        worst[name] = ((got[name].cpu().double() - r.double()).norm() / r.double().norm().clamp_min(1e-30)).item()
+    bad = {k: v for k, v in worst.items() if v > 3e-3}
+    print("worst chronos-2 full fine-tune gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+    assert not bad, bad
+    if with_text:
+        rf = oracle.fusion.projection[0].weight.grad
+        gf = dec.fusion.linears()[0].weight.grad.cpu()
+        assert ((gf.double() - rf.double()).norm() / rf.double().norm()).item() < 3e-3

@@ -293,18 +293,19 @@ def test_gradient_accumulation_and_bf16_mode():
 
 
 def test_full_finetune_of_an_adapter_without_that_path_is_refused_loudly():
-    """Only the TimesFM adapter has the wgrad path; an unfrozen Chronos-2 adapter must not silently train nothing."""
-    from tsfmx_b200.tsfm.chronos import Chronos2Adapter, Chronos2Module
-    from tsfmx_b200.tsfm.chronos import init_random_ as init_chronos_
+    """TimesFM and Chronos-2 have the wgrad path; an unfrozen Chronos-T5 adapter (not a reference adapter) must not
+    silently train nothing."""
+    from tsfmx_b200.tsfm.chronos_t5 import ChronosT5Adapter, ChronosT5Module
+    from tsfmx_b200.tsfm.chronos_t5 import init_random_ as init_t5_
 
-    module = Chronos2Module(1)
-    init_chronos_(module, 0)
-    dec = MultimodalDecoder(Chronos2Adapter(module), MultimodalDecoderConfig(384, 1, [])).to(DEV).train()
+    module = ChronosT5Module(num_layers=1)
+    init_t5_(module, 0)
+    adapter = ChronosT5Adapter(module)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(384, 1, [])).to(DEV).train()
     dec.adapter.unfreeze_parameters()
-    ctx, masks, _t, _ = O.synthetic_batch(2, 512, 16, patch_len=16)
-    text = torch.randn(2, 32, 384)
+    ctx, masks, text, _ = O.synthetic_batch(2, 64, 8)
     with pytest.raises(NotImplementedError, match="no full fine-tuning path"):
-        dec(16, ctx.to(DEV), masks.to(DEV), text.to(DEV))
+        dec(8, ctx.to(DEV), masks.to(DEV), adapter.expand_text_embeddings(text, 64).to(DEV))
 
 
 # ----------------------------------------------------------------------------- full fine-tuning ("baseline" mode)
@@ -365,3 +366,108 @@ def test_full_finetune_gradients_match_oracle(with_text, padded):
         assert ((gf.double() - rf.double()).norm() / rf.double().norm()).item() < 2e-3
     else:
         assert dec.fusion.linears()[0].weight.grad is None
+
+
+# ------------------------------------------------------------------------------------------------ loss curves
+def _samples(n, horizon=64, seed=77):
+    ctx, _m, text, hor = O.synthetic_batch(n, 512, horizon, seed=seed)
+    return [{"context": ctx[i].numpy(), "horizon": hor[i].numpy(), "text_embeddings": text[i].numpy(), "metadata": {"i": i}}
+            for i in range(n)]
+
+
+def _train_args(tmp_path, lr, **kw):
+    import types
+
+    base = dict(per_device_train_batch_size=4, per_device_eval_batch_size=4, gradient_accumulation_steps=1,
+                max_grad_norm=1.0, learning_rate=lr, weight_decay=0.01, num_train_epochs=1, seed=3, warmup_steps=0.25,
+                lr_scheduler_type="linear", save_strategy="no", checkpoint_dir=tmp_path / "ckpt")
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def _reference_loop(oracle, params, samples, args, collate, with_text):
+    """The reference's train_epoch (trainer.py:186-231) restated on the CPU oracle: same DataLoader order (same seeded
+    generator), MSE on the point forecast, clip, AdamW, linear warm-up schedule stepped per optimizer step."""
+    from torch.utils.data import DataLoader
+
+    from tsfmx_b200.trainer import linear_schedule_with_warmup
+
+    loader = DataLoader(samples, batch_size=args.per_device_train_batch_size, shuffle=True, num_workers=0, collate_fn=collate,
+                        generator=torch.Generator().manual_seed(args.seed))
+    total = args.num_train_epochs * len(loader)
+    opt = torch.optim.AdamW(params, lr=args.learning_rate, weight_decay=args.weight_decay)
+    import math
+    sched = linear_schedule_with_warmup(opt, math.ceil(total * args.warmup_steps), total)
+    losses = []
+    for batch in loader:
+        ctx, hor = batch["context"], batch["horizon"]
+        pad = torch.zeros_like(ctx, dtype=torch.bool)
+        point = oracle(hor.shape[-1], ctx, pad, batch["text_embeddings"] if with_text else None)
+        loss = torch.nn.functional.mse_loss(point, hor)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, args.max_grad_norm)
+        opt.step()
+        opt.zero_grad()
+        sched.step()
+        losses.append(loss.item())
+    return losses
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_fusion_finetune_loss_curve_matches_oracle(tmp_path, graphs):
+    """identical loss curve for >= 10 optimizer steps with the same seed and batches.  12 steps
+    of the reference's fine-tune loop (frozen adapter, trainable fusion) through MultimodalTrainer - eager, and with the
+    forward + backward replayed from a CUDA graph from the second batch on - against oracle autograd + torch AdamW."""
+    from tsfmx_b200.data import multimodal_collate_fn
+    from tsfmx_b200.trainer import MultimodalTrainer
+
+    dec, oracle = build(2)
+    dec.set_precision("bf16x3")
+    samples = _samples(48)
+    args = _train_args(tmp_path, lr=2e-3, cuda_graphs=graphs)
+    oracle.adapter.freeze_parameters()
+    ref_params = list(oracle.fusion.parameters())
+    for p in ref_params:
+        p.requires_grad_(True)
+    ref_losses = _reference_loop(oracle, ref_params, samples, args, multimodal_collate_fn, True)
+    trainer = MultimodalTrainer(dec, args, samples, samples[:8], "multimodal", torch.device(DEV))
+    got = []
+    micro = trainer._micro_batch
+    trainer._micro_batch = lambda batch, accum: got.append(micro(batch, accum)) or got[-1]
+    epoch_loss = trainer.train_epoch()
+    got = [float(x) for x in got]
+    assert len(got) == len(ref_losses) == 12 and trainer.global_step == 12
+    assert trainer.graph_replays == (11 if graphs else 0)
+    print("loss curve (product / oracle):", [f"{a:.5f}/{b:.5f}" for a, b in zip(got, ref_losses)])
+    for a, b in zip(got, ref_losses):
+        assert a == pytest.approx(b, rel=1e-3), (got, ref_losses)
+    assert ref_losses[-1] < ref_losses[0]  # and it is actually learning
+    assert epoch_loss == pytest.approx(sum(ref_losses) / 12, rel=1e-3)
+    w_ref = ref_params[0].detach()
+    assert rel_l2(dec.fusion.linears()[0].weight.detach().cpu(), w_ref) < 1e-3
+
+
+def test_full_finetune_loss_curve_matches_oracle(tmp_path):
+    """The same for the reference's "baseline" mode (trainer.py:78-79: every adapter parameter trained, no text): 10
+    optimizer steps, graph replay from the second batch on."""
+    from tsfmx_b200.data import baseline_collate_fn
+    from tsfmx_b200.trainer import MultimodalTrainer
+
+    dec, oracle = build(2)
+    dec.set_precision("bf16x3")
+    samples = [{k: v for k, v in s.items() if k != "text_embeddings"} for s in _samples(40, seed=78)]
+    args = _train_args(tmp_path, lr=2e-4, cuda_graphs=True)
+    oracle.adapter.unfreeze_parameters()
+    ref_params = list(oracle.adapter.parameters())
+    ref_losses = _reference_loop(oracle, ref_params, samples, args, baseline_collate_fn, False)
+    trainer = MultimodalTrainer(dec, args, samples, samples[:8], "baseline", torch.device(DEV))
+    got = []
+    micro = trainer._micro_batch
+    trainer._micro_batch = lambda batch, accum: got.append(micro(batch, accum)) or got[-1]
+    trainer.train_epoch()
+    got = [float(x) for x in got]
+    assert len(got) == len(ref_losses) == 10 and trainer.graph_replays == 9
+    print("full fine-tune loss curve (product / oracle):", [f"{a:.5f}/{b:.5f}" for a, b in zip(got, ref_losses)])
+    for a, b in zip(got, ref_losses):
+        assert a == pytest.approx(b, rel=2e-3), (got, ref_losses)
+    assert ref_losses[-1] < ref_losses[0]

@@ -127,8 +127,11 @@ def test_trainer_checkpoint_strategies(tmp_path):
     assert "adapter_state_dict" in base.build_checkpoint() and "fusion_state_dict" not in base.build_checkpoint()
     assert len(list(base._get_trainable_params())) == len(list(dec.adapter.parameters()))
     c2 = MultimodalDecoder(Chronos2Adapter(Chronos2Module(1)), MultimodalDecoderConfig())
+    MultimodalTrainer(c2, args, dummy, dummy, "baseline", torch.device("cpu"))   # Chronos-2: full fine-tuning too
+    assert all(p.requires_grad for p in c2.adapter.parameters())
+    t5 = MultimodalDecoder(ChronosT5Adapter(ChronosT5Module(num_layers=1)), MultimodalDecoderConfig())
     with pytest.raises(NotImplementedError):
-        MultimodalTrainer(c2, args, dummy, dummy, "baseline", torch.device("cpu"))
+        MultimodalTrainer(t5, args, dummy, dummy, "baseline", torch.device("cpu"))
     with pytest.raises(ValueError):
         MultimodalTrainer(dec, args, dummy, dummy, "something", torch.device("cpu"))
 

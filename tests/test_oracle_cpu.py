@@ -283,3 +283,82 @@ def test_decode_loop_reduces_to_forward_full_and_extends_it():
         emb[:, :8] = decoder.fusion(emb[:, :8], text)
         by_hand = adapter.postprocess(128, adapter(emb, pre.masks), pre.normalization_stats)
         assert (long[:, 128:256] - by_hand).abs().max() < 1e-4 * by_hand.abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ Chronos-2 sub-blocks
+def test_chronos2_blocks_coincide_with_transformers_t5():
+    """Chronos-2 is built from T5 parts (upstream subclasses / copies transformers' T5 modules).  Where the restated
+    oracle's sub-blocks coincide with `transformers.models.t5` they are pinned to it on identical weights: the RMS
+    LayerNorm, the ReLU feed-forward sub-layer (residual included), the bias-free un-scaled multi-head attention of the
+    group-attention sub-layer, and the rotary embedding (against transformers' Llama implementation: same rotate-half
+    convention and inv_freq).  What stays unpinned is listed in DESIGN.md section 3."""
+    from transformers import T5Config
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    from transformers.models.t5 import modeling_t5 as t5
+
+    from oracle import chronos2_oracle as C
+
+    torch.manual_seed(0)
+    cfg = C.Chronos2Config(num_layers=1)
+    tcfg = T5Config(d_model=cfg.d_model, d_kv=cfg.d_kv, num_heads=cfg.num_heads, d_ff=cfg.d_ff, dropout_rate=0.0,
+                    layer_norm_epsilon=cfg.layer_norm_epsilon, feed_forward_proj="relu", is_decoder=False)
+    block = C.EncoderBlock(cfg).eval()
+    for prm in block.parameters():
+        torch.nn.init.normal_(prm, std=0.05)
+    with torch.no_grad():
+        block.ff_ln.weight.add_(1.0), block.group_ln.weight.add_(1.0), block.time_ln.weight.add_(1.0)
+    h = torch.randn(3, 29, cfg.d_model)
+
+    # RMS LayerNorm == T5LayerNorm
+    ln = t5.T5LayerNorm(cfg.d_model, eps=cfg.layer_norm_epsilon)
+    ln.weight.data.copy_(block.ff_ln.weight)
+    assert torch.equal(ln(h), block.ff_ln(h))
+
+    # feed-forward sub-layer == T5LayerFF (pre-norm, ReLU, residual)
+    ff = t5.T5LayerFF(tcfg).eval()
+    ff.layer_norm.weight.data.copy_(block.ff_ln.weight)
+    ff.DenseReluDense.wi.weight.data.copy_(block.wi.weight)
+    ff.DenseReluDense.wo.weight.data.copy_(block.wo.weight)
+    with torch.no_grad():
+        mine = h + block.wo(torch.relu(block.wi(block.ff_ln(h))))
+        assert (ff(h) - mine).abs().max() < 1e-5 * mine.abs().max()
+
+    # attention without RoPE (group attention) == T5Attention without relative bias: no 1/sqrt(d), additive mask
+    att = t5.T5Attention(tcfg, has_relative_attention_bias=False).eval()
+    for name in "qkvo":
+        getattr(att, name).weight.data.copy_(getattr(block.group_attn, name).weight)
+    keep = torch.ones(3, 29)
+    keep[1, :7] = 0
+    mask = (1.0 - keep[:, None, None, :]) * torch.finfo(torch.float32).min
+    with torch.no_grad():
+        ref = att(h, mask=mask)[0]
+        got = block.group_attn(h, mask)
+    assert (ref - got).abs().max() < 1e-5 * ref.abs().max()
+
+    # RoPE: rotate-half convention and frequencies == transformers' Llama rotary embedding
+    q = torch.randn(3, cfg.num_heads, 29, cfg.d_kv)
+    k = torch.randn(3, cfg.num_heads, 29, cfg.d_kv)
+    pos = torch.arange(29)[None, :].expand(3, -1)
+    inv_freq = block.time_attn.inv_freq
+    freqs = pos[:, :, None].float() * inv_freq[None, None, :]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    q_ref, k_ref = apply_rotary_pos_emb(q, k, emb.cos(), emb.sin())
+    cos, sin = emb.cos()[:, None], emb.sin()[:, None]
+    assert torch.allclose(q * cos + C.rotate_half(q) * sin, q_ref, atol=1e-6)
+    assert torch.allclose(k * cos + C.rotate_half(k) * sin, k_ref, atol=1e-6)
+    llama_inv = 1.0 / (10000.0 ** (torch.arange(0, cfg.d_kv, 2, dtype=torch.int64).float() / cfg.d_kv))
+    assert torch.equal(inv_freq, llama_inv)
+
+    # time attention = the same T5 attention core applied to RoPE-rotated q / k (composition of the two pinned parts)
+    att_t = t5.T5Attention(tcfg, has_relative_attention_bias=False).eval()
+    for name in "qkvo":
+        getattr(att_t, name).weight.data.copy_(getattr(block.time_attn, name).weight)
+    with torch.no_grad():
+        def heads(t):
+            return t.view(3, 29, cfg.num_heads, cfg.d_kv).transpose(1, 2)
+        qh, kh, vh = heads(att_t.q(h)), heads(att_t.k(h)), heads(att_t.v(h))
+        qh, kh = apply_rotary_pos_emb(qh, kh, emb.cos(), emb.sin())
+        w = torch.softmax(qh @ kh.transpose(3, 2) + mask, dim=-1)
+        ref_t = att_t.o((w @ vh).transpose(1, 2).reshape(3, 29, -1))
+        got_t = block.time_attn(h, mask, pos)
+    assert (ref_t - got_t).abs().max() < 1e-5 * ref_t.abs().max()
