@@ -427,11 +427,13 @@ def run_b200_arm(args) -> None:
             # events around a GEMM launch measure that launch (with lanes the events would also count the time a
             # GEMM queues behind the other lane's GEMM for the SMs)
             dec.lanes = 1
+            adapter.stack_call = False  # one library call per kernel, so that each GEMM launch gets its own event pair
             roof_steps = max(1, min(args.steps, 4))
             step_resident(0)
             timer.enabled = True
             ms_serial = timed(step_resident, roof_steps) / roof_steps
             timer.enabled = False
+            adapter.stack_call = True
             dec.lanes = args.lanes
             # e2e with the FORECASTS coming back: MultimodalEvaluator.predict over the same pinned host batches, every
             # (B, horizon, 10) forecast copied device -> host inside the timed region (a forecast consumer's view; the

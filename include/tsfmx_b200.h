@@ -365,6 +365,50 @@ int tsfmx_mask_cast_rows(const float* in, int64_t rows, int32_t cols, const void
                          int64_t ld_mask, int32_t out_dtype, void* out, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Whole-stack entry point (one FFI crossing per forward instead of one per kernel)
+ * ---------------------------------------------------------------------- */
+
+/* Weights of one TimesFM 2.5 decoder layer, as the library consumes them: Linear weights K-major [out, in] packed to
+ * bf16 (precision BF16) or split bf16 [out, 2 * in] (BF16X3) with tsfmx_cast_rows; norm scales fp32. */
+typedef struct {
+  const void* qkv;   /* [3 D, D]   attn.qkv_proj.weight */
+  const void* out;   /* [D, D]     attn.out.weight */
+  const void* ff0;   /* [F, D]     ff0.weight */
+  const void* ff1;   /* [D, F]     ff1.weight */
+  const float* pre_attn_ln;  /* [D] */
+  const float* post_attn_ln; /* [D] */
+  const float* pre_ff_ln;    /* [D] */
+  const float* post_ff_ln;   /* [D] */
+  const float* q_ln;    /* [hd] attn.query_ln.scale */
+  const float* k_ln;    /* [hd] attn.key_ln.scale */
+  const float* q_scale; /* [hd] softplus(per_dim_scale) * 1.442695041 / sqrt(hd) */
+} tsfmx_timesfm_layer;
+
+typedef struct {
+  int32_t num_layers, model_dims, num_heads, head_dim, ff_dims;
+  int32_t precision; /* TSFMX_PREC_* */
+  float eps;
+  int32_t reserved;
+  const float* inv_freq;             /* [hd / 2] device */
+  const tsfmx_timesfm_layer* layers; /* HOST array of num_layers entries (device pointers inside) */
+} tsfmx_timesfm_stack;
+
+/* Bytes of scratch tsfmx_timesfm_stack_fwd needs for `batch` series of `num_patches` tokens (0 on a bad table). */
+size_t tsfmx_timesfm_stack_workspace_bytes(const tsfmx_timesfm_stack* stack, int64_t batch, int32_t num_patches);
+
+/*
+ * All decoder layers of TimesFM 2.5: replaces `for layer in stacked_xf: x = layer(x, masks[..., -1], None)`
+ * (reference tsfmx/tsfm/timesfm.py:95-98).  Per layer: qkv GEMM -> attention -> out GEMM -> post-norm + residual +
+ * pre-norm -> ff0 GEMM (SiLU) -> ff1 GEMM -> post-norm + residual + next pre-norm; the same kernels, in the same
+ * order, as the per-kernel entry points above.
+ *   x [B*N, D] fp32 (input embeddings, read only), patch_mask [B, N] u8 / num_masked [B] as in tsfmx_timesfm_attention,
+ *   workspace: caller-owned, 256-byte aligned, >= tsfmx_timesfm_stack_workspace_bytes(...);  y [B*N, D] fp32 (!= x).
+ */
+int tsfmx_timesfm_stack_fwd(const tsfmx_timesfm_stack* stack, int64_t batch, int32_t num_patches, const float* x,
+                            const uint8_t* patch_mask, const int32_t* num_masked, void* workspace,
+                            size_t workspace_bytes, float* y, void* stream);
+
+/* ------------------------------------------------------------------------
  * TimesFM 2.5 autoregressive decode (horizon > 128) and forecast extras.
  * Beyond the reference adapter, which raises for horizon > output_patch_len
  * (reference tsfmx/tsfm/timesfm.py:116-119); follows upstream timesfm's decode loop
@@ -414,7 +458,8 @@ int tsfmx_timesfm_forecast_finalize(const float* pf, const float* spread, const 
                                     int32_t use_continuous_quantile_head, int32_t infer_is_positive, float* out,
                                     void* stream);
 
-/* tuning hook: key 0 = series per warp of timesfm_patchify_norm, key 1 = its warps per block (0 = default) */
+/* tuning hook (A/B runs): key 0 = series per warp tile of timesfm_patchify_norm, key 1 = its warps per block,
+ * key 2 / key 3 != 0 force the generic fallback kernel of chronos_t5_tokenize / timesfm_patchify_norm (0 = default) */
 int tsfmx_tune(int32_t key, int32_t value);
 
 /* test hook: non-zero forces the fp32 SIMT attention kernel even where the tensor-core kernel applies */

@@ -31,6 +31,7 @@ SOURCES = [
     "chronos.cu",
     "t5.cu",
     "decode.cu",
+    "stack.cu",
 ]
 
 NVCC_FLAGS = [

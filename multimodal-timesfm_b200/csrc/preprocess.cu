@@ -186,227 +186,19 @@ __global__ void __launch_bounds__(WARPS * 32) timesfm_patchify_norm_generic_kern
 }
 
 // ----------------------------------------------------------------------------------------
-// TMA-pipelined variant (the default for context <= 4096): a persistent block walks over tiles of G consecutive
-// series.  One thread keeps a ring of STAGES tiles in flight with 1-D bulk copies (cp.async.bulk, completion on an
-// mbarrier), so the HBM reads of the next tiles overlap the arithmetic of the current one and cost no load
-// instructions; the block computes the per-patch statistics (8 lanes per patch), thread s runs the sequential merge
-// of series s (reference order: one dependent chain of divisions / square roots per series, paid once per tile for up
-// to 32 series side by side), and the block normalises from shared memory and streams the tokens out with full-line
-// 16-byte stores.  Slot layout: patch k of series s at (k * G + s) * 3 floats (stride 3: conflict-free merge scan).
+// Running-statistics helpers of the TimesFM kernels
 // ----------------------------------------------------------------------------------------
-constexpr int TF_THREADS = 256;
 constexpr int TF_BLOCKED_MIN_PATCHES = 16;  // contexts above 512 use the blocked fold of the running statistics
 
 struct RunStats {
   float n, mu, sigma;
 };
 
-// One step of the reference's update_running_stats: (n, mu, sigma) of the union of the running set and one patch.
-__device__ __forceinline__ RunStats merge_stats(RunStats run, float inc_n, float inc_mu, float inc_sigma) {
-  const float new_n = __fadd_rn(run.n, inc_n);
-  const float new_n_safe = new_n == 0.f ? 1.f : new_n;
-  float new_mu = __fdiv_rn(__fadd_rn(__fmul_rn(run.n, run.mu), __fmul_rn(inc_mu, inc_n)), new_n_safe);
-  if (new_n == 0.f) new_mu = 0.f;
-  const float d1 = __fsub_rn(run.mu, new_mu), d2 = __fsub_rn(inc_mu, new_mu);
-  const float t1 = __fmul_rn(run.n, __fmul_rn(run.sigma, run.sigma));
-  const float t2 = __fmul_rn(inc_n, __fmul_rn(inc_sigma, inc_sigma));
-  const float t3 = __fmul_rn(run.n, __fmul_rn(d1, d1));
-  const float t4 = __fmul_rn(inc_n, __fmul_rn(d2, d2));
-  float new_var = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4), new_n_safe);
-  if (new_n == 0.f) new_var = 0.f;
-  return RunStats{new_n, new_mu, sqrtf(fmaxf(new_var, 0.f))};
-}
-
-template <int OUT>
-__global__ void __launch_bounds__(TF_THREADS) timesfm_patchify_norm_tma_kernel(
-    const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, int group_size,
-    int stages, void* tokens, float* __restrict__ mu_out, float* __restrict__ sigma_out,
-    uint8_t* __restrict__ patch_mask_out, int32_t* __restrict__ num_masked_out) {
-  extern __shared__ __align__(128) uint8_t smem_tma[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int pg = tid >> 3, q = tid & 7;  // phase C: patch group (32 per block) and quad inside the patch
-  const int N = context >> 5;
-  const int G = group_size;
-  const int stage_bytes = (G * context * 5 + 127) & ~127;
-  // slot of patch k of series s: 4 floats at (k * G + s) * 4 -> the merge thread of series s reads/writes 16 bytes,
-  // consecutive threads consecutive slots (conflict-free)
-  float4* slots = reinterpret_cast<float4*>(smem_tma + stages * stage_bytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slots + G * N + G * ((N + 7) >> 3));
-  __shared__ int s_masked[32];
-  const float inv_n = 1.0f / static_cast<float>(N);
-  const int64_t num_tiles = (batch + G - 1) / G;
-
-  auto issue = [&](int64_t tile, int stage) {
-    const int64_t b0 = tile * G;
-    const uint32_t cnt = static_cast<uint32_t>(batch - b0 < G ? batch - b0 : G);
-    uint8_t* dst = smem_tma + stage * stage_bytes;
-    mbar_arrive_expect_tx(&full_bar[stage], cnt * context * 5u);
-    bulk_load_1d(dst, x + b0 * context, cnt * context * 4u, &full_bar[stage]);
-    bulk_load_1d(dst + G * context * 4, mask + b0 * context, cnt * context, &full_bar[stage]);
-  };
-
-  if (tid == 0) {
-    for (int i = 0; i < stages; ++i) mbar_init(&full_bar[i], 1);
-    fence_barrier_init();
-    for (int i = 0; i < stages; ++i) {
-      const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
-      if (tile < num_tiles) issue(tile, i);
-    }
-  }
-  __syncthreads();
-
-  // chunk rotation of phase A: lane l reads 16-byte chunk (j + rot) & 7 of its patch at step j, so that the 8 lanes
-  // of a quarter warp hit 8 different bank groups (patches are 128 bytes apart) and the 4-byte mask reads of the
-  // whole warp hit 32 different banks
-  const int rot = lane + (lane >> 3);
-  int stage = 0;
-  uint32_t parity = 0;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t b0 = tile * G;
-    const int cnt = static_cast<int>(batch - b0 < G ? batch - b0 : G);
-    const int P = cnt * N;
-    const float* sx = reinterpret_cast<const float*>(smem_tma + stage * stage_bytes);
-    const uint8_t* sm = smem_tma + stage * stage_bytes + G * context * 4;
-    mbar_wait(&full_bar[stage], parity);
-
-    // ---- phase A: statistics of every patch, one thread per patch (no shuffles)
-    for (int p = tid; p < P; p += TF_THREADS) {
-      const float4* xp = reinterpret_cast<const float4*>(sx + p * 32);
-      const uint32_t* mp = reinterpret_cast<const uint32_t*>(sm + p * 32);
-      float xv[32];
-      uint32_t mbits = 0;  // bit e = element e of the patch is padded
-      float c = 0.f, sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int ch = (j + rot) & 7;
-        const float4 v = xp[ch];
-        const uint32_t mk = mp[ch];
-        xv[4 * j + 0] = v.x, xv[4 * j + 1] = v.y, xv[4 * j + 2] = v.z, xv[4 * j + 3] = v.w;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool padded = ((mk >> (8 * k)) & 0xffu) != 0;
-          mbits |= (padded ? 1u : 0u) << (4 * j + k);
-          c += padded ? 0.f : 1.f;
-          sum += padded ? 0.f : xv[4 * j + k];
-        }
-      }
-      const float c_safe = c == 0.f ? 1.f : c;
-      const float inc_mu = c == 0.f ? 0.f : __fdiv_rn(sum, c_safe);
-      float sq = 0.f;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float d = ((mbits >> e) & 1u) ? 0.f : xv[e] - inc_mu;
-        sq = fmaf(d, d, sq);
-      }
-      const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
-      const int k = p - s * N;
-      // the patch counts as padded iff its LAST element is padded (timesfm.py:97)
-      const float flag = sm[p * 32 + 31] ? 1.f : 0.f;
-      slots[k * G + s] = make_float4(c, inc_mu, c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f)), flag);
-    }
-    __syncthreads();
-    // ---- phase B: merge of the running statistics (reference formula; HF twin modeling_timesfm2_5.py:528-568); the
-    //      slot becomes {cumulative mu, cumulative sigma, 1 / safe sigma, padded flag}
-    if (N <= TF_BLOCKED_MIN_PATCHES) {
-      // reference order exactly: thread s folds the N patches of series s one after the other
-      if (tid < cnt) {
-        RunStats st = {0.f, 0.f, 0.f};
-        int masked = 0;
-        for (int i = 0; i < N; ++i) {
-          const float4 inc = slots[i * G + tid];
-          st = merge_stats(st, inc.x, inc.y, inc.z);
-          slots[i * G + tid] = make_float4(st.mu, st.sigma, __fdiv_rn(1.0f, st.sigma < 1e-6f ? 1.f : st.sigma), inc.w);
-          masked += inc.w != 0.f ? 1 : 0;
-        }
-        if (num_masked_out != nullptr) num_masked_out[b0 + tid] = masked;
-      }
-    } else {
-      // long contexts: the N-step chain (two IEEE divisions and a square root per step) would leave the block idle, so
-      // the fold is cut into blocks of 8 patches: (1) every (series, block) thread folds its block from the empty
-      // state, (2) one thread per series folds the block summaries into the state BEFORE each block, (3) every
-      // (series, block) thread folds its patches again from that state.  Same merge formula at every step; the result
-      // differs from the strictly sequential fold only by fp32 rounding (a few 1e-7 relative).
-      const int NB = (N + 7) >> 3;
-      float4* blk = slots + G * N;  // [NB][G] block summaries, then the state before each block
-      for (int u = tid; u < cnt * NB; u += TF_THREADS) {
-        const int b = u / cnt, sr = u - b * cnt;
-        const int k1 = min(N, 8 * b + 8);
-        RunStats st = {0.f, 0.f, 0.f};
-        for (int i = 8 * b; i < k1; ++i) {
-          const float4 inc = slots[i * G + sr];
-          st = merge_stats(st, inc.x, inc.y, inc.z);
-        }
-        blk[b * G + sr] = make_float4(st.n, st.mu, st.sigma, 0.f);
-      }
-      __syncthreads();
-      if (tid < cnt) {
-        RunStats st = {0.f, 0.f, 0.f};
-        for (int b = 0; b < NB; ++b) {
-          const float4 inc = blk[b * G + tid];
-          blk[b * G + tid] = make_float4(st.n, st.mu, st.sigma, 0.f);  // exclusive prefix
-          st = merge_stats(st, inc.x, inc.y, inc.z);
-        }
-        s_masked[tid] = 0;
-      }
-      __syncthreads();
-      for (int u = tid; u < cnt * NB; u += TF_THREADS) {
-        const int b = u / cnt, sr = u - b * cnt;
-        const int k1 = min(N, 8 * b + 8);
-        const float4 pre = blk[b * G + sr];
-        RunStats st = {pre.x, pre.y, pre.z};
-        int masked = 0;
-        for (int i = 8 * b; i < k1; ++i) {
-          const float4 inc = slots[i * G + sr];
-          st = merge_stats(st, inc.x, inc.y, inc.z);
-          slots[i * G + sr] = make_float4(st.mu, st.sigma, __fdiv_rn(1.0f, st.sigma < 1e-6f ? 1.f : st.sigma), inc.w);
-          masked += inc.w != 0.f ? 1 : 0;
-        }
-        if (masked) atomicAdd(&s_masked[sr], masked);
-      }
-      __syncthreads();
-      if (tid < cnt && num_masked_out != nullptr) num_masked_out[b0 + tid] = s_masked[tid];
-    }
-    __syncthreads();
-    // ---- mu / sigma / patch mask out, coalesced (the tile's [cnt, N] block is contiguous in [B, N])
-    for (int i = tid; i < P; i += TF_THREADS) {
-      const int s = static_cast<int>((static_cast<float>(i) + 0.5f) * inv_n);
-      const int k = i - s * N;
-      const float4 st = slots[k * G + s];
-      if (mu_out != nullptr) mu_out[b0 * N + i] = st.x;
-      if (sigma_out != nullptr) sigma_out[b0 * N + i] = st.y;
-      if (patch_mask_out != nullptr) patch_mask_out[b0 * N + i] = st.w != 0.f ? 1 : 0;
-    }
-    // ---- phase C: RevIN with the cumulative stats of the own patch, zero the padded points, emit tokens
-    //      (8 lanes per patch: every store instruction writes whole 128-byte lines)
-    for (int p = pg; p < P; p += TF_THREADS / 8) {
-      const int s = static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
-      const int k = p - s * N;
-      const float4 st = slots[k * G + s];
-      const float4 v = *reinterpret_cast<const float4*>(sx + p * 32 + 4 * q);
-      const uint32_t mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
-      const float xv[4] = {v.x, v.y, v.z, v.w};
-      float val[4], msk[4];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const bool padded = ((mk >> (8 * kk)) & 0xffu) != 0;
-        msk[kk] = padded ? 1.f : 0.f;
-        val[kk] = padded ? 0.f : (xv[kk] - st.x) * st.z;
-      }
-      store_token_quad<OUT>(tokens, b0 * N + p, q, val, msk);
-    }
-    __syncthreads();  // every thread is done with this stage and with the slots
-    if (tid == 0) {
-      const int64_t next = tile + static_cast<int64_t>(stages) * gridDim.x;
-      if (next < num_tiles) issue(next, stage);
-    }
-    if (++stage == stages) { stage = 0; parity ^= 1; }
-  }
-}
-
 // ----------------------------------------------------------------------------------------
-// Warp-private TMA variant (the default for context <= 4096).  The block-wide kernel above leaves 240 of its 256
-// threads at a barrier while one thread per series runs the dependent merge chain (ncu: 5.9 barrier-stall cycles per
-// issued instruction, 24 % of the warp slots occupied).  Here every WARP owns its tiles — about 32 patches: 2 series
+// Warp-private TMA kernel (context <= 4096; longer or unaligned rows take the generic kernel at the top).  A
+// block-wide version of it left 240 of its 256 threads at a barrier while one thread per series ran the dependent merge
+// chain (ncu: 5.9 barrier-stall cycles per issued instruction, 24 % of the warp slots occupied; profiles/
+// r1e_ncu_patchify_blockwide.md).  Here every WARP owns its tiles — about 32 patches: 2 series
 // at context 512, one series from context 1024 — with its own two-deep ring of bulk copies and its own mbarriers, and
 // no block-wide barrier after start-up: while a few lanes of one warp walk their merge chain, the scheduler runs the
 // statistics and the token stores of the other warps.  Slots are series-major (slot of patch p of the tile at p).
@@ -426,8 +218,9 @@ __device__ __forceinline__ float div_known_recip(float a, float n, float r) {
   return __fdiv_rn(a, n);
 }
 
-// merge_stats with the new count and its reciprocal supplied (the counts do not depend on the values, so they are
-// scanned and inverted by all lanes in parallel before the dependent chain starts)
+// One step of the reference's update_running_stats - (n, mu, sigma) of the union of the running set and one patch -
+// with the new count and its reciprocal supplied (the counts do not depend on the values, so they are scanned and
+// inverted by all lanes in parallel before the dependent chain starts)
 __device__ __forceinline__ RunStats merge_stats_r(RunStats run, float inc_n, float inc_mu, float inc_sigma, float new_n,
                                                   float r) {
   const float new_n_safe = new_n == 0.f ? 1.f : new_n;
@@ -963,6 +756,23 @@ __global__ void __launch_bounds__(WARPS * 32) chronos_t5_tokenize_kernel(
   }
 }
 
+// Search of the boundary table kept in shared memory between two sentinels (-inf below, NaN above), so that it
+// needs no bounds checks: the uniform-grid guess is verified against its two neighbouring entries and only a miss walks
+// the table (exact for any ascending table).
+__device__ __forceinline__ int bucketize_right_sentinel(const float* __restrict__ sp, int nb, float v, float g_mul,
+                                                        float g_add) {
+  // sp[0] = -inf, sp[1 + i] = boundaries[i], sp[nb + 1] = NaN; returns #boundaries <= v (v is not NaN)
+  float g = fmaf(v, g_mul, g_add);
+  g = fminf(fmaxf(g, 0.f), static_cast<float>(nb));
+  int i = static_cast<int>(g);  // candidate count in [0, nb]
+  const float lo = sp[i], hi = sp[i + 1];
+  if (!(lo <= v) || hi <= v) {
+    while (!(sp[i] <= v)) --i;
+    while (sp[i + 1] <= v) ++i;
+  }
+  return i;
+}
+
 // Staged variant (the default for context % 4 == 0, context <= 2048).  Same arithmetic as the vectorised kernel
 // above, but the tokens and mask bytes of a series go through a per-warp shared-memory row first, so that what
 // leaves the SM is re-tiled to the ROW's alignment in global memory: every 16-byte id store is one aligned pair
@@ -1196,37 +1006,15 @@ int grid_for_series(int64_t batch) {
   return static_cast<int>(blocks < cap ? blocks : cap);
 }
 
-int g_tf_group = 0, g_tf_warps = 0, g_t5_variant = 0, g_tf_variant = 0;  // tuning hooks (0 = default)
+// tuning hooks (0 = default): series per warp tile / warps per block of the TimesFM kernel; g_t5_variant = 1 and
+// g_tf_variant = 1 force the generic fallback kernels (A/B runs, tests of the fallbacks)
+int g_tf_group = 0, g_tf_warps = 0, g_t5_variant = 0, g_tf_variant = 0;
 
 template <int OUT>
 int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, int context, void* tokens, float* mu,
                           float* sigma, uint8_t* patch_mask, int32_t* num_masked, cudaStream_t stream) {
   const int N = context >> 5;
-  if (g_tf_variant == 1) {  // A/B: warp-staged cp.async kernel
-    int G = g_tf_group > 0 ? g_tf_group : 2048 / context;
-    if (G > 4) G = 4;
-    if (G < 1) G = 1;
-    const int per_warp = ((G * context * 5 + G * (3 * N + 1) * 4) + 15) & ~15;
-    int warps = g_tf_warps > 0 ? g_tf_warps : 4;
-    while (warps > 1 && warps * per_warp > 100 * 1024) --warps;
-    const int smem = warps * per_warp;
-    auto kern = timesfm_patchify_norm_kernel<OUT>;
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) {
-        set_error("timesfm_patchify_norm: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
-        return TSFMX_ERR_CUDA;
-      }
-    }
-    const int64_t groups = (batch + G - 1) / G;
-    const int64_t blocks = (groups + warps - 1) / warps;
-    const int per_sm = (220 * 1024) / smem > 0 ? (220 * 1024) / smem : 1;
-    const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm * 2;
-    const int grid = static_cast<int>(blocks < cap ? blocks : cap);
-    kern<<<grid, warps * 32, smem, stream>>>(x, mask, batch, context, G, tokens, mu, sigma, patch_mask, num_masked);
-    return check_last_launch("timesfm_patchify_norm");
-  }
-  if ((g_tf_variant == 0 || g_tf_variant == 2) && context <= 4096) {  // warp-private tiles, no block-wide barriers
+  if (context <= 4096) {  // warp-private tiles, no block-wide barriers
     // series per tile: phase B keeps one lane per series busy, so more series per tile means fewer (mostly idle)
     // warp instructions per series; the tile still has to leave room for >= 12 warps per SM
     int g = g_tf_group > 0 ? g_tf_group : 2048 / context;
@@ -1262,38 +1050,8 @@ int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, in
                                              patch_mask, num_masked);
     return check_last_launch("timesfm_patchify_norm");
   }
-  // TMA-pipelined kernel: tiles of G series (<= 32: one merge thread per series), `stages` tiles in flight per block
-  int G = g_tf_group > 0 ? g_tf_group : (40 * 1024) / (context * 5);
-  if (G > 32) G = 32;
-  if (G < 1) G = 1;
-  int stages = g_tf_warps > 0 ? g_tf_warps : 2;
-  auto smem_for = [&](int g, int st) {
-    return st * ((g * context * 5 + 127) & ~127) + g * (N + ((N + 7) >> 3)) * 16 + st * 8 + 128;
-  };
-  while (stages > 1 && smem_for(G, stages) > 220 * 1024) --stages;
-  while (G > 1 && smem_for(G, stages) > 220 * 1024) --G;
-  const int smem = smem_for(G, stages);
-  TSFMX_REQUIRE(smem <= 227 * 1024, "timesfm_patchify_norm: context %d does not fit the staged kernel", context);
-  auto kern = timesfm_patchify_norm_tma_kernel<OUT>;
-  static int smem_set_dev[64] = {0};  // cudaFuncSetAttribute is per device
-  int& smem_set = smem_set_dev[current_device()];
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("timesfm_patchify_norm: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
-      return TSFMX_ERR_CUDA;
-    }
-    smem_set = smem;
-  }
-  const int64_t tiles = (batch + G - 1) / G;
-  int per_sm = (224 * 1024) / (smem + 1024);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2048 / TF_THREADS) per_sm = 2048 / TF_THREADS;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
-  const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-  kern<<<grid, TF_THREADS, smem, stream>>>(x, mask, batch, context, G, stages, tokens, mu, sigma, patch_mask,
-                                           num_masked);
-  return check_last_launch("timesfm_patchify_norm");
+  set_error("timesfm_patchify_norm: context %d is beyond the staged kernel", context);
+  return TSFMX_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -1331,7 +1089,7 @@ extern "C" int tsfmx_timesfm_patchify_norm(const float* x, const uint8_t* mask, 
   TSFMX_REQUIRE(tokens_dtype >= TSFMX_DT_F32 && tokens_dtype <= TSFMX_DT_BF16_SPLIT,
                 "timesfm_patchify_norm: bad tokens_dtype %d", tokens_dtype);
   if (batch == 0) return TSFMX_OK;
-  if (context <= 4096 && reinterpret_cast<uintptr_t>(mask) % 16 == 0) {
+  if (g_tf_variant == 0 && context <= 4096 && reinterpret_cast<uintptr_t>(mask) % 16 == 0) {
     switch (tokens_dtype) {
       case TSFMX_DT_F32:
         return launch_timesfm_staged<TSFMX_DT_F32>(x, mask, batch, context, tokens, mu, sigma, patch_mask, num_masked, stream);
@@ -1430,12 +1188,8 @@ extern "C" int tsfmx_chronos_t5_tokenize(const float* x, int64_t batch, int32_t 
   const int grid = grid_for_series(batch);
   const dim3 block(WARPS * 32);
   const size_t smem = static_cast<size_t>(n_boundaries) * sizeof(float);
-  const int variant = g_t5_variant > 0 ? g_t5_variant : (context <= 512 ? 1 : (context <= 2048 ? 2 : 3));
-  const bool vec_ok = (g_t5_variant == 0 || g_t5_variant == 4) && context % 4 == 0 && context <= 2048 && n_boundaries >= 4 && pad_id >= 0 &&
-                      reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(ids) % 16 == 0;
-  const size_t smem_vec = static_cast<size_t>(n_boundaries + 2) * sizeof(float);
-  // default: the staged kernel, any context that is a multiple of 4 (g_t5_variant == 4 keeps the direct-store
-  // vectorised kernel for A/B runs)
+  // default: the staged kernel, any context that is a multiple of 4; everything else (odd contexts, unaligned rows,
+  // tiny tables) takes the scalar kernel that re-reads the row
   const bool staged_ok = g_t5_variant == 0 && context % 4 == 0 && n_boundaries >= 4 && pad_id >= 0 &&
                          reinterpret_cast<uintptr_t>(x) % 16 == 0;
   if (staged_ok) {
@@ -1461,25 +1215,8 @@ extern "C" int tsfmx_chronos_t5_tokenize(const float* x, int64_t batch, int32_t 
           x, batch, context, boundaries, n_boundaries, n_special, n_tokens, pad_id, eos_id, ids, attn_mask, scale);
     return check_last_launch("chronos_t5_tokenize");
   }
-  if (vec_ok && context <= 512) {
-    chronos_t5_tokenize_vec_kernel<4><<<grid, block, smem_vec, stream>>>(x, batch, context, boundaries, n_boundaries,
-                                                                    n_special, n_tokens, pad_id, eos_id, ids, attn_mask,
-                                                                    scale);
-  } else if (vec_ok) {
-    chronos_t5_tokenize_vec_kernel<16><<<grid, block, smem_vec, stream>>>(x, batch, context, boundaries, n_boundaries,
-                                                                     n_special, n_tokens, pad_id, eos_id, ids, attn_mask,
-                                                                     scale);
-  } else if (variant == 1 && context <= 512) {
-    chronos_t5_tokenize_kernel<16><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries, n_special,
-                                                                 n_tokens, pad_id, eos_id, ids, attn_mask, scale);
-  } else if (variant == 2 && context <= 2048) {
-    chronos_t5_tokenize_kernel<64><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries,
-                                                                  n_special, n_tokens, pad_id, eos_id, ids, attn_mask,
-                                                                  scale);
-  } else {
-    chronos_t5_tokenize_kernel<0><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries, n_special,
-                                                                 n_tokens, pad_id, eos_id, ids, attn_mask, scale);
-  }
+  chronos_t5_tokenize_kernel<0><<<grid, block, smem, stream>>>(x, batch, context, boundaries, n_boundaries, n_special,
+                                                               n_tokens, pad_id, eos_id, ids, attn_mask, scale);
   return check_last_launch("chronos_t5_tokenize");
 }
 

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 import torch
@@ -66,6 +66,19 @@ class GemmArgs(Structure):
         ("ld_pre", c_int64),
         ("pre_act_dtype", c_int32),
         ("reserved", c_int32),
+    ]
+
+
+class TimesfmLayer(Structure):
+    _fields_ = [(name, c_void_p) for name in ("qkv", "out", "ff0", "ff1", "pre_attn_ln", "post_attn_ln", "pre_ff_ln",
+                                              "post_ff_ln", "q_ln", "k_ln", "q_scale")]
+
+
+class TimesfmStack(Structure):
+    _fields_ = [
+        ("num_layers", c_int32), ("model_dims", c_int32), ("num_heads", c_int32), ("head_dim", c_int32),
+        ("ff_dims", c_int32), ("precision", c_int32), ("eps", c_float), ("reserved", c_int32),
+        ("inv_freq", c_void_p), ("layers", POINTER(TimesfmLayer)),
     ]
 
 
@@ -162,6 +175,11 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "tsfmx_mask_cast_rows": (
         c_int32,
         [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p],
+    ),
+    "tsfmx_timesfm_stack_workspace_bytes": (c_size_t, [POINTER(TimesfmStack), c_int64, c_int32]),
+    "tsfmx_timesfm_stack_fwd": (
+        c_int32,
+        [POINTER(TimesfmStack), c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p],
     ),
     "tsfmx_timesfm_patchify_continue": (
         c_int32,

@@ -461,6 +461,44 @@ def mask_cast_rows(x: torch.Tensor, mask: torch.Tensor, out_dtype: int) -> torch
     return out
 
 
+# ----------------------------------------------------------------------------- whole-stack entry point
+def timesfm_stack_table(layers: Sequence[dict], inv_freq: torch.Tensor, model_dims: int, num_heads: int, head_dim: int,
+                        ff_dims: int, precision: int, eps: float):
+    """Pack the per-layer device pointers into the C ABI's ``tsfmx_timesfm_stack``.  The returned object keeps the
+    ctypes arrays (and the tensors they point at) alive; build it once per set of packed weights."""
+    arr = (_lib.TimesfmLayer * len(layers))()
+    for dst, lw in zip(arr, layers):
+        dst.qkv, dst.out, dst.ff0, dst.ff1 = (lw[k].data_ptr() for k in ("qkv", "out", "ff0", "ff1"))
+        dst.pre_attn_ln, dst.post_attn_ln = lw["pre_attn"].data_ptr(), lw["post_attn"].data_ptr()
+        dst.pre_ff_ln, dst.post_ff_ln = lw["pre_ff"].data_ptr(), lw["post_ff"].data_ptr()
+        dst.q_ln, dst.k_ln, dst.q_scale = lw["q_ln"].data_ptr(), lw["k_ln"].data_ptr(), lw["q_scale"].data_ptr()
+    table = _lib.TimesfmStack()
+    table.num_layers, table.model_dims, table.num_heads, table.head_dim = len(layers), model_dims, num_heads, head_dim
+    table.ff_dims, table.precision, table.eps = ff_dims, precision, eps
+    table.inv_freq = inv_freq.data_ptr()
+    table.layers = ctypes.cast(arr, ctypes.POINTER(_lib.TimesfmLayer))
+    table._keepalive = (arr, list(layers), inv_freq)
+    return table
+
+
+@_on_operand_device
+def timesfm_stack_fwd(table, x: torch.Tensor, batch: int, num_patches: int, patch_mask: torch.Tensor | None,
+                      num_masked: torch.Tensor | None) -> torch.Tensor:
+    """All decoder layers in one library call: x [B * N, D] fp32 -> y [B * N, D] fp32 (``tsfmx_timesfm_stack_fwd``)."""
+    lib = _lib.load()
+    _lib.require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    need = int(lib.tsfmx_timesfm_stack_workspace_bytes(ctypes.byref(table), batch, num_patches))
+    if need == 0 and batch > 0:
+        raise _lib.TsfmxError("tsfmx_timesfm_stack_workspace_bytes rejected the weight table")
+    workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=x.device)
+    y = torch.empty_like(x)
+    pm = None if patch_mask is None else _as_u8(patch_mask)
+    check(lib.tsfmx_timesfm_stack_fwd(ctypes.byref(table), batch, num_patches, ptr(x), ptr(pm), ptr(num_masked),
+                                      ptr(workspace), need, ptr(y), stream()))
+    return y
+
+
 def wgrad(dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, k_in: int, precision: int) -> torch.Tensor:
     """Weight gradient of ``y = x W^T``: dW [n_out, k_in] = dY^T X as a K-major tcgen05 GEMM with K = rows (both operands
     transposed once; split-K inside the GEMM when the tile count is small)."""

@@ -212,7 +212,38 @@ def _random_left_padding(b, c, gen):
     return torch.arange(c, device=DEV)[None, :] < pad[:, None]
 
 
-@pytest.mark.parametrize("context", [32, 512, 2048, 96, 1056, 4096])
+@pytest.fixture
+def generic_kernels():
+    """Force the generic fallback kernels (what rows longer than 4096 / unaligned rows / odd contexts take) through the
+    library's tuning hook, so that they stay covered next to the staged default kernels."""
+    lib = ops._lib.load()
+    ops._lib.check(lib.tsfmx_tune(2, 1))
+    ops._lib.check(lib.tsfmx_tune(3, 1))
+    yield
+    ops._lib.check(lib.tsfmx_tune(2, 0))
+    ops._lib.check(lib.tsfmx_tune(3, 0))
+
+
+def test_fallback_kernels_agree_with_the_staged_ones(generic_kernels):
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(67, 512, generator=gen, device=DEV) * 3 + 1
+    mask = _random_left_padding(67, 512, gen)
+    generic = ops.timesfm_patchify_norm(x, mask, 32, DT_F32)
+    ops._lib.check(ops._lib.load().tsfmx_tune(3, 0))
+    staged = ops.timesfm_patchify_norm(x, mask, 32, DT_F32)
+    assert torch.equal(generic[3], staged[3]) and torch.equal(generic[4], staged[4])
+    for g, s_ in zip(generic[:3], staged[:3]):
+        assert (g - s_).abs().max().item() < 2e-6 * max(1.0, s_.abs().max().item())
+    _centers, boundaries = _t5_tables()
+    xt = torch.randn(129, 512, generator=torch.Generator().manual_seed(1)).to(DEV) * 4
+    generic_ids = ops.chronos_t5_tokenize(xt, boundaries.to(DEV))
+    ops._lib.check(ops._lib.load().tsfmx_tune(2, 0))
+    staged_ids = ops.chronos_t5_tokenize(xt, boundaries.to(DEV))
+    for g, s_ in zip(generic_ids, staged_ids):
+        assert torch.equal(g, s_)
+
+
+@pytest.mark.parametrize("context", [32, 512, 2048, 96, 1056, 4096, 8192])
 @pytest.mark.parametrize("tokens_dtype", [DT_F32, DT_BF16, DT_BF16_SPLIT])
 def test_timesfm_patchify_norm(context, tokens_dtype):
     b = 67

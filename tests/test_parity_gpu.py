@@ -257,3 +257,45 @@ def test_series_lanes_bit_identical(model2, lanes_n, batch):
     finally:
         dec.lanes = saved
     assert torch.equal(one, many) and torch.equal(many, again)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_whole_stack_entry_point_is_bit_identical(model2, precision):
+    """tsfmx_timesfm_stack_fwd (one library call for all layers) launches the same
+    kernels in the same order as the per-kernel entry points: identical bits, padded batch, both precision modes."""
+    from tsfmx_b200 import ops
+    from tsfmx_b200._lib import TsfmxError
+
+    dec, _ = model2
+    dec.set_precision(precision)
+    ctx, masks, text, _ = O.synthetic_batch(40, 512, 128, padded=True, seed=17)
+    args = (128, ctx.to(DEV), masks.to(DEV), text.to(DEV))
+    saved = dec.adapter.stack_call
+    try:
+        with torch.no_grad():
+            dec.adapter.stack_call = False
+            launches0 = ops._lib.launch_count()
+            per_kernel = dec.forward_full(*args)
+            n_per_kernel = ops._lib.launch_count() - launches0
+            dec.adapter.stack_call = True
+            launches0 = ops._lib.launch_count()
+            whole = dec.forward_full(*args)
+            n_whole = ops._lib.launch_count() - launches0
+    finally:
+        dec.adapter.stack_call = saved
+    assert torch.equal(per_kernel, whole)
+    assert n_whole == n_per_kernel  # same kernels, fewer FFI crossings
+    w = dec.adapter._weights()
+    table = w["stack_table"]
+    lib = ops._lib.load()
+    import ctypes
+    need = lib.tsfmx_timesfm_stack_workspace_bytes(ctypes.byref(table), 40, 16)
+    per_token = 1280 * (2 + 6 + 2 + 2 + 2) if precision == "bf16" else 1280 * (4 + 12 + 4 + 4 + 4)
+    assert 40 * 16 * per_token <= need <= 40 * 16 * per_token + 5 * 256
+    x = torch.randn(40 * 16, 1280, device=DEV)
+    with pytest.raises(TsfmxError, match="workspace"):
+        ops._lib.check(lib.tsfmx_timesfm_stack_fwd(ctypes.byref(table), 40, 16, x.data_ptr(), None, None, x.data_ptr(), 16,
+                                                   torch.empty_like(x).data_ptr(), None))
+    with pytest.raises(TsfmxError, match="distinct"):
+        ops._lib.check(lib.tsfmx_timesfm_stack_fwd(ctypes.byref(table), 40, 16, x.data_ptr(), None, None, x.data_ptr(), need,
+                                                   x.data_ptr(), None))
