@@ -291,30 +291,53 @@ __global__ void __launch_bounds__(TFW_WARPS * 32) timesfm_patchify_norm_warp_ker
       const float4* xp = reinterpret_cast<const float4*>(sx + p * 32);
       const uint32_t* mp = reinterpret_cast<const uint32_t*>(sm + p * 32);
       float xv[32];
-      uint32_t mbits = 0;  // bit e = element e of the patch is padded
-      float c = 0.f, sum = 0.f;
+      uint32_t mw[8];
+      uint32_t any_padded = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int ch = (j + rot) & 7;
         const float4 v = xp[ch];
-        const uint32_t mk = mp[ch];
+        mw[j] = mp[ch];
+        any_padded |= mw[j];
         xv[4 * j + 0] = v.x, xv[4 * j + 1] = v.y, xv[4 * j + 2] = v.z, xv[4 * j + 3] = v.w;
+      }
+      float c, inc_mu, sq = 0.f;
+      if (any_padded == 0) {
+        // fully observed patch (every patch of the reference's own callers, which pass all-False masks, and all but
+        // the leading patches of a left-padded series): no per-element mask decoding - 3 instead of ~10 instructions
+        // per element; same summation order as the general path
+        float sum = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool padded = ((mk >> (8 * k)) & 0xffu) != 0;
-          mbits |= (padded ? 1u : 0u) << (4 * j + k);
-          c += padded ? 0.f : 1.f;
-          sum += padded ? 0.f : xv[4 * j + k];
+        for (int e = 0; e < 32; ++e) sum += xv[e];
+        c = 32.f;
+        inc_mu = sum * 0.03125f;  // == sum / 32 exactly
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float d = xv[e] - inc_mu;
+          sq = fmaf(d, d, sq);
+        }
+      } else {
+        uint32_t mbits = 0;  // bit e = element e of the patch is padded
+        float sum = 0.f;
+        c = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool padded = ((mw[j] >> (8 * k)) & 0xffu) != 0;
+            mbits |= (padded ? 1u : 0u) << (4 * j + k);
+            c += padded ? 0.f : 1.f;
+            sum += padded ? 0.f : xv[4 * j + k];
+          }
+        }
+        inc_mu = c == 0.f ? 0.f : __fdiv_rn(sum, c == 0.f ? 1.f : c);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float d = ((mbits >> e) & 1u) ? 0.f : xv[e] - inc_mu;
+          sq = fmaf(d, d, sq);
         }
       }
       const float c_safe = c == 0.f ? 1.f : c;
-      const float inc_mu = c == 0.f ? 0.f : __fdiv_rn(sum, c_safe);
-      float sq = 0.f;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float d = ((mbits >> e) & 1u) ? 0.f : xv[e] - inc_mu;
-        sq = fmaf(d, d, sq);
-      }
       // the patch counts as padded iff its LAST element is padded (timesfm.py:97)
       const float flag = sm[p * 32 + 31] ? 1.f : 0.f;
       slots[p] = make_float4(c, inc_mu, c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f)), flag);
@@ -421,11 +444,16 @@ __global__ void __launch_bounds__(TFW_WARPS * 32) timesfm_patchify_norm_warp_ker
       const uint32_t mk = *reinterpret_cast<const uint32_t*>(sm + p * 32 + 4 * q);
       const float xv[4] = {v.x, v.y, v.z, v.w};
       float val[4], msk[4];
+      if (mk == 0) {  // four observed points: no mask decoding
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const bool padded = ((mk >> (8 * kk)) & 0xffu) != 0;
-        msk[kk] = padded ? 1.f : 0.f;
-        val[kk] = padded ? 0.f : (xv[kk] - st.x) * st.z;
+        for (int kk = 0; kk < 4; ++kk) msk[kk] = 0.f, val[kk] = (xv[kk] - st.x) * st.z;
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const bool padded = ((mk >> (8 * kk)) & 0xffu) != 0;
+          msk[kk] = padded ? 1.f : 0.f;
+          val[kk] = padded ? 0.f : (xv[kk] - st.x) * st.z;
+        }
       }
       store_token_quad<OUT>(tokens, b0 * N + p, q, val, msk);
     }
