@@ -160,6 +160,33 @@ __global__ void __launch_bounds__(WARPS * 32) colsum_wgrad_kernel(const void* __
   }
 }
 
+// Bias gradient for any width that is a multiple of 4 (the 3072-wide hidden layers and the 336 -> 384 wide output
+// block of Chronos-2): dbias[c] = sum_r g[r, c].  A block owns 128 columns (32 threads x float4) and a slice of the
+// rows (8 row lanes); partials meet in shared memory and leave as one atomicAdd per column.
+__global__ void __launch_bounds__(256) colsum_bias_kernel(const void* __restrict__ g, int g_dtype, int64_t rows, int cols,
+                                                          int64_t rows_per_block, float* __restrict__ out) {
+  __shared__ float4 s_part[8][32];
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 128 + 4 * cq;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c0 < cols) {
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      const float4 v = load4(g, g_dtype, r * cols + c0);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  }
+  s_part[rl][cq] = acc;
+  __syncthreads();
+  if (rl == 0 && c0 < cols) {
+    float4 t = s_part[0][cq];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t.x += s_part[w][cq].x, t.y += s_part[w][cq].y, t.z += s_part[w][cq].z, t.w += s_part[w][cq].w;
+    atomicAdd(out + c0, t.x), atomicAdd(out + c0 + 1, t.y), atomicAdd(out + c0 + 2, t.z), atomicAdd(out + c0 + 3, t.w);
+  }
+}
+
 // ----------------------------------------------------------------------------------------
 // attention backward (fp32 SIMT; one warp per (series, head))
 // ----------------------------------------------------------------------------------------
@@ -617,9 +644,20 @@ extern "C" int tsfmx_colsum_wgrad(const void* v, int32_t v_dtype, const void* g,
   switch (cols) {
     case 1280: colsum_wgrad_kernel<10><<<grid, WARPS * 32, 0, stream>>>(v, v_dtype, g, g_dtype, rows, eps, normalize, out); break;
     case 768: colsum_wgrad_kernel<6><<<grid, WARPS * 32, 0, stream>>>(v, v_dtype, g, g_dtype, rows, eps, normalize, out); break;
-    default:
-      set_error("colsum_wgrad: cols=%d unsupported (1280 or 768)", cols);
-      return TSFMX_ERR_UNSUPPORTED;
+    default: {
+      if (normalize || cols <= 0 || cols % 4 != 0) {
+        set_error("colsum_wgrad: cols=%d unsupported (norm-scale gradients: 1280 or 768; bias gradients: any multiple of 4)",
+                  cols);
+        return TSFMX_ERR_UNSUPPORTED;
+      }
+      const int col_blocks = (cols + 127) / 128;
+      int64_t row_blocks = (static_cast<int64_t>(num_sms()) * 4 + col_blocks - 1) / col_blocks;
+      if (row_blocks > (rows + 63) / 64) row_blocks = (rows + 63) / 64;
+      if (row_blocks < 1) row_blocks = 1;
+      const int64_t rows_per_block = (rows + row_blocks - 1) / row_blocks;
+      colsum_bias_kernel<<<dim3(col_blocks, static_cast<unsigned>(row_blocks)), 256, 0, stream>>>(g, g_dtype, rows, cols,
+                                                                                                 rows_per_block, out);
+    }
   }
   return check_last_launch("colsum_wgrad");
 }

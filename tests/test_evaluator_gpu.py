@@ -150,3 +150,34 @@ def test_shuffled_store_with_a_lagging_copy_stream():
         got = ev.evaluate(store.batches(b, shuffle=True, generator=torch.Generator().manual_seed(seed)))
         assert got["mse"] == pytest.approx(in_order["mse"], rel=1e-5)
         assert got["mae"] == pytest.approx(in_order["mae"], rel=1e-5)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_predict_returns_every_forecast_on_the_host(graphs):
+    """MultimodalEvaluator.predict: staged H2D like evaluate, every forecast copied back on its own stream while the
+    next batch computes.  Forecasts equal direct forward_full calls, batch order and ragged tail preserved; copy=False
+    hands out views of the page-locked ring."""
+    dec = _small_decoder()
+    batches, want = [], []
+    for i, b in enumerate((12, 12, 12, 12, 12, 5)):
+        ctx, _m, text, hor = O.synthetic_batch(b, 512, 64, seed=40 + i)
+        batches.append({"context": ctx.pin_memory(), "horizon": hor.pin_memory(), "text_embeddings": text.pin_memory()})
+        with torch.no_grad():
+            want.append(dec.forward_full(64, ctx.cuda(), torch.zeros_like(ctx, dtype=torch.bool).cuda(), text.cuda()).cpu())
+    ev = MultimodalEvaluator(dec, torch.device("cuda"), graphs=graphs)
+    got = list(ev.predict(batches))
+    assert [g.shape for g in got] == [w.shape for w in want]
+    for g, w in zip(got, want):
+        assert not g.is_cuda and torch.equal(g, w)
+    points = list(ev.predict(iter(batches), horizon=32, full=False))
+    assert points[0].shape == (12, 32) and points[-1].shape == (5, 32)
+    with torch.no_grad():
+        ctx = batches[3]["context"]
+        ref = dec(32, ctx.cuda(), torch.zeros_like(ctx, dtype=torch.bool).cuda(), batches[3]["text_embeddings"].cuda()).cpu()
+    assert torch.equal(points[3], ref)
+    seen = 0
+    for g, w in zip(ev.predict(batches, copy=False), want):  # views: consumed before two more batches are requested
+        assert g.is_pinned() and torch.equal(g, w)
+        seen += 1
+    assert seen == len(want)
+    assert list(ev.predict([])) == []

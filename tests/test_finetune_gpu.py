@@ -185,6 +185,16 @@ def test_colsum_wgrad(cols):
     assert rel_l2(acc, 2 * ref_scale.float()) < 1e-5
 
 
+@pytest.mark.parametrize("rows,cols", [(1003, 384), (64, 3072), (5, 3072), (70000, 336), (3, 4)])
+def test_colsum_bias_any_width(rows, cols):
+    """Bias gradients of the blocks that are not model-wide (Chronos-2: 3072-wide hidden layers, the 336-wide head)."""
+    gen = torch.Generator(device=DEV).manual_seed(rows + cols)
+    g = torch.randn(rows, cols, generator=gen, device=DEV)
+    ref = g.double().sum(0).float()
+    assert rel_l2(ops.colsum_wgrad(g), ref) < 1e-5
+    assert rel_l2(ops.colsum_wgrad(g.to(torch.bfloat16)), g.to(torch.bfloat16).double().sum(0).float()) < 1e-5
+
+
 def test_gemm_grad_epilogues_and_pre_act():
     m, n, k = 200, 1280, 1280
     gen = torch.Generator(device=DEV).manual_seed(2)
