@@ -57,9 +57,12 @@ def parse_args():
     ap.add_argument("--no-graphs", action="store_true", help="time the eager launches instead of the CUDA-graph replay")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
     ap.add_argument("--no-stages", action="store_true", help="skip the HBM-bound stage rooflines")
-    ap.add_argument("--workload", default="forecast", choices=["forecast", "finetune", "full-finetune"],
+    ap.add_argument("--workload", default="forecast",
+                    choices=["forecast", "finetune", "full-finetune", "chronos2", "chronos-t5", "longctx-timesfm",
+                             "longctx-chronos2"],
                     help="forecast = BASELINE configs[1] (the driver's line); finetune = configs[3], the fusion fine-tune "
-                         "step with the NCCL gradient all-reduce; full-finetune = the reference's mode='baseline'")
+                         "step with the NCCL gradient all-reduce; full-finetune = the reference's mode='baseline'; chronos2 / "
+                         "chronos-t5 = configs[2]; longctx-* = configs[4] (ctx 2048 / horizon 256)")
     ap.add_argument("--finetune-batch", type=int, default=1024, help="series per GPU of a fine-tune step")
     ap.add_argument("--graph-collectives", action="store_true",
                     help="full fine-tune on several GPUs: capture the overlapped NCCL all-reduces into the step's CUDA graph")
@@ -755,6 +758,197 @@ def cpu_finetune_baseline(args, full: bool, sample: int = 16, repeats: int = 2) 
                       f"{cores} threads"}
 
 
+# ------------------------------------------------------------------------------------------------ other forecast configs
+def _d2(n):  # 2 * n: multiply-add
+    return 2.0 * n
+
+
+def workload_spec(name: str, layers: int) -> dict:
+    """BASELINE.json configs[2] and configs[4] as bench workloads: model factory, shapes, algorithmic FLOPs per series
+     and the CPU oracle that is timed beside them."""
+    d = 1280
+    if name in ("chronos2", "longctx-chronos2"):
+        long = name.startswith("longctx")
+        return {"model": "chronos2", "context": 2048 if long else 512, "horizon": 256 if long else 128, "patch": 16,
+                "batch": 2048, "flops": 40.79e9 if long else 20.14e9,
+                "label": "Chronos-2 (12 blocks x 768, the adapter the reference wraps) + 1-layer fusion"}
+    if name == "longctx-timesfm":
+        n, m = 64, 4
+        stack = layers * (_d2(n * 6 * d * d) + 2 * d * n * (n + 1))
+        tok = n * _d2(2 * 32 * d + d * d + 2 * 32 * d)
+        step = layers * _d2(m * 6 * d * d) + m * _d2(2 * 32 * d + d * d + 2 * 32 * d) + _d2(3 * d * d)
+        return {"model": "timesfm", "context": 2048, "horizon": 256, "patch": 32, "batch": 2048, "ar_decode": True,
+                "flops": float(tok + n * _d2(384 * d) + stack + _d2(3 * d * d) + step),
+                "label": f"TimesFM-2.5 layout, {layers} layers x 1280 + 1-layer fusion, autoregressive decode (prefill + one "
+                         "128-step decode step against the KV cache)"}
+    if name == "chronos-t5":
+        dm, ff, t, steps, nl = 768, 3072, 513, 64, 12
+        dec_step = nl * (_d2(6 * dm * dm) + _d2(2 * dm * ff)) + _d2(dm * 4096)
+        return {"model": "chronos-t5", "context": 512, "horizon": steps, "patch": 32, "batch": 2048,
+                "flops": 96.8e9 + steps * dec_step + t * nl * _d2(dm * 2 * dm),
+                "label": "Chronos-T5-base (12 + 12 layers x 768, vocab 4096) + per-token text fusion, mean-scale / bin "
+                         f"tokenisation, encoder over {t} tokens, greedy decoding of {steps} tokens"}
+    raise ValueError(name)
+
+
+def build_workload_model(spec: dict, layers: int, dev):
+    from tsfmx_b200.decoder import MultimodalDecoder, MultimodalDecoderConfig
+
+    if spec["model"] == "chronos2":
+        from tsfmx_b200.tsfm import chronos as C2
+
+        adapter = C2.Chronos2Adapter(precision="bf16")
+        C2.init_random_(adapter, seed=0)
+    elif spec["model"] == "chronos-t5":
+        from tsfmx_b200.tsfm import chronos_t5 as CT5
+
+        adapter = CT5.ChronosT5Adapter(CT5.ChronosT5Module(), precision="bf16")
+        CT5.init_random_(adapter._model, seed=0)
+    else:
+        from tsfmx_b200.tsfm.timesfm import ForecastOptions, TimesFM2p5Adapter, init_random_
+
+        adapter = TimesFM2p5Adapter(num_layers=layers, precision="bf16", with_quantile_head=False)
+        init_random_(adapter, seed=0)
+        adapter.forecast_options = ForecastOptions(ar_decode=bool(spec.get("ar_decode")))
+    torch.manual_seed(100)
+    dec = MultimodalDecoder(adapter, MultimodalDecoderConfig(TEXT_DIMS, 1, []))
+    return dec if dev is None else dec.to(dev).eval()
+
+
+def workload_oracle(spec: dict, dec):
+    if spec["model"] == "chronos2":
+        from oracle import chronos2_oracle as C
+
+        return C.oracle_from_product(dec)
+    if spec["model"] == "chronos-t5":
+        from oracle import chronos_t5_model_oracle as T
+
+        return T.oracle_from_product(dec)
+    from oracle import timesfm_oracle as O
+
+    return O.oracle_from_product(dec)
+
+
+def workload_batch(spec: dict, dec, batch: int, seed: int):
+    from oracle import timesfm_oracle as O
+
+    ctx, masks, text, hor = O.synthetic_batch(batch, spec["context"], spec["horizon"], seed=seed, patch_len=spec["patch"])
+    if spec["model"] == "chronos-t5":
+        text = dec.adapter.expand_text_embeddings(text, spec["context"])
+    return ctx, masks, text, hor
+
+
+def cpu_workload_baseline(spec: dict, layers: int, sample: int, repeats: int) -> dict:
+    torch.set_num_threads(os.cpu_count() or 1)
+    dec = build_workload_model(spec, layers, None)
+    oracle = workload_oracle(spec, dec)
+    ctx, masks, text, _ = workload_batch(spec, dec, sample, 1234)
+    h = spec["horizon"]
+    times = []
+    with torch.no_grad():
+        for i in range(1 + repeats):
+            t0 = time.perf_counter()
+            if spec.get("ar_decode"):
+                oracle.forecast(h, ctx, masks, text)
+            else:
+                oracle(h, ctx, masks, text)
+            if i:
+                times.append(time.perf_counter() - t0)
+    cores = torch.get_num_threads()
+    return {"value": sample / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} series, same model / ctx / horizon, fp32 oracle, best of {repeats} after 1 warm-up, {cores} threads"}
+
+
+def run_workload_arm(args) -> None:
+    """configs[2] / configs[4]: the forecast arm of bench.py for the other adapters and shapes - same timing rules, same
+    JSON line (value device-resident, e2e through MultimodalEvaluator.evaluate over pinned host batches, clocks, a
+    whole-step tensor roofline, the CPU oracle at N = 1)."""
+    import torch.distributed as dist
+
+    from tsfmx_b200 import _lib
+    from tsfmx_b200 import distributed as tdist
+    from tsfmx_b200.evaluator import MultimodalEvaluator
+
+    spec = workload_spec(args.workload, args.layers)
+    rank, world, local_rank = tdist.init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.check(_lib.load().tsfmx_device_check(local_rank))
+    B = args.batch if args.batch != BATCH_PER_GPU else spec["batch"]
+    h = spec["horizon"]
+    dec = build_workload_model(spec, args.layers, dev)
+    dec.set_precision("bf16")
+    host = []
+    for i in range(2):
+        ctx, masks, text, hor = workload_batch(spec, dec, B, 1234 + 17 * rank + i)
+        host.append({"context": ctx.pin_memory(), "horizon": hor.pin_memory(), "text_embeddings": text.pin_memory()})
+    resident = [(b["context"].to(dev), torch.zeros_like(b["context"], dtype=torch.bool).to(dev), b["text_embeddings"].to(dev))
+                for b in host]
+    evaluator = MultimodalEvaluator(dec, dev)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    graphs = not args.no_graphs and getattr(dec.adapter, "graph_safe", False)
+
+    def step_resident(i):
+        c, m, t = resident[i % 2]
+        return dec(h, c, m, t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return tdist.allreduce_max(e0.elapsed_time(e1), dev)
+
+    with torch.no_grad():
+        dec.graphs = graphs
+        for i in range(max(args.warmup, 4)):
+            step_resident(i)
+        evaluator.evaluate(host[i % 2] for i in range(2))
+        torch.cuda.synchronize()
+        launches0 = _lib.launch_count() + dec.graph_launches_replayed
+        with ClockSampler(local_rank, enabled=rank == 0) as clocks:
+            ms = timed(step_resident, args.steps)
+            launches = _lib.launch_count() + dec.graph_launches_replayed - launches0
+            dec.graphs = False
+            ms_e2e = timed(lambda i: evaluator.evaluate(host[j % 2] for j in range(args.steps)) if i == 0 else None, 1)
+    total = B * world * args.steps
+    value, e2e_value = total / (ms * 1e-3), total / (ms_e2e * 1e-3)
+    peaks = measured_peaks()
+    achieved = spec["flops"] * value / world / 1e12
+    line = {
+        "metric": f"forecast series/sec (ctx{spec['context']},h{h})", "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{spec['label']}, ctx {spec['context']} / horizon {h}, batch {B} series per GPU, forecast forward",
+                   "parallelism": f"series-sharded x{world}, no collectives",
+                   "launch": "CUDA-graph replay (one graph per resident batch)" if graphs else "eager launches",
+                   "weights": "random-init (seed 0)", "precision": "bf16 operands, fp32 accumulate",
+                   "l2": "per-step working set >> 126 MB L2; inputs alternate between two resident batches"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 16,
+                "ms_per_step": ms_e2e / args.steps,
+                "api": "MultimodalEvaluator.evaluate(loader of pinned host batches), per-batch (mse, mae) read back"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "whole forecast step (tcgen05 GEMMs + attention)",
+                     "algorithmic_flops_per_series": spec["flops"], "peak_source": f"{peaks['source']} bf16_tflops_sustained"},
+        "clocks": clocks.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_workload_baseline(spec, args.layers, 4 if spec["model"] != "chronos2" else 16, 1)
+    if rank == 0:
+        emit_json(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL prints its version banner there
     # whenever NCCL_DEBUG is set) is sent to stderr, and the JSON line goes to the saved descriptor
@@ -765,16 +959,21 @@ def main():
     args = parse_args()
     if args.impl == "reference" and args.workload != "forecast":
         if int(os.environ.get("RANK", "0")) == 0:
-            base = cpu_finetune_baseline(args, args.workload == "full-finetune", repeats=max(1, args.steps))
-            emit_json({"impl": "reference", "metric": FT_METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            if args.workload in ("finetune", "full-finetune"):
+                base = cpu_finetune_baseline(args, args.workload == "full-finetune", repeats=max(1, args.steps))
+            else:
+                base = cpu_workload_baseline(workload_spec(args.workload, args.layers), args.layers, 4, max(1, args.steps))
+            emit_json({"impl": "reference", "metric": FT_METRIC if "finetune" in args.workload else args.workload, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
                        "steps": args.steps, "warmup": 1, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                        "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "cpu_sample": base["sample"]},
                        "cpu_baseline": base, "gpu_launches": 0,
                        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     elif args.impl == "reference":
         run_reference_arm(args)
-    elif args.workload != "forecast":
+    elif args.workload in ("finetune", "full-finetune"):
         run_finetune_arm(args, args.workload == "full-finetune")
+    elif args.workload != "forecast":
+        run_workload_arm(args)
     else:
         run_b200_arm(args)
 

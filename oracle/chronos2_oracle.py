@@ -10,9 +10,15 @@ vendored nor installable here.  This file therefore
   8192) in plain fp32 torch, INCLUDING the O(B^2) group attention exactly as upstream runs it, and
 * follows the reference adapter's control flow line by line around it.
 
-PARITY PINNING: **parity unpinned** — there is no upstream source, test or golden vector to pin this restatement
-to; it is pinned only against itself (shapes, mask conventions, the degenerate-group-attention identity and the
-inverse-norm round trip; tests/test_oracle_cpu.py).
+PARITY PINNING: **parity unpinned** against upstream — there is no upstream source, test or golden vector to pin this
+restatement to.  What CAN be pinned is (tests/test_oracle_cpu.py): the sub-blocks that coincide with
+``transformers.models.t5`` (RMS LayerNorm == T5LayerNorm, the ReLU feed-forward sub-layer == T5LayerFF, the bias-free
+un-scaled attention of the group sub-layer == T5Attention without relative bias) and the rotary embedding
+(== transformers' Llama ``apply_rotary_pos_emb``, same inv_freq), on identical weights; plus self-consistency (shapes,
+mask conventions, the degenerate-group-attention identity, the inverse-norm round trip).  Still recalled, unpinned:
+the context preparation (instance-norm statistics, arcsinh, NaN left padding, the sign / scale of the time encoding),
+the [REG] token and future-patch layout, the group-attention masking rule, the head's (quantile, patch) output
+layout and the quantile list.
 """
 
 from __future__ import annotations
@@ -299,6 +305,23 @@ class OracleChronos2Adapter(nn.Module):
             blk.wo.weight.copy_(g(pre + "2.mlp.wo.weight"))
             blk.ff_ln.weight.copy_(g(pre + "2.layer_norm.weight"))
         m.final_layer_norm.weight.copy_(g("encoder.final_layer_norm.weight"))
+
+
+def oracle_from_product(decoder):
+    """Oracle twin (restated Chronos-2 + the reference decoder / fusion control flow) of a product ``MultimodalDecoder``
+    built around a ``Chronos2Adapter``, carrying the same weights."""
+    from . import timesfm_oracle as O
+
+    module = decoder.adapter._model
+    o_adapter = OracleChronos2Adapter(Chronos2Model(Chronos2Config(num_layers=len(module.encoder.block))))
+    o_adapter.load_upstream_state_dict({k: v.detach().cpu() for k, v in module.state_dict().items()})
+    fus = decoder.fusion
+    dims = [l.weight.shape[1] for l in fus.linears()] + [fus.linears()[-1].weight.shape[0]]
+    o = O.OracleDecoder(o_adapter, dims[0], len(dims) - 1, dims[1:-1])
+    with torch.no_grad():
+        for src, dst in zip(fus.linears(), [m for m in o.fusion.projection if isinstance(m, nn.Linear)]):
+            dst.weight.copy_(src.weight.detach().float().cpu())
+    return o.eval()
 
 
 def degenerate_group_attention(block: EncoderBlock, ht: torch.Tensor) -> torch.Tensor:
