@@ -297,7 +297,8 @@ class MultimodalTrainer:
             if (i + 1) % accum == 0 or (i + 1) == num_batches:
                 self.optimizer_step()
         total = torch.stack(losses).sum()
-        tdist.allreduce_([total], "sum")
+        if self.world_size > 1:
+            tdist.allreduce_([total], "sum")
         return float(total.item()) / num_batches
 
     def validate_epoch(self) -> float:
@@ -308,7 +309,8 @@ class MultimodalTrainer:
             raise RuntimeError("Validation dataset is empty.")
         with torch.no_grad():
             total = torch.stack([self._forward_loss(batch) for batch in self._staged(self.val_loader)]).sum()
-        tdist.allreduce_([total], "sum")
+        if self.world_size > 1:
+            tdist.allreduce_([total], "sum")
         return float(total.item()) / num_batches
 
     def train(self) -> None:

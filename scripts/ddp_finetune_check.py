@@ -59,13 +59,9 @@ def main():
     # single-process reference on the same global batches (world size forced to 1 for this trainer)
     ref = build(device)
     ref_trainer = MultimodalTrainer(ref, args, samples, samples[: per_rank * world], mode, device)
-    ref_trainer.rank, ref_trainer.world_size = 0, 1
-    saved = tdist.allreduce_mean_
-    tdist.allreduce_mean_ = lambda tensors, group=None: None
-    try:
-        ref_loss = ref_trainer.train_epoch()
-    finally:
-        tdist.allreduce_mean_ = saved
+    ref_trainer.rank, ref_trainer.world_size = 0, 1   # no sharding, no collectives
+    ref.grad_ready_hook = None
+    ref_loss = ref_trainer.train_epoch()
     w_ref = pick(ref).detach()
 
     rel = ((w_dist - w_ref).norm() / (w_ref - pick(build(device))).norm()).item()
@@ -75,7 +71,9 @@ def main():
         dist.all_gather(gathered, w_dist)
         same = all(torch.equal(gathered[0], g) for g in gathered)
     if rank == 0:
-        print(f"mode={mode} world={world} steps={trainer.global_step} loss dist={loss:.6f} ref={ref_loss:.6f} "
+        overlapped = dec.grad_ready_hook is not None
+        print(f"mode={mode} world={world} steps={trainer.global_step} overlapped_allreduce={overlapped} "
+              f"graph_replays={trainer.graph_replays} loss dist={loss:.6f} ref={ref_loss:.6f} "
               f"update rel diff={rel:.3e} identical_across_ranks={same}")
     assert same, "ranks diverged"
     assert abs(loss - ref_loss) < 1e-4 * max(1.0, abs(ref_loss)), (loss, ref_loss)
