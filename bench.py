@@ -723,6 +723,9 @@ def run_finetune_arm(args, full: bool) -> None:
     if rank == 0:
         emit_json(line)
     if world > 1:
+        trainer._train_graphs.clear()  # graphs that captured NCCL kernels must go before the communicator does
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

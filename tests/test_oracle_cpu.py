@@ -129,7 +129,20 @@ def test_t5_tokenizer_oracle_golden_and_properties():
     up_ids = torch.bucketize(x / up[:, None], boundaries, right=True) + 2
     up_ids.clamp_(0, 4095)
     up_ids[torch.isnan(x)] = 0
-    assert (up_ids != ids[:, :-1]).float().mean() < 1e-3
+    differ = up_ids != ids[:, :-1]
+    # measured (this container, 4096 x 512 inputs): 10 of 2 097 152 ids (5e-6) move, each to the NEIGHBOURING bin; the
+    # bound is that order of magnitude, not a blanket 1e-3
+    assert differ.float().mean() < 5e-5, differ.float().mean()
+    assert ((up_ids - ids[:, :-1]).abs()[differ] == 1).all()
+    # the same at scale: 4096 series x 512 steps of Gaussian data
+    gen = torch.Generator().manual_seed(0)
+    big = torch.randn(4096, 512, generator=gen) * torch.rand(4096, 1, generator=gen) * 10
+    b_ids, _am, b_scale = T5.tokenize(big, boundaries)
+    up_b = torch.nansum(big.abs(), -1) / 512
+    up_b_ids = (torch.bucketize(big / up_b[:, None], boundaries, right=True) + 2).clamp_(0, 4095)
+    moved = up_b_ids != b_ids[:, :-1]
+    assert moved.float().mean() < 2e-5, moved.float().mean()
+    assert ((up_b_ids - b_ids[:, :-1]).abs()[moved] == 1).all()
     # dequantise(tokenise(x)) is within half a bin of x (in scaled units) inside the bin range
     vals = T5.dequantize(ids[:, :-1], centers, scale)
     ok = ~torch.isnan(x) & ((x / scale[:, None]).abs() < 14.9)
