@@ -559,6 +559,7 @@ def run_b200_arm(args) -> None:
     if rank == 0:
         emit_json(line)
     if world > 1:
+        dist.barrier()  # ranks > 0 wait here while rank 0 runs its rank-0-only legs (parity, stages, CPU baseline)
         dist.destroy_process_group()
 
 
@@ -780,7 +781,10 @@ def workload_spec(name: str, layers: int) -> dict:
         stack = layers * (_d2(n * 6 * d * d) + 2 * d * n * (n + 1))
         tok = n * _d2(2 * 32 * d + d * d + 2 * 32 * d)
         step = layers * _d2(m * 6 * d * d) + m * _d2(2 * 32 * d + d * d + 2 * 32 * d) + _d2(3 * d * d)
+        # no graph replay here: a graph pins its own KV cache (the raw qkv of every layer: 1 GB per layer at 2048 series of
+        # 64 patches, 50 GB per forward) and two resident batches would hold two of them next to the eager warm-up's
         return {"model": "timesfm", "context": 2048, "horizon": 256, "patch": 32, "batch": 2048, "ar_decode": True,
+                "graphs": False,
                 "flops": float(tok + n * _d2(384 * d) + stack + _d2(3 * d * d) + step),
                 "label": f"TimesFM-2.5 layout, {layers} layers x 1280 + 1-layer fusion, autoregressive decode (prefill + one "
                          "128-step decode step against the KV cache)"}
@@ -889,7 +893,7 @@ def run_workload_arm(args) -> None:
                 for b in host]
     evaluator = MultimodalEvaluator(dec, dev)
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
-    graphs = not args.no_graphs and getattr(dec.adapter, "graph_safe", False)
+    graphs = not args.no_graphs and getattr(dec.adapter, "graph_safe", False) and spec.get("graphs", True)
 
     def step_resident(i):
         c, m, t = resident[i % 2]
@@ -949,6 +953,7 @@ def run_workload_arm(args) -> None:
     if rank == 0:
         emit_json(line)
     if world > 1:
+        dist.barrier()  # ranks > 0 wait here while rank 0 runs its rank-0-only legs (parity, stages, CPU baseline)
         dist.destroy_process_group()
 
 

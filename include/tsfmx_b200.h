@@ -301,6 +301,16 @@ int tsfmx_encoder_attention_bwd(const void* qkv, int32_t qkv_dtype, const void* 
  *   [num_heads, 2 seq - 1] indexed by (key - query) + seq - 1): qkv bf16 [B*seq, 3*H*64] = [q | k | v], out bf16
  *   [B*seq, H*64]; K and V of one (series, head) stay in shared memory, online softmax over 64-key chunks; seq <= 704.
  */
+/*
+ * Next-token choice of a Chronos-T5 decode step in one kernel (upstream ChronosModel.forward -> generate(do_sample=True,
+ * top_k=50, temperature=1.0), HF generation/logits_process.py TopKLogitsWarper + multinomial): logits [rows, vocab] fp32
+ * (not modified), `banned_id` (EOS while min_new_tokens holds; < 0: none) excluded, logits / temperature, the top_k
+ * largest kept (<= 0: all), softmax, inverse-CDF sampling in id order with uniform[row] in [0, 1).  top_k = 1 is greedy
+ * decoding (first maximum; uniform may be NULL).  out [rows] int64.
+ */
+int tsfmx_t5_sample_topk(const float* logits, int64_t rows, int32_t vocab, int32_t banned_id, float temperature,
+                         int32_t top_k, const float* uniform, int64_t* out, void* stream);
+
 int tsfmx_embed_rows(const int64_t* ids, int64_t rows, int32_t dims, int32_t vocab, const float* table, float* out,
                      void* stream);
 int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, int64_t q_batch_stride, const void* k, const void* v,

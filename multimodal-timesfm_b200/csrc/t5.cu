@@ -392,6 +392,160 @@ __global__ void __launch_bounds__(T5_WARPS * 32, 1) t5_encoder_attention_mma_ker
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Next-token choice of a decode step in ONE kernel: ban a token, temperature, top-k, softmax over the survivors,
+// inverse-CDF sampling with a caller-supplied uniform number - what upstream's generate(do_sample=True, top_k=50,
+// temperature=1.0) does with topk + softmax + multinomial (three eager launches and a [B, V] round trip each).
+// top_k = 1 is greedy decoding (the first maximum, like argmax).  One block per row; the k-th largest logit is found
+// with a 4-pass radix select on order-preserving keys; ties at the threshold are admitted lowest index first.
+// ----------------------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 256;
+constexpr int SAMPLE_MAX_PER_THREAD = 32;  // vocabularies up to 8192
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // ascending float order == ascending unsigned order
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) t5_sample_topk_kernel(const float* __restrict__ logits, int vocab,
+                                                                        int banned_id, float inv_temperature, int top_k,
+                                                                        const float* __restrict__ uniform,
+                                                                        int64_t* __restrict__ out) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_want;
+  __shared__ float s_red[SAMPLE_THREADS / 32];
+  __shared__ float s_scan[SAMPLE_THREADS];
+  __shared__ int s_tie_scan[SAMPLE_THREADS];
+  __shared__ float s_bcast;
+  __shared__ int s_pick;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row = blockIdx.x;
+  const float* lr = logits + row * vocab;
+  const int per = (vocab + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+  // thread t owns the CONTIGUOUS ids [t * per, (t + 1) * per): prefix sums over threads then follow id order
+  float v[SAMPLE_MAX_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+    const int id = tid * per + i;
+    v[i] = (i < per && id < vocab && id != banned_id) ? lr[id] * inv_temperature : -INFINITY;
+  }
+  const int k = (top_k <= 0 || top_k > vocab) ? vocab : top_k;
+  // ---- radix select: key of the k-th largest value
+  uint32_t prefix = 0, mask = 0;
+  uint32_t want = static_cast<uint32_t>(k);  // rank from the top inside the current prefix class
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    s_hist[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+      if (i < per) {
+        const uint32_t key = order_key(v[i]);
+        if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xffu], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t acc = 0;
+      int bin = 255;
+      for (; bin > 0; --bin) {
+        if (acc + s_hist[bin] >= want) break;
+        acc += s_hist[bin];
+      }
+      s_prefix = prefix | (static_cast<uint32_t>(bin) << shift);
+      s_want = want - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix, want = s_want;
+    mask |= 0xffu << shift;
+    __syncthreads();
+  }
+  const uint32_t thr_key = prefix;  // key of the k-th largest; `want` = how many values EQUAL to it are admitted
+  // ---- row maximum (for the softmax) and admission of ties in id order
+  float mx = -INFINITY;
+  int ties = 0;
+#pragma unroll
+  for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+    if (i < per) {
+      mx = fmaxf(mx, v[i]);
+      ties += order_key(v[i]) == thr_key ? 1 : 0;
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  s_tie_scan[tid] = ties;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_red[0];
+    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+    s_bcast = m;
+    int run = 0;
+    for (int t = 0; t < SAMPLE_THREADS; ++t) {  // exclusive scan of the tie counts
+      const int c = s_tie_scan[t];
+      s_tie_scan[t] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  mx = s_bcast;
+  int tie_rank = s_tie_scan[tid];
+  // ---- probabilities of the admitted values, thread-local sums
+  float p[SAMPLE_MAX_PER_THREAD];
+  float local = 0.f;
+#pragma unroll
+  for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+    p[i] = 0.f;
+    if (i < per) {
+      const uint32_t key = order_key(v[i]);
+      bool in = key > thr_key;
+      if (key == thr_key) in = tie_rank++ < static_cast<int>(want);
+      if (in && v[i] != -INFINITY) p[i] = __expf(v[i] - mx);
+      local += p[i];
+    }
+  }
+  s_scan[tid] = local;
+  __syncthreads();
+  if (tid == 0) {
+    float run = 0.f;
+    for (int t = 0; t < SAMPLE_THREADS; ++t) {
+      const float c = s_scan[t];
+      s_scan[t] = run;  // exclusive prefix
+      run += c;
+    }
+    s_bcast = run;
+    s_pick = -1;
+  }
+  __syncthreads();
+  const float total = s_bcast;
+  const float u = uniform != nullptr ? fminf(fmaxf(uniform[row], 0.f), 0.99999994f) : 0.f;
+  const float target = u * total;
+  // the thread whose [begin, begin + local) interval holds the target walks its values; the LAST admitted value catches
+  // a target that rounding pushed past the total
+  const float begin = s_scan[tid];
+  if (local > 0.f && target >= begin && (target < begin + local)) {
+    float run = begin;
+    int pick = -1;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i) {
+      if (i < per && p[i] > 0.f) {
+        pick = tid * per + i;
+        run += p[i];
+        if (target < run) break;
+      }
+    }
+    s_pick = pick;
+  }
+  __syncthreads();
+  if (s_pick < 0) {  // target == total after rounding: the last admitted id
+    int last = -1;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_MAX_PER_THREAD; ++i)
+      if (i < per && p[i] > 0.f) last = tid * per + i;
+    atomicMax(&s_pick, last);
+    __syncthreads();
+  }
+  if (tid == 0) out[row] = s_pick < 0 ? 0 : s_pick;
+}
+
 }  // namespace
 }  // namespace tsfmx
 
@@ -502,4 +656,18 @@ extern "C" int tsfmx_t5_encoder_attention_mma(const void* qkv, int64_t batch, in
       reinterpret_cast<const __nv_bfloat16*>(qkv), seq, seq_pad, num_heads, key_mask, bias,
       reinterpret_cast<__nv_bfloat16*>(out));
   return check_last_launch("t5_encoder_attention_mma");
+}
+
+extern "C" int tsfmx_t5_sample_topk(const float* logits, int64_t rows, int32_t vocab, int32_t banned_id, float temperature,
+                                    int32_t top_k, const float* uniform, int64_t* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(logits != nullptr && out != nullptr, "t5_sample_topk: NULL pointer");
+  TSFMX_REQUIRE(rows >= 0 && vocab > 0 && vocab <= SAMPLE_THREADS * SAMPLE_MAX_PER_THREAD,
+                "t5_sample_topk: vocab %d out of range (<= %d)", vocab, SAMPLE_THREADS * SAMPLE_MAX_PER_THREAD);
+  TSFMX_REQUIRE(temperature > 0.f, "t5_sample_topk: temperature must be positive");
+  TSFMX_REQUIRE(uniform != nullptr || top_k == 1, "t5_sample_topk: sampling needs one uniform number per row");
+  if (rows == 0) return TSFMX_OK;
+  t5_sample_topk_kernel<<<static_cast<unsigned>(rows), SAMPLE_THREADS, 0, stream>>>(logits, vocab, banned_id,
+                                                                                     1.0f / temperature, top_k, uniform, out);
+  return check_last_launch("t5_sample_topk");
 }

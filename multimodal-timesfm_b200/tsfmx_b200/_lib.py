@@ -124,6 +124,9 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     ),
     "tsfmx_attention_force_simt": (c_int32, [c_int32]),
     "tsfmx_tune": (c_int32, [c_int32, c_int32]),
+    "tsfmx_t5_sample_topk": (
+        c_int32, [c_void_p, c_int64, c_int32, c_int32, c_float, c_int32, c_void_p, c_void_p, c_void_p]
+    ),
     "tsfmx_embed_rows": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tsfmx_t5_attention": (
         c_int32,

@@ -714,6 +714,24 @@ def embed_rows(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
 
 
 @_on_operand_device
+def t5_sample_topk(logits: torch.Tensor, banned_id: int = -1, top_k: int = 1, temperature: float = 1.0,
+                   uniform: torch.Tensor | None = None) -> torch.Tensor:
+    """logits [rows, vocab] fp32 -> next ids [rows] int64: ban / temperature / top-k / softmax / inverse-CDF sampling in
+    one launch (``top_k = 1``: greedy, first maximum)."""
+    lib = _lib.load()
+    _lib.require_cuda(logits, uniform)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.is_contiguous()
+    rows, vocab = logits.shape
+    if uniform is not None:
+        uniform = uniform.reshape(-1).contiguous().float()
+        assert uniform.numel() == rows
+    out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    check(lib.tsfmx_t5_sample_topk(ptr(logits), rows, vocab, banned_id, float(temperature), int(top_k), ptr(uniform),
+                                   ptr(out), stream()))
+    return out
+
+
+@_on_operand_device
 def t5_attention(
     q: torch.Tensor,
     k: torch.Tensor,

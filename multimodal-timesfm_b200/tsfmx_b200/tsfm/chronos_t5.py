@@ -488,17 +488,15 @@ class ChronosT5Adapter(TsfmAdapter):
             ops.gemm([(xn, w["lm_head"], d)], b, m.vocab_size, logits, DT_F32, precision=prec)
             if all_logits is not None:
                 all_logits[:, step] = logits
-            logits[:, m.eos_token_id] = float("-inf")  # min_new_tokens = horizon: no EOS before the horizon is full
+            # min_new_tokens = horizon: EOS is banned until the horizon is full.  Greedy = top-1; otherwise temperature /
+            # top-k sampling as upstream's generate(do_sample=True, top_k=50, temperature=1.0) - ban, top-k, softmax and the
+            # draw in one kernel, fed one uniform number per path
             if samples == 1:
-                cur = logits.argmax(-1)
-            else:  # temperature / top-k sampling, as upstream's generate(do_sample=True, top_k=50, temperature=1.0)
-                scaled = logits / self.temperature if self.temperature != 1.0 else logits
-                if self.top_k and self.top_k < m.vocab_size:
-                    top_v, top_i = torch.topk(scaled, self.top_k, dim=-1)
-                    pick = torch.multinomial(torch.softmax(top_v, -1), 1, generator=self.generator)
-                    cur = top_i.gather(-1, pick).squeeze(-1)
-                else:
-                    cur = torch.multinomial(torch.softmax(scaled, -1), 1, generator=self.generator).squeeze(-1)
+                cur = ops.t5_sample_topk(logits, m.eos_token_id, top_k=1)
+            else:
+                u = torch.rand(b, device=dev, generator=self.generator)
+                cur = ops.t5_sample_topk(logits, m.eos_token_id, top_k=int(self.top_k or 0),
+                                         temperature=float(self.temperature), uniform=u)
             tokens[:, step] = cur
             if forced_ids is not None:
                 cur = forced_ids[:, step].to(torch.int64).contiguous()

@@ -185,3 +185,39 @@ def test_sampled_decoding_paths_and_quantiles():
     assert torch.equal(first, again)
     assert bool((first[..., 1:] >= first[..., :-1]).all())                            # quantiles are ordered
     assert point.shape == (5, 10) and torch.isfinite(first).all()
+
+
+def test_sample_topk_kernel():
+    """tsfmx_t5_sample_topk: greedy = first maximum with the banned id excluded; sampled ids come from softmax over the
+    top-k survivors (frequencies over 40 000 draws), never a banned or non-top-k id; u -> 1 picks the last survivor."""
+    from tsfmx_b200 import ops
+
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    logits = torch.randn(64, 4096, generator=gen, device=DEV) * 3
+    logits[0, 1] = 100.0  # the banned id would win
+    logits[1, 7] = logits[1, 99] = 50.0  # a tie: first index
+    greedy = ops.t5_sample_topk(logits, banned_id=1, top_k=1)
+    masked = logits.clone()
+    masked[:, 1] = float("-inf")
+    assert torch.equal(greedy, masked.argmax(-1)) and greedy[1].item() == 7
+    # one row, many draws
+    row = torch.randn(4096, generator=gen, device=DEV) * 2
+    row[1] = 30.0
+    draws = 40000
+    u = torch.rand(draws, generator=gen, device=DEV)
+    for top_k, temperature in ((5, 1.0), (50, 0.7), (0, 1.0)):
+        ids = ops.t5_sample_topk(row.expand(draws, -1).contiguous(), banned_id=1, top_k=top_k, temperature=temperature, uniform=u)
+        ref = row.clone()
+        ref[1] = float("-inf")
+        ref = ref / temperature
+        k = top_k if top_k else 4096
+        top_v, top_i = torch.topk(ref, k)
+        probs = torch.softmax(top_v, -1)
+        assert bool(torch.isin(ids, top_i).all()) and not bool((ids == 1).any())
+        freq = torch.bincount(ids, minlength=4096)[top_i].float() / draws
+        # binomial standard error of the largest probabilities is ~2.5e-3 at 40 000 draws
+        assert (freq - probs)[:5].abs().max().item() < 1.5e-2, (top_k, freq[:5], probs[:5])
+        assert abs(freq.sum().item() - 1.0) < 1e-6
+    last = ops.t5_sample_topk(row[None].contiguous(), banned_id=1, top_k=5, uniform=torch.ones(1, device=DEV))
+    top5 = torch.topk(torch.where(torch.arange(4096, device=DEV) == 1, float("-inf"), row), 5).indices
+    assert last.item() == top5.max().item()  # inverse CDF in id order: the highest id among the survivors
