@@ -494,9 +494,9 @@ class ChronosT5Adapter(TsfmAdapter):
             if samples == 1:
                 cur = ops.t5_sample_topk(logits, m.eos_token_id, top_k=1)
             else:
-                u = torch.rand(b, device=dev, generator=self.generator)
+                draws = torch.rand(b, device=dev, generator=self.generator)
                 cur = ops.t5_sample_topk(logits, m.eos_token_id, top_k=int(self.top_k or 0),
-                                         temperature=float(self.temperature), uniform=u)
+                                         temperature=float(self.temperature), uniform=draws)
             tokens[:, step] = cur
             if forced_ids is not None:
                 cur = forced_ids[:, step].to(torch.int64).contiguous()
