@@ -101,7 +101,7 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
                                                 const int32_t* __restrict__ num_masked,
                                                 const float* __restrict__ inv_freq, const float* __restrict__ q_ln_w,
                                                 const float* __restrict__ k_ln_w, const float* __restrict__ q_scale,
-                                                float eps, void* __restrict__ out) {
+                                                float eps, int rope_rows, void* __restrict__ out) {
   constexpr int DPL = (HD + 31) / 32;
   constexpr int HALF = HD / 2;
   constexpr int LDS = HD + 1;
@@ -110,6 +110,10 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int PER_WARP = (MQ + 2 * KT) * LDS + MQ * KT;
+  // per-block table of (cos, sin)(pos * inv_freq) for pos in [-n_ctx, total_tokens): every (series, head) of the block
+  // looks its rotations up instead of evaluating 3 sincosf per lane and key row (the kernel was SFU / range-reduction
+  // bound: 68 key rows x 80 rotations per pair at ctx 2048).  rope_rows = 0: table does not fit, evaluate directly.
+  float2* s_rope = reinterpret_cast<float2*>(smem_dec + warps_per_block * PER_WARP);
   float* sQ = smem_dec + warp * PER_WARP;
   float* sK = sQ + MQ * LDS;
   float* sV = sK + KT * LDS;
@@ -120,9 +124,18 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
   for (int r = 0; r < regions.count; ++r) total_tokens += regions.tokens[r];
   const int q_pos0 = total_tokens - MQ;  // sequence index of the first new token
   const void* q_region = regions.ptr[regions.count - 1];
+  if (rope_rows > 0) {
+    for (int i = threadIdx.x; i < rope_rows * HALF; i += blockDim.x) {
+      const int p = i / HALF, f = i - p * HALF;
+      float sn, cs;
+      sincosf(static_cast<float>(p - n_ctx) * __ldg(inv_freq + f), &sn, &cs);
+      s_rope[i] = make_float2(cs, sn);
+    }
+    __syncthreads();
+  }
 
   // RoPE (rotate-half) + RMSNorm over head_dim of one staged row, in place; `scale_w` = per-dim weight
-  auto condition_row = [&](float* row, float pos, const float* w1, const float* w2) {
+  auto condition_row = [&](float* row, int ipos, const float* w1, const float* w2) {
     float r[DPL];
     float ss = 0.f;
 #pragma unroll
@@ -132,7 +145,12 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
       if (d < HD) {
         const int f = d < HALF ? d : d - HALF;
         float sn, cs;
-        sincosf(pos * __ldg(inv_freq + f), &sn, &cs);
+        if (rope_rows > 0) {
+          const float2 e = s_rope[(ipos + n_ctx) * HALF + f];
+          cs = e.x, sn = e.y;
+        } else {
+          sincosf(static_cast<float>(ipos) * __ldg(inv_freq + f), &sn, &cs);
+        }
         const int dp = d < HALF ? d + HALF : d - HALF;
         const float sgn = d < HALF ? -1.f : 1.f;
         r[t] = row[d] * cs + sgn * row[dp] * sn;
@@ -169,7 +187,7 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
     }
     __syncwarp();
     for (int i = 0; i < MQ; ++i) {
-      condition_row(sQ + i * LDS, static_cast<float>(q_pos0 + i - nm), q_ln_w, q_scale);
+      condition_row(sQ + i * LDS, q_pos0 + i - nm, q_ln_w, q_scale);
       __syncwarp();
     }
     float m_run[MQ], l_run[MQ], o[MQ][DPL];
@@ -204,7 +222,7 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
       region = rr, region_start = rs;
       __syncwarp();
       for (int jj = 0; jj < tile; ++jj) {
-        condition_row(sK + jj * LDS, static_cast<float>(j0 + jj - nm), k_ln_w, nullptr);
+        condition_row(sK + jj * LDS, j0 + jj - nm, k_ln_w, nullptr);
         __syncwarp();
       }
       // scores: lane = key of the tile
@@ -384,8 +402,14 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
   if (batch == 0) return TSFMX_OK;
   constexpr int HD = 80, MQ = 4;
   const int per_warp = ((MQ + 64) * (HD + 1) + MQ * 32) * 4;
-  const int wpb = 4;
-  const int smem = wpb * per_warp;
+  int total_tokens = 0;
+  for (int r = 0; r < num_regions; ++r) total_tokens += region_tokens[r];
+  int rope_rows = n_ctx + total_tokens;  // positions -n_ctx .. total_tokens - 1 (num_masked <= n_ctx)
+  int rope_bytes = rope_rows * (HD / 2) * static_cast<int>(sizeof(float2));
+  if (rope_bytes > 96 * 1024) rope_rows = 0, rope_bytes = 0;
+  // 8 warps share one table where that still fits an SM's shared memory, else two blocks of 4 warps
+  const int wpb = (rope_rows > 0 && 8 * per_warp + rope_bytes <= 224 * 1024) ? 8 : 4;
+  const int smem = wpb * per_warp + rope_bytes;
   const int64_t total = batch * num_heads;
   const int64_t blocks = (total + wpb - 1) / wpb;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
@@ -397,7 +421,7 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
       return TSFMX_ERR_CUDA;
     }
     kern<<<grid, wpb * 32, smem, stream>>>(regions, batch, num_heads, n_ctx, patch_mask, num_masked, inv_freq, q_ln_w,
-                                            k_ln_w, q_scale, eps, out);
+                                            k_ln_w, q_scale, eps, rope_rows, out);
     return check_last_launch("timesfm_attention_decode");
   };
   if (qkv_dtype == TSFMX_DT_BF16) {

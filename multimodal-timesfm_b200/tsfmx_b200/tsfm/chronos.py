@@ -722,6 +722,12 @@ class Chronos2Adapter(TsfmAdapter):
         instance.load_checkpoint(hf_hub_download(repo_id=repo_id, filename="model.safetensors"))
         return instance
 
+    @property
+    def graph_safe(self) -> bool:
+        """The forecast path makes no host synchronisation (lazily built tables are filled by the eager pass that
+        precedes a capture), so ``MultimodalDecoder`` / ``MultimodalEvaluator`` may replay it from a CUDA graph."""
+        return True
+
     def freeze_parameters(self) -> None:
         for param in self.parameters():
             param.requires_grad = False

@@ -432,7 +432,7 @@ def synthetic_batch(batch: int, context: int, horizon: int, text_dims: int = 384
 _BF16_OUTPUT_LINEARS = ("q_proj", "k_proj", "v_proj", "o_proj", "fc2")
 
 
-def bf16_oracle(oracle: OracleDecoder) -> OracleDecoder:
+def bf16_oracle(oracle: nn.Module, output_linears: tuple[str, ...] = _BF16_OUTPUT_LINEARS) -> nn.Module:
     """A copy of ``oracle`` that computes the way a bf16 deployment of the reference would: every ``nn.Linear`` sees
     bf16-rounded weights and bf16-rounded inputs and accumulates in fp32; the outputs of the attention projections and
     of the second MLP matrix are rounded to bf16 as well (they are stored as bf16 activations).  Everything else -
@@ -441,7 +441,10 @@ def bf16_oracle(oracle: OracleDecoder) -> OracleDecoder:
     Its distance to the fp32 oracle is what bf16 operands cost on THIS model and THESE inputs, independent of any
     kernel: SURVEY.md section 8(d) asks for the bf16 tolerance to be "calibrated against the oracle itself run with
     bf16 weights/activations".  tests/test_parity_gpu.py and bench.py bound the product's bf16 error by a stated
-    multiple of it instead of a hand-set constant."""
+    multiple of it instead of a hand-set constant.
+
+    ``output_linears``: last name components (or dotted suffixes) of the Linears whose OUTPUT is stored in bf16 by a
+    bf16 deployment - TimesFM's by default; ``CHRONOS2_BF16_OUTPUTS`` / ``T5_BF16_OUTPUTS`` for the other oracles."""
     import copy
 
     twin = copy.deepcopy(oracle).eval()
@@ -460,7 +463,7 @@ def bf16_oracle(oracle: OracleDecoder) -> OracleDecoder:
             if isinstance(module, nn.Linear):
                 module.weight.copy_(to_bf16(module.weight))
                 module.register_forward_pre_hook(round_inputs)
-                if name.rsplit(".", 1)[-1] in _BF16_OUTPUT_LINEARS:
+                if name.rsplit(".", 1)[-1] in output_linears or name.endswith(tuple("." + o for o in output_linears if "." in o)):
                     module.register_forward_hook(round_output)
     return twin
 
@@ -473,6 +476,9 @@ def rel_max(a: torch.Tensor, b: torch.Tensor) -> float:
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
+
+CHRONOS2_BF16_OUTPUTS = ("time_attn.q", "time_attn.k", "time_attn.v", "time_attn.o", "group_attn.o", "wo")
+T5_BF16_OUTPUTS = ("q", "k", "v", "o", "wo")
 
 # the product's bf16 mode may deviate from the fp32 oracle by at most this multiple of the bf16 oracle's own deviation
 # (two independent bf16 realisations of the same computation differ from each other by about sqrt(2) of it; the product
