@@ -444,14 +444,16 @@ int tsfmx_timesfm_patchify_continue(const float* x, int64_t x_series_stride, int
  * (causal).  Region r is a raw qkv matrix [B * region_tokens[r], 3 * H * hd] (f32 or bf16) exactly as
  * tsfmx_gemm left it - region 0 the prefill's, then one per earlier decode step - so the "KV cache" needs no
  * copy.  region_ptrs / region_tokens are HOST arrays (num_regions <= TSFMX_MAX_KV_REGIONS).  patch_mask
- * [B, n_ctx] / num_masked [B] describe the left padding of region 0 as in tsfmx_timesfm_attention.
+ * [B, n_ctx] / num_masked [B] describe the left padding of region 0 as in tsfmx_timesfm_attention.  rope_table
+ * [rope_len, hd / 2, 2] fp32 = (cos, sin)(position * inv_freq) from tsfmx_rope_table (positions beyond it, or
+ * rope_len = 0, are evaluated directly).
  *   out [B * q_tokens, H * hd] of out_dtype.
  */
 int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, const int32_t* region_tokens, int32_t num_regions,
                                    int32_t qkv_dtype, int64_t batch, int32_t num_heads, int32_t head_dim, int32_t n_ctx,
-                                   const uint8_t* patch_mask, const int32_t* num_masked, const float* inv_freq,
-                                   const float* q_ln_w, const float* k_ln_w, const float* q_scale, float eps,
-                                   int32_t out_dtype, void* out, void* stream);
+                                   const uint8_t* patch_mask, const int32_t* num_masked, const float* rope_table,
+                                   int32_t rope_len, const float* inv_freq, const float* q_ln_w, const float* k_ln_w,
+                                   const float* q_scale, float eps, int32_t out_dtype, void* out, void* stream);
 
 /*
  * Forecast extras in one pass (HF modeling_timesfm2_5.py:797-837): flip-invariance combination

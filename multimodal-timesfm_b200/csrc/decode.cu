@@ -10,7 +10,8 @@
 //                                      simply the raw qkv matrices earlier launches left in HBM: the prefill's
 //                                      [B * N, 3 D] and one [B * 4, 3 D] per decode step, passed as a list of regions
 //                                      (no copy, no re-layout).  Keys are conditioned (RoPE, RMSNorm, k_ln) on the
-//                                      fly in 32-key tiles with an online softmax, so any context length fits.
+//                                      fly in 32-key tiles (one lane per key) with an online softmax, so any
+//                                      context length fits.
 //   timesfm_forecast_finalize_kernel : flip-invariance combination, continuous quantile head, positivity clamp and
 //                                      horizon slice (HF modeling_timesfm2_5.py:797-837) in one pass.
 #include <math.h>
@@ -94,80 +95,50 @@ __device__ __forceinline__ float ld_qkv(const void* p, int64_t idx) {
   else return reinterpret_cast<const float*>(p)[idx];
 }
 
-// One warp per (series, head).  MQ = number of new tokens (queries) = tokens of the last region.
+// One warp per (series, head).  MQ = 4 new tokens (queries) = tokens of the last region.
+//
+// Work layout (second version; the first one conditioned every key row with the lanes spread over head_dim - a warp
+// reduction and ~60 instructions per key row - and staged V in shared memory although every V element is used once):
+//   * queries: conditioned with lanes over head_dim (4 rows only), pre-multiplied by k_ln_w, stored TRANSPOSED
+//     (sQT[d][4]) so that one 16-byte shared-memory load feeds the four dot products of a key;
+//   * keys: a tile of 32 raw key rows is staged through shared memory (coalesced global reads), then LANE j owns key
+//     j: it pulls its row into registers, rotates it with (cos, sin) from a global table (L1-resident, built once per
+//     inv_freq by tsfmx_rope_table), accumulates its own sum of squares (no shuffles) and keeps 1 / rms as a scalar
+//     that multiplies the score instead of the 80 elements;
+//   * values: read straight from global memory in the P.V loop (lanes over head_dim, 160 contiguous bytes per row).
 template <int HD, int MQ, int QKV_BF16, int OUT>
-__global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch, int num_heads, int n_ctx,
-                                                const uint8_t* __restrict__ patch_mask,
-                                                const int32_t* __restrict__ num_masked,
-                                                const float* __restrict__ inv_freq, const float* __restrict__ q_ln_w,
-                                                const float* __restrict__ k_ln_w, const float* __restrict__ q_scale,
-                                                float eps, int rope_rows, void* __restrict__ out) {
+__global__ void __launch_bounds__(256) timesfm_attention_decode_kernel(
+    KvRegions regions, int64_t batch, int num_heads, int n_ctx, const uint8_t* __restrict__ patch_mask,
+    const int32_t* __restrict__ num_masked, const float2* __restrict__ rope, int rope_len,
+    const float* __restrict__ inv_freq, const float* __restrict__ q_ln_w, const float* __restrict__ k_ln_w,
+    const float* __restrict__ q_scale, float eps, void* __restrict__ out) {
+  static_assert(MQ == 4, "the transposed query tile is read as float4");
   constexpr int DPL = (HD + 31) / 32;
   constexpr int HALF = HD / 2;
   constexpr int LDS = HD + 1;
   constexpr int KT = 32;  // keys per tile
-  extern __shared__ float smem_dec[];
+  extern __shared__ __align__(16) float smem_dec[];
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int PER_WARP = (MQ + 2 * KT) * LDS + MQ * KT;
-  // per-block table of (cos, sin)(pos * inv_freq) for pos in [-n_ctx, total_tokens): every (series, head) of the block
-  // looks its rotations up instead of evaluating 3 sincosf per lane and key row (the kernel was SFU / range-reduction
-  // bound: 68 key rows x 80 rotations per pair at ctx 2048).  rope_rows = 0: table does not fit, evaluate directly.
-  float2* s_rope = reinterpret_cast<float2*>(smem_dec + warps_per_block * PER_WARP);
-  float* sQ = smem_dec + warp * PER_WARP;
-  float* sK = sQ + MQ * LDS;
-  float* sV = sK + KT * LDS;
-  float* sP = sV + KT * LDS;  // [MQ][KT]
+  constexpr int PER_WARP = HD * MQ + KT * LDS + MQ * KT + MQ * LDS;  // sQT | sK | sP | sQ (row-major scratch)
+  float* sQT = smem_dec + warp * PER_WARP;
+  float* sK = sQT + HD * MQ;
+  float* sP = sK + KT * LDS;   // [KT][MQ]
+  float* sQ = sP + MQ * KT;    // [MQ][LDS]
   const int width = num_heads * HD;
   const int64_t ld = 3 * static_cast<int64_t>(width);
   int total_tokens = 0;
   for (int r = 0; r < regions.count; ++r) total_tokens += regions.tokens[r];
   const int q_pos0 = total_tokens - MQ;  // sequence index of the first new token
   const void* q_region = regions.ptr[regions.count - 1];
-  if (rope_rows > 0) {
-    for (int i = threadIdx.x; i < rope_rows * HALF; i += blockDim.x) {
-      const int p = i / HALF, f = i - p * HALF;
-      float sn, cs;
-      sincosf(static_cast<float>(p - n_ctx) * __ldg(inv_freq + f), &sn, &cs);
-      s_rope[i] = make_float2(cs, sn);
-    }
-    __syncthreads();
-  }
 
-  // RoPE (rotate-half) + RMSNorm over head_dim of one staged row, in place; `scale_w` = per-dim weight
-  auto condition_row = [&](float* row, int ipos, const float* w1, const float* w2) {
-    float r[DPL];
-    float ss = 0.f;
-#pragma unroll
-    for (int t = 0; t < DPL; ++t) {
-      const int d = lane + 32 * t;
-      r[t] = 0.f;
-      if (d < HD) {
-        const int f = d < HALF ? d : d - HALF;
-        float sn, cs;
-        if (rope_rows > 0) {
-          const float2 e = s_rope[(ipos + n_ctx) * HALF + f];
-          cs = e.x, sn = e.y;
-        } else {
-          sincosf(static_cast<float>(ipos) * __ldg(inv_freq + f), &sn, &cs);
-        }
-        const int dp = d < HALF ? d + HALF : d - HALF;
-        const float sgn = d < HALF ? -1.f : 1.f;
-        r[t] = row[d] * cs + sgn * row[dp] * sn;
-        ss += r[t] * r[t];
-      }
-    }
-    ss = warp_sum(ss);
-    const float rs = 1.0f / sqrtf(ss / static_cast<float>(HD) + eps);
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < DPL; ++t) {
-      const int d = lane + 32 * t;
-      if (d < HD) {
-        float v = __ldg(w1 + d) * (r[t] * rs);
-        if (w2 != nullptr) v *= __ldg(w2 + d);
-        row[d] = v;
-      }
+  auto rotation = [&](int ipos, int f, float& cs, float& sn) {
+    const int ap = ipos < 0 ? -ipos : ipos;
+    if (ap < rope_len) {
+      const float2 e = __ldg(rope + static_cast<int64_t>(ap) * HALF + f);
+      cs = e.x, sn = ipos < 0 ? -e.y : e.y;
+    } else {
+      sincosf(static_cast<float>(ipos) * __ldg(inv_freq + f), &sn, &cs);
     }
   };
 
@@ -176,7 +147,7 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
     const int64_t b = w / num_heads;
     const int h = static_cast<int>(w - b * num_heads);
     const int nm = num_masked != nullptr ? num_masked[b] : 0;
-    // ---- the new tokens' queries
+    // ---- the new tokens' queries: RoPE, RMSNorm, q_ln * q_scale, and k_ln folded in; lanes over head_dim
     for (int i = 0; i < MQ; ++i) {
       const int64_t base = (b * MQ + i) * ld + h * HD;
 #pragma unroll
@@ -187,9 +158,31 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
     }
     __syncwarp();
     for (int i = 0; i < MQ; ++i) {
-      condition_row(sQ + i * LDS, q_pos0 + i - nm, q_ln_w, q_scale);
-      __syncwarp();
+      float r[DPL];
+      float ss = 0.f;
+#pragma unroll
+      for (int t = 0; t < DPL; ++t) {
+        const int d = lane + 32 * t;
+        r[t] = 0.f;
+        if (d < HD) {
+          const int f = d < HALF ? d : d - HALF;
+          float sn, cs;
+          rotation(q_pos0 + i - nm, f, cs, sn);
+          const int dp = d < HALF ? d + HALF : d - HALF;
+          const float sgn = d < HALF ? -1.f : 1.f;
+          r[t] = sQ[i * LDS + d] * cs + sgn * sQ[i * LDS + dp] * sn;
+          ss += r[t] * r[t];
+        }
+      }
+      ss = warp_sum(ss);
+      const float rs = 1.0f / sqrtf(ss / static_cast<float>(HD) + eps);
+#pragma unroll
+      for (int t = 0; t < DPL; ++t) {
+        const int d = lane + 32 * t;
+        if (d < HD) sQT[d * MQ + i] = __ldg(q_ln_w + d) * (r[t] * rs) * __ldg(q_scale + d) * __ldg(k_ln_w + d);
+      }
     }
+    __syncwarp();
     float m_run[MQ], l_run[MQ], o[MQ][DPL];
 #pragma unroll
     for (int i = 0; i < MQ; ++i) {
@@ -201,42 +194,53 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
     int region = 0, region_start = 0;  // sequence index of the region's first token
     for (int j0 = 0; j0 < total_tokens; j0 += KT) {
       const int tile = min(KT, total_tokens - j0);
-      // stage raw k, v rows of the tile (a tile may straddle regions)
-      int rr = region, rs = region_start;
+      // stage the raw key rows of the tile (a tile may straddle regions); remember where the tile starts
+      const int tile_region = region, tile_region_start = region_start;
+      int rr = region, rs_ = region_start;
       for (int jj = 0; jj < tile; ++jj) {
         const int j = j0 + jj;
-        while (j >= rs + regions.tokens[rr]) {
-          rs += regions.tokens[rr];
+        while (j >= rs_ + regions.tokens[rr]) {
+          rs_ += regions.tokens[rr];
           ++rr;
         }
-        const int64_t base = (b * regions.tokens[rr] + (j - rs)) * ld + h * HD;
+        const int64_t base = (b * regions.tokens[rr] + (j - rs_)) * ld + h * HD + width;
 #pragma unroll
         for (int t = 0; t < DPL; ++t) {
           const int d = lane + 32 * t;
-          if (d < HD) {
-            sK[jj * LDS + d] = ld_qkv<QKV_BF16>(regions.ptr[rr], base + width + d);
-            sV[jj * LDS + d] = ld_qkv<QKV_BF16>(regions.ptr[rr], base + 2 * width + d);
-          }
+          if (d < HD) sK[jj * LDS + d] = ld_qkv<QKV_BF16>(regions.ptr[rr], base + d);
         }
       }
-      region = rr, region_start = rs;
+      region = rr, region_start = rs_;
       __syncwarp();
-      for (int jj = 0; jj < tile; ++jj) {
-        condition_row(sK + jj * LDS, j0 + jj - nm, k_ln_w, nullptr);
-        __syncwarp();
-      }
-      // scores: lane = key of the tile
+      // lane = key: rotate the own row in registers, own sum of squares, scores against the four queries
       const int j = j0 + lane;
       const bool key_ok = lane < tile && (j >= n_ctx || patch_mask == nullptr || patch_mask[b * n_ctx + j] == 0);
+      float s4[MQ] = {0.f, 0.f, 0.f, 0.f};
+      float krs = 0.f;
+      if (lane < tile) {
+        const float* krow = sK + lane * LDS;
+        const int ipos = j - nm;
+        float ss = 0.f;
+#pragma unroll 8
+        for (int f = 0; f < HALF; ++f) {
+          float cs, sn;
+          rotation(ipos, f, cs, sn);
+          const float a = krow[f], c = krow[f + HALF];
+          const float r1 = a * cs - c * sn, r2 = c * cs + a * sn;
+          ss = fmaf(r1, r1, fmaf(r2, r2, ss));
+          const float4 q1 = *reinterpret_cast<const float4*>(sQT + f * MQ);
+          const float4 q2 = *reinterpret_cast<const float4*>(sQT + (f + HALF) * MQ);
+          s4[0] = fmaf(q1.x, r1, fmaf(q2.x, r2, s4[0]));
+          s4[1] = fmaf(q1.y, r1, fmaf(q2.y, r2, s4[1]));
+          s4[2] = fmaf(q1.z, r1, fmaf(q2.z, r2, s4[2]));
+          s4[3] = fmaf(q1.w, r1, fmaf(q2.w, r2, s4[3]));
+        }
+        krs = 1.0f / sqrtf(ss / static_cast<float>(HD) + eps);
+      }
+      float p4[MQ];
 #pragma unroll
       for (int i = 0; i < MQ; ++i) {
-        float s = -INFINITY;
-        if (key_ok && j <= q_pos0 + i) {
-          float acc = 0.f;
-#pragma unroll 8
-          for (int d = 0; d < HD; ++d) acc = fmaf(sQ[i * LDS + d], sK[lane * LDS + d], acc);
-          s = acc;
-        }
+        const float s = (key_ok && j <= q_pos0 + i) ? s4[i] * krs : -INFINITY;
         const float m_new = fmaxf(m_run[i], warp_max(s));
         // a new token always sees itself, so m_new is finite from the tile that holds it on; before that every
         // probability of the tile is zero and the running state stays empty
@@ -244,19 +248,31 @@ __global__ void timesfm_attention_decode_kernel(KvRegions regions, int64_t batch
         const float corr = (m_run[i] == -INFINITY) ? 0.f : expf(m_run[i] - m_new);
         l_run[i] = l_run[i] * corr + warp_sum(p);
         m_run[i] = m_new;
-        sP[i * KT + lane] = p;
+        p4[i] = p;
 #pragma unroll
         for (int t = 0; t < DPL; ++t) o[i][t] *= corr;
       }
+      *reinterpret_cast<float4*>(sP + lane * MQ) = make_float4(p4[0], p4[1], p4[2], p4[3]);
       __syncwarp();
+      // P.V with the value rows read from global memory (each element is used exactly once)
+      rr = tile_region, rs_ = tile_region_start;
       for (int jj = 0; jj < tile; ++jj) {
+        const int jv = j0 + jj;
+        while (jv >= rs_ + regions.tokens[rr]) {
+          rs_ += regions.tokens[rr];
+          ++rr;
+        }
+        const int64_t base = (b * regions.tokens[rr] + (jv - rs_)) * ld + h * HD + 2 * width;
+        const float4 p = *reinterpret_cast<const float4*>(sP + jj * MQ);
 #pragma unroll
-        for (int i = 0; i < MQ; ++i) {
-          const float p = sP[i * KT + jj];
-#pragma unroll
-          for (int t = 0; t < DPL; ++t) {
-            const int d = lane + 32 * t;
-            if (d < HD) o[i][t] = fmaf(p, sV[jj * LDS + d], o[i][t]);
+        for (int t = 0; t < DPL; ++t) {
+          const int d = lane + 32 * t;
+          if (d < HD) {
+            const float v = ld_qkv<QKV_BF16>(regions.ptr[rr], base + d);
+            o[0][t] = fmaf(p.x, v, o[0][t]);
+            o[1][t] = fmaf(p.y, v, o[1][t]);
+            o[2][t] = fmaf(p.z, v, o[2][t]);
+            o[3][t] = fmaf(p.w, v, o[3][t]);
           }
         }
       }
@@ -372,9 +388,10 @@ extern "C" int tsfmx_timesfm_patchify_continue(const float* x, int64_t x_series_
 extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, const int32_t* region_tokens,
                                               int32_t num_regions, int32_t qkv_dtype, int64_t batch, int32_t num_heads,
                                               int32_t head_dim, int32_t n_ctx, const uint8_t* patch_mask,
-                                              const int32_t* num_masked, const float* inv_freq, const float* q_ln_w,
-                                              const float* k_ln_w, const float* q_scale, float eps, int32_t out_dtype,
-                                              void* out, void* stream_) {
+                                              const int32_t* num_masked, const float* rope_table, int32_t rope_len,
+                                              const float* inv_freq, const float* q_ln_w, const float* k_ln_w,
+                                              const float* q_scale, float eps, int32_t out_dtype, void* out,
+                                              void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TSFMX_REQUIRE(region_ptrs != nullptr && region_tokens != nullptr && out != nullptr && inv_freq != nullptr &&
                     q_ln_w != nullptr && k_ln_w != nullptr && q_scale != nullptr,
@@ -385,6 +402,7 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
   TSFMX_REQUIRE(qkv_dtype == TSFMX_DT_F32 || qkv_dtype == TSFMX_DT_BF16,
                 "timesfm_attention_decode: qkv must be f32 or bf16");
   TSFMX_REQUIRE(out_dtype >= TSFMX_DT_F32 && out_dtype <= TSFMX_DT_BF16_SPLIT, "timesfm_attention_decode: bad out_dtype");
+  TSFMX_REQUIRE(rope_len >= 0 && (rope_len == 0 || rope_table != nullptr), "timesfm_attention_decode: bad rope table");
   KvRegions regions;
   regions.count = num_regions;
   for (int r = 0; r < num_regions; ++r) {
@@ -401,18 +419,12 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
   }
   if (batch == 0) return TSFMX_OK;
   constexpr int HD = 80, MQ = 4;
-  const int per_warp = ((MQ + 64) * (HD + 1) + MQ * 32) * 4;
-  int total_tokens = 0;
-  for (int r = 0; r < num_regions; ++r) total_tokens += region_tokens[r];
-  int rope_rows = n_ctx + total_tokens;  // positions -n_ctx .. total_tokens - 1 (num_masked <= n_ctx)
-  int rope_bytes = rope_rows * (HD / 2) * static_cast<int>(sizeof(float2));
-  if (rope_bytes > 96 * 1024) rope_rows = 0, rope_bytes = 0;
-  // 8 warps share one table where that still fits an SM's shared memory, else two blocks of 4 warps
-  const int wpb = (rope_rows > 0 && 8 * per_warp + rope_bytes <= 224 * 1024) ? 8 : 4;
-  const int smem = wpb * per_warp + rope_bytes;
+  const int per_warp = (HD * MQ + 32 * (HD + 1) + MQ * 32 + MQ * (HD + 1)) * 4;  // 13.5 KB
+  const int wpb = 8;
+  const int smem = wpb * per_warp;  // 108 KB: two blocks (16 warps) per SM
   const int64_t total = batch * num_heads;
   const int64_t blocks = (total + wpb - 1) / wpb;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
   auto launch = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -420,8 +432,9 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
       set_error("timesfm_attention_decode: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
       return TSFMX_ERR_CUDA;
     }
-    kern<<<grid, wpb * 32, smem, stream>>>(regions, batch, num_heads, n_ctx, patch_mask, num_masked, inv_freq, q_ln_w,
-                                            k_ln_w, q_scale, eps, rope_rows, out);
+    kern<<<grid, wpb * 32, smem, stream>>>(regions, batch, num_heads, n_ctx, patch_mask, num_masked,
+                                            reinterpret_cast<const float2*>(rope_table), rope_len, inv_freq, q_ln_w, k_ln_w,
+                                            q_scale, eps, out);
     return check_last_launch("timesfm_attention_decode");
   };
   if (qkv_dtype == TSFMX_DT_BF16) {

@@ -192,7 +192,7 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "tsfmx_timesfm_attention_decode": (
         c_int32,
         [POINTER(c_void_p), POINTER(c_int32), c_int32, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
-         c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p],
+         c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p],
     ),
     "tsfmx_timesfm_forecast_finalize": (
         c_int32,

@@ -576,10 +576,12 @@ def timesfm_attention_decode(
         out = alloc(batch * tokens[-1], num_heads * head_dim, out_dtype, regions[0].device)
     pm = None if patch_mask is None else _as_u8(patch_mask)
     n_ctx = 0 if pm is None else pm.shape[1]
+    rope_len = (max(sum(tokens), n_ctx) + 63) // 64 * 64  # |position| < max(total tokens, padded prefix); cached per length
+    table = rope_table(inv_freq, rope_len)
     check(
         lib.tsfmx_timesfm_attention_decode(
-            ptrs, toks, n, _dt(regions[0]), batch, num_heads, head_dim, n_ctx, ptr(pm), ptr(num_masked), ptr(inv_freq),
-            ptr(q_ln_w), ptr(k_ln_w), ptr(q_scale), eps, out_dtype, ptr(out), stream(),
+            ptrs, toks, n, _dt(regions[0]), batch, num_heads, head_dim, n_ctx, ptr(pm), ptr(num_masked), ptr(table),
+            rope_len, ptr(inv_freq), ptr(q_ln_w), ptr(k_ln_w), ptr(q_scale), eps, out_dtype, ptr(out), stream(),
         )
     )
     return out
