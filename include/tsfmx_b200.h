@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TSFMX_ABI_VERSION 1
+#define TSFMX_ABI_VERSION 2
 
 enum {
   TSFMX_OK = 0,

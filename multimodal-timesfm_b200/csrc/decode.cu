@@ -190,27 +190,40 @@ __global__ void __launch_bounds__(256) timesfm_attention_decode_kernel(
 #pragma unroll
       for (int t = 0; t < DPL; ++t) o[i][t] = 0.f;
     }
-    // ---- keys / values tile by tile over all regions
-    int region = 0, region_start = 0;  // sequence index of the region's first token
+    // ---- keys / values tile by tile over all regions.  Region 0 holds n0 tokens per series, every later region MQ
+    //      (one per decode step; checked by the launcher), so a sequence index maps to (region, row) without a search
+    const int n0 = regions.tokens[0];
+    auto row_base = [&](int j, const void*& ptr) -> int64_t {  // element index of q[0] of head h of sequence token j
+      const int r = j < n0 ? 0 : 1 + (j - n0) / MQ;
+      const int local = j < n0 ? j : (j - n0) % MQ;
+      ptr = regions.ptr[r];
+      return (b * (r == 0 ? n0 : MQ) + local) * ld + h * HD;
+    };
     for (int j0 = 0; j0 < total_tokens; j0 += KT) {
       const int tile = min(KT, total_tokens - j0);
-      // stage the raw key rows of the tile (a tile may straddle regions); remember where the tile starts
-      const int tile_region = region, tile_region_start = region_start;
-      int rr = region, rs_ = region_start;
-      for (int jj = 0; jj < tile; ++jj) {
-        const int j = j0 + jj;
-        while (j >= rs_ + regions.tokens[rr]) {
-          rs_ += regions.tokens[rr];
-          ++rr;
-        }
-        const int64_t base = (b * regions.tokens[rr] + (j - rs_)) * ld + h * HD + width;
+      // stage the raw key rows of the tile: 16-byte chunks, every lane keeps several independent loads in flight (a
+      // row-by-row loop exposed one global-memory latency per key row: 68 x ~0.7 us per (series, head))
+      constexpr int CPR = QKV_BF16 ? HD / 8 : HD / 4;  // 16-byte chunks per row
+#pragma unroll 5
+      for (int idx = lane; idx < tile * CPR; idx += 32) {
+        const int jj = idx / CPR, ch = idx - jj * CPR;
+        const void* ptr;
+        const int64_t base = row_base(j0 + jj, ptr) + width;
+        if constexpr (QKV_BF16) {
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ptr) + base + 8 * ch);
+          const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+          float* dst = sK + jj * LDS + 8 * ch;
 #pragma unroll
-        for (int t = 0; t < DPL; ++t) {
-          const int d = lane + 32 * t;
-          if (d < HD) sK[jj * LDS + d] = ld_qkv<QKV_BF16>(regions.ptr[rr], base + d);
+          for (int k = 0; k < 4; ++k) {
+            dst[2 * k] = __uint_as_float(wv[k] << 16);
+            dst[2 * k + 1] = __uint_as_float(wv[k] & 0xffff0000u);
+          }
+        } else {
+          const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ptr) + base + 4 * ch);
+          float* dst = sK + jj * LDS + 4 * ch;
+          dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
         }
       }
-      region = rr, region_start = rs_;
       __syncwarp();
       // lane = key: rotate the own row in registers, own sum of squares, scores against the four queries
       const int j = j0 + lane;
@@ -254,21 +267,18 @@ __global__ void __launch_bounds__(256) timesfm_attention_decode_kernel(
       }
       *reinterpret_cast<float4*>(sP + lane * MQ) = make_float4(p4[0], p4[1], p4[2], p4[3]);
       __syncwarp();
-      // P.V with the value rows read from global memory (each element is used exactly once)
-      rr = tile_region, rs_ = tile_region_start;
+      // P.V with the value rows read from global memory (each element is used exactly once); unrolled so that the loads
+      // of several key rows are in flight together
+#pragma unroll 8
       for (int jj = 0; jj < tile; ++jj) {
-        const int jv = j0 + jj;
-        while (jv >= rs_ + regions.tokens[rr]) {
-          rs_ += regions.tokens[rr];
-          ++rr;
-        }
-        const int64_t base = (b * regions.tokens[rr] + (jv - rs_)) * ld + h * HD + 2 * width;
+        const void* ptr;
+        const int64_t base = row_base(j0 + jj, ptr) + 2 * width;
         const float4 p = *reinterpret_cast<const float4*>(sP + jj * MQ);
 #pragma unroll
         for (int t = 0; t < DPL; ++t) {
           const int d = lane + 32 * t;
           if (d < HD) {
-            const float v = ld_qkv<QKV_BF16>(regions.ptr[rr], base + d);
+            const float v = ld_qkv<QKV_BF16>(ptr, base + d);
             o[0][t] = fmaf(p.x, v, o[0][t]);
             o[1][t] = fmaf(p.y, v, o[1][t]);
             o[2][t] = fmaf(p.z, v, o[2][t]);
@@ -412,6 +422,11 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
   }
   TSFMX_REQUIRE(n_ctx >= 0 && (num_regions == 1 || n_ctx <= region_tokens[0]) && (patch_mask == nullptr || n_ctx > 0),
                 "timesfm_attention_decode: n_ctx (%d) must be the padded-mask length of region 0", n_ctx);
+  for (int r = 1; r < num_regions; ++r)
+    TSFMX_REQUIRE(region_tokens[r] == 4, "timesfm_attention_decode: region %d holds %d tokens per series; every region after "
+                  "the prefill's must hold the 4 tokens of one decode step", r, region_tokens[r]);
+  for (int r = 0; r < num_regions; ++r)
+    TSFMX_REQUIRE(reinterpret_cast<uintptr_t>(region_ptrs[r]) % 16 == 0, "timesfm_attention_decode: region %d is not 16-byte aligned", r);
   if (head_dim != 80 || region_tokens[num_regions - 1] != 4) {
     set_error("timesfm_attention_decode: head_dim %d / %d new tokens unsupported (TimesFM 2.5: 80, 128 / 32 = 4)",
               head_dim, region_tokens[num_regions - 1]);

@@ -17,6 +17,7 @@ _CSRC = Path(__file__).resolve().parent.parent / "csrc"
 LIB_PATH = _CSRC / "libtsfmx_b200.so"
 
 OK = 0
+ABI_VERSION = 2  # TSFMX_ABI_VERSION of include/tsfmx_b200.h this binding was written against
 PREC_BF16, PREC_BF16X3 = 0, 1
 DT_F32, DT_BF16, DT_BF16_SPLIT = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SILU_GRAD, ACT_RELU_GRAD = 0, 1, 2, 3, 4
@@ -225,8 +226,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tsfmx_abi_version() != 1:
-        raise TsfmxError(f"ABI version mismatch: library reports {lib.tsfmx_abi_version()}, binding expects 1")
+    if lib.tsfmx_abi_version() != ABI_VERSION:
+        raise TsfmxError(f"ABI version mismatch: library reports {lib.tsfmx_abi_version()}, binding expects {ABI_VERSION}")
     if lib.tsfmx_sizeof_gemm_args() != ctypes.sizeof(GemmArgs):
         raise TsfmxError(
             f"tsfmx_gemm_args layout mismatch: library {lib.tsfmx_sizeof_gemm_args()} bytes, binding "
