@@ -468,9 +468,12 @@ def run_b200_arm(args) -> None:
 
         hbm_peak = H.peak_gbs()
         cases = H.stage_cases(dev, [(512, 262144), (2048, 65536)])
+        torch.cuda.synchronize()
+        time.sleep(3.0)  # an independent leg: let the power state of the forecast legs (1 kW cap, ~1.5 GHz) decay first
         with ClockSampler(local_rank) as sc:
             stages = H.measure(cases, 20, hbm_peak)
         stage_clocks = sc.summary()
+        stage_clocks["note"] = "measured after 3 s of idle; the stage kernels are issue-bound, so their GB/s follow the SM clock"
         del cases
         torch.cuda.empty_cache()
     parity = None

@@ -446,7 +446,7 @@ int tsfmx_timesfm_patchify_continue(const float* x, int64_t x_series_stride, int
  * copy.  region_ptrs / region_tokens are HOST arrays (num_regions <= TSFMX_MAX_KV_REGIONS).  patch_mask
  * [B, n_ctx] / num_masked [B] describe the left padding of region 0 as in tsfmx_timesfm_attention.  rope_table
  * [rope_len, hd / 2, 2] fp32 = (cos, sin)(position * inv_freq) from tsfmx_rope_table (positions beyond it, or
- * rope_len = 0, are evaluated directly).
+ * every |position|: rope_len >= max(total tokens, n_ctx).
  *   out [B * q_tokens, H * hd] of out_dtype.
  */
 int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, const int32_t* region_tokens, int32_t num_regions,

@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(256) timesfm_attention_decode_kernel(
   extern __shared__ __align__(16) float smem_dec[];
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int PER_WARP = HD * MQ + KT * LDS + MQ * KT + MQ * LDS;  // sQT | sK | sP | sQ (row-major scratch)
+  constexpr int PER_WARP = HD * MQ + MQ * KT + MQ * LDS;  // sQT | sP | sQ (row-major scratch); a multiple of 4 floats
+  static_assert(PER_WARP % 4 == 0, "float4 alignment of the per-warp tiles");
   float* sQT = smem_dec + warp * PER_WARP;
-  float* sK = sQT + HD * MQ;
-  float* sP = sK + KT * LDS;   // [KT][MQ]
+  float* sP = sQT + HD * MQ;   // [KT][MQ]
   float* sQ = sP + MQ * KT;    // [MQ][LDS]
   const int width = num_heads * HD;
   const int64_t ld = 3 * static_cast<int64_t>(width);
@@ -132,14 +132,10 @@ __global__ void __launch_bounds__(256) timesfm_attention_decode_kernel(
   const int q_pos0 = total_tokens - MQ;  // sequence index of the first new token
   const void* q_region = regions.ptr[regions.count - 1];
 
-  auto rotation = [&](int ipos, int f, float& cs, float& sn) {
+  auto rotation = [&](int ipos, int f, float& cs, float& sn) {  // the launcher checks that the table covers |ipos|
     const int ap = ipos < 0 ? -ipos : ipos;
-    if (ap < rope_len) {
-      const float2 e = __ldg(rope + static_cast<int64_t>(ap) * HALF + f);
-      cs = e.x, sn = ipos < 0 ? -e.y : e.y;
-    } else {
-      sincosf(static_cast<float>(ipos) * __ldg(inv_freq + f), &sn, &cs);
-    }
+    const float2 e = __ldg(rope + static_cast<int64_t>(ap) * HALF + f);
+    cs = e.x, sn = ipos < 0 ? -e.y : e.y;
   };
 
   for (int64_t w = static_cast<int64_t>(blockIdx.x) * warps_per_block + warp; w < batch * num_heads;
@@ -201,52 +197,69 @@ __global__ void __launch_bounds__(256) timesfm_attention_decode_kernel(
     };
     for (int j0 = 0; j0 < total_tokens; j0 += KT) {
       const int tile = min(KT, total_tokens - j0);
-      // stage the raw key rows of the tile: 16-byte chunks, every lane keeps several independent loads in flight (a
-      // row-by-row loop exposed one global-memory latency per key row: 68 x ~0.7 us per (series, head))
-      constexpr int CPR = QKV_BF16 ? HD / 8 : HD / 4;  // 16-byte chunks per row
-#pragma unroll 5
-      for (int idx = lane; idx < tile * CPR; idx += 32) {
-        const int jj = idx / CPR, ch = idx - jj * CPR;
-        const void* ptr;
-        const int64_t base = row_base(j0 + jj, ptr) + width;
-        if constexpr (QKV_BF16) {
-          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ptr) + base + 8 * ch);
-          const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-          float* dst = sK + jj * LDS + 8 * ch;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            dst[2 * k] = __uint_as_float(wv[k] << 16);
-            dst[2 * k + 1] = __uint_as_float(wv[k] & 0xffff0000u);
-          }
-        } else {
-          const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ptr) + base + 4 * ch);
-          float* dst = sK + jj * LDS + 4 * ch;
-          dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
-        }
-      }
-      __syncwarp();
-      // lane = key: rotate the own row in registers, own sum of squares, scores against the four queries
+      // lane = key: the lane pulls its own raw key row (160 / 320 contiguous bytes) and its row of the rotation table
+      // straight into registers - all loads independent, nothing staged in shared memory, so the SM keeps its L1 for
+      // the table - rotates, accumulates its own sum of squares and the four dot products
       const int j = j0 + lane;
       const bool key_ok = lane < tile && (j >= n_ctx || patch_mask == nullptr || patch_mask[b * n_ctx + j] == 0);
       float s4[MQ] = {0.f, 0.f, 0.f, 0.f};
       float krs = 0.f;
       if (lane < tile) {
-        const float* krow = sK + lane * LDS;
+        float kf[HD];
+        {
+          const void* ptr;
+          const int64_t base = row_base(j, ptr) + width;
+          if constexpr (QKV_BF16) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ptr) + base);
+            uint4 raw[HD / 8];
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) raw[c] = src[c];
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+              const uint32_t wv[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                kf[8 * c + 2 * k] = __uint_as_float(wv[k] << 16);
+                kf[8 * c + 2 * k + 1] = __uint_as_float(wv[k] & 0xffff0000u);
+              }
+            }
+          } else {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ptr) + base);
+#pragma unroll
+            for (int c = 0; c < HD / 4; ++c) {
+              const float4 v = src[c];
+              kf[4 * c] = v.x, kf[4 * c + 1] = v.y, kf[4 * c + 2] = v.z, kf[4 * c + 3] = v.w;
+            }
+          }
+        }
         const int ipos = j - nm;
+        const int ap = ipos < 0 ? -ipos : ipos;
+        const float sgn = ipos < 0 ? -1.f : 1.f;  // sin(-x) = -sin(x): the table holds non-negative positions
+        const float4* trow = reinterpret_cast<const float4*>(rope + static_cast<int64_t>(ap) * HALF);
         float ss = 0.f;
-#pragma unroll 8
-        for (int f = 0; f < HALF; ++f) {
-          float cs, sn;
-          rotation(ipos, f, cs, sn);
-          const float a = krow[f], c = krow[f + HALF];
-          const float r1 = a * cs - c * sn, r2 = c * cs + a * sn;
-          ss = fmaf(r1, r1, fmaf(r2, r2, ss));
-          const float4 q1 = *reinterpret_cast<const float4*>(sQT + f * MQ);
-          const float4 q2 = *reinterpret_cast<const float4*>(sQT + (f + HALF) * MQ);
-          s4[0] = fmaf(q1.x, r1, fmaf(q2.x, r2, s4[0]));
-          s4[1] = fmaf(q1.y, r1, fmaf(q2.y, r2, s4[1]));
-          s4[2] = fmaf(q1.z, r1, fmaf(q2.z, r2, s4[2]));
-          s4[3] = fmaf(q1.w, r1, fmaf(q2.w, r2, s4[3]));
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          float4 t[HALF / 4];
+#pragma unroll
+          for (int g = 0; g < HALF / 4; ++g) t[g] = __ldg(trow + part * (HALF / 4) + g);
+#pragma unroll
+          for (int g = 0; g < HALF / 4; ++g) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int f = part * (HALF / 2) + 2 * g + e;
+              const float cs = e == 0 ? t[g].x : t[g].z;
+              const float sn = sgn * (e == 0 ? t[g].y : t[g].w);
+              const float a = kf[f], c = kf[f + HALF];
+              const float r1 = a * cs - c * sn, r2 = c * cs + a * sn;
+              ss = fmaf(r1, r1, fmaf(r2, r2, ss));
+              const float4 q1 = *reinterpret_cast<const float4*>(sQT + f * MQ);
+              const float4 q2 = *reinterpret_cast<const float4*>(sQT + (f + HALF) * MQ);
+              s4[0] = fmaf(q1.x, r1, fmaf(q2.x, r2, s4[0]));
+              s4[1] = fmaf(q1.y, r1, fmaf(q2.y, r2, s4[1]));
+              s4[2] = fmaf(q1.z, r1, fmaf(q2.z, r2, s4[2]));
+              s4[3] = fmaf(q1.w, r1, fmaf(q2.w, r2, s4[3]));
+            }
+          }
         }
         krs = 1.0f / sqrtf(ss / static_cast<float>(HD) + eps);
       }
@@ -412,7 +425,7 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
   TSFMX_REQUIRE(qkv_dtype == TSFMX_DT_F32 || qkv_dtype == TSFMX_DT_BF16,
                 "timesfm_attention_decode: qkv must be f32 or bf16");
   TSFMX_REQUIRE(out_dtype >= TSFMX_DT_F32 && out_dtype <= TSFMX_DT_BF16_SPLIT, "timesfm_attention_decode: bad out_dtype");
-  TSFMX_REQUIRE(rope_len >= 0 && (rope_len == 0 || rope_table != nullptr), "timesfm_attention_decode: bad rope table");
+  TSFMX_REQUIRE(rope_len > 0 && rope_table != nullptr, "timesfm_attention_decode: rotation table missing");
   KvRegions regions;
   regions.count = num_regions;
   for (int r = 0; r < num_regions; ++r) {
@@ -434,19 +447,19 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
   }
   if (batch == 0) return TSFMX_OK;
   constexpr int HD = 80, MQ = 4;
-  const int per_warp = (HD * MQ + 32 * (HD + 1) + MQ * 32 + MQ * (HD + 1)) * 4;  // 13.5 KB
+  const int per_warp = (HD * MQ + MQ * 32 + MQ * (HD + 1)) * 4;  // 3.1 KB: the SM keeps its L1 for the rotation table
   const int wpb = 8;
-  const int smem = wpb * per_warp;  // 108 KB: two blocks (16 warps) per SM
+  const int smem = wpb * per_warp;
+  int total_tokens = 0;
+  for (int r = 0; r < num_regions; ++r) total_tokens += region_tokens[r];
+  TSFMX_REQUIRE(rope_len >= total_tokens && rope_len >= n_ctx,
+                "timesfm_attention_decode: the rotation table (%d positions) must cover %d tokens", rope_len,
+                total_tokens > n_ctx ? total_tokens : n_ctx);
   const int64_t total = batch * num_heads;
   const int64_t blocks = (total + wpb - 1) / wpb;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
   auto launch = [&](auto kern) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("timesfm_attention_decode: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
-      return TSFMX_ERR_CUDA;
-    }
     kern<<<grid, wpb * 32, smem, stream>>>(regions, batch, num_heads, n_ctx, patch_mask, num_masked,
                                             reinterpret_cast<const float2*>(rope_table), rope_len, inv_freq, q_ln_w, k_ln_w,
                                             q_scale, eps, out);
