@@ -128,8 +128,11 @@ class MultimodalDecoder(nn.Module):
                 self.lanes = lanes_before
             while len(self._graph_cache) >= self.GRAPH_CACHE_ENTRIES:
                 self._graph_cache.pop(next(iter(self._graph_cache)))
-            # the inputs are kept alive with the graph: their addresses are baked into it
-            entry = (graph, out, (inputs, masks, text_embeddings), launches)
+            # the inputs are kept alive with the graph: their addresses are baked into it.  So are the packed weight
+            # copies the eager pass built: switching the precision mode and back clears the modules' caches, but this
+            # entry's key would match again and its replay must still find the weights it was captured with
+            packed = [dict(getattr(m, "_packed", {})) for m in (self.adapter, self.fusion)]
+            entry = (graph, out, (inputs, masks, text_embeddings), launches, packed)
             self._graph_cache[key] = entry
             self.graph_captures += 1
         entry[0].replay()

@@ -416,6 +416,9 @@ class _GraphedMicroBatch:
             loss = trainer._forward_loss(self.static)
             loss.backward()
         self.loss = loss.detach()
+        # the graph reads packed weight copies that were built BEFORE the capture (a frozen adapter's, cached by the eager
+        # first step) at their addresses: hold them, so that clearing a cache later cannot free memory a replay still reads
+        self.keepalive = [dict(getattr(m, "_packed", {})) for m in (trainer.model.adapter, trainer.model.fusion)]
         # with the overlapped reducer active the per-layer all-reduces were captured as well: a replay leaves globally
         # summed gradients behind, which optimizer_step has to be told
         self.reducer = trainer.model.grad_ready_hook

@@ -418,9 +418,11 @@ class ChronosT5Adapter(TsfmAdapter):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 tokens, _ = self._decode_eager(static_enc, static_mask, horizon, None, False)
-            entry = (graph, static_enc, static_mask, tokens)
+            # the packed weights the capture read are kept alive with it (a precision round trip clears self._packed while
+            # this key can match again)
+            entry = (graph, static_enc, static_mask, tokens, dict(self._packed))
             self._graphs[key] = entry
-        graph, static_enc, static_mask, tokens = entry
+        graph, static_enc, static_mask, tokens, _packed = entry
         static_enc.copy_(encoder_states)
         static_mask.copy_(attention_mask.bool())
         graph.replay()

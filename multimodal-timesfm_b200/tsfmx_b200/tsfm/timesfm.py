@@ -337,7 +337,11 @@ class TimesFM2p5Adapter(TsfmAdapter):
             kv_cache.extend([] for _ in layers)
         xn = ops.rmsnorm(x, layers[0]["pre_attn"], m.eps, adt)
         yield
+        # one scratch qkv when nothing is kept; with a KV cache one allocation holds every layer's qkv (50 x 1 GB at
+        # 2048 series of 64 patches: a single block that the caching allocator hands back whole on the next forecast,
+        # instead of 50 blocks that fragment against the activations of the other lane)
         qkv = ops.alloc(rows, 3 * d, mid_dt, dev) if kv_cache is None else None
+        qkv_all = None if kv_cache is None else ops.alloc(len(layers) * rows, 3 * d, mid_dt, dev)
         attn = ops.alloc(rows, d, adt, dev)
         a = ops.alloc(rows, d, mid_dt, dev)
         hbuf = ops.alloc(rows, m.ff, adt, dev)
@@ -345,7 +349,7 @@ class TimesFM2p5Adapter(TsfmAdapter):
             last = i == len(layers) - 1
             nxt = None if last else layers[i + 1]["pre_attn"]
             if kv_cache is not None:
-                qkv = ops.alloc(rows, 3 * d, mid_dt, dev)
+                qkv = qkv_all[i * rows : (i + 1) * rows]
                 kv_cache[i].append(qkv)
             ops.gemm([(xn, lw["qkv"], d)], rows, 3 * d, qkv, mid_dt, precision=prec)
             yield

@@ -181,3 +181,24 @@ def test_predict_returns_every_forecast_on_the_host(graphs):
         seen += 1
     assert seen == len(want)
     assert list(ev.predict([])) == []
+
+
+def test_graph_survives_a_precision_round_trip():
+    """set_precision("bf16x3") and back re-packs the weights into new buffers; the bf16 graph captured before has the
+    same cache key again and must still read the (kept alive) weights it was captured with."""
+    dec = _small_decoder()
+    ctx, masks, text, _ = O.synthetic_batch(24, 512, 128, seed=5)
+    ctx, masks, text = ctx.cuda(), masks.cuda(), text.cuda()
+    with torch.no_grad():
+        dec.set_precision("bf16")
+        eager = dec.forward_full(128, ctx, masks, text).clone()
+        dec.graphs = True
+        assert torch.equal(dec.forward_full(128, ctx, masks, text), eager)
+        dec.set_precision("bf16x3")
+        precise = dec.forward_full(128, ctx, masks, text).clone()
+        junk = [torch.randn(64, 1280, 1280, device="cuda") for _ in range(4)]  # churn the allocator over freed blocks
+        dec.set_precision("bf16")
+        again = dec.forward_full(128, ctx, masks, text).clone()
+        dec.graphs = False
+    del junk
+    assert torch.equal(again, eager) and not torch.equal(precise, eager)
