@@ -64,8 +64,9 @@ def parse_args():
                          "step with the NCCL gradient all-reduce; full-finetune = the reference's mode='baseline'; chronos2 / "
                          "chronos-t5 = configs[2]; longctx-* = configs[4] (ctx 2048 / horizon 256)")
     ap.add_argument("--finetune-batch", type=int, default=1024, help="series per GPU of a fine-tune step")
-    ap.add_argument("--graph-collectives", action="store_true",
-                    help="full fine-tune on several GPUs: capture the overlapped NCCL all-reduces into the step's CUDA graph")
+    ap.add_argument("--no-graph-collectives", dest="graph_collectives", action="store_false",
+                    help="full fine-tune on several GPUs: keep the overlapped NCCL all-reduces (and with them the whole step) "
+                         "out of CUDA graphs; by default they are captured into the step's graph")
     return ap.parse_args()
 
 
@@ -727,8 +728,7 @@ def run_finetune_arm(args, full: bool) -> None:
     if rank == 0:
         emit_json(line)
     if world > 1:
-        trainer._train_graphs.clear()  # graphs that captured NCCL kernels must go before the communicator does
-        torch.cuda.synchronize()
+        trainer.release_graphs()  # graphs that captured NCCL kernels must go before the communicator does
         dist.barrier()
         dist.destroy_process_group()
 

@@ -244,6 +244,15 @@ class MultimodalTrainer:
         self._backward(loss, batch["global_size"])
         return loss.detach() * accum
 
+    def release_graphs(self) -> None:
+        """Drop the captured training graphs (and the activations they pin).  With ``args.graph_collectives`` the graphs
+        hold captured NCCL kernels: call this BEFORE ``torch.distributed.destroy_process_group()`` - tearing the
+        communicator down while such a graph is alive hangs the process."""
+        self._train_graphs.clear()
+        self._graph_seen.clear()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
     def _backward(self, loss: torch.Tensor, global_size: int | None = None) -> None:
         """``loss.backward()``.  A global batch with fewer samples than ranks leaves some rank with an empty shard, a
         constant loss and no backward pass; every rank can tell from ``global_size`` alone, so for such a batch ALL
