@@ -471,7 +471,8 @@ int tsfmx_timesfm_forecast_finalize(const float* pf, const float* spread, const 
                                     void* stream);
 
 /* tuning hook (A/B runs): key 0 = series per warp tile of timesfm_patchify_norm, key 1 = its warps per block,
- * key 2 / key 3 != 0 force the generic fallback kernel of chronos_t5_tokenize / timesfm_patchify_norm (0 = default) */
+ * key 2 / key 3 != 0 force the generic fallback kernel of chronos_t5_tokenize / timesfm_patchify_norm, key 5 != 0 the
+ * general tsfmx_t5_attention kernel also for a decode step's cross-attention (0 = default) */
 int tsfmx_tune(int32_t key, int32_t value);
 
 /* test hook: non-zero forces the fp32 SIMT attention kernel even where the tensor-core kernel applies */

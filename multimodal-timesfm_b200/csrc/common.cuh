@@ -33,6 +33,7 @@ int current_device();  // index of the calling thread's CUDA device, clamped to 
 int launch_timesfm_attention_bwd_mma(const void* qkv, const void* dout, int64_t batch, int N, int H, const uint8_t* pm,
                                      const int32_t* nm, const float* inv_freq, const float* qw, const float* kw,
                                      const float* qs, float eps, void* dqkv, float* dparams, cudaStream_t stream);
+extern int g_t5_general_attention;  // t5.cu: 1 = general attention kernel also for decode-step cross-attention
 extern int g_force_simt_attention;  // test hook: fp32 SIMT attention kernels even where the tensor-core ones apply
 
 // ---------------------------------------------------------------- device PTX

@@ -1093,6 +1093,7 @@ extern "C" int tsfmx_tune(int32_t key, int32_t value) {
     case 1: g_tf_warps = value; return TSFMX_OK;
     case 2: g_t5_variant = value; return TSFMX_OK;
     case 3: g_tf_variant = value; return TSFMX_OK;
+    case 5: g_t5_general_attention = value; return TSFMX_OK;
     default:
       set_error("tune: unknown key %d", key);
       return TSFMX_ERR_INVALID_ARGUMENT;

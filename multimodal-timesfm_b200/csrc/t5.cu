@@ -186,6 +186,130 @@ __global__ void __launch_bounds__(128) t5_attention_kernel(const T5AttnParams p)
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Cross-attention of a decode step (one query row per path, bf16 keys / values, no bias, not causal): the kernel that
+// bounds Chronos-T5 decoding - every step streams the 513 x 12 heads x (64 k + 64 v) bf16 of every series, 3.2 GB per
+// layer at 2048 series.  The general kernel above keeps one key row per lane in flight as 64 fp32 registers next to
+// q[64] and acc[64]: ~200 registers, 8 warps per SM, 32 KB in flight per SM - 3.9 TB/s (ncu: 825 us per launch).
+// Here a lane keeps TWO rows in flight as packed bf16 (2 x 32 registers) and unpacks while it multiplies, which fits
+// three 4-warp blocks per SM: ~100 KB in flight per SM.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void t5_load_row_packed(const __nv_bfloat16* row, uint4 (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = ld_stream_u4(reinterpret_cast<const uint4*>(row) + i);
+}
+__device__ __forceinline__ float t5_dot_packed(const float (&q)[T5_HD], const uint4 (&r)[8]) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t w[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+    a0 = fmaf(q[8 * i + 0], __uint_as_float(w[0] << 16), a0);
+    a1 = fmaf(q[8 * i + 1], __uint_as_float(w[0] & 0xffff0000u), a1);
+    a2 = fmaf(q[8 * i + 2], __uint_as_float(w[1] << 16), a2);
+    a3 = fmaf(q[8 * i + 3], __uint_as_float(w[1] & 0xffff0000u), a3);
+    a0 = fmaf(q[8 * i + 4], __uint_as_float(w[2] << 16), a0);
+    a1 = fmaf(q[8 * i + 5], __uint_as_float(w[2] & 0xffff0000u), a1);
+    a2 = fmaf(q[8 * i + 6], __uint_as_float(w[3] << 16), a2);
+    a3 = fmaf(q[8 * i + 7], __uint_as_float(w[3] & 0xffff0000u), a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ void t5_axpy_packed(float (&acc)[T5_HD], float p, const uint4 (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t w[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[8 * i + 2 * e] = fmaf(p, __uint_as_float(w[e] << 16), acc[8 * i + 2 * e]);
+      acc[8 * i + 2 * e + 1] = fmaf(p, __uint_as_float(w[e] & 0xffff0000u), acc[8 * i + 2 * e + 1]);
+    }
+  }
+}
+
+template <int OUT>
+__global__ void __launch_bounds__(128, 3) t5_cross_decode_kernel(const T5AttnParams p) {
+  extern __shared__ float s_scores[];  // [4 warps][tk]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sc = s_scores + warp * p.tk;
+  const int b = blockIdx.y;
+  const int tk = p.tk;
+  for (int h = blockIdx.x * 4 + warp; h < p.num_heads; h += gridDim.x * 4) {
+    float q[T5_HD];
+    t5_load_row64(p.q, p.q_dtype, b * p.q_batch_stride + h * T5_HD, q);
+    const int64_t bk = b / p.kv_batch_div;
+    const uint8_t* km = p.key_mask != nullptr ? p.key_mask + bk * tk : nullptr;
+    const __nv_bfloat16* kbase = reinterpret_cast<const __nv_bfloat16*>(p.k) + bk * p.kv_batch_stride + h * T5_HD;
+    const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + bk * p.kv_batch_stride + h * T5_HD;
+    // ---- scores: lane l owns keys l, l + 32, ...; the row of the NEXT key is in flight while this one is multiplied
+    float mx = -INFINITY;
+    bool any = false;
+    uint4 cur[8], nxt[8];
+    if (lane < tk) t5_load_row_packed(kbase + static_cast<int64_t>(lane) * p.ldk, cur);
+    for (int j = lane; j < tk; j += 32) {
+      const int jn = j + 32;
+      if (jn < tk) t5_load_row_packed(kbase + static_cast<int64_t>(jn) * p.ldk, nxt);
+      float s = -INFINITY;
+      if (km == nullptr || km[j] != 0) {
+        s = t5_dot_packed(q, cur);
+        any = true;
+      }
+      sc[j] = s;
+      mx = fmaxf(mx, s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
+    mx = warp_max(mx);
+    any = __any_sync(0xffffffffu, any);
+    float sum = 0.f;
+    for (int j = lane; j < tk; j += 32) {
+      const float e = any ? (sc[j] == -INFINITY ? 0.f : expf(sc[j] - mx)) : 1.f;  // all masked: uniform (finfo.min mask)
+      sc[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+    // ---- P V: same ownership, value rows double-buffered the same way, then the butterfly reduce-scatter
+    float acc[T5_HD];
+#pragma unroll
+    for (int d = 0; d < T5_HD; ++d) acc[d] = 0.f;
+    if (lane < tk) t5_load_row_packed(vbase + static_cast<int64_t>(lane) * p.ldv, cur);
+    for (int j = lane; j < tk; j += 32) {
+      const int jn = j + 32;
+      if (jn < tk) t5_load_row_packed(vbase + static_cast<int64_t>(jn) * p.ldv, nxt);
+      t5_axpy_packed(acc, sc[j], cur);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
+#pragma unroll
+    for (int half = 32, m = 16; m >= 1; half >>= 1, m >>= 1) {
+      const bool upper = (lane & m) != 0;
+#pragma unroll
+      for (int d = 0; d < half; ++d) {
+        const float mine = upper ? acc[d + half] : acc[d];
+        const float theirs = upper ? acc[d] : acc[d + half];
+        acc[d] = mine + __shfl_xor_sync(0xffffffffu, theirs, m);
+      }
+    }
+    const float o0 = acc[0] * inv, o1 = acc[1] * inv;
+    const int64_t ooff = b * p.o_batch_stride;
+    const int c = h * T5_HD + 2 * lane;
+    const int width = p.num_heads * T5_HD;
+    if constexpr (OUT == TSFMX_DT_F32) {
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + ooff + c) = make_float2(o0, o1);
+    } else if constexpr (OUT == TSFMX_DT_BF16) {
+      *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c) = pack_bf16x2(o0, o1);
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + 2 * ooff;
+      uint32_t hi, lo;
+      split_bf16x2(o0, o1, hi, lo);
+      *reinterpret_cast<uint32_t*>(o + c) = hi;
+      *reinterpret_cast<uint32_t*>(o + width + c) = lo;
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ tensor-core encoder
 constexpr int T5_LD = 72;     // padded bf16 row (144 B)
 constexpr int T5_WARPS = 8;
@@ -549,6 +673,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) t5_sample_topk_kernel(const fl
 }  // namespace
 }  // namespace tsfmx
 
+namespace tsfmx {
+int g_t5_general_attention = 0;  // tune key 5: 1 = the general kernel also for decode-step cross-attention (A/B, tests)
+}
+
 using namespace tsfmx;
 
 extern "C" int tsfmx_embed_rows(const int64_t* ids, int64_t rows, int32_t dims, int32_t vocab, const float* table,
@@ -620,6 +748,12 @@ extern "C" int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, i
     kern<<<grid, 128, smem, stream>>>(p);
     return check_last_launch("t5_attention");
   };
+  // a decode step's cross-attention: one query row, bf16 keys / values, no bias, not causal, every row 16-byte aligned
+  if (tq == 1 && kv_dtype == TSFMX_DT_BF16 && !causal && bias == nullptr && ldv % 8 == 0 && tk >= 64 && !g_t5_general_attention) {
+    if (out_dtype == TSFMX_DT_F32) return launch(t5_cross_decode_kernel<TSFMX_DT_F32>);
+    if (out_dtype == TSFMX_DT_BF16) return launch(t5_cross_decode_kernel<TSFMX_DT_BF16>);
+    return launch(t5_cross_decode_kernel<TSFMX_DT_BF16_SPLIT>);
+  }
   if (out_dtype == TSFMX_DT_F32) return launch(t5_attention_kernel<TSFMX_DT_F32>);
   if (out_dtype == TSFMX_DT_BF16) return launch(t5_attention_kernel<TSFMX_DT_BF16>);
   return launch(t5_attention_kernel<TSFMX_DT_BF16_SPLIT>);

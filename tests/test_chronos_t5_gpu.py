@@ -227,3 +227,34 @@ def test_sample_topk_kernel():
     last = ops.t5_sample_topk(row[None].contiguous(), banned_id=1, top_k=5, uniform=torch.ones(1, device=DEV))
     top5 = torch.topk(torch.where(torch.arange(4096, device=DEV) == 1, float("-inf"), row), 5).indices
     assert last.item() == top5.max().item()  # inverse CDF in id order: the highest id among the survivors
+
+
+@pytest.mark.parametrize("tk,samples", [(513, 1), (129, 3), (64, 1), (700, 2)])
+def test_cross_attention_decode_kernel_matches_the_general_kernel(tk, samples):
+    """The decode step's cross-attention (one query row per path, bf16 K / V, key mask, sample paths sharing their
+    series' keys) through its specialised kernel and through the general tsfmx_t5_attention kernel (tuning hook 5)."""
+    from tsfmx_b200 import ops
+    from tsfmx_b200._lib import DT_BF16, DT_F32
+
+    gen = torch.Generator(device=DEV).manual_seed(tk)
+    series, heads, inner = 7, 12, 768
+    b = series * samples
+    q = (torch.randn(b, inner, generator=gen, device=DEV) * 0.5).to(torch.bfloat16)
+    kv = (torch.randn(series * tk, 2 * inner, generator=gen, device=DEV) * 0.5).to(torch.bfloat16)
+    km = torch.rand(series, tk, generator=gen, device=DEV) > 0.2
+    km[1] = False  # every key masked: uniform weights
+    km[2] = True
+    outs = {}
+    for general in (1, 0):
+        ops._lib.check(ops._lib.load().tsfmx_tune(5, general))
+        try:
+            for dt in (DT_F32, DT_BF16):
+                out = ops.alloc(b, inner, dt, q.device)
+                ops.t5_attention(q, kv, kv[:, inner:], b, 1, tk, heads, dt, out, q_rows=(inner, inner),
+                                 kv_rows=(2 * inner, tk * 2 * inner), out_rows=(inner, inner), key_mask=km, kv_batch_div=samples)
+                outs[(general, dt)] = out.float()
+        finally:
+            ops._lib.check(ops._lib.load().tsfmx_tune(5, 0))
+    ref = outs[(1, DT_F32)]
+    assert (outs[(0, DT_F32)] - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert (outs[(0, DT_BF16)] - outs[(1, DT_BF16)]).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
