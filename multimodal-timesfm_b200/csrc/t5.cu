@@ -191,8 +191,11 @@ __global__ void __launch_bounds__(128) t5_attention_kernel(const T5AttnParams p)
 // bounds Chronos-T5 decoding - every step streams the 513 x 12 heads x (64 k + 64 v) bf16 of every series, 3.2 GB per
 // layer at 2048 series.  The general kernel above keeps one key row per lane in flight as 64 fp32 registers next to
 // q[64] and acc[64]: ~200 registers, 8 warps per SM, 32 KB in flight per SM - 3.9 TB/s (ncu: 825 us per launch).
-// Here a lane keeps TWO rows in flight as packed bf16 (2 x 32 registers) and unpacks while it multiplies, which fits
-// three 4-warp blocks per SM: ~100 KB in flight per SM.
+// Two changes: (1) ONE block holds all heads of a series (12 warps), so that the block as a whole walks the [K | V] rows
+// of its series front to back - 3 KB contiguous per key - instead of four warps picking 128-byte pieces out of every
+// 3 KB row (a DRAM row miss per access: the general kernel's 3.9 TB/s is what strided 128-byte reads get);
+// (2) a lane keeps TWO rows in flight as packed bf16 (2 x 32 registers) and unpacks while it multiplies: ~100 KB in
+// flight per SM with 12 warps.
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void t5_load_row_packed(const __nv_bfloat16* row, uint4 (&r)[8]) {
 #pragma unroll
@@ -227,13 +230,14 @@ __device__ __forceinline__ void t5_axpy_packed(float (&acc)[T5_HD], float p, con
 }
 
 template <int OUT>
-__global__ void __launch_bounds__(128, 3) t5_cross_decode_kernel(const T5AttnParams p) {
-  extern __shared__ float s_scores[];  // [4 warps][tk]
+__global__ void __launch_bounds__(384, 1) t5_cross_decode_kernel(const T5AttnParams p) {
+  extern __shared__ float s_scores[];  // [warps][tk]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sc = s_scores + warp * p.tk;
   const int b = blockIdx.y;
   const int tk = p.tk;
-  for (int h = blockIdx.x * 4 + warp; h < p.num_heads; h += gridDim.x * 4) {
+  const int wpb = blockDim.x >> 5;
+  for (int h = blockIdx.x * wpb + warp; h < p.num_heads; h += gridDim.x * wpb) {
     float q[T5_HD];
     t5_load_row64(p.q, p.q_dtype, b * p.q_batch_stride + h * T5_HD, q);
     const int64_t bk = b / p.kv_batch_div;
@@ -750,9 +754,25 @@ extern "C" int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, i
   };
   // a decode step's cross-attention: one query row, bf16 keys / values, no bias, not causal, every row 16-byte aligned
   if (tq == 1 && kv_dtype == TSFMX_DT_BF16 && !causal && bias == nullptr && ldv % 8 == 0 && tk >= 64 && !g_t5_general_attention) {
-    if (out_dtype == TSFMX_DT_F32) return launch(t5_cross_decode_kernel<TSFMX_DT_F32>);
-    if (out_dtype == TSFMX_DT_BF16) return launch(t5_cross_decode_kernel<TSFMX_DT_BF16>);
-    return launch(t5_cross_decode_kernel<TSFMX_DT_BF16_SPLIT>);
+    const int wpb = num_heads <= 12 ? num_heads : 12;  // all heads of a series in one block (T5-base: 12)
+    const int smem_x = wpb * tk * static_cast<int>(sizeof(float));
+    const dim3 grid_x((num_heads + wpb - 1) / wpb, static_cast<unsigned>(batch));
+    auto launch_x = [&](auto kern) -> int {
+      if (smem_x > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x);
+        if (e != cudaSuccess) {
+          set_error("t5_attention: cudaFuncSetAttribute(%d): %s", smem_x, cudaGetErrorString(e));
+          return TSFMX_ERR_CUDA;
+        }
+      }
+      kern<<<grid_x, wpb * 32, smem_x, stream>>>(p);
+      return check_last_launch("t5_cross_decode");
+    };
+    if (smem_x <= 200 * 1024) {
+      if (out_dtype == TSFMX_DT_F32) return launch_x(t5_cross_decode_kernel<TSFMX_DT_F32>);
+      if (out_dtype == TSFMX_DT_BF16) return launch_x(t5_cross_decode_kernel<TSFMX_DT_BF16>);
+      return launch_x(t5_cross_decode_kernel<TSFMX_DT_BF16_SPLIT>);
+    }
   }
   if (out_dtype == TSFMX_DT_F32) return launch(t5_attention_kernel<TSFMX_DT_F32>);
   if (out_dtype == TSFMX_DT_BF16) return launch(t5_attention_kernel<TSFMX_DT_BF16>);
