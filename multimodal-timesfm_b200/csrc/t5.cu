@@ -189,81 +189,82 @@ __global__ void __launch_bounds__(128) t5_attention_kernel(const T5AttnParams p)
 // ----------------------------------------------------------------------------------------
 // Cross-attention of a decode step (one query row per path, bf16 keys / values, no bias, not causal): the kernel that
 // bounds Chronos-T5 decoding - every step streams the 513 x 12 heads x (64 k + 64 v) bf16 of every series, 3.2 GB per
-// layer at 2048 series.  The general kernel above keeps one key row per lane in flight as 64 fp32 registers next to
-// q[64] and acc[64]: ~200 registers, 8 warps per SM, 32 KB in flight per SM - 3.9 TB/s (ncu: 825 us per launch).
-// Two changes: (1) ONE block holds all heads of a series (12 warps), so that the block as a whole walks the [K | V] rows
-// of its series front to back - 3 KB contiguous per key - instead of four warps picking 128-byte pieces out of every
-// 3 KB row (a DRAM row miss per access: the general kernel's 3.9 TB/s is what strided 128-byte reads get);
-// (2) a lane keeps TWO rows in flight as packed bf16 (2 x 32 registers) and unpacks while it multiplies: ~100 KB in
-// flight per SM with 12 warps.
+// layer at 2048 series.  The general kernel above gives every lane a whole 128-byte key row: a warp-level 16-byte load
+// then touches 32 different lines and uses half of each 32-byte sector, the other half being fetched again by the next
+// load - ncu: 825 us per launch, 3.9 TB/s, and keeping two rows in flight per lane or putting all heads of a series
+// into one block changed nothing (844 us).  Here EIGHT lanes share a key row (8 x 16 B = one full line per key, four
+// keys per warp-level load, every sector used once), a lane keeps only its 8 of the 64 dimensions of q, of the
+// accumulator and of eight rows in flight (~60 registers), partial dot products meet with three shuffles, and one
+// block holds all heads of a series so that it walks the [K | V] rows of its series front to back.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void t5_load_row_packed(const __nv_bfloat16* row, uint4 (&r)[8]) {
+__device__ __forceinline__ void t5_unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = ld_stream_u4(reinterpret_cast<const uint4*>(row) + i);
-}
-__device__ __forceinline__ float t5_dot_packed(const float (&q)[T5_HD], const uint4 (&r)[8]) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t w[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
-    a0 = fmaf(q[8 * i + 0], __uint_as_float(w[0] << 16), a0);
-    a1 = fmaf(q[8 * i + 1], __uint_as_float(w[0] & 0xffff0000u), a1);
-    a2 = fmaf(q[8 * i + 2], __uint_as_float(w[1] << 16), a2);
-    a3 = fmaf(q[8 * i + 3], __uint_as_float(w[1] & 0xffff0000u), a3);
-    a0 = fmaf(q[8 * i + 4], __uint_as_float(w[2] << 16), a0);
-    a1 = fmaf(q[8 * i + 5], __uint_as_float(w[2] & 0xffff0000u), a1);
-    a2 = fmaf(q[8 * i + 6], __uint_as_float(w[3] << 16), a2);
-    a3 = fmaf(q[8 * i + 7], __uint_as_float(w[3] & 0xffff0000u), a3);
-  }
-  return (a0 + a1) + (a2 + a3);
-}
-__device__ __forceinline__ void t5_axpy_packed(float (&acc)[T5_HD], float p, const uint4 (&r)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t w[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      acc[8 * i + 2 * e] = fmaf(p, __uint_as_float(w[e] << 16), acc[8 * i + 2 * e]);
-      acc[8 * i + 2 * e + 1] = fmaf(p, __uint_as_float(w[e] & 0xffff0000u), acc[8 * i + 2 * e + 1]);
-    }
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
   }
 }
 
 template <int OUT>
-__global__ void __launch_bounds__(384, 1) t5_cross_decode_kernel(const T5AttnParams p) {
+__global__ void __launch_bounds__(384) t5_cross_decode_kernel(const T5AttnParams p) {
   extern __shared__ float s_scores[];  // [warps][tk]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int part = lane & 7, kq = lane >> 3;  // 16-byte chunk of the row / which of the four keys of a load
   float* sc = s_scores + warp * p.tk;
   const int b = blockIdx.y;
   const int tk = p.tk;
   const int wpb = blockDim.x >> 5;
+  constexpr int U = 8;  // loads in flight per lane: 8 x 4 keys = 32 keys per round
   for (int h = blockIdx.x * wpb + warp; h < p.num_heads; h += gridDim.x * wpb) {
-    float q[T5_HD];
-    t5_load_row64(p.q, p.q_dtype, b * p.q_batch_stride + h * T5_HD, q);
+    float q[8];
+    {
+      const int64_t qoff = b * p.q_batch_stride + h * T5_HD + 8 * part;
+      if (p.q_dtype == TSFMX_DT_F32) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.q) + qoff);
+        const float4 c = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.q) + qoff + 4);
+        q[0] = a.x, q[1] = a.y, q[2] = a.z, q[3] = a.w, q[4] = c.x, q[5] = c.y, q[6] = c.z, q[7] = c.w;
+      } else {
+        t5_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.q) + qoff), q);
+      }
+    }
     const int64_t bk = b / p.kv_batch_div;
     const uint8_t* km = p.key_mask != nullptr ? p.key_mask + bk * tk : nullptr;
-    const __nv_bfloat16* kbase = reinterpret_cast<const __nv_bfloat16*>(p.k) + bk * p.kv_batch_stride + h * T5_HD;
-    const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + bk * p.kv_batch_stride + h * T5_HD;
-    // ---- scores: lane l owns keys l, l + 32, ...; the row of the NEXT key is in flight while this one is multiplied
+    const __nv_bfloat16* kbase = reinterpret_cast<const __nv_bfloat16*>(p.k) + bk * p.kv_batch_stride + h * T5_HD + 8 * part;
+    const __nv_bfloat16* vbase = reinterpret_cast<const __nv_bfloat16*>(p.v) + bk * p.kv_batch_stride + h * T5_HD + 8 * part;
+    // ---- scores
     float mx = -INFINITY;
     bool any = false;
-    uint4 cur[8], nxt[8];
-    if (lane < tk) t5_load_row_packed(kbase + static_cast<int64_t>(lane) * p.ldk, cur);
-    for (int j = lane; j < tk; j += 32) {
-      const int jn = j + 32;
-      if (jn < tk) t5_load_row_packed(kbase + static_cast<int64_t>(jn) * p.ldk, nxt);
-      float s = -INFINITY;
-      if (km == nullptr || km[j] != 0) {
-        s = t5_dot_packed(q, cur);
-        any = true;
-      }
-      sc[j] = s;
-      mx = fmaxf(mx, s);
+    for (int j0 = 0; j0 < tk; j0 += 4 * U) {
+      uint4 r[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 4 * u + kq;
+        r[u] = j < tk ? ld_stream_u4(kbase + static_cast<int64_t>(j) * p.ldk) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 4 * u + kq;
+        float kf[8];
+        t5_unpack8(r[u], kf);
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) s = fmaf(q[d], kf[d], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (j < tk) {
+          const bool ok = km == nullptr || km[j] != 0;
+          s = ok ? s : -INFINITY;
+          any = any || ok;
+          mx = fmaxf(mx, s);
+          if (part == 0) sc[j] = s;
+        }
+      }
     }
     mx = warp_max(mx);
     any = __any_sync(0xffffffffu, any);
+    __syncwarp();
     float sum = 0.f;
     for (int j = lane; j < tk; j += 32) {
       const float e = any ? (sc[j] == -INFINITY ? 0.f : expf(sc[j] - mx)) : 1.f;  // all masked: uniform (finfo.min mask)
@@ -273,42 +274,53 @@ __global__ void __launch_bounds__(384, 1) t5_cross_decode_kernel(const T5AttnPar
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     __syncwarp();
-    // ---- P V: same ownership, value rows double-buffered the same way, then the butterfly reduce-scatter
-    float acc[T5_HD];
+    // ---- P V: the same ownership; a lane accumulates its 8 dimensions over its quarter of the keys
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 < tk; j0 += 4 * U) {
+      uint4 r[U];
 #pragma unroll
-    for (int d = 0; d < T5_HD; ++d) acc[d] = 0.f;
-    if (lane < tk) t5_load_row_packed(vbase + static_cast<int64_t>(lane) * p.ldv, cur);
-    for (int j = lane; j < tk; j += 32) {
-      const int jn = j + 32;
-      if (jn < tk) t5_load_row_packed(vbase + static_cast<int64_t>(jn) * p.ldv, nxt);
-      t5_axpy_packed(acc, sc[j], cur);
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 4 * u + kq;
+        r[u] = j < tk ? ld_stream_u4(vbase + static_cast<int64_t>(j) * p.ldv) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-    }
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 4 * u + kq;
+        const float pj = j < tk ? sc[j] : 0.f;
+        float vf[8];
+        t5_unpack8(r[u], vf);
 #pragma unroll
-    for (int half = 32, m = 16; m >= 1; half >>= 1, m >>= 1) {
-      const bool upper = (lane & m) != 0;
-#pragma unroll
-      for (int d = 0; d < half; ++d) {
-        const float mine = upper ? acc[d + half] : acc[d];
-        const float theirs = upper ? acc[d] : acc[d + half];
-        acc[d] = mine + __shfl_xor_sync(0xffffffffu, theirs, m);
+        for (int d = 0; d < 8; ++d) acc[d] = fmaf(pj, vf[d], acc[d]);
       }
     }
-    const float o0 = acc[0] * inv, o1 = acc[1] * inv;
-    const int64_t ooff = b * p.o_batch_stride;
-    const int c = h * T5_HD + 2 * lane;
-    const int width = p.num_heads * T5_HD;
-    if constexpr (OUT == TSFMX_DT_F32) {
-      *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + ooff + c) = make_float2(o0, o1);
-    } else if constexpr (OUT == TSFMX_DT_BF16) {
-      *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c) = pack_bf16x2(o0, o1);
-    } else {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + 2 * ooff;
-      uint32_t hi, lo;
-      split_bf16x2(o0, o1, hi, lo);
-      *reinterpret_cast<uint32_t*>(o + c) = hi;
-      *reinterpret_cast<uint32_t*>(o + width + c) = lo;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 8);
+      acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 16);
+      acc[d] *= inv;
+    }
+    if (kq == 0) {
+      const int64_t ooff = b * p.o_batch_stride;
+      const int c = h * T5_HD + 8 * part;
+      const int width = p.num_heads * T5_HD;
+      if constexpr (OUT == TSFMX_DT_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + ooff + c;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else if constexpr (OUT == TSFMX_DT_BF16) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + c) =
+            make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                       pack_bf16x2(acc[6], acc[7]));
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + 2 * ooff;  // split rows: [hi(width) | lo(width)]
+        uint4 hi, lo;
+        split_bf16x2(acc[0], acc[1], hi.x, lo.x);
+        split_bf16x2(acc[2], acc[3], hi.y, lo.y);
+        split_bf16x2(acc[4], acc[5], hi.z, lo.z);
+        split_bf16x2(acc[6], acc[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(o + c) = hi;
+        *reinterpret_cast<uint4*>(o + width + c) = lo;
+      }
     }
     __syncwarp();
   }
@@ -753,7 +765,8 @@ extern "C" int tsfmx_t5_attention(const void* q, int32_t q_dtype, int64_t ldq, i
     return check_last_launch("t5_attention");
   };
   // a decode step's cross-attention: one query row, bf16 keys / values, no bias, not causal, every row 16-byte aligned
-  if (tq == 1 && kv_dtype == TSFMX_DT_BF16 && !causal && bias == nullptr && ldv % 8 == 0 && tk >= 64 && !g_t5_general_attention) {
+  const bool out16 = reinterpret_cast<uintptr_t>(out) % 16 == 0 && o_batch_stride % 8 == 0;
+  if (tq == 1 && kv_dtype == TSFMX_DT_BF16 && !causal && bias == nullptr && ldv % 8 == 0 && tk >= 64 && out16 && !g_t5_general_attention) {
     const int wpb = num_heads <= 12 ? num_heads : 12;  // all heads of a series in one block (T5-base: 12)
     const int smem_x = wpb * tk * static_cast<int>(sizeof(float));
     const dim3 grid_x((num_heads + wpb - 1) / wpb, static_cast<unsigned>(batch));
