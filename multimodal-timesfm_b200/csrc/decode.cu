@@ -328,249 +328,6 @@ __global__ void __launch_bounds__(256) timesfm_attention_decode_kernel(
   }
 }
 
-// Fourth version, bf16 qkv (the throughput mode).  In v3 every lane pulls a whole 160-byte key row: a warp-level 16-byte
-// load touches 32 lines and uses half of every sector (the Chronos-T5 cross-attention kernel had the same pattern and
-// gained 1.4 x from fixing it).  Here FIVE lanes share a key row - lane p of an 8-lane group owns dims [8p, 8p + 8) and
-// their rotation partners [40 + 8p, 48 + 8p), four keys per warp-level load, every sector used once - the partial sums
-// of squares and dot products meet with three shuffles, scores go through a small per-warp shared-memory tile
-// ([4 queries][T]) and the values are accumulated with the same ownership.
-template <int OUT>
-__global__ void __launch_bounds__(256) timesfm_attention_decode_g8_kernel(
-    KvRegions regions, int64_t batch, int num_heads, int n_ctx, const uint8_t* __restrict__ patch_mask,
-    const int32_t* __restrict__ num_masked, const float2* __restrict__ rope, const float* __restrict__ q_ln_w,
-    const float* __restrict__ k_ln_w, const float* __restrict__ q_scale, float eps, int total_tokens,
-    void* __restrict__ out) {
-  constexpr int HD = 80, HALF = 40, MQ = 4, LDS = HD + 1, DPL = 3, U = 4;
-  extern __shared__ __align__(16) float smem_dec[];
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 3, part = lane & 7;
-  const bool active = part < 5;
-  const int T = total_tokens;
-  const int per_warp = ((MQ * T + 3) & ~3) + HD * MQ + MQ * LDS;
-  float* sc = smem_dec + warp * per_warp;          // [MQ][T] scores, then probabilities
-  float* sQT = sc + ((MQ * T + 3) & ~3);            // [HD][MQ]
-  float* sQ = sQT + HD * MQ;                        // [MQ][LDS] scratch
-  const int width = num_heads * HD;
-  const int64_t ld = 3 * static_cast<int64_t>(width);
-  const int q_pos0 = T - MQ;
-  const int n0 = regions.tokens[0];
-  const __nv_bfloat16* q_region = reinterpret_cast<const __nv_bfloat16*>(regions.ptr[regions.count - 1]);
-
-  for (int64_t w = static_cast<int64_t>(blockIdx.x) * warps_per_block + warp; w < batch * num_heads;
-       w += static_cast<int64_t>(gridDim.x) * warps_per_block) {
-    const int64_t b = w / num_heads;
-    const int h = static_cast<int>(w - b * num_heads);
-    const int nm = num_masked != nullptr ? num_masked[b] : 0;
-    auto row_ptr = [&](int j) -> const __nv_bfloat16* {  // q[0] of head h of sequence token j
-      const int r = j < n0 ? 0 : 1 + (j - n0) / MQ;
-      const int local = j < n0 ? j : (j - n0) % MQ;
-      return reinterpret_cast<const __nv_bfloat16*>(regions.ptr[r]) + (b * (r == 0 ? n0 : MQ) + local) * ld + h * HD;
-    };
-    // ---- queries: RoPE, RMSNorm, q_ln * q_scale * k_ln, lanes over head_dim; stored transposed
-    for (int i = 0; i < MQ; ++i) {
-      const int64_t base = (b * MQ + i) * ld + h * HD;
-#pragma unroll
-      for (int t = 0; t < DPL; ++t) {
-        const int d = lane + 32 * t;
-        if (d < HD) sQ[i * LDS + d] = __bfloat162float(q_region[base + d]);
-      }
-    }
-    __syncwarp();
-    for (int i = 0; i < MQ; ++i) {
-      const int ipos = q_pos0 + i - nm;
-      const int ap = ipos < 0 ? -ipos : ipos;
-      float r[DPL];
-      float ss = 0.f;
-#pragma unroll
-      for (int t = 0; t < DPL; ++t) {
-        const int d = lane + 32 * t;
-        r[t] = 0.f;
-        if (d < HD) {
-          const int f = d < HALF ? d : d - HALF;
-          const float2 e = __ldg(rope + static_cast<int64_t>(ap) * HALF + f);
-          const float sn = ipos < 0 ? -e.y : e.y;
-          const int dp = d < HALF ? d + HALF : d - HALF;
-          const float sgn = d < HALF ? -1.f : 1.f;
-          r[t] = sQ[i * LDS + d] * e.x + sgn * sQ[i * LDS + dp] * sn;
-          ss += r[t] * r[t];
-        }
-      }
-      ss = warp_sum(ss);
-      const float rs = 1.0f / sqrtf(ss / static_cast<float>(HD) + eps);
-#pragma unroll
-      for (int t = 0; t < DPL; ++t) {
-        const int d = lane + 32 * t;
-        if (d < HD) sQT[d * MQ + i] = __ldg(q_ln_w + d) * (r[t] * rs) * __ldg(q_scale + d) * __ldg(k_ln_w + d);
-      }
-    }
-    __syncwarp();
-    float4 qa[8], qb[8];  // the lane's 8 rotary pairs of the four conditioned queries
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int f = active ? 8 * part + e : 0;
-      qa[e] = *reinterpret_cast<const float4*>(sQT + f * MQ);
-      qb[e] = *reinterpret_cast<const float4*>(sQT + (f + HALF) * MQ);
-    }
-    // ---- pass 1: scores of the four queries against every key
-    for (int j0 = 0; j0 < T; j0 += 4 * U) {
-      uint4 k1[U], k2[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 4 * u + g;
-        if (j < T && active) {
-          const __nv_bfloat16* kr = row_ptr(j) + width + 8 * part;
-          k1[u] = ld_stream_u4(kr);
-          k2[u] = ld_stream_u4(kr + HALF);
-        } else {
-          k1[u] = k2[u] = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 4 * u + g;
-        const int jc = j < T ? j : T - 1;
-        const int ipos = jc - nm;
-        const int ap = ipos < 0 ? -ipos : ipos;
-        const float sgn = ipos < 0 ? -1.f : 1.f;
-        const float4* trow = reinterpret_cast<const float4*>(rope + static_cast<int64_t>(ap) * HALF + (active ? 8 * part : 0));
-        const uint32_t w1[4] = {k1[u].x, k1[u].y, k1[u].z, k1[u].w}, w2[4] = {k2[u].x, k2[u].y, k2[u].z, k2[u].w};
-        float ss = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {
-          const float4 t = __ldg(trow + e2);  // (cos, sin) of two consecutive frequencies
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int e = 2 * e2 + hh;
-            const float a = hh == 0 ? __uint_as_float(w1[e2] << 16) : __uint_as_float(w1[e2] & 0xffff0000u);
-            const float c = hh == 0 ? __uint_as_float(w2[e2] << 16) : __uint_as_float(w2[e2] & 0xffff0000u);
-            const float cs = hh == 0 ? t.x : t.z, sn = sgn * (hh == 0 ? t.y : t.w);
-            const float r1 = a * cs - c * sn, r2 = c * cs + a * sn;
-            ss = fmaf(r1, r1, fmaf(r2, r2, ss));
-            s0 = fmaf(qa[e].x, r1, fmaf(qb[e].x, r2, s0));
-            s1 = fmaf(qa[e].y, r1, fmaf(qb[e].y, r2, s1));
-            s2 = fmaf(qa[e].z, r1, fmaf(qb[e].z, r2, s2));
-            s3 = fmaf(qa[e].w, r1, fmaf(qb[e].w, r2, s3));
-          }
-        }
-#pragma unroll
-        for (int m = 1; m <= 4; m <<= 1) {
-          ss += __shfl_xor_sync(0xffffffffu, ss, m);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, m);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-          s3 += __shfl_xor_sync(0xffffffffu, s3, m);
-        }
-        if (j < T && part == 0) {
-          const float krs = 1.0f / sqrtf(ss / static_cast<float>(HD) + eps);
-          const bool ok = j >= n_ctx || patch_mask == nullptr || patch_mask[b * n_ctx + j] == 0;
-          sc[0 * T + j] = (ok && j <= q_pos0 + 0) ? s0 * krs : -INFINITY;
-          sc[1 * T + j] = (ok && j <= q_pos0 + 1) ? s1 * krs : -INFINITY;
-          sc[2 * T + j] = (ok && j <= q_pos0 + 2) ? s2 * krs : -INFINITY;
-          sc[3 * T + j] = (ok && j <= q_pos0 + 3) ? s3 * krs : -INFINITY;
-        }
-      }
-    }
-    __syncwarp();
-    // ---- softmax per query (a new token always sees itself: the maximum is finite)
-    float inv[MQ];
-#pragma unroll
-    for (int i = 0; i < MQ; ++i) {
-      float mx = -INFINITY;
-      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, sc[i * T + j]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int j = lane; j < T; j += 32) {
-        const float v = sc[i * T + j];
-        const float e = v == -INFINITY ? 0.f : expf(v - mx);
-        sc[i * T + j] = e;
-        sum += e;
-      }
-      inv[i] = 1.0f / warp_sum(sum);
-    }
-    __syncwarp();
-    // ---- pass 2: P.V, the same ownership (a lane accumulates its 16 dimensions over its quarter of the keys)
-    float o[MQ][16];
-#pragma unroll
-    for (int i = 0; i < MQ; ++i)
-#pragma unroll
-      for (int d = 0; d < 16; ++d) o[i][d] = 0.f;
-    for (int j0 = 0; j0 < T; j0 += 4 * U) {
-      uint4 v1[U], v2[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 4 * u + g;
-        if (j < T && active) {
-          const __nv_bfloat16* vr = row_ptr(j) + 2 * width + 8 * part;
-          v1[u] = ld_stream_u4(vr);
-          v2[u] = ld_stream_u4(vr + HALF);
-        } else {
-          v1[u] = v2[u] = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 4 * u + g;
-        const int jc = j < T ? j : T - 1;
-        float pj[MQ];
-#pragma unroll
-        for (int i = 0; i < MQ; ++i) pj[i] = j < T ? sc[i * T + jc] : 0.f;
-        const uint32_t w1[4] = {v1[u].x, v1[u].y, v1[u].z, v1[u].w}, w2[4] = {v2[u].x, v2[u].y, v2[u].z, v2[u].w};
-#pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {
-          const float a0 = __uint_as_float(w1[e2] << 16), a1 = __uint_as_float(w1[e2] & 0xffff0000u);
-          const float c0 = __uint_as_float(w2[e2] << 16), c1 = __uint_as_float(w2[e2] & 0xffff0000u);
-#pragma unroll
-          for (int i = 0; i < MQ; ++i) {
-            o[i][2 * e2] = fmaf(pj[i], a0, o[i][2 * e2]);
-            o[i][2 * e2 + 1] = fmaf(pj[i], a1, o[i][2 * e2 + 1]);
-            o[i][8 + 2 * e2] = fmaf(pj[i], c0, o[i][8 + 2 * e2]);
-            o[i][8 + 2 * e2 + 1] = fmaf(pj[i], c1, o[i][8 + 2 * e2 + 1]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < MQ; ++i)
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        float v = o[i][d];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        o[i][d] = v * inv[i];
-      }
-    if (g == 0 && active) {
-#pragma unroll
-      for (int i = 0; i < MQ; ++i) {
-        const int64_t row = b * MQ + i;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c = h * HD + half * HALF + 8 * part;
-          const float* v = &o[i][8 * half];
-          if constexpr (OUT == TSFMX_DT_F32) {
-            float* dst = reinterpret_cast<float*>(out) + row * width + c;
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          } else if constexpr (OUT == TSFMX_DT_BF16) {
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + row * width + c) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out) + row * 2 * width + c;
-            uint4 hi, lo;
-            split_bf16x2(v[0], v[1], hi.x, lo.x);
-            split_bf16x2(v[2], v[3], hi.y, lo.y);
-            split_bf16x2(v[4], v[5], hi.z, lo.z);
-            split_bf16x2(v[6], v[7], hi.w, lo.w);
-            *reinterpret_cast<uint4*>(dst) = hi;
-            *reinterpret_cast<uint4*>(dst + width) = lo;
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ forecast finalize
 // One block per series.  pf [(1 + flip) * B, ht, Q] (rows B.. = forecasts of the negated inputs), spread
 // [(1 + flip) * B, hs, Q] or NULL, inputs [B, C] (positivity test: min over the context >= 0) -> out [B, horizon, Q].
@@ -708,33 +465,6 @@ extern "C" int tsfmx_timesfm_attention_decode(const void* const* region_ptrs, co
                                             q_scale, eps, out);
     return check_last_launch("timesfm_attention_decode");
   };
-  if (qkv_dtype == TSFMX_DT_BF16 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && !g_t5_general_attention) {
-    // five lanes per key row (v4); scores of the four queries live in a [4][T] tile per warp
-    const int per_warp4 = (((MQ * total_tokens + 3) & ~3) + HD * MQ + MQ * (HD + 1)) * 4;
-    int wpb4 = 8;
-    while (wpb4 > 1 && wpb4 * per_warp4 > 100 * 1024) wpb4 >>= 1;
-    const int smem4 = wpb4 * per_warp4;
-    if (smem4 <= 200 * 1024) {
-      const int64_t blocks4 = (total + wpb4 - 1) / wpb4;
-      const int grid4 = static_cast<int>(blocks4 < cap ? blocks4 : cap);
-      auto launch4 = [&](auto kern) -> int {
-        if (smem4 > 48 * 1024) {
-          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
-          if (e != cudaSuccess) {
-            set_error("timesfm_attention_decode: cudaFuncSetAttribute(%d): %s", smem4, cudaGetErrorString(e));
-            return TSFMX_ERR_CUDA;
-          }
-        }
-        kern<<<grid4, wpb4 * 32, smem4, stream>>>(regions, batch, num_heads, n_ctx, patch_mask, num_masked,
-                                                  reinterpret_cast<const float2*>(rope_table), q_ln_w, k_ln_w, q_scale, eps,
-                                                  total_tokens, out);
-        return check_last_launch("timesfm_attention_decode");
-      };
-      if (out_dtype == TSFMX_DT_F32) return launch4(timesfm_attention_decode_g8_kernel<TSFMX_DT_F32>);
-      if (out_dtype == TSFMX_DT_BF16) return launch4(timesfm_attention_decode_g8_kernel<TSFMX_DT_BF16>);
-      return launch4(timesfm_attention_decode_g8_kernel<TSFMX_DT_BF16_SPLIT>);
-    }
-  }
   if (qkv_dtype == TSFMX_DT_BF16) {
     if (out_dtype == TSFMX_DT_F32) return launch(timesfm_attention_decode_kernel<HD, MQ, 1, TSFMX_DT_F32>);
     if (out_dtype == TSFMX_DT_BF16) return launch(timesfm_attention_decode_kernel<HD, MQ, 1, TSFMX_DT_BF16>);
