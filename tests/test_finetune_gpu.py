@@ -481,3 +481,40 @@ def test_full_finetune_loss_curve_matches_oracle(tmp_path):
     for a, b in zip(got, ref_losses):
         assert a == pytest.approx(b, rel=2e-3), (got, ref_losses)
     assert ref_losses[-1] < ref_losses[0]
+
+
+def test_trainer_full_loop_with_graphs_validation_and_checkpoints(tmp_path):
+    """MultimodalTrainer.train() end to end on the GPU: two epochs of graph-replayed training steps interleaved with
+    eval-mode validation passes (which re-pack the just-updated fusion weights outside the graph), best-model
+    checkpointing and the reload at the end - the interplay of the training graph, the weight caches and the eager
+    forecast path."""
+    from tsfmx_b200.trainer import MultimodalTrainer
+
+    dec, _ = build(2)
+    dec.set_precision("bf16")
+    train, val = _samples(32, seed=91), _samples(8, seed=92)
+    args = _train_args(tmp_path, lr=2e-3, cuda_graphs=True, num_train_epochs=3, save_strategy="best",
+                       eval_strategy="epoch", load_best_model_at_end=True, logging_strategy="epoch")
+    logged = []
+
+    class Run:
+        def log(self, metrics, step):
+            logged.append((step, dict(metrics)))
+
+    trainer = MultimodalTrainer(dec, args, train, val, "multimodal", torch.device(DEV), wandb_run=Run())
+    w0 = dec.fusion.linears()[0].weight.detach().clone()
+    before = trainer.validate_epoch()
+    trainer.train()
+    assert trainer.global_step == 3 * 8 and trainer.graph_replays == 3 * 8 - 1
+    assert [s for s, _ in logged] == [8, 16, 24]
+    vals = [m["val/loss"] for _, m in logged]
+    assert min(vals) < before and trainer.best_val_loss == pytest.approx(min(vals))
+    assert all(m["train/loss"] == m["train/loss"] for _, m in logged)  # no NaN
+    best = torch.load(args.checkpoint_dir / "best_model.pt", weights_only=True)
+    assert best["best_val_loss"] == pytest.approx(min(vals))
+    # the best fusion weights are back in the model, and an eager validation pass reproduces their loss
+    assert torch.equal(dec.fusion.linears()[0].weight.detach().cpu(), best["fusion_state_dict"]["projection.0.weight"].cpu())
+    assert not torch.equal(dec.fusion.linears()[0].weight.detach(), w0)
+    assert trainer.validate_epoch() == pytest.approx(min(vals), rel=1e-4)
+    trainer.release_graphs()
+    assert not trainer._train_graphs
