@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, call W (1 GPU): driver-style sequence on the final tree - smoke, full GPU suite, bench (+ reference arm)
+mkdir -p gpurun_out
+python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/r2w_pytest.log 2>&1
+echo "pytest rc=$?"; tail -4 gpurun_out/r2w_pytest.log
+python bench.py > gpurun_out/r2w_bench.json 2> gpurun_out/r2w_bench.err
+echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/r2w_bench.json')); print(round(d['value']), 'series/s', 'e2e', round(d['e2e']['value']), 'parity ok', d['parity']['ok'], d['parity']['bf16']['ratio_to_bf16_oracle'], 'roofline', round(d['roofline']['frac'],3), d['clocks'])"
