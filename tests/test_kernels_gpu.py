@@ -65,6 +65,30 @@ def test_gemm_bf16_plain(cta_group, m, n, k):
         _lib.check(lib.tsfmx_gemm_set_cta_group(0))
 
 
+@pytest.mark.parametrize("n,act,d_dtype", [(3840, ACT_NONE, DT_BF16), (1280, ACT_SILU, DT_BF16), (1280, ACT_NONE, DT_F32)])
+def test_gemm_at_the_benchmarked_size(n, act, d_dtype):
+    """The decoder-layer GEMMs exactly as bench.py launches them: M = 65 536 token rows (4096 series x 16 patches),
+    K = 1280, N = 3840 (qkv) / 1280 (ff0 with the SiLU epilogue, attn-out / ff1), every one of the 256 x 15 (or 5) tiles
+    checked against torch's fp32 matmul of the same bf16 operands."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, k = 65536, 1280
+    gen = torch.Generator(device=DEV).manual_seed(n + act)
+    a, af = _make_operand(m, k, PREC_BF16, gen)
+    b, bf = _make_operand(n, k, PREC_BF16, gen)
+    af *= 0.05
+    a = af.to(torch.bfloat16)
+    af = a.float()
+    out = torch.full((m, n), float("nan"), device=DEV, dtype=torch.float32 if d_dtype == DT_F32 else torch.bfloat16)
+    ops.gemm([(a, b, k)], m, n, out, d_dtype, act=act)
+    ref = af @ bf.t()
+    if act == ACT_SILU:
+        ref = torch.nn.functional.silu(ref)
+    tol = 2e-5 if d_dtype == DT_F32 else 5e-3  # bf16 storage of the output: 2^-9 relative per element
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, err
+    assert torch.isfinite(out.float()).all()
+
+
 @pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("split", [0, 3, 16])
 @pytest.mark.parametrize("m,n,k", [(1280, 1280, 16384), (3840, 1280, 4096), (300, 336, 8192)])
