@@ -79,7 +79,11 @@ class MultimodalTrainer:
             self.model.adapter.freeze_parameters()
         elif mode == "baseline":
             # full fine-tuning of the adapter, no text (reference trainer.py:78-79, baseline_collate_fn)
-            if not hasattr(self.model.adapter, "preprocess_backward"):
+            # the C-ABI adapters compute their gradients by hand: one without the weight-gradient path would silently
+            # train nothing (a plain autograd adapter, e.g. the CPU oracle, needs no such path)
+            from .tsfm.base import TsfmAdapter
+
+            if isinstance(self.model.adapter, TsfmAdapter) and not hasattr(self.model.adapter, "preprocess_backward"):
                 raise NotImplementedError(
                     f"mode='baseline' needs backbone weight gradients, which {type(self.model.adapter).__name__} does "
                     "not produce on the B200 path yet (TimesFM2p5Adapter does)"
