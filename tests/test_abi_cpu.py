@@ -38,7 +38,9 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.tsfmx_abi_version() == 1
+    header = (ROOT / "include" / "tsfmx_b200.h").read_text()
+    declared = int(re.search(r"#define\s+TSFMX_ABI_VERSION\s+(\d+)", header).group(1))
+    assert lib.tsfmx_abi_version() == declared == _lib.ABI_VERSION == 2
     assert isinstance(lib.tsfmx_last_error(), bytes)
 
 
