@@ -188,6 +188,16 @@ int tsfmx_gemm_set_cta_group(int cta_group);
 int tsfmx_gemm_set_split_k(int mode);
 
 /*
+ * Weight gradient of y = x W^T (full fine-tuning, reference trainer.py:78-79,123: every Linear of the adapter trains):
+ *   dw [n_out, k_in] fp32 = dy[rows, n_out]^T x[rows, k_in],  dy / x bf16 row-major as the backward pass left them.
+ * K = tokens: the operands are MN-major for this product and are consumed as such (TMA boxes of 64 features x 64
+ * tokens, MN-major UMMA descriptors) - no transposed copies; tokens beyond `rows` are zero-filled by TMA; split-K as
+ * in tsfmx_gemm.  ld_dy / ld_x in elements (multiples of 8), pointers 16-byte aligned, n_out / k_in multiples of 8.
+ */
+int tsfmx_gemm_wgrad(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t rows, int32_t n_out,
+                     int32_t k_in, float* dw, int64_t ld_dw, void* stream);
+
+/*
  * GEMM with the norm / residual junction of a transformer layer fused into its epilogue (one launch instead
  * of tsfmx_gemm + tsfmx_norm_residual_norm; the GEMM result never goes to HBM):
  *   a = A W^T;  y = RMSNorm(a) * w_post + x  (w_post NULL: y = a + x);  yn = RMSNorm(y) * w_next  (w_next NULL: yn = y)
@@ -346,6 +356,13 @@ int tsfmx_chronos2_finalize(const float* preds, int64_t batch, int32_t num_patch
 int tsfmx_rmsnorm_bwd_chain(const float* g_res, const void* v1, int32_t v1_dtype, const float* w1, const void* g1,
                             int32_t g1_dtype, const void* v2, int32_t v2_dtype, const float* w2, int64_t rows,
                             int32_t cols, float eps, float* g_total, int32_t g2_dtype, void* g2, void* stream);
+/* The same pass with the gradients of the two norm scales riding along (full fine-tuning, reference trainer.py:78-79):
+ *   dw1[c] += sum_r g1[r, c] * v1_hat[r, c],   dw2[c] += sum_r g_total[r, c] * v2_hat[r, c]
+ * (v_hat = RMS-normalised v; dw1 / dw2 fp32 [cols], accumulated into, either may be NULL). */
+int tsfmx_rmsnorm_bwd_chain_wgrad(const float* g_res, const void* v1, int32_t v1_dtype, const float* w1, const void* g1,
+                                  int32_t g1_dtype, const void* v2, int32_t v2_dtype, const float* w2, int64_t rows,
+                                  int32_t cols, float eps, float* g_total, int32_t g2_dtype, void* g2, float* dw1,
+                                  float* dw2, void* stream);
 
 /*
  * Gradient of tsfmx_timesfm_attention w.r.t. its qkv input: recomputes the conditioned q / k and the

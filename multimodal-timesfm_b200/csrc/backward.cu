@@ -43,21 +43,33 @@ __device__ __forceinline__ void store4(void* out, int64_t row, int cols, int c, 
 }
 
 // dv = r * (w*g) - v * r^3 * mean(v * w * g),  r = (mean(v^2) + eps)^-1/2     (in place on g)
+// acc (full fine-tune): this warp's partial of the scale gradient, acc[c] += g[c] * v[c] * r, in shared memory.
 template <int NV>
 __device__ __forceinline__ void rms_bwd_row(const float4 (&v)[NV], float4 (&g)[NV], const float* __restrict__ w,
-                                            int lane, float eps) {
+                                            int lane, float eps, float* acc = nullptr) {
   constexpr int COLS = NV * 128;
   float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+  ss = warp_sum(ss);
+  const float r = 1.0f / sqrtf(ss / static_cast<float>(COLS) + eps);
+  if (acc != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float4* ap = reinterpret_cast<float4*>(acc + 4 * (lane + 32 * j));
+      float4 a = *ap;
+      a.x = fmaf(g[j].x, v[j].x * r, a.x), a.y = fmaf(g[j].y, v[j].y * r, a.y);
+      a.z = fmaf(g[j].z, v[j].z * r, a.z), a.w = fmaf(g[j].w, v[j].w * r, a.w);
+      *ap = a;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const float4 ww = __ldg(reinterpret_cast<const float4*>(w + 4 * (lane + 32 * j)));
     g[j].x *= ww.x, g[j].y *= ww.y, g[j].z *= ww.z, g[j].w *= ww.w;
-    ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
     dot += v[j].x * g[j].x + v[j].y * g[j].y + v[j].z * g[j].z + v[j].w * g[j].w;
   }
-  ss = warp_sum(ss);
   dot = warp_sum(dot);
-  const float r = 1.0f / sqrtf(ss / static_cast<float>(COLS) + eps);
   const float c = r * r * r * dot / static_cast<float>(COLS);
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
@@ -66,13 +78,26 @@ __device__ __forceinline__ void rms_bwd_row(const float4 (&v)[NV], float4 (&g)[N
   }
 }
 
-template <int NV, int OUT>
-__global__ void __launch_bounds__(WARPS * 32) rmsnorm_bwd_chain_kernel(
+// WG (full fine-tune): the gradients of the two norm scales leave the same pass - dw1[c] += sum_r g1 * v1_hat,
+// dw2[c] += sum_r g_total * v2_hat - through warp-private column partials in shared memory, folded per block and added
+// to the pre-zeroed outputs (the separate colsum_wgrad launches re-read g and v: 4 more passes per layer).
+template <int NV, int OUT, bool WG = false>
+__global__ void __launch_bounds__(WARPS * 32, 2) rmsnorm_bwd_chain_kernel(
     const float* g_res, const void* __restrict__ v1, int v1_dtype, const float* __restrict__ w1,
     const void* __restrict__ g1, int g1_dtype, const void* __restrict__ v2, int v2_dtype,
-    const float* __restrict__ w2, int64_t rows, float eps, float* g_total, void* g2) {
+    const float* __restrict__ w2, int64_t rows, float eps, float* g_total, void* g2, float* __restrict__ dw1 = nullptr,
+    float* __restrict__ dw2 = nullptr) {
   constexpr int COLS = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) float s_wg[];  // WG: [2][WARPS][COLS]
+  float* acc1 = nullptr;
+  float* acc2 = nullptr;
+  if constexpr (WG) {
+    for (int i = threadIdx.x; i < 2 * WARPS * COLS; i += blockDim.x) s_wg[i] = 0.f;
+    __syncthreads();
+    if (dw1 != nullptr) acc1 = s_wg + warp * COLS;
+    if (dw2 != nullptr) acc2 = s_wg + (WARPS + warp) * COLS;
+  }
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * WARPS + warp; r < rows;
        r += static_cast<int64_t>(gridDim.x) * WARPS) {
     float4 g[NV], v[NV];
@@ -83,7 +108,7 @@ __global__ void __launch_bounds__(WARPS * 32) rmsnorm_bwd_chain_kernel(
         v[j] = load4(v1, v1_dtype, idx);
         g[j] = load4(g1, g1_dtype, idx);
       }
-      rms_bwd_row<NV>(v, g, w1, lane, eps);
+      rms_bwd_row<NV>(v, g, w1, lane, eps, acc1);
     } else {
 #pragma unroll
       for (int j = 0; j < NV; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -102,9 +127,21 @@ __global__ void __launch_bounds__(WARPS * 32) rmsnorm_bwd_chain_kernel(
     if (v2 != nullptr) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) v[j] = load4(v2, v2_dtype, r * COLS + 4 * (lane + 32 * j));
-      rms_bwd_row<NV>(v, g, w2, lane, eps);
+      rms_bwd_row<NV>(v, g, w2, lane, eps, acc2);
 #pragma unroll
       for (int j = 0; j < NV; ++j) store4<OUT>(g2, r, COLS, 4 * (lane + 32 * j), g[j]);
+    }
+  }
+  if constexpr (WG) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * COLS; i += blockDim.x) {
+      const int which = i / COLS, c = i - which * COLS;
+      float* dst = which == 0 ? dw1 : dw2;
+      if (dst == nullptr) continue;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) t += s_wg[(which * WARPS + w) * COLS + c];
+      atomicAdd(dst + c, t);
     }
   }
 }
@@ -582,9 +619,33 @@ int grid_for_rows(int64_t rows) {
 template <int NV>
 int launch_bwd_chain(const float* g_res, const void* v1, int v1_dtype, const float* w1, const void* g1, int g1_dtype,
                      const void* v2, int v2_dtype, const float* w2, int64_t rows, float eps, float* g_total,
-                     int g2_dtype, void* g2, cudaStream_t stream) {
-  const int grid = grid_for_rows(rows);
+                     int g2_dtype, void* g2, float* dw1, float* dw2, cudaStream_t stream) {
   const dim3 block(WARPS * 32);
+  if (dw1 != nullptr || dw2 != nullptr) {
+    // scale gradients ride along: few, fat blocks (every block ends with one atomicAdd per column and output)
+    constexpr int SMEM = 2 * WARPS * NV * 128 * 4;
+    const int64_t blocks = (rows + WARPS - 1) / WARPS, cap = static_cast<int64_t>(num_sms()) * 2;
+    const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+    auto go = [&](auto kern) -> int {
+      static bool attr_set_dev[64] = {false};
+      bool& attr_set = attr_set_dev[current_device()];
+      if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) {
+          set_error("rmsnorm_bwd_chain: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+          return TSFMX_ERR_CUDA;
+        }
+        attr_set = true;
+      }
+      kern<<<grid, block, SMEM, stream>>>(g_res, v1, v1_dtype, w1, g1, g1_dtype, v2, v2_dtype, w2, rows, eps, g_total, g2,
+                                          dw1, dw2);
+      return check_last_launch("rmsnorm_bwd_chain");
+    };
+    if (g2_dtype == TSFMX_DT_F32) return go(rmsnorm_bwd_chain_kernel<NV, TSFMX_DT_F32, true>);
+    if (g2_dtype == TSFMX_DT_BF16) return go(rmsnorm_bwd_chain_kernel<NV, TSFMX_DT_BF16, true>);
+    return go(rmsnorm_bwd_chain_kernel<NV, TSFMX_DT_BF16_SPLIT, true>);
+  }
+  const int grid = grid_for_rows(rows);
   if (g2_dtype == TSFMX_DT_F32)
     rmsnorm_bwd_chain_kernel<NV, TSFMX_DT_F32><<<grid, block, 0, stream>>>(g_res, v1, v1_dtype, w1, g1, g1_dtype, v2,
                                                                           v2_dtype, w2, rows, eps, g_total, g2);
@@ -602,16 +663,18 @@ int launch_bwd_chain(const float* g_res, const void* v1, int v1_dtype, const flo
 
 using namespace tsfmx;
 
-extern "C" int tsfmx_rmsnorm_bwd_chain(const float* g_res, const void* v1, int32_t v1_dtype, const float* w1,
-                                       const void* g1, int32_t g1_dtype, const void* v2, int32_t v2_dtype,
-                                       const float* w2, int64_t rows, int32_t cols, float eps, float* g_total,
-                                       int32_t g2_dtype, void* g2, void* stream_) {
+extern "C" int tsfmx_rmsnorm_bwd_chain_wgrad(const float* g_res, const void* v1, int32_t v1_dtype, const float* w1,
+                                             const void* g1, int32_t g1_dtype, const void* v2, int32_t v2_dtype,
+                                             const float* w2, int64_t rows, int32_t cols, float eps, float* g_total,
+                                             int32_t g2_dtype, void* g2, float* dw1, float* dw2, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TSFMX_REQUIRE(rows >= 0, "rmsnorm_bwd_chain: bad rows");
   TSFMX_REQUIRE(g_res != nullptr || v1 != nullptr, "rmsnorm_bwd_chain: no gradient input");
   TSFMX_REQUIRE(v1 == nullptr || (w1 != nullptr && g1 != nullptr), "rmsnorm_bwd_chain: v1 needs w1 and g1");
   TSFMX_REQUIRE(v2 == nullptr || (w2 != nullptr && g2 != nullptr), "rmsnorm_bwd_chain: v2 needs w2 and g2");
   TSFMX_REQUIRE(g_total != nullptr || g2 != nullptr, "rmsnorm_bwd_chain: no output requested");
+  TSFMX_REQUIRE((dw1 == nullptr || v1 != nullptr) && (dw2 == nullptr || v2 != nullptr),
+                "rmsnorm_bwd_chain: a scale gradient needs its norm (dw1 with v1, dw2 with v2)");
   auto dt_ok = [](int d) { return d == TSFMX_DT_F32 || d == TSFMX_DT_BF16; };
   TSFMX_REQUIRE((v1 == nullptr || (dt_ok(v1_dtype) && dt_ok(g1_dtype))) && (v2 == nullptr || dt_ok(v2_dtype)),
                 "rmsnorm_bwd_chain: inputs must be f32 or bf16");
@@ -620,14 +683,22 @@ extern "C" int tsfmx_rmsnorm_bwd_chain(const float* g_res, const void* v1, int32
   switch (cols) {
     case 1280:
       return launch_bwd_chain<10>(g_res, v1, v1_dtype, w1, g1, g1_dtype, v2, v2_dtype, w2, rows, eps, g_total, g2_dtype,
-                                  g2, stream);
+                                  g2, dw1, dw2, stream);
     case 768:
       return launch_bwd_chain<6>(g_res, v1, v1_dtype, w1, g1, g1_dtype, v2, v2_dtype, w2, rows, eps, g_total, g2_dtype,
-                                 g2, stream);
+                                 g2, dw1, dw2, stream);
     default:
       set_error("rmsnorm_bwd_chain: cols=%d unsupported (1280 or 768)", cols);
       return TSFMX_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int tsfmx_rmsnorm_bwd_chain(const float* g_res, const void* v1, int32_t v1_dtype, const float* w1,
+                                       const void* g1, int32_t g1_dtype, const void* v2, int32_t v2_dtype,
+                                       const float* w2, int64_t rows, int32_t cols, float eps, float* g_total,
+                                       int32_t g2_dtype, void* g2, void* stream_) {
+  return tsfmx_rmsnorm_bwd_chain_wgrad(g_res, v1, v1_dtype, w1, g1, g1_dtype, v2, v2_dtype, w2, rows, cols, eps, g_total,
+                                       g2_dtype, g2, nullptr, nullptr, stream_);
 }
 
 extern "C" int tsfmx_colsum_wgrad(const void* v, int32_t v_dtype, const void* g, int32_t g_dtype, int64_t rows, int32_t cols,

@@ -286,7 +286,20 @@ __device__ __forceinline__ uint64_t make_umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                       // layout type: SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
+// MN-major operand tile (the operand's M / N index is the contiguous one in shared memory), 128-byte swizzle: atoms of
+// 64 elements (128 B) x 8 k-rows; LBO = byte stride between 64-element chunks along M / N, SBO = between 8-row groups
+// along K (CUTLASS cute/atom/mma_traits_sm100.hpp, "make_umma_desc<Major::MN>": ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units).
+__device__ __forceinline__ uint64_t make_umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;  // LBO, bits [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;  // SBO, bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major (bits 15 / 16 set = MN-major A / B).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int umma_m, int umma_n) {
   return (1u << 4)                                   // D format: F32
          | (1u << 7)                                 // A format: BF16

@@ -311,9 +311,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
-template <int BN, int CG>
+// TOKEN_MAJOR (weight gradients dW = dY^T X, K = tokens): both operands are read as they lie in HBM, [tokens, features]
+// row-major, i.e. MN-major for this product.  One stage still holds 128 x 64 elements per operand, but as 64-feature
+// chunks of [64 tokens][128 B] (one TMA box each, 128B swizzle): the UMMA descriptors then walk MN in steps of one
+// chunk (LBO = 8 KB) and K in 8-token groups of 1 KB (SBO); one UMMA_K = 16 tokens = 2 KB.  Tokens beyond the last row
+// are zero-filled by TMA, so K needs no padding - and nothing is transposed through HBM any more.
+template <int BN, int CG, bool TOKEN_MAJOR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, CG>;
+  constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64-feature x 64-token box
   constexpr int STAGES = C::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -380,7 +386,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
             mbar_wait(&empty_bar[stage], phase ^ 1);
             void* sa = smem_a + stage * C::A_BYTES;
             void* sb = smem_b + stage * C::B_BYTES;
-            if constexpr (CG == 1) {
+            if constexpr (TOKEN_MAJOR) {
+              static_assert(!TOKEN_MAJOR || CG == 2, "token-major operands: CTA pairs only");
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * 2);
+              else        mbar_arrive_cluster(&full_bar[stage], 0);
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c)
+                tma_load_2d_pair(static_cast<uint8_t*>(sa) + c * CHUNK_BYTES, ta, &full_bar[stage], a_row + 64 * c, kb * BK);
+#pragma unroll
+              for (int c = 0; c < C::B_ROWS / 64; ++c)
+                tma_load_2d_pair(static_cast<uint8_t*>(sb) + c * CHUNK_BYTES, tb, &full_bar[stage], b_row + 64 * c, kb * BK);
+            } else if constexpr (CG == 1) {
               mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
               tma_load_2d(sa, ta, &full_bar[stage], sg.a_koff + kb * BK, a_row);
               tma_load_2d(sb, tb, &full_bar[stage], sg.b_koff + kb * BK, b_row);
@@ -398,7 +414,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN) | (TOKEN_MAJOR ? (1u << 15) | (1u << 16) : 0u);
       uint32_t stage = 0, phase = 0, iter = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
         const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
@@ -412,13 +428,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tcgen05_kernel(const
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint64_t da = make_umma_desc_sw128(smem_u32(smem_a + stage * C::A_BYTES));
-            const uint64_t db = make_umma_desc_sw128(smem_u32(smem_b + stage * C::B_BYTES));
+            if constexpr (TOKEN_MAJOR) {
+              constexpr uint32_t SBO = 8 * 128;  // 8 tokens x 128 B
+              const uint64_t da = make_umma_desc_mn_sw128(smem_u32(smem_a + stage * C::A_BYTES), CHUNK_BYTES, SBO);
+              const uint64_t db = make_umma_desc_mn_sw128(smem_u32(smem_b + stage * C::B_BYTES), CHUNK_BYTES, SBO);
+              constexpr uint32_t kstep = (UMMA_K / 8) * SBO >> 4;  // 16 tokens = two 8-token groups (descriptor units of 16 B)
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-              umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                umma_bf16<CG>(tmem_d, da + kstep * k, db + kstep * k, idesc, accumulate);
+                accumulate = 1;
+              }
+            } else {
+              const uint64_t da = make_umma_desc_sw128(smem_u32(smem_a + stage * C::A_BYTES));
+              const uint64_t db = make_umma_desc_sw128(smem_u32(smem_b + stage * C::B_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+                umma_bf16<CG>(tmem_d, da + 2 * k, db + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
             }
             if constexpr (CG == 1) umma_commit(&empty_bar[stage]);
             else                   umma_commit_pair(&empty_bar[stage], 0b11);
@@ -929,10 +957,10 @@ int make_tmap_f32_chunk(CUtensorMap* map, const void* base, int64_t rows, int64_
   return TSFMX_OK;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool TOKEN_MAJOR = false>
 int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, CG>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, CG, TOKEN_MAJOR>;
   static bool attr_set_dev[64] = {false};  // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
@@ -972,6 +1000,41 @@ int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 
 int g_force_cta_group = 0;  // test hook: 0 = auto, 1 / 2 = force
 int g_split_k_mode = 0;     // tune key 4: 0 = auto, 1 = never split K, n > 1 = force n splits where splitting is legal
+
+// split-K for short-and-wide problems (weight gradients: M, N = features, K = tokens): a 1280 x 1280 output is 25
+// tiles for 74 CTA pairs.  Only for a plain fp32 store (or an in-place accumulation into D), where the partial sums
+// can be added with vector reductions into a zero-filled D, and only from K = 4096 up: the order of those
+// reductions varies from run to run, which is fine for a gradient summed over tokens but would take away the
+// run-to-run bit-reproducibility of the model GEMMs (K <= 3840 in every adapter here).
+int choose_split_k(GemmParams& p, int cg, bool plain_f32_store, bool in_place, cudaStream_t stream) {
+  p.split_k = 1;
+  const int units = cg == 2 ? num_sms() / 2 : num_sms();
+  const int base = p.tiles_m * p.tiles_n;
+  int min_nkb = 1 << 30;
+  for (int s = 0; s < p.num_xseg; ++s) min_nkb = p.xseg[s].nkb < min_nkb ? p.xseg[s].nkb : min_nkb;
+  if (g_split_k_mode != 1 && base * 10 < units * 9 && plain_f32_store && (min_nkb >= 64 || g_split_k_mode > 1)) {
+    double best = static_cast<double>(base) / units;  // no split: one partial wave
+    for (int sk = 2; sk <= 16 && min_nkb / sk >= 16; ++sk) {  // at least 16 k-blocks (1024 of K) per split
+      const int tiles = base * sk, waves = (tiles + units - 1) / units;
+      const double kbs = static_cast<double>(min_nkb) / sk;
+      const double score = static_cast<double>(tiles) / (waves * units) * kbs / (kbs + 4.0);
+      if (score > best * 1.03) best = score, p.split_k = sk;
+    }
+    if (g_split_k_mode > 1) p.split_k = g_split_k_mode < min_nkb ? g_split_k_mode : min_nkb;
+  }
+  if (p.split_k > 1) {
+    p.residual = nullptr;  // in-place accumulation: the reductions add to what D already holds
+    if (!in_place) {
+      const cudaError_t e = cudaMemset2DAsync(p.d, static_cast<size_t>(p.ldd) * 4, 0, static_cast<size_t>(p.n_store) * 4,
+                                              static_cast<size_t>(p.m), stream);
+      if (e != cudaSuccess) {
+        set_error("gemm: cudaMemset2DAsync: %s", cudaGetErrorString(e));
+        return TSFMX_ERR_CUDA;
+      }
+    }
+  }
+  return TSFMX_OK;
+}
 
 }  // namespace
 }  // namespace tsfmx
@@ -1084,41 +1147,13 @@ extern "C" int tsfmx_gemm(const tsfmx_gemm_args* a, void* stream_) {
   }
   p.num_xseg = nx;
 
-  // split-K for short-and-wide problems (weight gradients: M, N = features, K = tokens): a 1280 x 1280 output is 25
-  // tiles for 74 CTA pairs.  Only for a plain fp32 store (or an in-place accumulation into D), where the partial sums
-  // can be added with vector reductions into a zero-filled D, and only from K = 4096 up: the order of those
-  // reductions varies from run to run, which is fine for a gradient summed over tokens but would take away the
-  // run-to-run bit-reproducibility of the model GEMMs (K <= 3840 in every adapter here).
-  p.split_k = 1;
   {
-    const int units = cg == 2 ? num_sms() / 2 : num_sms();
-    const int base = p.tiles_m * p.tiles_n;
     const bool in_place = a->residual != nullptr && a->residual == a->d && a->ldr == a->ldd;
-    int min_nkb = 1 << 30;
-    for (int s = 0; s < nx; ++s) min_nkb = p.xseg[s].nkb < min_nkb ? p.xseg[s].nkb : min_nkb;
-    if (g_split_k_mode != 1 && base * 10 < units * 9 && a->d_dtype == TSFMX_DT_F32 && a->act == TSFMX_ACT_NONE &&
-        a->bias == nullptr && a->row_scale == nullptr && a->pre_act == nullptr && (a->residual == nullptr || in_place) &&
-        reinterpret_cast<uintptr_t>(a->d) % 16 == 0 && a->ldd % 4 == 0 && (min_nkb >= 64 || g_split_k_mode > 1)) {
-      double best = static_cast<double>(base) / units;  // no split: one partial wave
-      for (int sk = 2; sk <= 16 && min_nkb / sk >= 16; ++sk) {  // at least 16 k-blocks (1024 of K) per split
-        const int tiles = base * sk, waves = (tiles + units - 1) / units;
-        const double kbs = static_cast<double>(min_nkb) / sk;
-        const double score = static_cast<double>(tiles) / (waves * units) * kbs / (kbs + 4.0);
-        if (score > best * 1.03) best = score, p.split_k = sk;
-      }
-      if (g_split_k_mode > 1) p.split_k = g_split_k_mode < min_nkb ? g_split_k_mode : min_nkb;
-    }
-    if (p.split_k > 1) {
-      p.residual = nullptr;  // in-place accumulation: the reductions add to what D already holds
-      if (!in_place) {
-        const cudaError_t e = cudaMemset2DAsync(a->d, static_cast<size_t>(a->ldd) * 4, 0, static_cast<size_t>(p.n_store) * 4,
-                                                static_cast<size_t>(a->m), stream);
-        if (e != cudaSuccess) {
-          set_error("gemm: cudaMemset2DAsync: %s", cudaGetErrorString(e));
-          return TSFMX_ERR_CUDA;
-        }
-      }
-    }
+    const bool plain = a->d_dtype == TSFMX_DT_F32 && a->act == TSFMX_ACT_NONE && a->bias == nullptr &&
+                       a->row_scale == nullptr && a->pre_act == nullptr && (a->residual == nullptr || in_place) &&
+                       reinterpret_cast<uintptr_t>(a->d) % 16 == 0 && a->ldd % 4 == 0;
+    const int rc = choose_split_k(p, cg, plain, in_place, stream);
+    if (rc != TSFMX_OK) return rc;
   }
 
   if (cg == 2) return launch_gemm<256, 2>(p, stream);
@@ -1225,4 +1260,40 @@ extern "C" int tsfmx_gemm_rownorm(const tsfmx_gemm_segment* seg, int64_t m, int3
     return TSFMX_ERR_CUDA;
   }
   return check_last_launch("gemm_rownorm_tcgen05");
+}
+
+extern "C" int tsfmx_gemm_wgrad(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t rows, int32_t n_out,
+                                int32_t k_in, float* dw, int64_t ld_dw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TSFMX_REQUIRE(dy != nullptr && x != nullptr && dw != nullptr, "gemm_wgrad: NULL operand");
+  TSFMX_REQUIRE(rows > 0 && rows < (int64_t(1) << 31) - 64, "gemm_wgrad: bad token count %lld", (long long)rows);
+  TSFMX_REQUIRE(n_out > 0 && k_in > 0 && n_out % 8 == 0 && k_in % 8 == 0,
+                "gemm_wgrad: n_out (%d) and k_in (%d) must be positive multiples of 8", n_out, k_in);
+  TSFMX_REQUIRE(ld_dy >= n_out && ld_x >= k_in && ld_dy % 8 == 0 && ld_x % 8 == 0,
+                "gemm_wgrad: row strides must cover the row and be multiples of 8 elements");
+  TSFMX_REQUIRE(reinterpret_cast<uintptr_t>(dy) % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(dw) % 16 == 0 && ld_dw % 4 == 0 && ld_dw >= k_in,
+                "gemm_wgrad: operands must be 16-byte aligned (ld_dw a multiple of 4, >= k_in)");
+  GemmParams p = {};
+  p.m = n_out;
+  p.n = k_in;
+  p.tiles_m = (n_out + 2 * BM - 1) / (2 * BM);
+  p.tiles_n = (k_in + 255) / 256;
+  p.act = TSFMX_ACT_NONE;
+  p.d_dtype = TSFMX_DT_F32;
+  p.d = dw;
+  p.ldd = ld_dw;
+  p.n_store = k_in;
+  p.split_off = k_in;
+  p.vec_ok = 1;
+  // boxes of 64 features x 64 tokens straight out of the [tokens, features] matrices
+  int rc = make_tmap_bf16(&p.tma_a[0], dy, rows, n_out, ld_dy, 64);
+  if (rc != TSFMX_OK) return rc;
+  rc = make_tmap_bf16(&p.tma_b[0], x, rows, k_in, ld_x, 64);
+  if (rc != TSFMX_OK) return rc;
+  p.xseg[0] = XSeg{0, 0, 0, 0, static_cast<int32_t>((rows + BK - 1) / BK)};
+  p.num_xseg = 1;
+  rc = choose_split_k(p, 2, true, false, stream);
+  if (rc != TSFMX_OK) return rc;
+  return launch_gemm<256, 2, true>(p, stream);
 }

@@ -112,6 +112,9 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "tsfmx_gemm": (c_int32, [POINTER(GemmArgs), c_void_p]),
     "tsfmx_gemm_set_cta_group": (c_int32, [c_int32]),
     "tsfmx_gemm_set_split_k": (c_int32, [c_int32]),
+    "tsfmx_gemm_wgrad": (
+        c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p],
+    ),
     "tsfmx_gemm_rownorm": (
         c_int32,
         [POINTER(GemmSegment), c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
@@ -165,6 +168,11 @@ SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int32,
         [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_int32,
          c_float, c_void_p, c_int32, c_void_p, c_void_p],
+    ),
+    "tsfmx_rmsnorm_bwd_chain_wgrad": (
+        c_int32,
+        [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_int32,
+         c_float, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "tsfmx_timesfm_attention_bwd": (
         c_int32,

@@ -360,13 +360,19 @@ def rmsnorm_bwd_chain(
     g2: torch.Tensor | None,
     rows: int,
     cols: int,
+    dw1: torch.Tensor | None = None,
+    dw2: torch.Tensor | None = None,
 ) -> None:
+    """``dw1`` / ``dw2`` (full fine-tuning): fp32 [cols], ACCUMULATED into - the gradients of the scales ``w1`` / ``w2``
+    from the same pass over the rows."""
     lib = _lib.load()
+    for t in (dw1, dw2):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == cols)
     check(
-        lib.tsfmx_rmsnorm_bwd_chain(
+        lib.tsfmx_rmsnorm_bwd_chain_wgrad(
             ptr(g_res), ptr(v1), _dt(v1) if v1 is not None else 0, ptr(w1), ptr(g1), _dt(g1) if g1 is not None else 0,
             ptr(v2), _dt(v2) if v2 is not None else 0, ptr(w2), rows, cols, eps, ptr(g_total), g2_dtype, ptr(g2),
-            stream(),
+            ptr(dw1), ptr(dw2), stream(),
         )
     )
 
@@ -499,9 +505,23 @@ def timesfm_stack_fwd(table, x: torch.Tensor, batch: int, num_patches: int, patc
     return y
 
 
+def _token_major_ok(t: torch.Tensor, cols: int) -> bool:
+    return (t.dtype == torch.bfloat16 and t.dim() == 2 and t.shape[1] == cols and t.stride(1) == 1
+            and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0)
+
+
+@_on_operand_device
 def wgrad(dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, k_in: int, precision: int) -> torch.Tensor:
-    """Weight gradient of ``y = x W^T``: dW [n_out, k_in] = dY^T X as a K-major tcgen05 GEMM with K = rows (both operands
-    transposed once; split-K inside the GEMM when the tile count is small)."""
+    """Weight gradient of ``y = x W^T``: dW [n_out, k_in] = dY^T X, a tcgen05 GEMM with K = rows (split-K inside the GEMM
+    when the tile count is small).  bf16 operands are consumed where they lie, [tokens, features] row-major = MN-major
+    for this product (``tsfmx_gemm_wgrad``); fp32 / split operands (parity mode, fp32 head gradients) are transposed
+    to K-major copies first."""
+    if precision == PREC_BF16 and _token_major_ok(dy, n_out) and _token_major_ok(x, k_in) and n_out % 8 == 0 and k_in % 8 == 0:
+        lib = _lib.load()
+        _lib.require_cuda(dy, x)
+        gw = torch.empty(n_out, k_in, dtype=torch.float32, device=dy.device)
+        check(lib.tsfmx_gemm_wgrad(ptr(dy), dy.stride(0), ptr(x), x.stride(0), rows, n_out, k_in, ptr(gw), k_in, stream()))
+        return gw
     adt = act_dtype(precision)
     dy_t, kpad = transpose_mask(dy, rows, n_out, adt)
     x_t, _ = transpose_mask(x, rows, k_in, adt)

@@ -187,7 +187,11 @@ class TimesFM2p5Adapter(TsfmAdapter):
 
         def pack_t(lin: nn.Linear) -> torch.Tensor:
             """W^T, K-major: the B operand of the dgrad GEMM dX = dY W (built lazily, only for training)."""
-            return ops.cast_rows(lin.weight.detach().float().t().contiguous(), adt)
+            wt = lin.weight.detach()
+            n_out, k_in = wt.shape
+            if wt.dtype == torch.float32 and wt.is_contiguous() and n_out % 64 == 0:
+                return ops.transpose_mask(wt, n_out, k_in, adt)[0]  # transpose + cast in one kernel
+            return ops.cast_rows(wt.float().t().contiguous(), adt)
 
         def f32(t: torch.Tensor) -> torch.Tensor:
             return t.detach().float().contiguous()
@@ -610,9 +614,21 @@ class TimesFM2p5Adapter(TsfmAdapter):
         gmid = ops.alloc(rows, d, mid_dt, dev)
         datt = ops.alloc(rows, d, mid_dt, dev)
         dqkv = ops.alloc(rows, 3 * d, adt, dev)
-        # top of the stack: da2 = RMSNorm_bwd(a2, post_ff, dz)
-        ops.rmsnorm_bwd_chain(g, None, None, None, sl[-1]["a2"], layers[-1]["post_ff"], m.eps, None, adt, g2, rows, d)
         pg = param_grads
+        # full fine-tuning: the four norm-scale gradients of a layer leave the junction kernels' own pass over the rows
+        # (views of one zero-filled buffer: the kernels accumulate into them)
+        dscale = torch.zeros(len(layers), 4, d, dtype=torch.float32, device=dev) if pg is not None else None
+
+        def slot(i: int, name: str):
+            if dscale is None or i < 0:
+                return None
+            j = ("pre_attn_ln", "post_attn_ln", "pre_ff_ln", "post_ff_ln").index(name)
+            pg[f"stacked_xf.{i}.{name}.scale"] = dscale[i, j]
+            return dscale[i, j]
+
+        # top of the stack: da2 = RMSNorm_bwd(a2, post_ff, dz)
+        ops.rmsnorm_bwd_chain(g, None, None, None, sl[-1]["a2"], layers[-1]["post_ff"], m.eps, None, adt, g2, rows, d,
+                              dw2=slot(len(layers) - 1, "post_ff_ln"))
         for i in reversed(range(len(layers))):
             lw, tw, s = layers[i], tlayers[i], sl[i]
             pre = f"stacked_xf.{i}."
@@ -620,7 +636,6 @@ class TimesFM2p5Adapter(TsfmAdapter):
                 done = f"stacked_xf.{i + 1}."  # the layer above is complete: hand its gradients over
                 on_grads([v for k, v in pg.items() if k.startswith(done)])
             if pg is not None:  # g = dL/dz, g2 = da2 at this point
-                pg[pre + "post_ff_ln.scale"] = ops.colsum_wgrad(g, s["a2"], m.eps)
                 pg[pre + "ff1.weight"] = self._wgrad(g2, s["h"], rows, d, m.ff)
             # dhff = da2 W1 ; du = dhff * silu'(u)
             ops.gemm([(g2, tw["ff1"], d)], rows, m.ff, du, adt, precision=prec, act=ACT_SILU_GRAD, aux=s["u"])
@@ -628,11 +643,10 @@ class TimesFM2p5Adapter(TsfmAdapter):
             ops.gemm([(du, tw["ff0"], m.ff)], rows, d, gmid, mid_dt, precision=prec)
             if pg is not None:
                 pg[pre + "ff0.weight"] = self._wgrad(du, s["xn2"], rows, m.ff, d)
-                pg[pre + "pre_ff_ln.scale"] = ops.colsum_wgrad(gmid, s["y"], m.eps)
             # dy = dz + RMSNorm_bwd(y, pre_ff, dyn) ; da1 = RMSNorm_bwd(a1, post_attn, dy)
-            ops.rmsnorm_bwd_chain(g, s["y"], lw["pre_ff"], gmid, s["a1"], lw["post_attn"], m.eps, g, adt, g2, rows, d)
+            ops.rmsnorm_bwd_chain(g, s["y"], lw["pre_ff"], gmid, s["a1"], lw["post_attn"], m.eps, g, adt, g2, rows, d,
+                                  dw1=slot(i, "pre_ff_ln"), dw2=slot(i, "post_attn_ln"))
             if pg is not None:  # g = dL/dy, g2 = da1
-                pg[pre + "post_attn_ln.scale"] = ops.colsum_wgrad(g, s["a1"], m.eps)
                 pg[pre + "attn.out.weight"] = self._wgrad(g2, s["attn"], rows, d, d)
             # datt = da1 Wo
             ops.gemm([(g2, tw["out"], d)], rows, d, datt, mid_dt, precision=prec)
@@ -644,7 +658,6 @@ class TimesFM2p5Adapter(TsfmAdapter):
             ops.gemm([(dqkv, tw["qkv"], 3 * d)], rows, d, gmid, mid_dt, precision=prec)
             if pg is not None:
                 pg[pre + "attn.qkv_proj.weight"] = self._wgrad(dqkv, s["xn1"], rows, 3 * d, d)
-                pg[pre + "pre_attn_ln.scale"] = ops.colsum_wgrad(gmid, s["x"], m.eps)
                 # q' = (q_ln * softplus(per_dim) * c) * qhat: chain rule for the three 80-vectors
                 xf = m.stacked_xf[i].attn
                 per_dim = xf.per_dim_scale.per_dim_scale.detach().float()
@@ -657,7 +670,8 @@ class TimesFM2p5Adapter(TsfmAdapter):
             below = i - 1
             ops.rmsnorm_bwd_chain(g, s["x"], lw["pre_attn"], gmid, sl[below]["a2"] if below >= 0 else None,
                                   layers[below]["post_ff"] if below >= 0 else None, m.eps, g, adt,
-                                  g2 if below >= 0 else None, rows, d)
+                                  g2 if below >= 0 else None, rows, d,
+                                  dw1=slot(i, "pre_attn_ln"), dw2=slot(below, "post_ff_ln"))
         if pg is not None and on_grads is not None:
             on_grads([v for k, v in pg.items() if k.startswith("stacked_xf.0.")])
         return g

@@ -121,6 +121,52 @@ def test_gemm_split_k(cta_group, split, m, n, k):
         _lib.check(lib.tsfmx_gemm_set_split_k(0))
 
 
+@pytest.mark.parametrize("split", [0, 1, 5])
+@pytest.mark.parametrize(
+    "rows,n_out,k_in",
+    [(4096 + 37, 1280, 1280), (16384, 3840, 1280), (1000, 336, 768), (513, 64, 1280), (200, 1280, 64), (70, 8, 264)],
+)
+def test_wgrad_token_major(split, rows, n_out, k_in):
+    """dW = dY^T X with both operands read as they lie in HBM ([tokens, features] = MN-major UMMA descriptors, no
+    transposed copies): ragged token counts (TMA zero-fills the last k-block), feature counts off the 64-element chunk
+    and the 256-wide tile, strided operands, with and without split-K - against torch fp32 and against the transposing
+    path (same products, same accumulation order inside a tile)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lib = _lib.load()
+    _lib.check(lib.tsfmx_gemm_set_split_k(split))
+    try:
+        gen = torch.Generator(device=DEV).manual_seed(rows + n_out)
+        dy_full = torch.randn(rows, n_out + 24, device=DEV, generator=gen).to(torch.bfloat16)
+        dy = dy_full[:, 8 : 8 + n_out]  # strided rows, 16-byte aligned start
+        x = torch.randn(rows, k_in, device=DEV, generator=gen).to(torch.bfloat16)
+        got = ops.wgrad(dy, x, rows, n_out, k_in, PREC_BF16)
+        ref = dy.float().t() @ x.float()
+        assert _rel(got, ref) < 3e-5
+        dy_t, kpad = ops.transpose_mask(dy.contiguous(), rows, n_out, DT_BF16)
+        x_t, _ = ops.transpose_mask(x, rows, k_in, DT_BF16)
+        old = torch.empty(n_out, k_in, dtype=torch.float32, device=DEV)
+        ops.gemm([(dy_t, x_t, kpad)], n_out, k_in, old, DT_F32, precision=PREC_BF16)
+        if split == 1:  # one tile per output block: the two paths add the same products in the same order
+            assert torch.equal(got, old)
+        else:
+            assert _rel(got, old) < 1e-5
+    finally:
+        _lib.check(lib.tsfmx_gemm_set_split_k(0))
+
+
+def test_wgrad_falls_back_for_fp32_and_split_operands():
+    """Parity mode (split operands) and fp32 gradients keep the transposing path; both give the fp32 product."""
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    rows, n_out, k_in = 777, 128, 192
+    dy = torch.randn(rows, n_out, device=DEV, generator=gen)
+    x = torch.randn(rows, k_in, device=DEV, generator=gen)
+    ref = dy.t() @ x
+    got = ops.wgrad(ops.cast_rows(dy, DT_BF16_SPLIT), ops.cast_rows(x, DT_BF16_SPLIT), rows, n_out, k_in, PREC_BF16X3)
+    assert _rel(got, ref) < 1e-4
+    got = ops.wgrad(dy, x.to(torch.bfloat16), rows, n_out, k_in, PREC_BF16)  # fp32 dY: cast while transposing
+    assert _rel(got, dy.to(torch.bfloat16).float().t() @ x.to(torch.bfloat16).float()) < 3e-5
+
+
 @pytest.mark.parametrize("cta_group", [1, 2])
 def test_gemm_bf16x3_close_to_fp32(cta_group):
     lib = _lib.load()
