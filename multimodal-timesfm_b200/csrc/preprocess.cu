@@ -188,8 +188,6 @@ __global__ void __launch_bounds__(WARPS * 32) timesfm_patchify_norm_generic_kern
 // ----------------------------------------------------------------------------------------
 // Running-statistics helpers of the TimesFM kernels
 // ----------------------------------------------------------------------------------------
-constexpr int TF_BLOCKED_MIN_PATCHES = 16;  // contexts above 512 use the blocked fold of the running statistics
-
 struct RunStats {
   float n, mu, sigma;
 };
@@ -236,24 +234,37 @@ __device__ __forceinline__ RunStats merge_stats_r(RunStats run, float inc_n, flo
   return RunStats{new_n, new_mu, sqrtf(fmaxf(new_var, 0.f))};
 }
 
+// Statistics of the union of two disjoint sets (the same update, with the count and its IEEE reciprocal formed here):
+// the operator of the parallel scan.
+__device__ __forceinline__ RunStats merge_sets(RunStats a, RunStats b) {
+  const float new_n = __fadd_rn(a.n, b.n);  // exact: small integers
+  return merge_stats_r(a, b.n, b.mu, b.sigma, new_n, __frcp_rn(new_n == 0.f ? 1.f : new_n));
+}
+// the same for the scan steps, where either side may be an empty set (nothing to round then)
+__device__ __forceinline__ RunStats merge_sets_scan(RunStats a, RunStats b) {
+  if (a.n == 0.f) return b;
+  if (b.n == 0.f) return a;
+  return merge_sets(a, b);
+}
+__device__ __forceinline__ RunStats shfl_up_stats(RunStats v, int d) {
+  return RunStats{__shfl_up_sync(0xffffffffu, v.n, d), __shfl_up_sync(0xffffffffu, v.mu, d),
+                  __shfl_up_sync(0xffffffffu, v.sigma, d)};
+}
+
 template <int OUT>
 __global__ void __launch_bounds__(TFW_WARPS * 32) timesfm_patchify_norm_warp_kernel(
     const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t batch, int context, int warps,
     int warp_bytes, int g, int stages, void* tokens, float* __restrict__ mu_out, float* __restrict__ sigma_out,
     uint8_t* __restrict__ patch_mask_out, int32_t* __restrict__ num_masked_out) {
-  // g = series per tile (<= 32; 1 when the context has more than 16 patches), stages = 1 or 2 tiles in flight
+  // g = series per tile (a power of two <= 32 with N <= 4 * 32 / g), stages = 1 or 2 tiles in flight
   extern __shared__ __align__(128) uint8_t smem_tfw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pg = lane >> 3, q = lane & 7;
   const int N = context >> 5;
   const int stage_bytes = (g * context * 5 + 127) & ~127;
-  const int NB = (N + 7) >> 3;
-  const float inv_n = 1.0f / static_cast<float>(N);
   uint8_t* wbase = smem_tfw + warp * warp_bytes;
   float4* slots = reinterpret_cast<float4*>(wbase + stages * stage_bytes);  // {count, mean, sigma, padded flag} per patch
-  float4* aux = slots + g * N;  // {count so far, its reciprocal, count so far inside the block of 8, its reciprocal}
-  float4* blk = aux + g * N;    // blocked fold: [g][NB] block summaries, then the state before each block
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(blk + g * NB);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slots + g * N);
   const int64_t num_tiles = (batch + g - 1) / g;
   const int64_t first = static_cast<int64_t>(blockIdx.x) * warps + warp;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * warps;
@@ -343,86 +354,50 @@ __global__ void __launch_bounds__(TFW_WARPS * 32) timesfm_patchify_norm_warp_ker
       slots[p] = make_float4(c, inc_mu, c == 0.f ? 0.f : sqrtf(fmaxf(__fdiv_rn(sq, c_safe), 0.f)), flag);
     }
     __syncwarp();
-    // ---- running counts and their reciprocals, one lane per patch: the counts are exact small integers (any order
-    //      of the additions gives the same value) and do not depend on the data values, so they leave the dependent
-    //      chain of phase B and all lanes take part in the IEEE reciprocals
-    for (int p = lane; p < P; p += 32) {
-      const int sr = g == 1 ? 0 : static_cast<int>((static_cast<float>(p) + 0.5f) * inv_n);
-      const int k = p - sr * N;
-      const float4* row = slots + sr * N;
-      float n_before_block = 0.f, n_loc = 0.f;
-      for (int i = 0; i < (k & ~7); ++i) n_before_block += row[i].x;
-      for (int i = k & ~7; i <= k; ++i) n_loc += row[i].x;
-      const float n_cum = n_before_block + n_loc;
-      aux[p] = make_float4(n_cum, __frcp_rn(n_cum == 0.f ? 1.f : n_cum), n_loc,
-                           N > TF_BLOCKED_MIN_PATCHES ? __frcp_rn(n_loc == 0.f ? 1.f : n_loc) : 1.f);
-    }
-    __syncwarp();
-    // ---- phase B: merge of the running statistics; the slot becomes {cumulative mu, cumulative sigma,
-    //      1 / safe sigma, padded flag}
-    if (N <= TF_BLOCKED_MIN_PATCHES) {
-      // reference order exactly: lane s folds the N patches of series s one after the other
-      if (lane < cnt) {
-        RunStats st = {0.f, 0.f, 0.f};
-        int masked = 0;
-        float4* row = slots + lane * N;
-        const float4* arow = aux + lane * N;
-        for (int i = 0; i < N; ++i) {
-          const float4 inc = row[i];
-          const float4 cn = arow[i];
-          st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.x, cn.y);
-          row[i] = make_float4(st.mu, st.sigma, 0.f, inc.w);
-          masked += inc.w != 0.f ? 1 : 0;
+    // ---- phase B: running statistics; the slot becomes {cumulative mu, cumulative sigma, 1 / safe sigma, padded flag}
+    {
+      // parallel scan.  The 32 / g lanes of a series own E <= 4 consecutive patches each: fold them locally, scan the
+      // lane aggregates with shuffles (log2 steps of one set-union each), then apply the exclusive prefix - 2 E +
+      // log2(32 / g) dependent merges with all lanes busy.  The folds this replaces kept one lane per series busy for N
+      // dependent merges (ctx <= 512) or ran 24 dependent merges per series with 8 or 1 lanes active (blocked fold, ctx
+      // 2048), plus a count pre-pass: ~1 600 of the kernel's 3 450 warp instructions per series at ctx 2048
+      // (profiles/r2ac_ncu_patchify_ctx2048.md).  Every statistic is still the union of exact sub-set statistics
+      // (update_running_stats' own formula); only the association order of the fp32 roundings differs from the
+      // reference's patch-by-patch loop (timesfm.py:63-66) - a few 1e-7, inside the 2e-6 bound the tests hold.
+      const int L = 32 / g, E = (N + L - 1) / L;
+      const int sr = lane / L, ls = lane - sr * L, k0 = ls * E;
+      const bool act = sr < cnt;
+      RunStats loc[4];
+      float flag[4];
+      RunStats st = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        flag[e] = 0.f;
+        if (e < E && k0 + e < N && act) {
+          const float4 inc = slots[sr * N + k0 + e];
+          flag[e] = inc.w;
+          st = merge_sets(st, RunStats{inc.x, inc.y, inc.z});
         }
-        if (num_masked_out != nullptr) num_masked_out[b0 + lane] = masked;
+        loc[e] = st;
       }
-    } else {
-      // blocked fold exactly as in the block-wide kernel (blocks of 8 patches), one lane per (series, block)
-      for (int u = lane; u < cnt * NB; u += 32) {
-        const int sr = u / NB, b = u - sr * NB;
-        const int k1 = min(N, 8 * b + 8);
-        RunStats st = {0.f, 0.f, 0.f};
-        for (int i = 8 * b; i < k1; ++i) {
-          const float4 inc = slots[sr * N + i];
-          const float4 cn = aux[sr * N + i];
-          st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.z, cn.w);
-        }
-        blk[u] = make_float4(st.n, st.mu, st.sigma, 0.f);
+      RunStats agg = st;
+      for (int d = 1; d < L; d <<= 1) {
+        const RunStats up = shfl_up_stats(agg, d);
+        if (ls >= d) agg = merge_sets_scan(up, agg);
       }
-      __syncwarp();
-      if (lane < cnt) {
-        RunStats st = {0.f, 0.f, 0.f};
-        for (int b = 0; b < NB; ++b) {
-          const float4 inc = blk[lane * NB + b];
-          const float4 cn = aux[lane * N + min(N, 8 * b + 8) - 1];  // count at the end of block b
-          blk[lane * NB + b] = make_float4(st.n, st.mu, st.sigma, 0.f);  // exclusive prefix
-          st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.x, cn.y);
+      RunStats pre = shfl_up_stats(agg, 1);
+      if (ls == 0) pre = RunStats{0.f, 0.f, 0.f};
+      int masked = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (e < E && k0 + e < N && act) {
+          const RunStats out = merge_sets_scan(pre, loc[e]);
+          slots[sr * N + k0 + e] = make_float4(out.mu, out.sigma, 0.f, flag[e]);
+          masked += flag[e] != 0.f ? 1 : 0;
         }
       }
-      __syncwarp();
-      for (int u = lane; u < ((cnt * NB + 31) & ~31); u += 32) {
-        int masked = 0;
-        const int sr = u / NB, b = u - sr * NB;
-        if (u < cnt * NB) {
-          const int k1 = min(N, 8 * b + 8);
-          const float4 pre = blk[u];
-          RunStats st = {pre.x, pre.y, pre.z};
-          for (int i = 8 * b; i < k1; ++i) {
-            const float4 inc = slots[sr * N + i];
-            const float4 cn = aux[sr * N + i];
-            st = merge_stats_r(st, inc.x, inc.y, inc.z, cn.x, cn.y);
-            slots[sr * N + i] = make_float4(st.mu, st.sigma, 0.f, inc.w);
-            masked += inc.w != 0.f ? 1 : 0;
-          }
-        }
-        // padded-patch count of every series: sum over its NB lanes (NB <= 8 here, a series never straddles rounds
-        // when NB divides 32; otherwise fall back to one atomic per lane)
-        if (num_masked_out != nullptr && u < cnt * NB) {
-          if (b == 0) num_masked_out[b0 + sr] = 0;
-        }
-        __syncwarp();
-        if (num_masked_out != nullptr && u < cnt * NB && masked) atomicAdd(&num_masked_out[b0 + sr], masked);
-      }
+      for (int d = 1; d < L; d <<= 1) masked += __shfl_xor_sync(0xffffffffu, masked, d);
+      if (num_masked_out != nullptr && act && ls == 0) num_masked_out[b0 + sr] = masked;
     }
     __syncwarp();
     // ---- mu / sigma / patch mask out, coalesced (the tile's [cnt, N] block is contiguous in [B, N]); the
@@ -1045,13 +1020,15 @@ int launch_timesfm_staged(const float* x, const uint8_t* mask, int64_t batch, in
   if (context <= 4096) {  // warp-private tiles, no block-wide barriers
     // series per tile: phase B keeps one lane per series busy, so more series per tile means fewer (mostly idle)
     // warp instructions per series; the tile still has to leave room for >= 12 warps per SM
-    int g = g_tf_group > 0 ? g_tf_group : 2048 / context;
-    if (g > 32) g = 32;
-    if (g < 1) g = 1;
+    // series per tile: a power of two (32 / g lanes scan one series, at most 4 patches per lane); the tile still has
+    // to leave room for >= 12 warps per SM
+    int want = g_tf_group > 0 ? g_tf_group : 2048 / context;
+    int g = 1;
+    while (2 * g <= want && 2 * g <= 32 && N <= 4 * (32 / (2 * g))) g *= 2;
     int stages = (g_tf_warps >> 8) > 0 ? (g_tf_warps >> 8) : (g * context * 5 <= 6 * 1024 ? 2 : 1);
     if (stages > 2) stages = 2;
     const int stage_bytes = (g * context * 5 + 127) & ~127;
-    const int warp_bytes = (stages * stage_bytes + (2 * g * N + g * ((N + 7) >> 3)) * 16 + 16 + 127) & ~127;
+    const int warp_bytes = (stages * stage_bytes + g * N * 16 + 16 + 127) & ~127;
     int warps = (g_tf_warps & 0xff) > 0 ? (g_tf_warps & 0xff) : TFW_WARPS;
     if (warps > TFW_WARPS) warps = TFW_WARPS;
     while (warps > 1 && warps * warp_bytes > 110 * 1024) --warps;  // at least two blocks per SM
