@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
   constexpr int HALF = MMA_HD / 2;          // 40 rotary pairs
   constexpr int TILE = ROWS * MMA_LD;       // elements per q / k / v tile
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  float2* s_rope = reinterpret_cast<float2*>(smem_attn);                  // [2 * ROWS][40] (cos, sin)
-  float* s_wq = reinterpret_cast<float*>(s_rope + 2 * ROWS * HALF);       // [80] q_ln_w * q_scale
+  float* s_rope = reinterpret_cast<float*>(smem_attn);                    // [2 * ROWS][cos 40 | sin 40 | -sin 40]
+  float* s_wq = s_rope + 2 * ROWS * 3 * HALF;                             // [80] q_ln_w * q_scale
   float* s_wk = s_wq + MMA_HD;                                            // [80] k_ln_w
   __nv_bfloat16* s_tiles = reinterpret_cast<__nv_bfloat16*>(s_wk + MMA_HD);
   const int warps_per_block = blockDim.x >> 5;
@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
     const int p = i / HALF, f = i - p * HALF;
     float sn, cs;
     sincosf(static_cast<float>(p - N) * __ldg(inv_freq + f), &sn, &cs);
-    s_rope[i] = make_float2(cs, sn);
+    float* row = s_rope + p * 3 * HALF;
+    row[f] = cs, row[HALF + f] = sn, row[2 * HALF + f] = -sn;
   }
   for (int i = threadIdx.x; i < MMA_HD; i += blockDim.x) {
     s_wq[i] = __ldg(q_ln_w + i) * __ldg(q_scale + i);
@@ -310,11 +311,14 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
       if (rt < ntk) {
         const int hf = lane & 1;
         const bool live = r < N;
-        const float2* rope = s_rope + (live ? (r - nm + N) : 0) * HALF + 20 * hf;
+        // rotation, sum of squares and scaling on packed fp32 pairs (dims idx, idx + 1 of one tensor): FFMA2 / FMUL2
+        // halve the instruction count of what was ~600 of this kernel's ~1 160 warp instructions per (series, head)
+        const float* rope = s_rope + (live ? (r - nm + N) : 0) * 3 * HALF + 20 * hf;
         __nv_bfloat16* qrow = sQ + r * MMA_LD + 20 * hf;
         __nv_bfloat16* krow = sK + r * MMA_LD + 20 * hf;
-        float q1[20], q2[20], k1[20], k2[20];
-        float qss = 0.f, kss = 0.f;
+        float2 q1[10], q2[10], k1[10], k2[10];
+        float2 qss2 = make_float2(0.f, 0.f), kss2 = make_float2(0.f, 0.f);
+        auto unpack = [](uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
           const uint2 a1 = *reinterpret_cast<const uint2*>(qrow + 4 * i);
@@ -323,44 +327,46 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
           const uint2 c2 = *reinterpret_cast<const uint2*>(krow + HALF + 4 * i);
           const uint32_t aw1[2] = {a1.x, a1.y}, aw2[2] = {a2.x, a2.y}, cw1[2] = {c1.x, c1.y}, cw2[2] = {c2.x, c2.y};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int idx = 4 * i + e;
-            const float2 cssn = rope[idx];
-            auto pick = [&](const uint32_t(&w)[2]) {
-              const uint32_t word = w[e >> 1];
-              return __uint_as_float((e & 1) ? (word & 0xffff0000u) : (word << 16));
-            };
-            const float x1 = pick(aw1), x2 = pick(aw2), y1 = pick(cw1), y2 = pick(cw2);
-            q1[idx] = x1 * cssn.x - x2 * cssn.y;
-            q2[idx] = x2 * cssn.x + x1 * cssn.y;
-            k1[idx] = y1 * cssn.x - y2 * cssn.y;
-            k2[idx] = y2 * cssn.x + y1 * cssn.y;
-            qss += q1[idx] * q1[idx] + q2[idx] * q2[idx];
-            kss += k1[idx] * k1[idx] + k2[idx] * k2[idx];
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * i + e;  // pair index: dims 2j, 2j + 1 of this lane's 20
+            const float2 cs = *reinterpret_cast<const float2*>(rope + 2 * j);
+            const float2 sn = *reinterpret_cast<const float2*>(rope + HALF + 2 * j);
+            const float2 ns = *reinterpret_cast<const float2*>(rope + 2 * HALF + 2 * j);
+            const float2 x1 = unpack(aw1[e]), x2 = unpack(aw2[e]), y1 = unpack(cw1[e]), y2 = unpack(cw2[e]);
+            q1[j] = fma2(x2, ns, mul2(x1, cs));  // x1 cos - x2 sin
+            q2[j] = fma2(x1, sn, mul2(x2, cs));  // x2 cos + x1 sin
+            k1[j] = fma2(y2, ns, mul2(y1, cs));
+            k2[j] = fma2(y1, sn, mul2(y2, cs));
+            qss2 = fma2(q2[j], q2[j], fma2(q1[j], q1[j], qss2));
+            kss2 = fma2(k2[j], k2[j], fma2(k1[j], k1[j], kss2));
           }
         }
+        float qss = qss2.x + qss2.y, kss = kss2.x + kss2.y;
         qss += __shfl_xor_sync(0xffffffffu, qss, 1);
         kss += __shfl_xor_sync(0xffffffffu, kss, 1);
         const float qrs = rsqrtf(qss * (1.0f / MMA_HD) + eps);
         const float krs = rsqrtf(kss * (1.0f / MMA_HD) + eps);
+        const float2 qrs2 = make_float2(qrs, qrs), krs2 = make_float2(krs, krs);
         const float* wq1 = s_wq + 20 * hf;
         const float* wk1 = s_wk + 20 * hf;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          uint2 o1, o2, p1, p2;
-          o1.x = pack_bf16x2(q1[4 * i] * qrs * wq1[4 * i], q1[4 * i + 1] * qrs * wq1[4 * i + 1]);
-          o1.y = pack_bf16x2(q1[4 * i + 2] * qrs * wq1[4 * i + 2], q1[4 * i + 3] * qrs * wq1[4 * i + 3]);
-          o2.x = pack_bf16x2(q2[4 * i] * qrs * wq1[HALF + 4 * i], q2[4 * i + 1] * qrs * wq1[HALF + 4 * i + 1]);
-          o2.y = pack_bf16x2(q2[4 * i + 2] * qrs * wq1[HALF + 4 * i + 2], q2[4 * i + 3] * qrs * wq1[HALF + 4 * i + 3]);
-          p1.x = pack_bf16x2(k1[4 * i] * krs * wk1[4 * i], k1[4 * i + 1] * krs * wk1[4 * i + 1]);
-          p1.y = pack_bf16x2(k1[4 * i + 2] * krs * wk1[4 * i + 2], k1[4 * i + 3] * krs * wk1[4 * i + 3]);
-          p2.x = pack_bf16x2(k2[4 * i] * krs * wk1[HALF + 4 * i], k2[4 * i + 1] * krs * wk1[HALF + 4 * i + 1]);
-          p2.y = pack_bf16x2(k2[4 * i + 2] * krs * wk1[HALF + 4 * i + 2], k2[4 * i + 3] * krs * wk1[HALF + 4 * i + 3]);
+          uint32_t o1[2], o2[2], p1[2], p2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * i + e;
+            const float2 a = mul2(q1[j], mul2(*reinterpret_cast<const float2*>(wq1 + 2 * j), qrs2));
+            const float2 b2 = mul2(q2[j], mul2(*reinterpret_cast<const float2*>(wq1 + HALF + 2 * j), qrs2));
+            const float2 c = mul2(k1[j], mul2(*reinterpret_cast<const float2*>(wk1 + 2 * j), krs2));
+            const float2 d = mul2(k2[j], mul2(*reinterpret_cast<const float2*>(wk1 + HALF + 2 * j), krs2));
+            o1[e] = pack_bf16x2(a.x, a.y), o2[e] = pack_bf16x2(b2.x, b2.y);
+            p1[e] = pack_bf16x2(c.x, c.y), p2[e] = pack_bf16x2(d.x, d.y);
+          }
           if (live) {
-            *reinterpret_cast<uint2*>(qrow + 4 * i) = o1;
-            *reinterpret_cast<uint2*>(qrow + HALF + 4 * i) = o2;
-            *reinterpret_cast<uint2*>(krow + 4 * i) = p1;
-            *reinterpret_cast<uint2*>(krow + HALF + 4 * i) = p2;
+            *reinterpret_cast<uint2*>(qrow + 4 * i) = make_uint2(o1[0], o1[1]);
+            *reinterpret_cast<uint2*>(qrow + HALF + 4 * i) = make_uint2(o2[0], o2[1]);
+            *reinterpret_cast<uint2*>(krow + 4 * i) = make_uint2(p1[0], p1[1]);
+            *reinterpret_cast<uint2*>(krow + HALF + 4 * i) = make_uint2(p2[0], p2[1]);
           }
         }
       }
@@ -503,7 +509,7 @@ int launch_attention_mma(const void* qkv, int64_t batch, int N, int H, const uin
                          cudaStream_t stream) {
   constexpr int ROWS = 16 * NT;
   constexpr int per_unit = 3 * ROWS * MMA_LD * 2;
-  constexpr int fixed = 2 * ROWS * 40 * 8 + 2 * MMA_HD * 4;
+  constexpr int fixed = 2 * ROWS * 3 * 40 * 4 + 2 * MMA_HD * 4;  // rope table (cos | sin | -sin) + folded norm weights
   int upb = (200 * 1024 - fixed) / per_unit;                 // units ((series, head) pairs) per block
   const int max_units = NT == 1 ? 8 : 512 / (32 * NT);       // NT warps per unit, <= 512 threads per block
   if (upb > max_units) upb = max_units;

@@ -309,6 +309,30 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int umma_m, int umma_n) {
          | (static_cast<uint32_t>(umma_m >> 4) << 24); // M >> 4
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2: one issue slot for two fp32 operations; the issue-bound SIMT stages
+// - q / k conditioning of the attention kernels - are made of exactly such pairs).  Same IEEE result per element as the
+// scalar instruction.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // ---- bf16 helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
