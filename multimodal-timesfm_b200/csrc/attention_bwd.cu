@@ -52,6 +52,32 @@ __device__ __forceinline__ uint32_t bw_movmatrix(uint32_t x) {
 __device__ __forceinline__ float bw_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bw_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// dst[0..20) += sum over the 16 lanes of equal parity of v[0..20) (lane bit 0 selects the destination and is not summed)
+__device__ __forceinline__ void bw_fold20(const float (&v)[20], int lane, float* dst) {
+  const bool up1 = (lane & 2) != 0, up2 = (lane & 4) != 0;
+  float w10[10], w5[5];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float send = up1 ? v[i] : v[i + 10], keep = up1 ? v[i + 10] : v[i];
+    w10[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const float send = up2 ? w10[i] : w10[i + 5], keep = up2 ? w10[i + 5] : w10[i];
+    w5[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    w5[i] += __shfl_xor_sync(0xffffffffu, w5[i], 8);
+    w5[i] += __shfl_xor_sync(0xffffffffu, w5[i], 16);
+  }
+  if ((lane & 24) == 0) {
+    float* d = dst + (up1 ? 10 : 0) + (up2 ? 5 : 0);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) d[i] += w5[i];
+  }
+}
+
 template <int NT>  // 16-row tiles: N <= 16 * NT
 __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
     const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, int64_t batch, int num_patches,
@@ -493,21 +519,23 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
         const float fq = rq * rq * rq * cq * (1.0f / BW_HD), fk = rk * rk * rk * ck * (1.0f / BW_HD);
         if (dparams != nullptr) {
           // parameter gradients: the 16 lanes with the same half (one per row of the tile) hold contributions to the
-          // same 40 dims -> fold them with shuffles, one lane per half adds into the warp's private slot
+          // same 40 dims.  Summing every value over all 16 lanes cost 4 shuffles per value - 1 480 of this kernel's
+          // 4 835 warp instructions per (series, head) in the full fine-tune step (profiles/r2aa_ncu_finetune_backward.md)
+          // - so the first two exchange steps HALVE the set instead (a lane keeps 10, then 5 of its 20 sums and
+          // hands the others over), and only the last two steps are plain butterflies: 25 shuffles per 20 values.
+          float v[20];  // one group of 20 at a time: the register file is full here
 #pragma unroll
-          for (int idx = 0; idx < 20; ++idx) {
-            float a = dqp[idx] * q1[idx] * rq, bq2 = dqp[HALF + idx] * q2[idx] * rq;
-            float c = dkp[idx] * k1[idx] * rk, d2 = dkp[HALF + idx] * k2[idx] * rk;
+          for (int idx = 0; idx < 20; ++idx) v[idx] = dqp[idx] * q1[idx] * rq;
+          bw_fold20(v, lane, my_dw + 20 * hf);
 #pragma unroll
-            for (int o = 2; o < 32; o <<= 1) {
-              a += __shfl_xor_sync(0xffffffffu, a, o), bq2 += __shfl_xor_sync(0xffffffffu, bq2, o);
-              c += __shfl_xor_sync(0xffffffffu, c, o), d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-            }
-            if (lane < 2) {  // lane 0: half 0, lane 1: half 1
-              my_dw[20 * hf + idx] += a, my_dw[20 * hf + HALF + idx] += bq2;
-              my_dw[BW_HD + 20 * hf + idx] += c, my_dw[BW_HD + 20 * hf + HALF + idx] += d2;
-            }
-          }
+          for (int idx = 0; idx < 20; ++idx) v[idx] = dqp[HALF + idx] * q2[idx] * rq;
+          bw_fold20(v, lane, my_dw + 20 * hf + HALF);
+#pragma unroll
+          for (int idx = 0; idx < 20; ++idx) v[idx] = dkp[idx] * k1[idx] * rk;
+          bw_fold20(v, lane, my_dw + BW_HD + 20 * hf);
+#pragma unroll
+          for (int idx = 0; idx < 20; ++idx) v[idx] = dkp[HALF + idx] * k2[idx] * rk;
+          bw_fold20(v, lane, my_dw + BW_HD + 20 * hf + HALF);
         }
         __nv_bfloat16* qrow = sQ + r * BW_LD + 20 * hf;
         __nv_bfloat16* krow = sK + r * BW_LD + 20 * hf;
