@@ -49,8 +49,9 @@ __device__ __forceinline__ uint32_t bw_movmatrix(uint32_t x) {
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
-__device__ __forceinline__ float bw_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bw_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float2 bw_pair(uint32_t w) {  // the two bf16 of a word as fp32
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
 
 // dst[0..20) += sum over the 16 lanes of equal parity of v[0..20) (lane bit 0 selects the destination and is not summed)
 __device__ __forceinline__ void bw_fold20(const float (&v)[20], int lane, float* dst) {
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
   constexpr int TILEF = ROWS * BW_LDF;  // floats
   constexpr int PER_WARP = 6 * TILE * 2 + 2 * TILEF * 4 + 4 * ROWS * 4;
   extern __shared__ __align__(16) uint8_t smem_bw[];
-  float2* s_rope = reinterpret_cast<float2*>(smem_bw);             // [2 * ROWS][40] (cos, sin), positions -N .. N-1
-  float* s_wq = reinterpret_cast<float*>(s_rope + 2 * ROWS * HALF);  // [80] q_ln_w * q_scale
+  float* s_rope = reinterpret_cast<float*>(smem_bw);  // [2 * ROWS][cos 40 | sin 40 | -sin 40], positions -N .. N-1
+  float* s_wq = s_rope + 2 * ROWS * 3 * HALF;         // [80] q_ln_w * q_scale
   float* s_wk = s_wq + BW_HD;
   float* s_dw = s_wk + BW_HD;  // [warps][2 * 80] per-warp sums of dq' * qhat and dk' * khat (full fine-tune only)
   uint8_t* warp_base = reinterpret_cast<uint8_t*>(s_dw + 8 * 2 * BW_HD);
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
     const int p = i / HALF, f = i - p * HALF;
     float sn, cs;
     sincosf(static_cast<float>(p - N) * __ldg(inv_freq + f), &sn, &cs);
-    s_rope[i] = make_float2(cs, sn);
+    float* trow = s_rope + p * 3 * HALF;
+    trow[f] = cs, trow[HALF + f] = sn, trow[2 * HALF + f] = -sn;
   }
   for (int i = threadIdx.x; i < BW_HD; i += blockDim.x) {
     s_wq[i] = __ldg(q_ln_w + i) * __ldg(q_scale + i);
@@ -173,11 +175,12 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
       if (rt < ntk) {
         const int hf = lane & 1;
         const bool live = r < N;
-        const float2* rope = s_rope + (live ? (r - nm + N) : 0) * HALF + 20 * hf;
+        // packed fp32 pairs (dims 2j, 2j + 1 of this lane's 20): FFMA2 / FMUL2, as in the forward kernel
+        const float* rope = s_rope + (live ? (r - nm + N) : 0) * 3 * HALF + 20 * hf;
         const __nv_bfloat16* qraw = sQraw + r * BW_LD + 20 * hf;
         const __nv_bfloat16* kraw = sKraw + r * BW_LD + 20 * hf;
-        float q1[20], q2[20], k1[20], k2[20];
-        float qss = 0.f, kss = 0.f;
+        float2 q1[10], q2[10], k1[10], k2[10];
+        float2 qss2 = make_float2(0.f, 0.f), kss2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
           const uint2 a1 = live ? *reinterpret_cast<const uint2*>(qraw + 4 * i) : make_uint2(0u, 0u);
@@ -186,25 +189,26 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
           const uint2 c2 = live ? *reinterpret_cast<const uint2*>(kraw + HALF + 4 * i) : make_uint2(0u, 0u);
           const uint32_t aw1[2] = {a1.x, a1.y}, aw2[2] = {a2.x, a2.y}, cw1[2] = {c1.x, c1.y}, cw2[2] = {c2.x, c2.y};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int idx = 4 * i + e;
-            const float2 cssn = rope[idx];
-            const float x1 = (e & 1) ? bw_hi(aw1[e >> 1]) : bw_lo(aw1[e >> 1]);
-            const float x2 = (e & 1) ? bw_hi(aw2[e >> 1]) : bw_lo(aw2[e >> 1]);
-            const float y1 = (e & 1) ? bw_hi(cw1[e >> 1]) : bw_lo(cw1[e >> 1]);
-            const float y2 = (e & 1) ? bw_hi(cw2[e >> 1]) : bw_lo(cw2[e >> 1]);
-            q1[idx] = x1 * cssn.x - x2 * cssn.y;
-            q2[idx] = x2 * cssn.x + x1 * cssn.y;
-            k1[idx] = y1 * cssn.x - y2 * cssn.y;
-            k2[idx] = y2 * cssn.x + y1 * cssn.y;
-            qss += q1[idx] * q1[idx] + q2[idx] * q2[idx];
-            kss += k1[idx] * k1[idx] + k2[idx] * k2[idx];
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * i + e;
+            const float2 cs = *reinterpret_cast<const float2*>(rope + 2 * j);
+            const float2 sn = *reinterpret_cast<const float2*>(rope + HALF + 2 * j);
+            const float2 ns = *reinterpret_cast<const float2*>(rope + 2 * HALF + 2 * j);
+            const float2 x1 = bw_pair(aw1[e]), x2 = bw_pair(aw2[e]), y1 = bw_pair(cw1[e]), y2 = bw_pair(cw2[e]);
+            q1[j] = fma2(x2, ns, mul2(x1, cs));
+            q2[j] = fma2(x1, sn, mul2(x2, cs));
+            k1[j] = fma2(y2, ns, mul2(y1, cs));
+            k2[j] = fma2(y1, sn, mul2(y2, cs));
+            qss2 = fma2(q2[j], q2[j], fma2(q1[j], q1[j], qss2));
+            kss2 = fma2(k2[j], k2[j], fma2(k1[j], k1[j], kss2));
           }
         }
+        float qss = qss2.x + qss2.y, kss = kss2.x + kss2.y;
         qss += __shfl_xor_sync(0xffffffffu, qss, 1);
         kss += __shfl_xor_sync(0xffffffffu, kss, 1);
         const float qrs = rsqrtf(qss * (1.0f / BW_HD) + eps);
         const float krs = rsqrtf(kss * (1.0f / BW_HD) + eps);
+        const float2 qrs2 = make_float2(qrs, qrs), krs2 = make_float2(krs, krs);
         const float* wq1 = s_wq + 20 * hf;
         const float* wk1 = s_wk + 20 * hf;
         __nv_bfloat16* qrow = sQ + r * BW_LD + 20 * hf;
@@ -212,19 +216,21 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
         if (live) {
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
-            uint2 o1, o2, p1, p2;
-            o1.x = pack_bf16x2(q1[4 * i] * qrs * wq1[4 * i], q1[4 * i + 1] * qrs * wq1[4 * i + 1]);
-            o1.y = pack_bf16x2(q1[4 * i + 2] * qrs * wq1[4 * i + 2], q1[4 * i + 3] * qrs * wq1[4 * i + 3]);
-            o2.x = pack_bf16x2(q2[4 * i] * qrs * wq1[HALF + 4 * i], q2[4 * i + 1] * qrs * wq1[HALF + 4 * i + 1]);
-            o2.y = pack_bf16x2(q2[4 * i + 2] * qrs * wq1[HALF + 4 * i + 2], q2[4 * i + 3] * qrs * wq1[HALF + 4 * i + 3]);
-            p1.x = pack_bf16x2(k1[4 * i] * krs * wk1[4 * i], k1[4 * i + 1] * krs * wk1[4 * i + 1]);
-            p1.y = pack_bf16x2(k1[4 * i + 2] * krs * wk1[4 * i + 2], k1[4 * i + 3] * krs * wk1[4 * i + 3]);
-            p2.x = pack_bf16x2(k2[4 * i] * krs * wk1[HALF + 4 * i], k2[4 * i + 1] * krs * wk1[HALF + 4 * i + 1]);
-            p2.y = pack_bf16x2(k2[4 * i + 2] * krs * wk1[HALF + 4 * i + 2], k2[4 * i + 3] * krs * wk1[HALF + 4 * i + 3]);
-            *reinterpret_cast<uint2*>(qrow + 4 * i) = o1;
-            *reinterpret_cast<uint2*>(qrow + HALF + 4 * i) = o2;
-            *reinterpret_cast<uint2*>(krow + 4 * i) = p1;
-            *reinterpret_cast<uint2*>(krow + HALF + 4 * i) = p2;
+            uint32_t o1[2], o2[2], p1[2], p2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = 2 * i + e;
+              const float2 a = mul2(q1[j], mul2(*reinterpret_cast<const float2*>(wq1 + 2 * j), qrs2));
+              const float2 b2 = mul2(q2[j], mul2(*reinterpret_cast<const float2*>(wq1 + HALF + 2 * j), qrs2));
+              const float2 c = mul2(k1[j], mul2(*reinterpret_cast<const float2*>(wk1 + 2 * j), krs2));
+              const float2 d = mul2(k2[j], mul2(*reinterpret_cast<const float2*>(wk1 + HALF + 2 * j), krs2));
+              o1[e] = pack_bf16x2(a.x, a.y), o2[e] = pack_bf16x2(b2.x, b2.y);
+              p1[e] = pack_bf16x2(c.x, c.y), p2[e] = pack_bf16x2(d.x, d.y);
+            }
+            *reinterpret_cast<uint2*>(qrow + 4 * i) = make_uint2(o1[0], o1[1]);
+            *reinterpret_cast<uint2*>(qrow + HALF + 4 * i) = make_uint2(o2[0], o2[1]);
+            *reinterpret_cast<uint2*>(krow + 4 * i) = make_uint2(p1[0], p1[1]);
+            *reinterpret_cast<uint2*>(krow + HALF + 4 * i) = make_uint2(p2[0], p2[1]);
           }
         }
       }
@@ -476,15 +482,17 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
       if (rt < ntk) {
         const int hf = lane & 1;
         const bool live = r < N;
-        const float2* rope = s_rope + (live ? (r - nm + N) : 0) * HALF + 20 * hf;
+        const float* rope = s_rope + (live ? (r - nm + N) : 0) * 3 * HALF + 20 * hf;
         const __nv_bfloat16* qraw = sQraw + r * BW_LD + 20 * hf;
         const __nv_bfloat16* kraw = sKraw + r * BW_LD + 20 * hf;
         const float* dqp = sDQ + r * BW_LDF + 20 * hf;
         const float* dkp = sDK + r * BW_LDF + 20 * hf;
         const float* wq1 = s_wq + 20 * hf;
         const float* wk1 = s_wk + 20 * hf;
-        float q1[20], q2[20], k1[20], k2[20];
-        float qss = 0.f, kss = 0.f, cq = 0.f, ck = 0.f;
+        auto ld2 = [](const float* p_) { return *reinterpret_cast<const float2*>(p_); };
+        float2 q1[10], q2[10], k1[10], k2[10];
+        float2 qss2 = make_float2(0.f, 0.f), kss2 = make_float2(0.f, 0.f);
+        float2 cq2 = make_float2(0.f, 0.f), ck2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
           const uint2 a1 = live ? *reinterpret_cast<const uint2*>(qraw + 4 * i) : make_uint2(0u, 0u);
@@ -493,24 +501,24 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
           const uint2 c2 = live ? *reinterpret_cast<const uint2*>(kraw + HALF + 4 * i) : make_uint2(0u, 0u);
           const uint32_t aw1[2] = {a1.x, a1.y}, aw2[2] = {a2.x, a2.y}, cw1[2] = {c1.x, c1.y}, cw2[2] = {c2.x, c2.y};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int idx = 4 * i + e;
-            const float2 cssn = rope[idx];
-            const float x1 = (e & 1) ? bw_hi(aw1[e >> 1]) : bw_lo(aw1[e >> 1]);
-            const float x2 = (e & 1) ? bw_hi(aw2[e >> 1]) : bw_lo(aw2[e >> 1]);
-            const float y1 = (e & 1) ? bw_hi(cw1[e >> 1]) : bw_lo(cw1[e >> 1]);
-            const float y2 = (e & 1) ? bw_hi(cw2[e >> 1]) : bw_lo(cw2[e >> 1]);
-            q1[idx] = x1 * cssn.x - x2 * cssn.y;
-            q2[idx] = x2 * cssn.x + x1 * cssn.y;
-            k1[idx] = y1 * cssn.x - y2 * cssn.y;
-            k2[idx] = y2 * cssn.x + y1 * cssn.y;
-            qss += q1[idx] * q1[idx] + q2[idx] * q2[idx];
-            kss += k1[idx] * k1[idx] + k2[idx] * k2[idx];
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * i + e;
+            const float2 cs = ld2(rope + 2 * j), sn = ld2(rope + HALF + 2 * j), ns = ld2(rope + 2 * HALF + 2 * j);
+            const float2 x1 = bw_pair(aw1[e]), x2 = bw_pair(aw2[e]), y1 = bw_pair(cw1[e]), y2 = bw_pair(cw2[e]);
+            q1[j] = fma2(x2, ns, mul2(x1, cs));
+            q2[j] = fma2(x1, sn, mul2(x2, cs));
+            k1[j] = fma2(y2, ns, mul2(y1, cs));
+            k2[j] = fma2(y1, sn, mul2(y2, cs));
+            qss2 = fma2(q2[j], q2[j], fma2(q1[j], q1[j], qss2));
+            kss2 = fma2(k2[j], k2[j], fma2(k1[j], k1[j], kss2));
             // t = w * dL/dq' ; c = <rope(q), t>
-            cq += q1[idx] * (wq1[idx] * dqp[idx]) + q2[idx] * (wq1[HALF + idx] * dqp[HALF + idx]);
-            ck += k1[idx] * (wk1[idx] * dkp[idx]) + k2[idx] * (wk1[HALF + idx] * dkp[HALF + idx]);
+            cq2 = fma2(q1[j], mul2(ld2(wq1 + 2 * j), ld2(dqp + 2 * j)), cq2);
+            cq2 = fma2(q2[j], mul2(ld2(wq1 + HALF + 2 * j), ld2(dqp + HALF + 2 * j)), cq2);
+            ck2 = fma2(k1[j], mul2(ld2(wk1 + 2 * j), ld2(dkp + 2 * j)), ck2);
+            ck2 = fma2(k2[j], mul2(ld2(wk1 + HALF + 2 * j), ld2(dkp + HALF + 2 * j)), ck2);
           }
         }
+        float qss = qss2.x + qss2.y, kss = kss2.x + kss2.y, cq = cq2.x + cq2.y, ck = ck2.x + ck2.y;
         qss += __shfl_xor_sync(0xffffffffu, qss, 1);
         kss += __shfl_xor_sync(0xffffffffu, kss, 1);
         cq += __shfl_xor_sync(0xffffffffu, cq, 1);
@@ -525,42 +533,46 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
           // hands the others over), and only the last two steps are plain butterflies: 25 shuffles per 20 values.
           float v[20];  // one group of 20 at a time: the register file is full here
 #pragma unroll
-          for (int idx = 0; idx < 20; ++idx) v[idx] = dqp[idx] * q1[idx] * rq;
+          for (int j = 0; j < 10; ++j) v[2 * j] = dqp[2 * j] * q1[j].x * rq, v[2 * j + 1] = dqp[2 * j + 1] * q1[j].y * rq;
           bw_fold20(v, lane, my_dw + 20 * hf);
 #pragma unroll
-          for (int idx = 0; idx < 20; ++idx) v[idx] = dqp[HALF + idx] * q2[idx] * rq;
+          for (int j = 0; j < 10; ++j)
+            v[2 * j] = dqp[HALF + 2 * j] * q2[j].x * rq, v[2 * j + 1] = dqp[HALF + 2 * j + 1] * q2[j].y * rq;
           bw_fold20(v, lane, my_dw + 20 * hf + HALF);
 #pragma unroll
-          for (int idx = 0; idx < 20; ++idx) v[idx] = dkp[idx] * k1[idx] * rk;
+          for (int j = 0; j < 10; ++j) v[2 * j] = dkp[2 * j] * k1[j].x * rk, v[2 * j + 1] = dkp[2 * j + 1] * k1[j].y * rk;
           bw_fold20(v, lane, my_dw + BW_HD + 20 * hf);
 #pragma unroll
-          for (int idx = 0; idx < 20; ++idx) v[idx] = dkp[HALF + idx] * k2[idx] * rk;
+          for (int j = 0; j < 10; ++j)
+            v[2 * j] = dkp[HALF + 2 * j] * k2[j].x * rk, v[2 * j + 1] = dkp[HALF + 2 * j + 1] * k2[j].y * rk;
           bw_fold20(v, lane, my_dw + BW_HD + 20 * hf + HALF);
         }
         __nv_bfloat16* qrow = sQ + r * BW_LD + 20 * hf;
         __nv_bfloat16* krow = sK + r * BW_LD + 20 * hf;
         if (live) {
+          const float2 rq2 = make_float2(rq, rq), rk2 = make_float2(rk, rk);
+          const float2 nfq2 = make_float2(-fq, -fq), nfk2 = make_float2(-fk, -fk);
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
-            float gq1[4], gq2[4], gk1[4], gk2[4];
+            uint32_t gq1[2], gq2[2], gk1[2], gk2[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int idx = 4 * i + e;
-              const float2 cssn = rope[idx];
-              // d/d rope(q), then the transposed rotation
-              const float a = rq * (wq1[idx] * dqp[idx]) - q1[idx] * fq;
-              const float bq = rq * (wq1[HALF + idx] * dqp[HALF + idx]) - q2[idx] * fq;
-              const float c = rk * (wk1[idx] * dkp[idx]) - k1[idx] * fk;
-              const float d = rk * (wk1[HALF + idx] * dkp[HALF + idx]) - k2[idx] * fk;
-              gq1[e] = a * cssn.x + bq * cssn.y;
-              gq2[e] = bq * cssn.x - a * cssn.y;
-              gk1[e] = c * cssn.x + d * cssn.y;
-              gk2[e] = d * cssn.x - c * cssn.y;
+            for (int e = 0; e < 2; ++e) {
+              const int j = 2 * i + e;
+              const float2 cs = ld2(rope + 2 * j), sn = ld2(rope + HALF + 2 * j), ns = ld2(rope + 2 * HALF + 2 * j);
+              // d/d rope(q) = rq (w dq') - rope(q) fq, then the transposed rotation
+              const float2 a = fma2(mul2(ld2(wq1 + 2 * j), ld2(dqp + 2 * j)), rq2, mul2(q1[j], nfq2));
+              const float2 bq = fma2(mul2(ld2(wq1 + HALF + 2 * j), ld2(dqp + HALF + 2 * j)), rq2, mul2(q2[j], nfq2));
+              const float2 c = fma2(mul2(ld2(wk1 + 2 * j), ld2(dkp + 2 * j)), rk2, mul2(k1[j], nfk2));
+              const float2 d = fma2(mul2(ld2(wk1 + HALF + 2 * j), ld2(dkp + HALF + 2 * j)), rk2, mul2(k2[j], nfk2));
+              const float2 g1 = fma2(bq, sn, mul2(a, cs)), g2 = fma2(a, ns, mul2(bq, cs));
+              const float2 h1 = fma2(d, sn, mul2(c, cs)), h2 = fma2(c, ns, mul2(d, cs));
+              gq1[e] = pack_bf16x2(g1.x, g1.y), gq2[e] = pack_bf16x2(g2.x, g2.y);
+              gk1[e] = pack_bf16x2(h1.x, h1.y), gk2[e] = pack_bf16x2(h2.x, h2.y);
             }
-            *reinterpret_cast<uint2*>(qrow + 4 * i) = make_uint2(pack_bf16x2(gq1[0], gq1[1]), pack_bf16x2(gq1[2], gq1[3]));
-            *reinterpret_cast<uint2*>(qrow + HALF + 4 * i) = make_uint2(pack_bf16x2(gq2[0], gq2[1]), pack_bf16x2(gq2[2], gq2[3]));
-            *reinterpret_cast<uint2*>(krow + 4 * i) = make_uint2(pack_bf16x2(gk1[0], gk1[1]), pack_bf16x2(gk1[2], gk1[3]));
-            *reinterpret_cast<uint2*>(krow + HALF + 4 * i) = make_uint2(pack_bf16x2(gk2[0], gk2[1]), pack_bf16x2(gk2[2], gk2[3]));
+            *reinterpret_cast<uint2*>(qrow + 4 * i) = make_uint2(gq1[0], gq1[1]);
+            *reinterpret_cast<uint2*>(qrow + HALF + 4 * i) = make_uint2(gq2[0], gq2[1]);
+            *reinterpret_cast<uint2*>(krow + 4 * i) = make_uint2(gk1[0], gk1[1]);
+            *reinterpret_cast<uint2*>(krow + HALF + 4 * i) = make_uint2(gk2[0], gk2[1]);
           }
         }
       }
@@ -593,7 +605,7 @@ int launch_bwd_mma(const void* qkv, const void* dout, int64_t batch, int N, int 
                    float* dparams, cudaStream_t stream) {
   constexpr int ROWS = 16 * NT;
   constexpr int per_warp = 6 * ROWS * BW_LD * 2 + 2 * ROWS * BW_LDF * 4 + 4 * ROWS * 4;
-  constexpr int fixed = 2 * ROWS * 40 * 8 + 2 * BW_HD * 4 + 8 * 2 * BW_HD * 4;
+  constexpr int fixed = 2 * ROWS * 3 * 40 * 4 + 2 * BW_HD * 4 + 8 * 2 * BW_HD * 4;
   int wpb = (220 * 1024 - fixed) / per_warp;
   if (wpb > 8) wpb = 8;
   if (wpb < 1) {
