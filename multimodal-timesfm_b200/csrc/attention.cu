@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         float sum0 = 0.f, sum1 = 0.f;
+        const float ml0 = mx0 * LOG2E_F, ml1 = mx1 * LOG2E_F;  // finite unless the row is dead (handled below)
 #pragma unroll
         for (int kj = 0; kj < NT; ++kj)
 #pragma unroll
@@ -439,10 +440,9 @@ __global__ void __launch_bounds__(NT == 1 ? 256 : 512) timesfm_attention_mma_ker
             for (int e = 0; e < 4; ++e) {
               const int key = kj * 16 + nt * 8 + 2 * t + (e & 1);
               const bool dead = (e & 2) ? dead1 : dead0;
-              const float mx = (e & 2) ? mx1 : mx0;
               float p;
               if (dead) p = key < N ? 1.f : 0.f;
-              else p = s[kj][nt][e] == -INFINITY ? 0.f : __expf(s[kj][nt][e] - mx);
+              else p = exp_sub(s[kj][nt][e], (e & 2) ? ml1 : ml0);  // masked scores are -inf -> 0
               s[kj][nt][e] = p;
               if (e & 2) sum1 += p; else sum0 += p;
             }

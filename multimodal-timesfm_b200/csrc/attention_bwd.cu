@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         float sum0 = 0.f, sum1 = 0.f;
+        const float ml0 = mx0 * LOG2E_F, ml1 = mx1 * LOG2E_F;  // row maxima in the exp2 domain (kept for pass B)
 #pragma unroll
         for (int kj = 0; kj < NT; ++kj)
 #pragma unroll
@@ -306,10 +307,9 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
             for (int e = 0; e < 4; ++e) {
               const int key = kj * 16 + nt * 8 + 2 * t + (e & 1);
               const bool dead = (e & 2) ? dead1 : dead0;
-              const float mx = (e & 2) ? mx1 : mx0;
               float p;
               if (dead) p = key < N ? 1.f : 0.f;
-              else p = s[kj][nt][e] == -INFINITY ? 0.f : __expf(s[kj][nt][e] - mx);
+              else p = exp_sub(s[kj][nt][e], (e & 2) ? ml1 : ml0);  // masked scores are -inf -> 0
               s[kj][nt][e] = p;
               if (e & 2) sum1 += p; else sum0 += p;
             }
@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
         dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
         dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
         if (t == 0) {
-          sMx[row0] = mx0, sInv[row0] = inv0, sDelta[row0] = dl0, sDead[row0] = dead0 ? 1.f : 0.f;
-          sMx[row1] = mx1, sInv[row1] = inv1, sDelta[row1] = dl1, sDead[row1] = dead1 ? 1.f : 0.f;
+          sMx[row0] = ml0, sInv[row0] = inv0, sDelta[row0] = dl0, sDead[row0] = dead0 ? 1.f : 0.f;
+          sMx[row1] = ml1, sInv[row1] = inv1, sDelta[row1] = dl1, sDead[row1] = dead1 ? 1.f : 0.f;
         }
         float dq[10][4];
 #pragma unroll
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256) timesfm_attention_bwd_mma_kernel(
                   const bool ok = kj <= qi && key <= row && ((kmask >> key) & 1ull);
                   float pv;
                   if (dead) pv = key < N ? 1.f : 0.f;
-                  else pv = ok ? __expf(s2[nt][e] - ((e & 2) ? mx1 : mx0)) : 0.f;
+                  else pv = ok ? exp_sub(s2[nt][e], (e & 2) ? mx1 : mx0) : 0.f;  // sMx holds mx * log2e
                   pv *= (e & 2) ? inv1 : inv0;
                   if (row >= N) pv = 0.f;
                   p[nt][e] = pv;

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (NT <= 9 ? 2 : 1)) encoder_att
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_enc);
   __nv_bfloat16* sK = sQ + TILE;
   __nv_bfloat16* sV = sK + TILE;
-  uint8_t* s_valid = reinterpret_cast<uint8_t*>(sV + TILE);  // [ROWS] 1 = key exists and may be attended
+  float* s_bias = reinterpret_cast<float*>(sV + TILE);  // [ROWS] additive key mask: 0 = may be attended, -inf = not
   __shared__ int s_any;
   const int T = seq;
   const int b = blockIdx.x / num_heads, h = blockIdx.x - b * num_heads;
@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (NT <= 9 ? 2 : 1)) encoder_att
   {
     int any = 0;
     for (int j = threadIdx.x; j < ROWS; j += blockDim.x) {
-      const uint8_t v = j < T && (key_mask == nullptr || key_mask[static_cast<int64_t>(b) * T + j] != 0) ? 1 : 0;
-      s_valid[j] = v;
+      const int v = j < T && (key_mask == nullptr || key_mask[static_cast<int64_t>(b) * T + j] != 0) ? 1 : 0;
+      s_bias[j] = v ? 0.f : -INFINITY;
       any |= v;
     }
     if (any) s_any = 1;  // benign race: every writer stores 1
@@ -234,6 +234,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (NT <= 9 ? 2 : 1)) encoder_att
   __syncthreads();
 
   const bool has_key = s_any != 0;  // every key masked: uniform weights over all T keys (finfo.min semantics)
+  if (!has_key) {
+    for (int j = threadIdx.x; j < ROWS; j += blockDim.x) s_bias[j] = j < T ? 0.f : -INFINITY;
+    __syncthreads();
+  }
   const int g = lane >> 2, t = lane & 3;
   const int ntk = (T + 15) >> 4;
   const uint32_t sq_addr = smem_u32(sQ), sk_addr = smem_u32(sK), sv_addr = smem_u32(sV);
@@ -264,20 +268,19 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (NT <= 9 ? 2 : 1)) encoder_att
         }
       }
     }
-    // mask + row max (rows g and g + 8 of the tile; this thread holds keys 2t, 2t + 1 of every 8-key group)
+    // mask + row max (rows g and g + 8 of the tile; this thread holds keys 2t, 2t + 1 of every 8-key group): the key
+    // mask is an additive 0 / -inf row in shared memory (one 8-byte load and four adds per 8-key group; the select
+    // chains it replaces were 19 % of the kernel's instructions).  Every key masked (rare, block-uniform): the
+    // staging phase rewrote the mask row to "every existing key" and the scores count as 0, i.e. uniform weights.
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int kj = 0; kj < NT; ++kj)
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         const int key = kj * 16 + nt * 8 + 2 * t;
-        const uint32_t vv = *reinterpret_cast<const uint16_t*>(s_valid + key);
-        const bool ok0 = has_key ? (vv & 0xffu) != 0 : key < T;
-        const bool ok1 = has_key ? (vv >> 8) != 0 : key + 1 < T;
-        s[kj][nt][0] = ok0 ? (has_key ? s[kj][nt][0] : 0.f) : -INFINITY;
-        s[kj][nt][1] = ok1 ? (has_key ? s[kj][nt][1] : 0.f) : -INFINITY;
-        s[kj][nt][2] = ok0 ? (has_key ? s[kj][nt][2] : 0.f) : -INFINITY;
-        s[kj][nt][3] = ok1 ? (has_key ? s[kj][nt][3] : 0.f) : -INFINITY;
+        const float2 bias = *reinterpret_cast<const float2*>(s_bias + key);
+        s[kj][nt][0] = (has_key ? s[kj][nt][0] : 0.f) + bias.x, s[kj][nt][1] = (has_key ? s[kj][nt][1] : 0.f) + bias.y;
+        s[kj][nt][2] = (has_key ? s[kj][nt][2] : 0.f) + bias.x, s[kj][nt][3] = (has_key ? s[kj][nt][3] : 0.f) + bias.y;
         mx0 = fmaxf(mx0, fmaxf(s[kj][nt][0], s[kj][nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[kj][nt][2], s[kj][nt][3]));
       }
@@ -286,14 +289,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (NT <= 9 ? 2 : 1)) encoder_att
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
+    const float ml0 = mx0 * LOG2E_F, ml1 = mx1 * LOG2E_F;  // finite: at least one key of the row carries a score
 #pragma unroll
     for (int kj = 0; kj < NT; ++kj)
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float mx = (e & 2) ? mx1 : mx0;
-          const float p = s[kj][nt][e] == -INFINITY ? 0.f : __expf(s[kj][nt][e] - mx);
+          const float p = exp_sub(s[kj][nt][e], (e & 2) ? ml1 : ml0);
           s[kj][nt][e] = p;
           if (e & 2) sum1 += p; else sum0 += p;
         }
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (NT <= 9 ? 2 : 1)) encoder_att
 template <int NT>
 int launch_encoder_attention_mma(const void* qkv, int64_t batch, int seq, int num_heads, const uint8_t* key_mask,
                                  const float* rope, void* out, cudaStream_t stream) {
-  constexpr int smem = 3 * 16 * NT * ENC_LD * 2 + 16 * NT;
+  constexpr int smem = 3 * 16 * NT * ENC_LD * 2 + 16 * NT * 4;
   auto kern = encoder_attention_mma_kernel<NT>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -535,14 +538,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 1) encoder_attention_bwd_mma_k
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
+    const float ml0 = mx0 * LOG2E_F, ml1 = mx1 * LOG2E_F;  // row maxima in the exp2 domain (kept for pass B)
 #pragma unroll
     for (int kj = 0; kj < NT; ++kj)
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float mx = (e & 2) ? mx1 : mx0;
-          const float p = s[kj][nt][e] == -INFINITY ? 0.f : __expf(s[kj][nt][e] - mx);
+          const float p = exp_sub(s[kj][nt][e], (e & 2) ? ml1 : ml0);  // masked scores are -inf -> 0
           s[kj][nt][e] = p;
           if (e & 2) sum1 += p; else sum0 += p;
         }
@@ -568,8 +571,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 1) encoder_attention_bwd_mma_k
     dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
     const int row0 = qi * 16 + g, row1 = row0 + 8;
     if (t == 0) {
-      sMx[row0] = mx0, sInv[row0] = inv0, sDelta[row0] = dl0;
-      sMx[row1] = mx1, sInv[row1] = inv1, sDelta[row1] = dl1;
+      sMx[row0] = ml0, sInv[row0] = inv0, sDelta[row0] = dl0;
+      sMx[row1] = ml1, sInv[row1] = inv1, sDelta[row1] = dl1;
     }
     float dq[8][4];
 #pragma unroll
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 1) encoder_attention_bwd_mma_k
           const int row = (e & 2) ? row1 : row0;
           float pv = 0.f;
           if (okk[nt][e & 1] && row < T)
-            pv = has_key ? __expf(s2[nt][e] - ((e & 2) ? mx1 : mx0)) * ((e & 2) ? inv1 : inv0) : inv_T;
+            pv = has_key ? exp_sub(s2[nt][e], (e & 2) ? mx1 : mx0) * ((e & 2) ? inv1 : inv0) : inv_T;  // sMx: mx * log2e
           p[nt][e] = pv;
           ds[nt][e] = pv * (dp2[nt][e] - ((e & 2) ? dl1 : dl0));
         }

@@ -333,6 +333,17 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   return d;
 }
 
+// ---- softmax numerator exp(s - mx) as ONE FFMA and ONE MUFU.EX2: ex2(s * log2e - mx * log2e).  `__expf(s - mx)` behind
+// an `s == -inf ? 0 : ...` guard compiled to ~10 instructions per element (denormal scaling around ex2.approx, the
+// subtraction, the compare / select) and was 31 % of the Chronos-2 encoder attention's instructions (ncu source view,
+// profiles/r2aj_ncu_encoder_attention.md).  s = -inf gives exactly 0; mxl = mx * LOG2E_F must be finite.
+constexpr float LOG2E_F = 1.4426950408889634f;
+__device__ __forceinline__ float exp_sub(float s, float mxl) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(s, LOG2E_F, -mxl)));
+  return y;
+}
+
 // ---- bf16 helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
