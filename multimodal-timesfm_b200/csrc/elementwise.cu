@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(WARPS * 32) norm_residual_norm_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * WARPS + warp; r < rows;
        r += static_cast<int64_t>(gridDim.x) * WARPS) {
-    float4 v[NV];
+    float4 v[NV], xx[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = 4 * (lane + 32 * j);
@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(WARPS * 32) norm_residual_norm_kernel(
         v[j] = ld_stream_f4(reinterpret_cast<const float*>(a) + r * COLS + c);
       }
     }
+    // the residual row is fetched NOW, together with a: y may alias x (in-place update), so the compiler would not lift
+    // these loads above the stores below by itself, and the row would be read one 16-byte chunk per round trip after the
+    // first reduction.  A lane only ever overwrites the elements it has read itself.
+#pragma unroll
+    for (int j = 0; j < NV; ++j) xx[j] = ld_stream_f4(x + r * COLS + 4 * (lane + 32 * j));
     if (w_post != nullptr) {
       const float rs = row_rsqrt_mean_sq<NV>(v, COLS, eps);
 #pragma unroll
@@ -96,8 +101,7 @@ __global__ void __launch_bounds__(WARPS * 32) norm_residual_norm_kernel(
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = 4 * (lane + 32 * j);
-      const float4 xx = ld_stream_f4(x + r * COLS + c);
-      v[j].x += xx.x, v[j].y += xx.y, v[j].z += xx.z, v[j].w += xx.w;
+      v[j].x += xx[j].x, v[j].y += xx[j].y, v[j].z += xx[j].z, v[j].w += xx[j].w;
       if (y != nullptr) st_stream_f4(y + r * COLS + c, v[j]);
     }
     if (yn != nullptr) {
