@@ -177,3 +177,19 @@ def test_warmup_steps_follow_the_reference_semantics():
         for ws in (0.0, 0.1, 0.5, 1.0, 5.0):
             ref = TrainingArguments(output_dir=d, warmup_steps=ws)
             assert trainer(warmup_steps=ws)._warmup_steps(total) == ref.get_warmup_steps(total)
+
+
+def test_wgrad_takes_token_major_operands_only_when_they_qualify():
+    """`ops.wgrad` hands bf16 row-major operands (16-byte aligned rows) to the token-major GEMM; split, fp32, strided-by-odd
+    or narrow views go through the transposing path.  (Host-side dispatch only: no kernel runs here.)"""
+    import torch
+
+    from tsfmx_b200 import ops
+
+    x = torch.zeros(64, 1280, dtype=torch.bfloat16)
+    assert ops._token_major_ok(x, 1280)
+    assert ops._token_major_ok(x[:, 8:72], 64)  # aligned column window of a wider matrix
+    assert not ops._token_major_ok(x[:, 4:68], 64)  # starts 8 bytes into a row
+    assert not ops._token_major_ok(x.float(), 1280)
+    assert not ops._token_major_ok(torch.zeros(64, 2560, dtype=torch.bfloat16), 1280)  # split storage [hi | lo]
+    assert not ops._token_major_ok(torch.zeros(64, 36, dtype=torch.bfloat16)[:, :32], 32)  # row stride not a multiple of 8
