@@ -8,8 +8,9 @@ datasets, checkpoint dictionary keys (types.py:42-61), the warm-up semantics of 
 weights its loss by slice size / batch size and the gradients are summed with NCCL all-reduces per optimizer step,
 before the clip (equal to the single-process global-batch step for any slice sizes, empty ones included); the slice of
 the next batch is copied host -> device on a copy stream while the current one computes; checkpoints are written by
-rank 0.  "baseline" = full fine-tuning of the adapter without text (trainer.py:78-79):
-available for the TimesFM adapter (weight-gradient GEMMs for every Linear, all-reduce of all 231 M gradients).
+rank 0.  "baseline" = full fine-tuning of the adapter without text (trainer.py:78-79): available for both reference
+adapters, TimesFM 2.5 and Chronos-2 (weight-gradient GEMMs for every Linear, every gradient all-reduced, layer by layer
+under the backward pass).
 """
 
 from __future__ import annotations
@@ -53,7 +54,7 @@ def cosine_schedule_with_warmup(optimizer: Optimizer, warmup_steps: int, total_s
 
 
 class MultimodalTrainer:
-    """Trainer for the fusion fine-tune ("multimodal" mode) on one or several B200s."""
+    """Trainer for the fusion fine-tune ("multimodal" mode) and the full fine-tune ("baseline") on one or several B200s."""
 
     def __init__(
         self,
@@ -86,7 +87,7 @@ class MultimodalTrainer:
             if isinstance(self.model.adapter, TsfmAdapter) and not hasattr(self.model.adapter, "preprocess_backward"):
                 raise NotImplementedError(
                     f"mode='baseline' needs backbone weight gradients, which {type(self.model.adapter).__name__} does "
-                    "not produce on the B200 path yet (TimesFM2p5Adapter does)"
+                    "not produce on the B200 path (TimesFM2p5Adapter and Chronos2Adapter do)"
                 )
             self.model.adapter.unfreeze_parameters()
         else:
