@@ -981,6 +981,11 @@ def main():
                        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     elif args.impl == "reference":
         run_reference_arm(args)
+    elif not torch.cuda.is_available():
+        # the product arm has no CPU or PyTorch fallback: fail loudly instead of timing something else
+        sys.stderr.write("bench.py: no CUDA device - tsfmx_b200 runs on B200 only (there is no CPU fallback); "
+                         "`--impl reference` times the CPU oracle\n")
+        raise SystemExit(2)
     elif args.workload in ("finetune", "full-finetune"):
         run_finetune_arm(args, args.workload == "full-finetune")
     elif args.workload != "forecast":

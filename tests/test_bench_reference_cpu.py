@@ -44,3 +44,13 @@ def test_reference_arm_other_ranks_exit_without_work():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29533"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "0", "--layers", "2"],
+                       capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+    assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
