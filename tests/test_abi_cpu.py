@@ -60,3 +60,47 @@ def test_gemm_args_struct_layout():
 
     assert ctypes.sizeof(_lib.GemmSegment) == 40
     assert ctypes.sizeof(_lib.GemmArgs) == 8 + 4 + 4 + 80 + 4 + 4 + 8 * 4 + 8 + 8 + 8 + 4 * 4 + 8 * 4 + 4 + 4
+
+
+C_CONSUMER = r"""
+#include <stdio.h>
+#include <string.h>
+#include "tsfmx_b200.h"
+
+int main(void) {
+  tsfmx_gemm_args args;
+  memset(&args, 0, sizeof(args));
+  if (tsfmx_abi_version() != TSFMX_ABI_VERSION) return 10;
+  if (tsfmx_sizeof_gemm_args() != (int)sizeof(tsfmx_gemm_args)) return 11;
+  if (tsfmx_launch_count() != 0) return 12;
+  /* no GPU in this container: a compute entry point must fail with a status and a message, never crash */
+  int rc = tsfmx_device_check(-1);
+  printf("%d|%s\n", rc, tsfmx_last_error());
+  return 0;
+}
+"""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_header_is_plain_c_and_links_from_a_c_program(lib, tmp_path):
+    """The boundary is a C ABI, not a C++ or torch one: a strict-C99 translation unit that includes the header compiles
+    without warnings, links against the in-tree library alone and gets status codes + messages back."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "consumer.c"
+    src.write_text(C_CONSUMER)
+    exe = tmp_path / "consumer"
+    r = subprocess.run(
+        [gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+         f"-L{_lib.LIB_PATH.parent}", "-ltsfmx_b200", f"-Wl,-rpath,{_lib.LIB_PATH.parent}"],
+        capture_output=True, text=True,
+    )
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    status, message = run.stdout.strip().split("|", 1)
+    assert int(status) == 3 and "no CPU fallback" in message  # TSFMX_ERR_NO_DEVICE
