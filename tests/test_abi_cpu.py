@@ -63,6 +63,7 @@ def test_gemm_args_struct_layout():
 
 
 C_CONSUMER = r"""
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include "tsfmx_b200.h"
@@ -76,6 +77,26 @@ int main(void) {
   /* no GPU in this container: a compute entry point must fail with a status and a message, never crash */
   int rc = tsfmx_device_check(-1);
   printf("%d|%s\n", rc, tsfmx_last_error());
+#define OFF(T, f) printf(#T "." #f " %d\n", (int)offsetof(T, f))
+  printf("tsfmx_gemm_segment.sizeof %d\n", (int)sizeof(tsfmx_gemm_segment));
+  OFF(tsfmx_gemm_segment, a); OFF(tsfmx_gemm_segment, lda); OFF(tsfmx_gemm_segment, b); OFF(tsfmx_gemm_segment, ldb);
+  OFF(tsfmx_gemm_segment, k);
+  printf("tsfmx_gemm_args.sizeof %d\n", (int)sizeof(tsfmx_gemm_args));
+  OFF(tsfmx_gemm_args, m); OFF(tsfmx_gemm_args, n); OFF(tsfmx_gemm_args, num_segments); OFF(tsfmx_gemm_args, seg);
+  OFF(tsfmx_gemm_args, precision); OFF(tsfmx_gemm_args, act); OFF(tsfmx_gemm_args, bias); OFF(tsfmx_gemm_args, row_scale);
+  OFF(tsfmx_gemm_args, row_shift); OFF(tsfmx_gemm_args, residual); OFF(tsfmx_gemm_args, ldr); OFF(tsfmx_gemm_args, d);
+  OFF(tsfmx_gemm_args, ldd); OFF(tsfmx_gemm_args, d_dtype); OFF(tsfmx_gemm_args, n_store); OFF(tsfmx_gemm_args, split_off);
+  OFF(tsfmx_gemm_args, aux_dtype); OFF(tsfmx_gemm_args, aux); OFF(tsfmx_gemm_args, ld_aux); OFF(tsfmx_gemm_args, pre_act);
+  OFF(tsfmx_gemm_args, ld_pre); OFF(tsfmx_gemm_args, pre_act_dtype);
+  printf("tsfmx_timesfm_layer.sizeof %d\n", (int)sizeof(tsfmx_timesfm_layer));
+  OFF(tsfmx_timesfm_layer, qkv); OFF(tsfmx_timesfm_layer, out); OFF(tsfmx_timesfm_layer, ff0); OFF(tsfmx_timesfm_layer, ff1);
+  OFF(tsfmx_timesfm_layer, pre_attn_ln); OFF(tsfmx_timesfm_layer, post_attn_ln); OFF(tsfmx_timesfm_layer, pre_ff_ln);
+  OFF(tsfmx_timesfm_layer, post_ff_ln); OFF(tsfmx_timesfm_layer, q_ln); OFF(tsfmx_timesfm_layer, k_ln);
+  OFF(tsfmx_timesfm_layer, q_scale);
+  printf("tsfmx_timesfm_stack.sizeof %d\n", (int)sizeof(tsfmx_timesfm_stack));
+  OFF(tsfmx_timesfm_stack, num_layers); OFF(tsfmx_timesfm_stack, model_dims); OFF(tsfmx_timesfm_stack, num_heads);
+  OFF(tsfmx_timesfm_stack, head_dim); OFF(tsfmx_timesfm_stack, ff_dims); OFF(tsfmx_timesfm_stack, precision);
+  OFF(tsfmx_timesfm_stack, eps); OFF(tsfmx_timesfm_stack, inv_freq); OFF(tsfmx_timesfm_stack, layers);
   return 0;
 }
 """
@@ -85,6 +106,7 @@ int main(void) {
 def test_header_is_plain_c_and_links_from_a_c_program(lib, tmp_path):
     """The boundary is a C ABI, not a C++ or torch one: a strict-C99 translation unit that includes the header compiles
     without warnings, links against the in-tree library alone and gets status codes + messages back."""
+    import ctypes
     import shutil
     import subprocess
 
@@ -102,5 +124,75 @@ def test_header_is_plain_c_and_links_from_a_c_program(lib, tmp_path):
     assert r.returncode == 0, r.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
-    status, message = run.stdout.strip().split("|", 1)
+    first, *layout = run.stdout.strip().splitlines()
+    status, message = first.split("|", 1)
     assert int(status) == 3 and "no CPU fallback" in message  # TSFMX_ERR_NO_DEVICE
+    # struct layouts as the C compiler sees them == the ctypes Structures of the binding, field by field
+    structs = {"tsfmx_gemm_segment": _lib.GemmSegment, "tsfmx_gemm_args": _lib.GemmArgs,
+               "tsfmx_timesfm_layer": _lib.TimesfmLayer, "tsfmx_timesfm_stack": _lib.TimesfmStack}
+    seen = 0
+    for line in layout:
+        key, value = line.split()
+        cname, field = key.split(".")
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if field == "sizeof" else getattr(cls, field).offset
+        assert int(value) == want, (key, int(value), want)
+        seen += 1
+    assert seen == 4 + 5 + 22 + 11 + 9
+
+
+def _prototypes(text: str, definitions: bool = False):
+    """(name -> (return kind, [argument kinds])) of every `tsfmx_*` function declared or defined in C / CUDA source."""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    out = {}
+    prefix = r'extern\s+"C"\s+' if definitions else r"(?<![\w\"])"
+    for ret, name, args in re.findall(
+            prefix + r"((?:const\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\**)\s*\b(tsfmx_[a-z0-9_]+)\s*\(([^;{)]*)\)\s*[;{]", text):
+        kinds = []
+        args = " ".join(args.split())
+        if args not in ("", "void"):
+            for a in args.split(","):
+                a = a.strip()
+                ctype = a[: a.rfind(" ")] if " " in a and not a.endswith("*") else a  # drop the parameter name
+                if "*" in a:
+                    ctype = a[: a.rfind("*") + 1]
+                kinds.append(_kind(ctype))
+        out[name] = (_kind(ret), kinds)
+    return out
+
+
+def _kind(ctype: str) -> str:
+    c = ctype.replace("const", "").replace(" ", "")
+    if c.endswith("*"):
+        return "char*" if c == "char*" else "ptr"
+    return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "float": "f32", "size_t": "u64", "uint64_t": "u64"}[c]  # LP64
+
+
+def _ctypes_kind(t) -> str:
+    import ctypes
+
+    if t in (ctypes.c_void_p,) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+        return "ptr"
+    return {ctypes.c_char_p: "char*", ctypes.c_int32: "i32", ctypes.c_int64: "i64", ctypes.c_float: "f32",
+            ctypes.c_size_t: "u64", ctypes.c_uint64: "u64"}[t]
+
+
+def test_binding_and_definitions_agree_with_the_header_argument_by_argument():
+    """Width and order of every argument: header declaration == ctypes signature == the `extern "C"` definition in csrc.
+    (A 32- vs 64-bit slip in a binding does not fail at call time; it reads a garbage size.)"""
+    header = _prototypes((ROOT / "include" / "tsfmx_b200.h").read_text())
+    assert len(header) == len(_lib.SIGNATURES)
+    for name, (ret, kinds) in header.items():
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert _ctypes_kind(restype) == ret, name
+        assert [_ctypes_kind(t) for t in argtypes] == kinds, name
+    defined = {}
+    for src in sorted((ROOT / "multimodal-timesfm_b200" / "csrc").glob("*.cu")):
+        for name, proto in _prototypes(src.read_text(), definitions=True).items():
+            assert name in header, f"{src.name} defines {name}, which the header does not declare"
+            defined[name] = proto
+    missing = sorted(set(header) - set(defined))
+    assert not missing, missing
+    for name, proto in defined.items():
+        assert proto == header[name], (name, proto, header[name])
