@@ -196,3 +196,59 @@ def test_binding_and_definitions_agree_with_the_header_argument_by_argument():
     assert not missing, missing
     for name, proto in defined.items():
         assert proto == header[name], (name, proto, header[name])
+
+
+_NO_ARGUMENT_CHECKS = {  # version / accounting queries and test hooks: nothing to refuse
+    "tsfmx_abi_version", "tsfmx_last_error", "tsfmx_launch_count", "tsfmx_sizeof_gemm_args", "tsfmx_device_check",
+    "tsfmx_gemm_set_cta_group", "tsfmx_gemm_set_split_k", "tsfmx_attention_force_simt", "tsfmx_tune",
+}
+
+
+def test_every_compute_entry_point_refuses_null_arguments_with_a_status(lib):
+    """The ABI never throws and never crashes: all-NULL / all-zero arguments come back as TSFMX_ERR_INVALID_ARGUMENT with
+    a message, before any device work (SURVEY 8(b) error conventions: errors are raised before any compute)."""
+    import ctypes
+
+    def zero(t):
+        if t is ctypes.c_float:
+            return 0.0
+        return None if t in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(t, ctypes._Pointer) else 0
+
+    launches = lib.tsfmx_launch_count()
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        if name in _NO_ARGUMENT_CHECKS:
+            continue
+        status = getattr(lib, name)(*[zero(t) for t in argtypes])
+        if name == "tsfmx_timesfm_stack_workspace_bytes":
+            assert status == 0  # size query: 0 bytes for a bad table
+        else:
+            assert status == 1, (name, status, lib.tsfmx_last_error())  # TSFMX_ERR_INVALID_ARGUMENT
+        assert lib.tsfmx_last_error(), name
+    assert lib.tsfmx_launch_count() == launches
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_argument_errors_come_before_device_errors(lib):
+    """Shape / dtype / alignment errors are reported as such even on a machine without a GPU; well-formed calls fail with
+    a device status (never a crash, never a silent success)."""
+    import ctypes
+
+    p = 0x10000  # a well-aligned fake device address: never dereferenced on the host
+    assert lib.tsfmx_rmsnorm(p, 8, 1000, p, 1e-6, 1, p, None) == 4  # TSFMX_ERR_UNSUPPORTED
+    assert b"cols=1000 unsupported" in lib.tsfmx_last_error()
+    assert lib.tsfmx_rmsnorm(p + 4, 8, 1280, p, 1e-6, 1, p, None) == 1
+    assert b"16-byte aligned" in lib.tsfmx_last_error()
+    assert lib.tsfmx_norm_residual_norm(p, 7, p, 8, 1280, p, p, 1e-6, p, 1, p, None) == 1
+    # the reference's ValueError for ctx % patch_len != 0 (tsfmx/tsfm/timesfm.py:48-49) exists at the C level too
+    assert lib.tsfmx_timesfm_patchify_norm(p, p, 4, 500, 32, 0, p, p, p, p, p, None) == 1
+    assert b"must be divisible by patch length" in lib.tsfmx_last_error()
+    args = _lib.GemmArgs()
+    args.m, args.n, args.num_segments = 128, 128, 1
+    args.seg[0].a, args.seg[0].b, args.seg[0].lda, args.seg[0].ldb, args.seg[0].k = p, p, 64, 64, 60
+    args.d, args.ldd = p, 128
+    assert lib.tsfmx_gemm(ctypes.byref(args), None) == 1
+    assert b"multiple of 64" in lib.tsfmx_last_error()
+    args.seg[0].k = 64
+    assert lib.tsfmx_gemm(ctypes.byref(args), None) in (2, 3)  # TSFMX_ERR_CUDA / TSFMX_ERR_NO_DEVICE
+    assert lib.tsfmx_rmsnorm(p, 8, 1280, p, 1e-6, 1, p, None) in (2, 3)
+    assert lib.tsfmx_timesfm_patchify_norm(p, p, 4, 512, 32, 0, p, p, p, p, p, None) in (2, 3)
