@@ -252,3 +252,24 @@ def test_argument_errors_come_before_device_errors(lib):
     assert lib.tsfmx_gemm(ctypes.byref(args), None) in (2, 3)  # TSFMX_ERR_CUDA / TSFMX_ERR_NO_DEVICE
     assert lib.tsfmx_rmsnorm(p, 8, 1280, p, 1e-6, 1, p, None) in (2, 3)
     assert lib.tsfmx_timesfm_patchify_norm(p, p, 4, 512, 32, 0, p, p, p, p, p, None) in (2, 3)
+
+
+def test_stack_workspace_query_is_pure_host_arithmetic(lib):
+    """the caller sizes the scratch of the whole-stack call with a query that needs no device."""
+    import ctypes
+
+    layers = (_lib.TimesfmLayer * 50)()
+    table = _lib.TimesfmStack(num_layers=50, model_dims=1280, num_heads=16, head_dim=80, ff_dims=1280,
+                              precision=_lib.PREC_BF16, eps=1e-6, layers=layers)
+    rows = 4096 * 16
+    # xn, attn (operands) + qkv, a (GEMM outputs) + h, all bf16 in throughput mode: 7 x rows x 1280 x 2 bytes
+    assert lib.tsfmx_timesfm_stack_workspace_bytes(ctypes.byref(table), 4096, 16) == 7 * rows * 1280 * 2
+    table.precision = _lib.PREC_BF16X3  # split operands and fp32 intermediates: twice the bytes
+    assert lib.tsfmx_timesfm_stack_workspace_bytes(ctypes.byref(table), 4096, 16) == 7 * rows * 1280 * 4
+    table.precision = _lib.PREC_BF16
+    small = lib.tsfmx_timesfm_stack_workspace_bytes(ctypes.byref(table), 3, 5)  # every buffer rounded up to 256 bytes
+    assert small % 256 == 0 and small >= 7 * 15 * 1280 * 2
+    assert lib.tsfmx_timesfm_stack_workspace_bytes(ctypes.byref(table), 0, 16) == 0
+    table.head_dim = 64  # heads x head_dim != model_dims
+    assert lib.tsfmx_timesfm_stack_workspace_bytes(ctypes.byref(table), 4096, 16) == 0
+    assert b"heads x head_dim" in lib.tsfmx_last_error()
