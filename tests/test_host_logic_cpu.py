@@ -193,3 +193,27 @@ def test_wgrad_takes_token_major_operands_only_when_they_qualify():
     assert not ops._token_major_ok(x.float(), 1280)
     assert not ops._token_major_ok(torch.zeros(64, 2560, dtype=torch.bfloat16), 1280)  # split storage [hi | lo]
     assert not ops._token_major_ok(torch.zeros(64, 36, dtype=torch.bfloat16)[:, :32], 32)  # row stride not a multiple of 8
+
+
+def test_the_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may import it (a product path routed through the CPU
+    restatement would void every parity claim), and the package imports neither triton nor torch.compile."""
+    import ast
+    from pathlib import Path
+
+    pkg = Path(__file__).resolve().parent.parent / "multimodal-timesfm_b200" / "tsfmx_b200"
+    files = sorted(pkg.rglob("*.py"))
+    assert len(files) >= 15
+    for path in files:
+        tree = ast.parse(path.read_text(), str(path))
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            for name in names:
+                root = name.split(".")[0]
+                assert root not in ("oracle", "triton", "tilelang"), f"{path.name} imports {name}"
+            if isinstance(node, ast.Attribute) and node.attr == "compile" and isinstance(node.value, ast.Name):
+                assert node.value.id != "torch", f"{path.name} uses torch.compile"
